@@ -1,0 +1,178 @@
+/*
+ * virconv_b200 — C ABI of the B200 (sm_100a) sparse-convolution hot path of VirConv.
+ *
+ * The reference (hailanyi/VirConv) has no FFI of its own for this path: every sparse operator is a
+ * call into the third-party Python package spconv 2.1 (`import spconv.pytorch as spconv`,
+ * pcdet/utils/spconv_utils.py:33-36).  Each entry point below therefore cites the reference CALL
+ * SITE (file:line under /root/reference) whose spconv work it replaces; the Python classes in
+ * `virconv_b200/spconv_compat.py` re-create the spconv.pytorch surface on top of these calls
+ * (binding shown in INTEGRATION.md).
+ *
+ * Contract:
+ *   - plain pointers + sizes; all pointers are DEVICE pointers unless marked "host";
+ *   - the caller (PyTorch) owns every input, output and workspace buffer; the library never
+ *     allocates, frees or retains a pointer past the call;
+ *   - all work is enqueued on the cudaStream_t passed as `stream`; no hidden device sync,
+ *     re-entrant, one host thread per device;
+ *   - return 0 on success, <0 on error (message: vc_last_error(), thread-local); no exceptions,
+ *     no exit();
+ *   - row-major everywhere: features [N, C]; indices [N, 1+ndim] int32 = (batch, z, y, x) or
+ *     (batch, u, v); conv weight in spconv-2.x layout [C_out, K, C_in] with K = prod(kernel) and
+ *     offsets numbered z-major (k = (kz*Ky+ky)*Kx+kx), see detector3d_template.py:358-370;
+ *   - a rulebook is a NEIGHBOUR TABLE nbr[K, N_out] int32: input row feeding output row o through
+ *     kernel offset k, or -1 (canonical form; oracle/rulebook.py is the definition).
+ */
+#ifndef VIRCONV_B200_H
+#define VIRCONV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VC_OK 0
+#define VC_ERR_INVALID (-1)      /* bad argument */
+#define VC_ERR_CUDA (-2)         /* CUDA runtime error (launch / config) */
+#define VC_ERR_WORKSPACE (-3)    /* workspace too small */
+#define VC_ERR_UNSUPPORTED (-4)  /* channel count / ndim not compiled in */
+
+#define VC_MAX_NDIM 3
+#define VC_TILE_ROWS 128         /* output rows per CTA tile in the conv kernels (BN partial granularity) */
+
+typedef void* vc_stream_t;       /* cudaStream_t */
+
+int vc_version(void);
+const char* vc_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Rulebooks.  Replaces spconv `ops.get_indice_pairs`, reached from every conv call site:
+ * spconv_backbone.py:89 (SubMConv3d), :113 (SubMConv2d on image indices built at :217-222),
+ * :92-93 and :563-564 (SparseConv3d).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Submanifold: output rows == input rows.  Hash table of linearised coordinates (lowest row wins on
+ * duplicate coordinates), 1 thread per (row, offset) probe, per-offset pair counts through a
+ * shared-memory histogram.  ws >= vc_subm_rulebook_ws_bytes(n). */
+size_t vc_subm_rulebook_ws_bytes(int n);
+int vc_subm_rulebook(const int32_t* indices, int n, int ndim, int batch_size,
+                     const int32_t* spatial_shape /*host[ndim]*/, const int32_t* ksize /*host[ndim]*/,
+                     const int32_t* dilation /*host[ndim]*/, int32_t* nbr /*[K,n]*/,
+                     int32_t* pair_num /*[K], may be NULL*/, void* ws, size_t ws_bytes, vc_stream_t stream);
+
+/* Regular (strided) sparse conv, two phases because the output row count is data dependent.
+ *   count: marks every reachable output cell in a bitmap over the OUTPUT grid and ranks it (prefix sum
+ *          of popcounts) -> *n_out_dev; also writes out_shape (host).  Output rows are therefore
+ *          ordered by ascending linear index, batch most significant (voxel_query_utils.py:85-91 needs
+ *          batch-contiguous rows).
+ *   fill : after the caller has read n_out and allocated, emits out_indices, nbr_fwd[K,n_out],
+ *          nbr_bwd[K,n] (output row per input row; the dgrad table) and pair counts.
+ * The same `ws` (>= vc_conv_rulebook_ws_bytes) must be passed to both calls, untouched in between. */
+size_t vc_conv_rulebook_ws_bytes(int ndim, int batch_size, const int32_t* out_shape /*host[ndim]*/);
+int vc_conv_out_shape(int ndim, const int32_t* spatial_shape, const int32_t* ksize, const int32_t* stride,
+                      const int32_t* padding, const int32_t* dilation, int32_t* out_shape /*host[ndim]*/);
+int vc_conv_rulebook_count(const int32_t* indices, int n, int ndim, int batch_size,
+                           const int32_t* spatial_shape, const int32_t* ksize, const int32_t* stride,
+                           const int32_t* padding, const int32_t* dilation,
+                           int32_t* n_out_dev /*device int32[1]*/, void* ws, size_t ws_bytes, vc_stream_t stream);
+int vc_conv_rulebook_fill(const int32_t* indices, int n, int ndim, int batch_size,
+                          const int32_t* spatial_shape, const int32_t* ksize, const int32_t* stride,
+                          const int32_t* padding, const int32_t* dilation, int n_out,
+                          int32_t* out_indices /*[n_out,1+ndim]*/, int32_t* nbr_fwd /*[K,n_out]*/,
+                          int32_t* nbr_bwd /*[K,n]*/, int32_t* pair_num /*[K], may be NULL*/,
+                          void* ws, size_t ws_bytes, vc_stream_t stream);
+
+/* spconv-style `indice_pairs [2,K,n]` (-1 padded) + `indice_pair_num [K]` from a neighbour table, each
+ * offset's pairs ordered by ascending output row.  Only for API parity / tests; the conv kernels
+ * consume the neighbour table directly. */
+int vc_pairs_from_nbr(const int32_t* nbr, int K, int n, int32_t* pairs /*[2,K,n]*/,
+                      int32_t* pair_num /*[K]*/, vc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Convolution (output-stationary implicit gather-GEMM).  Replaces spconv `ops.indice_conv` and its
+ * autograd backward for the same call sites.  fp32 in / fp32 accumulate / fp32 out.
+ * Supported channel counts: cin, cout in {8,16,32,64}.
+ * fwd / dgrad take a workspace of vc_conv_ws_bytes(cin, cout, K) for the re-laid-out weights
+ * ([K, C_in, C_out] for forward, [K, C_out, C_in] for dgrad), rebuilt on every call.
+ * ---------------------------------------------------------------------------------------------- */
+size_t vc_conv_ws_bytes(int cin, int cout, int K);
+
+/* out[o, co] = sum_k sum_ci in[nbr[k,o], ci] * w[co, k, ci].
+ * bn_partial (may be NULL): [ceil(n_out/VC_TILE_ROWS), 2, cout] per-tile channel sums (sum x, sum x^2)
+ * of the output, for the BatchNorm1d that follows every conv (spconv_backbone.py:101-105). */
+int vc_conv_fwd_f32(const float* in, const float* w, const int32_t* nbr, float* out, int n_out, int cin,
+                    int cout, int K, float* bn_partial, void* ws, size_t ws_bytes, vc_stream_t stream);
+
+/* din[i, ci] = sum_k sum_co dout[nbr_t[k,i], co] * w[co, kk, ci],  kk = mirror ? K-1-k : k.
+ * nbr_t is the table indexed by INPUT row: the rulebook's nbr_bwd for a regular conv, or the
+ * submanifold table itself with mirror=1 (valid when coordinates are unique). */
+int vc_conv_dgrad_f32(const float* dout, const float* w, const int32_t* nbr_t, float* din, int n_in, int cin,
+                      int cout, int K, int mirror, void* ws, size_t ws_bytes, vc_stream_t stream);
+
+/* din[nbr[k,o], :] += dout[o, :] @ w[:, k, :]  with float atomics; din must be zeroed by the caller.
+ * Needed for the 2-D image branch, whose table is many-to-one (duplicate pixel coordinates). */
+int vc_conv_dgrad_scatter_f32(const float* dout, const float* w, const int32_t* nbr, float* din, int n_out,
+                              int cin, int cout, int K, void* ws, size_t ws_bytes, vc_stream_t stream);
+
+/* dw[co, k, ci] = sum_o in[nbr[k,o], ci] * dout[o, co].  Deterministic two-pass reduction.
+ * ws >= vc_conv_wgrad_ws_bytes(n_out, cin, cout, K). */
+size_t vc_conv_wgrad_ws_bytes(int n_out, int cin, int cout, int K);
+int vc_conv_wgrad_f32(const float* in, const float* dout, const int32_t* nbr, float* dw, int n_out, int cin,
+                      int cout, int K, void* ws, size_t ws_bytes, vc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * BatchNorm1d(eps, momentum) + ReLU over the active rows.  Replaces the `norm_fn(out_channels)`,
+ * `nn.ReLU()` members of every `spconv.SparseSequential` (spconv_backbone.py:101-105, :160, :561-567).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Train mode: reduce conv partials -> batch mean / biased var; scale = gamma*invstd,
+ * shift = beta - mean*scale; running stats updated in place with the unbiased variance
+ * (torch.nn.BatchNorm1d semantics).  save_mean/save_invstd [c] are kept for backward. */
+int vc_bn_train_finalize(const float* bn_partial, int n_tiles, int n_rows, int c, const float* gamma,
+                         const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                         float* scale, float* shift, float* save_mean, float* save_invstd, vc_stream_t stream);
+/* Eval mode: scale/shift from the running statistics. */
+int vc_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean,
+                      const float* running_var, float eps, int c, float* scale, float* shift,
+                      float* save_mean, float* save_invstd, vc_stream_t stream);
+/* y = max(x*scale + shift, 0) (relu != 0) — in place allowed. */
+int vc_affine_relu_f32(const float* x, const float* scale, const float* shift, float* y, int n, int c, int relu,
+                       vc_stream_t stream);
+/* Backward of y = relu(gamma*(x-mean)*invstd + beta):
+ *   g = dy * (y > 0); dbeta = sum g; dgamma = sum g*xhat;
+ *   train: dx = gamma*invstd*(g - dbeta/n - xhat*dgamma/n);   eval: dx = gamma*invstd*g.
+ * ws >= vc_bn_bwd_ws_bytes(n, c). */
+size_t vc_bn_bwd_ws_bytes(int n, int c);
+int vc_bn_relu_bwd_f32(const float* dy, const float* x, const float* y, const float* gamma,
+                       const float* save_mean, const float* save_invstd, float* dx, float* dgamma, float* dbeta,
+                       int n, int c, int training, void* ws, size_t ws_bytes, vc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Voxel index -> image pixel index.  Replaces `index2uv` + `index2points` + the per-sample
+ * `X_TRANS.backward_with_param` / `Calibration.lidar_to_rect_cuda` / `rect_to_img_cuda` loop
+ * (spconv_backbone.py:8-24, :54-83; X_transform.py:139-154; calibration_kitti.py:120-153).
+ * params: [batch_size, 28] float32 per sample:
+ *   [0..11]  M = V2C^T @ R0^T  (4x3, row major)        [12..19] first two columns of P2^T (4x2)
+ *   [20] has_transform  [21] scale  [22] flip  [23] cos(-rot)  [24] sin(-rot)  [25..27] unused
+ * grid: 6 floats (vx, vy, vz, min_x, min_y, min_z) = voxel size * stride and range min + half voxel.
+ * uv_out [n,3] int32 = (batch, clamp(u,0,u_max-1)/stride, clamp(v,0,v_max-1)/stride).
+ * ---------------------------------------------------------------------------------------------- */
+int vc_index2uv(const int32_t* indices /*[n,4] b,z,y,x*/, int n, int batch_size, const float* params,
+                const float* grid /*host[6]*/, int stride, int u_max, int v_max, int32_t* uv_out,
+                vc_stream_t stream);
+
+/* `SparseConvTensor.dense()` (height_compression.py:29): out [B, C, *shape] must be zeroed by the caller. */
+int vc_dense_f32(const float* features, const int32_t* indices, int n, int c, int ndim, int batch_size,
+                 const int32_t* spatial_shape, float* out, vc_stream_t stream);
+/* Gradient of dense(): dfeatures[n, c] = dout[b, c, coords]. */
+int vc_dense_bwd_f32(const float* dout, const int32_t* indices, int n, int c, int ndim, int batch_size,
+                     const int32_t* spatial_shape, float* dfeatures, vc_stream_t stream);
+
+/* Row gather for StVD layer discard (spconv_backbone.py:134-147): out[r] = in[rows[r]]. */
+int vc_gather_rows(const void* in, const int32_t* rows, void* out, int n_rows, int row_bytes, vc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIRCONV_B200_H */

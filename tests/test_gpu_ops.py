@@ -1,0 +1,306 @@
+"""GPU parity tests, operator level: every C-ABI kernel against the CPU oracle on the same seeded inputs.
+Integer / index work must be bit exact; fp32 features within 1e-4 (max|d| / max|ref|, BASELINE north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import rulebook as orb
+from oracle import spconv_cpu as osp
+from oracle import index2uv as ouv
+from oracle.testing import rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _dev():
+    return torch.device('cuda:0')
+
+
+def _coords(rng, n, batch, shape, unique=True):
+    cols = [rng.integers(0, batch, n)] + [rng.integers(0, s, n) for s in shape]
+    c = np.stack(cols, 1).astype(np.int32)
+    if unique:
+        c = np.unique(c, axis=0)
+        rng.shuffle(c)
+    return np.ascontiguousarray(c)
+
+
+# ---------------------------------------------------------------------------------------------- rulebooks
+@pytest.mark.parametrize('n,batch,shape', [(0, 1, [5, 6, 7]), (1, 1, [3, 3, 3]), (700, 2, [9, 10, 11]),
+                                           (20000, 2, [41, 160, 141]), (3000, 3, [81, 1600, 1408])])
+def test_subm3d_rulebook_bit_exact(lib_built, n, batch, shape):
+    from virconv_b200 import ops
+    rng = np.random.default_rng(n + 1)
+    c = _coords(rng, n, batch, shape) if n else np.zeros((0, 4), np.int32)
+    rb = ops.build_subm_rulebook(torch.from_numpy(c).to(_dev()), batch, shape, 3)
+    want = orb.subm_rulebook(c, shape, 3)
+    assert np.array_equal(rb.nbr.cpu().numpy(), want)
+    assert np.array_equal(rb.pair_num.cpu().numpy(), (want >= 0).sum(1))
+    pairs, num = rb.indice_pairs()
+    wp, wn = orb.pairs_from_nbr(want)
+    assert np.array_equal(num.cpu().numpy(), wn)
+    if c.shape[0]:
+        assert np.array_equal(pairs.cpu().numpy(), wp)
+
+
+@pytest.mark.parametrize('n,shape', [(500, [12, 9]), (30000, [1600, 600]), (30000, [175, 75])])
+def test_subm2d_rulebook_with_duplicates(lib_built, n, shape):
+    from virconv_b200 import ops
+    rng = np.random.default_rng(n)
+    c = _coords(rng, n, 2, shape, unique=False)
+    rb = ops.build_subm_rulebook(torch.from_numpy(c).to(_dev()), 2, shape, 3)
+    want = orb.subm_rulebook(c, shape, 3)
+    assert not rb.unique_coords
+    assert np.array_equal(rb.nbr.cpu().numpy(), want)   # lowest row index wins on duplicate pixels
+
+
+GEOS = [dict(ksize=3, stride=2, padding=1), dict(ksize=3, stride=2, padding=(0, 1, 1)),
+        dict(ksize=(3, 1, 1), stride=(2, 1, 1), padding=0), dict(ksize=3, stride=1, padding=1),
+        dict(ksize=(3, 3, 3), stride=(2, 2, 2), padding=0), dict(ksize=2, stride=2, padding=0)]
+
+
+@pytest.mark.parametrize('geo', GEOS)
+@pytest.mark.parametrize('n,batch,shape', [(1, 1, [5, 5, 5]), (900, 2, [9, 10, 11]), (25000, 2, [81, 400, 352])])
+def test_conv_rulebook_bit_exact(lib_built, geo, n, batch, shape):
+    from virconv_b200 import ops
+    rng = np.random.default_rng(n)
+    c = _coords(rng, n, batch, shape)
+    rb = ops.build_conv_rulebook(torch.from_numpy(c).to(_dev()), batch, shape, geo['ksize'], geo['stride'],
+                                 geo['padding'])
+    oi, osh, nf, nb = orb.conv_rulebook(c, shape, geo['ksize'], geo['stride'], geo['padding'])
+    assert rb.out_shape == osh
+    assert np.array_equal(rb.out_indices.cpu().numpy(), oi)           # ascending linear index, batch major
+    assert np.array_equal(rb.nbr.cpu().numpy(), nf)
+    assert np.array_equal(rb.nbr_bwd.cpu().numpy(), nb)
+    assert np.array_equal(rb.pair_num.cpu().numpy(), (nf >= 0).sum(1))
+    assert np.all(np.diff(rb.out_indices[:, 0].cpu().numpy()) >= 0)   # batch-contiguous rows
+
+
+def test_virconv_shape_chain(lib_built):
+    """z 81->41->21->10->4, y 1600->800->400->200, x 1408->704->352->176."""
+    from virconv_b200 import _lib
+    lib = _lib.load()
+    shape = [81, 1600, 1408]
+    for pad in [(1, 1, 1), (1, 1, 1), (0, 1, 1)]:
+        o = _lib.host_i32([0, 0, 0])
+        assert lib.vc_conv_out_shape(3, _lib.host_i32(shape), _lib.host_i32([3, 3, 3]), _lib.host_i32([2, 2, 2]),
+                                     _lib.host_i32(pad), _lib.host_i32([1, 1, 1]), o) == 0
+        shape = list(o)
+    assert shape == [10, 200, 176]
+    o = _lib.host_i32([0, 0, 0])
+    lib.vc_conv_out_shape(3, _lib.host_i32(shape), _lib.host_i32([3, 1, 1]), _lib.host_i32([2, 1, 1]),
+                          _lib.host_i32([0, 0, 0]), _lib.host_i32([1, 1, 1]), o)
+    assert list(o) == [4, 200, 176]
+
+
+# ---------------------------------------------------------------------------------------------- convolution
+CH = [(8, 8), (16, 16), (16, 32), (32, 16), (32, 32), (32, 64), (64, 32), (64, 64), (8, 16), (64, 8)]
+
+
+def _oracle_conv(feats, weight, nbr, n_out, subm, dout):
+    f = feats.clone().requires_grad_(True)
+    w = weight.clone().requires_grad_(True)
+    out = osp.native_conv(f, w.reshape(w.shape[0], -1, w.shape[-1]), torch.from_numpy(nbr).long(), n_out, subm)
+    out.backward(dout)
+    return out.detach(), f.grad, w.grad
+
+
+@pytest.mark.parametrize('cin,cout', CH)
+def test_subm3d_conv_fwd_bwd(lib_built, cin, cout):
+    from virconv_b200 import ops
+    rng = np.random.default_rng(cin * 100 + cout)
+    shape = [12, 40, 40]
+    c = _coords(rng, 6000, 2, shape)
+    n = c.shape[0]
+    torch.manual_seed(cin + cout)
+    feats = torch.randn(n, cin)
+    weight = torch.randn(cout, 3, 3, 3, cin) * 0.1
+    dout = torch.randn(n, cout)
+    rb = ops.build_subm_rulebook(torch.from_numpy(c).to(_dev()), 2, shape, 3)
+    f = feats.to(_dev()).requires_grad_(True)
+    w = weight.to(_dev()).requires_grad_(True)
+    out = ops.SparseConvFn.apply(f, w, rb)
+    out.backward(dout.to(_dev()))
+    ro, rdf, rdw = _oracle_conv(feats, weight, orb.subm_rulebook(c, shape, 3), n, True, dout)
+    assert rel_err(out.detach().cpu(), ro) < TOL
+    assert rel_err(f.grad.cpu(), rdf) < TOL
+    assert rel_err(w.grad.cpu(), rdw) < TOL
+
+
+@pytest.mark.parametrize('cin,cout', [(16, 32), (32, 64), (64, 64), (8, 8)])
+@pytest.mark.parametrize('geo', GEOS[:3])
+def test_strided_conv_fwd_bwd(lib_built, cin, cout, geo):
+    from virconv_b200 import ops
+    rng = np.random.default_rng(cin + cout)
+    shape = [21, 40, 36]
+    c = _coords(rng, 5000, 2, shape)
+    n = c.shape[0]
+    torch.manual_seed(1)
+    ks = geo['ksize'] if isinstance(geo['ksize'], tuple) else (geo['ksize'],) * 3
+    feats = torch.randn(n, cin)
+    weight = torch.randn(cout, *ks, cin) * 0.1
+    rb = ops.build_conv_rulebook(torch.from_numpy(c).to(_dev()), 2, shape, geo['ksize'], geo['stride'], geo['padding'])
+    oi, osh, nf, nb = orb.conv_rulebook(c, shape, geo['ksize'], geo['stride'], geo['padding'])
+    dout = torch.randn(oi.shape[0], cout)
+    f = feats.to(_dev()).requires_grad_(True)
+    w = weight.to(_dev()).requires_grad_(True)
+    out = ops.SparseConvFn.apply(f, w, rb)
+    out.backward(dout.to(_dev()))
+    ro, rdf, rdw = _oracle_conv(feats, weight, nf, oi.shape[0], False, dout)
+    assert rel_err(out.detach().cpu(), ro) < TOL
+    assert rel_err(f.grad.cpu(), rdf) < TOL
+    assert rel_err(w.grad.cpu(), rdw) < TOL
+
+
+@pytest.mark.parametrize('c', [8, 16, 32])
+def test_subm2d_conv_duplicates_fwd_bwd(lib_built, c):
+    """image branch: many rows per pixel; dgrad goes through the scatter kernel."""
+    from virconv_b200 import ops
+    rng = np.random.default_rng(c)
+    shape = [60, 40]
+    co = _coords(rng, 7000, 2, shape, unique=False)
+    n = co.shape[0]
+    torch.manual_seed(c)
+    feats, weight, dout = torch.randn(n, c), torch.randn(c, 3, 3, c) * 0.1, torch.randn(n, c)
+    rb = ops.build_subm_rulebook(torch.from_numpy(co).to(_dev()), 2, shape, 3)
+    f = feats.to(_dev()).requires_grad_(True)
+    w = weight.to(_dev()).requires_grad_(True)
+    out = ops.SparseConvFn.apply(f, w, rb)
+    out.backward(dout.to(_dev()))
+    ro, rdf, rdw = _oracle_conv(feats, weight, orb.subm_rulebook(co, shape, 3), n, True, dout)
+    assert rel_err(out.detach().cpu(), ro) < TOL
+    assert rel_err(f.grad.cpu(), rdf) < TOL
+    assert rel_err(w.grad.cpu(), rdw) < TOL
+
+
+def test_conv_against_dense_conv3d(lib_built):
+    """Ground truth independent of the oracle: brute-force dense torch conv3d on a tiny grid."""
+    import torch.nn.functional as F
+    from virconv_b200 import spconv_compat as sp
+    rng = np.random.default_rng(3)
+    shape, B = [9, 10, 11], 2
+    c = _coords(rng, 500, B, shape)
+    feats = torch.randn(c.shape[0], 16)
+    x = sp.SparseConvTensor(feats.to(_dev()), torch.from_numpy(c).to(_dev()), shape, B)
+    dense_in = x.dense().cpu()
+    for cls, kw, dkw in [(sp.SubMConv3d, dict(kernel_size=3), dict(padding=1)),
+                         (sp.SparseConv3d, dict(kernel_size=3, stride=2, padding=1), dict(stride=2, padding=1)),
+                         (sp.SparseConv3d, dict(kernel_size=(3, 1, 1), stride=(2, 1, 1), padding=0),
+                          dict(stride=(2, 1, 1), padding=0))]:
+        m = cls(16, 32, bias=False, **kw).to(_dev())
+        y = m(x)
+        ref = F.conv3d(dense_in, m.weight.detach().cpu().permute(0, 4, 1, 2, 3), **dkw)
+        if m.subm:
+            got = y.features.detach().cpu()
+            want = ref[c[:, 0], :, c[:, 1], c[:, 2], c[:, 3]]
+            assert rel_err(got, want) < TOL
+        else:
+            assert list(y.dense().shape) == list(ref.shape)
+            assert rel_err(y.dense().detach().cpu(), ref) < TOL
+
+
+def test_empty_and_tail_tiles(lib_built):
+    from virconv_b200 import ops
+    shape = [5, 6, 7]
+    for n in (1, 127, 128, 129):
+        rng = np.random.default_rng(n)
+        c = _coords(rng, n, 1, shape)
+        rb = ops.build_subm_rulebook(torch.from_numpy(c).to(_dev()), 1, shape, 3)
+        feats, weight = torch.randn(c.shape[0], 8), torch.randn(16, 3, 3, 3, 8)
+        out, _ = ops.conv_forward(feats.to(_dev()), weight.to(_dev()), rb)
+        ro = osp.native_conv(feats, weight.reshape(16, 27, 8), torch.from_numpy(orb.subm_rulebook(c, shape, 3)).long(),
+                             c.shape[0], True)
+        assert rel_err(out.cpu(), ro) < TOL
+
+
+# ---------------------------------------------------------------------------------------------- BN + ReLU
+@pytest.mark.parametrize('training', [True, False])
+@pytest.mark.parametrize('cin,cout', [(8, 8), (32, 16), (64, 64)])
+def test_conv_bn_relu_fused(lib_built, training, cin, cout):
+    from virconv_b200 import ops
+    rng = np.random.default_rng(5)
+    shape = [12, 30, 30]
+    c = _coords(rng, 5000, 2, shape)
+    n = c.shape[0]
+    torch.manual_seed(0)
+    feats, weight, dy = torch.randn(n, cin), torch.randn(cout, 3, 3, 3, cin) * 0.1, torch.randn(n, cout)
+    bn = torch.nn.BatchNorm1d(cout, eps=1e-3, momentum=0.01)
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.normal_(0, 0.1)
+        bn.running_mean.normal_(0, 0.1)
+        bn.running_var.uniform_(0.5, 1.5)
+    bn.train(training)
+    import copy
+    bn_g = copy.deepcopy(bn).to(_dev())
+    rb = ops.build_subm_rulebook(torch.from_numpy(c).to(_dev()), 2, shape, 3)
+    f = feats.to(_dev()).requires_grad_(True)
+    w = weight.to(_dev()).requires_grad_(True)
+    y = ops.ConvBNReLUFn.apply(f, w, bn_g.weight, bn_g.bias, bn_g.running_mean, bn_g.running_var, rb, training, 1e-3,
+                               0.01)
+    y.backward(dy.to(_dev()))
+    fr = feats.clone().requires_grad_(True)
+    wr = weight.clone().requires_grad_(True)
+    xr = osp.native_conv(fr, wr.reshape(cout, 27, cin), torch.from_numpy(orb.subm_rulebook(c, shape, 3)).long(), n, True)
+    yr = torch.relu(bn(xr))
+    yr.backward(dy)
+    assert rel_err(y.detach().cpu(), yr.detach()) < TOL
+    assert rel_err(f.grad.cpu(), fr.grad) < 5e-4
+    assert rel_err(w.grad.cpu(), wr.grad) < 5e-4
+    assert rel_err(bn_g.weight.grad.cpu(), bn.weight.grad) < 5e-4
+    assert rel_err(bn_g.bias.grad.cpu(), bn.bias.grad) < 5e-4
+    assert rel_err(bn_g.running_mean.cpu(), bn.running_mean) < 1e-5
+    assert rel_err(bn_g.running_var.cpu(), bn.running_var) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------- index2uv
+def test_index2uv_bit_exact_and_golden(lib_built):
+    import os
+    from virconv_b200 import ops, scenes
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'index2uv.npz'))
+    for ci in range(int(g['n_cases'])):
+        idx, want, stride, aug = g[f'idx{ci}'], g[f'uv{ci}'], int(g[f'stride{ci}']), g[f'aug{ci}']
+        aug = aug if aug.shape[0] else None
+        calibs = [scenes.Calib(), scenes.Calib()]
+        params = ops.projection_params(calibs, aug, 2, _dev())
+        uv = ops.index2uv(torch.from_numpy(idx).to(_dev()), 2, params, stride).cpu().numpy()
+        assert np.array_equal(uv, ouv.index2uv(idx, 2, calibs, stride, aug))   # oracle: bit exact
+        assert np.array_equal(uv, want)                                        # the reference's own output
+
+
+def test_index2uv_edge_cases(lib_built):
+    """voxels behind / at the camera plane: inf, NaN and negative pixel coordinates must clamp like the oracle."""
+    from virconv_b200 import ops, scenes
+    rng = np.random.default_rng(0)
+    idx = np.stack([rng.integers(0, 2, 4000), rng.integers(0, 81, 4000), rng.integers(0, 1600, 4000),
+                    rng.integers(0, 12, 4000)], 1).astype(np.int32)        # x < 0.6 m: rect z around 0
+    calibs = [scenes.Calib(), scenes.Calib()]
+    aug = np.array([[0.7, 1, 0.95], [-0.7, 0, 1.05]], np.float32)
+    for stride in (1, 8):
+        params = ops.projection_params(calibs, aug, 2, _dev())
+        uv = ops.index2uv(torch.from_numpy(idx).to(_dev()), 2, params, stride).cpu().numpy()
+        assert np.array_equal(uv, ouv.index2uv(idx, 2, calibs, stride, aug))
+
+
+# ---------------------------------------------------------------------------------------------- dense / gather
+def test_dense_and_gather(lib_built):
+    from virconv_b200 import ops, spconv_compat as sp
+    rng = np.random.default_rng(1)
+    shape = [4, 20, 17]
+    c = _coords(rng, 900, 2, shape)
+    feats = torch.randn(c.shape[0], 64)
+    x = sp.SparseConvTensor(feats.to(_dev()).requires_grad_(True), torch.from_numpy(c).to(_dev()), shape, 2)
+    d = x.dense()
+    ref = osp.SparseConvTensor(feats, torch.from_numpy(c), shape, 2).dense()
+    assert torch.equal(d.detach().cpu(), ref)
+    n, cc, dd, h, w = d.shape
+    assert d.view(n, cc * dd, h, w).shape == (2, 256, 20, 17)          # height_compression.py:30-31
+    g = torch.randn_like(d)
+    d.backward(g)
+    want = g.cpu()[c[:, 0], :, c[:, 1], c[:, 2], c[:, 3]]
+    assert torch.equal(x.features.grad.cpu(), want)
+    rows = torch.from_numpy(np.sort(rng.permutation(c.shape[0])[:500]).astype(np.int32)).to(_dev())
+    assert torch.equal(ops.gather_rows(feats.to(_dev()), rows).cpu(), feats[rows.cpu().long()])
+    idx = torch.from_numpy(c).to(_dev())
+    assert torch.equal(ops.gather_rows(idx, rows).cpu(), torch.from_numpy(c)[rows.cpu().long()])
