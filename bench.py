@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py — VirConv-L backbone scenes/s (forward+backward) on synthetic KITTI-shaped scenes.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+A "step" = one forward+backward pass of the VirConv-L 3-D backbone (20 sparse convs + BN/ReLU + 4x index2uv,
+scalar loss = sum of mean features of x_conv1..4 and the encoded tensor) over one batch of 2 synthetic
+scenes per GPU (BASELINE.json configs[1]: 16k LiDAR + 80k virtual points per scene, 40 000-voxel cap,
+reference grid [81,1600,1408]).  One JSON line on rank 0 (contract: task statement "Measurement").
+
+  value     scenes/s with inputs resident in HBM, per-step CUDA-event time, max over ranks
+  e2e       same step driven from PINNED HOST buffers: H2D of voxel features/coords/params, D2H of the loss
+  roofline  the dominant kernel (gather-GEMM: conv forward + dgrad launches): algorithmic bytes / event time
+  cpu_baseline / --impl reference : the restated reference algorithm (spconv "Native": CPU hash-map rulebook +
+            per-offset torch.mm + index_add_) from oracle/, timed on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CFG = dict(RETURN_NUM_FEATURES_AS_DICT=True, OUT_FEATURES=64, LAYER_DISCARD_RATE=0.1, NUM_FILTERS=[16, 32, 64, 64])
+SCENES_PER_GPU = 2          # VirConv-L.yaml:284 BATCH_SIZE_PER_GPU
+N_LIDAR, N_VIRTUAL, MAX_VOXELS = 16384, 80000, 40000
+POOL = 4                    # distinct batches rotated through the timed steps
+WORKLOAD = ('VirConv-L 3D backbone fwd+bwd, synthetic KITTI scenes 16k LiDAR + 80k virtual pts, '
+            '40000-voxel cap/scene, grid [81,1600,1408], batch 2/GPU')
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--ref-budget-s', type=float, default=150.0)
+    ap.add_argument('--ncu-step', action='store_true',
+                    help='profiling aid: W warm-up steps, then exactly one step between cudaProfilerStart/Stop; no JSON')
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+             'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(suffix='.csv')
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(gpu_index), f'--query-gpu={self.QUERY}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(',')]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle's CPU restatement (the only place bench.py executes oracle/)
+# ------------------------------------------------------------------------------------------------------
+def cpu_step(model, batch):
+    vf = torch.from_numpy(batch.voxel_features.copy())
+    vc = torch.from_numpy(batch.voxel_coords.copy())
+    model.zero_grad(set_to_none=True)
+    o = model(vf, vc, batch.batch_size, batch.calib, batch.aug_param)
+    loss = o['out'].features.mean() + sum(o['x_conv%d' % i].features.mean() for i in range(1, 5))
+    loss.backward()
+    return float(loss.detach())
+
+
+def make_cpu_model():
+    from oracle import spconv_cpu
+    from oracle.backbone import VirConvL8x as OracleL
+    spconv_cpu.RULEBOOK_BACKEND = 'c'            # sequential hash-map indexing, like spconv's CPU path
+    torch.manual_seed(666)
+    m = OracleL()
+    m.train()
+    return m
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from virconv_b200 import scenes
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = make_cpu_model()
+    batches = [scenes.make_batch([2 * i, 2 * i + 1], N_LIDAR, N_VIRTUAL, MAX_VOXELS, training=True) for i in range(2)]
+    t0 = time.time()
+    for w in range(min(args.warmup, 1)):
+        cpu_step(model, batches[w % 2])
+    warm = time.time() - t0
+    per = max(warm, 1e-3)
+    k = max(1, min(args.steps, int(max(args.ref_budget_s - warm, per) / per))) if warm > 0 else args.steps
+    times = []
+    for s in range(k):
+        t = time.time()
+        cpu_step(model, batches[s % 2])
+        times.append(time.time() - t)
+    ms = 1e3 * float(np.mean(times))
+    val = SCENES_PER_GPU / (ms / 1e3)
+    sample = (f'{k} step(s) of one batch of {SCENES_PER_GPU} scenes (same workload), after {min(args.warmup, 1)} warm-up; '
+              f'steps capped by a {args.ref_budget_s:.0f} s budget')
+    line = {'impl': 'reference', 'metric': 'VirConv-L scenes/sec (fwd+bwd)', 'value': val, 'unit': 'scenes/s',
+            'n_gpus': args.gpus, 'steps': k, 'warmup': min(args.warmup, 1), 'ms_per_step': ms, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'scenes_per_step': SCENES_PER_GPU,
+                       'what': 'restated reference algorithm on CPU (spconv Native: C hash-map rulebook + per-offset '
+                               'torch.mm + index_add_, autograd backward); spconv itself is not installable here'},
+            'cpu_baseline': {'value': val, 'unit': 'scenes/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': val, 'unit': 'scenes/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from virconv_b200 import _lib, ops, scenes
+    from virconv_b200.backbone import VirConvL8x
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (the product has no CPU path); use --impl reference for the CPU arm')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    lib = _lib.load()
+
+    torch.manual_seed(666)
+    model = VirConvL8x(CFG, 8, [1408, 1600, 80]).to(dev).train()
+    params = [p for p in model.parameters()]
+    # one flat gradient bucket: .grad of every parameter is a view into it -> one all-reduce per step
+    flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=dev)
+    off = 0
+    for p in params:
+        p.grad = flat[off:off + p.numel()].view_as(p)
+        off += p.numel()
+    if world > 1:
+        for p in params:
+            dist.broadcast(p.data, 0)
+
+    host, devb = [], []
+    h2d = 0
+    for i in range(POOL):
+        sid = 1000 * rank + 2 * i
+        b = scenes.make_batch([sid, sid + 1], N_LIDAR, N_VIRTUAL, MAX_VOXELS, training=True)
+        hv = torch.from_numpy(b.voxel_features).pin_memory()
+        hc = torch.from_numpy(b.voxel_coords).pin_memory()
+        host.append((hv, hc, b))
+        devb.append((hv.to(dev), hc.to(dev), b))
+        h2d = hv.numel() * 4 + hc.numel() * 4 + b.batch_size * 28 * 4
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def step(vf, vc, b, sync_loss):
+        flat.zero_()
+        bd = {'voxel_features': vf, 'voxel_coords': vc, 'batch_size': b.batch_size, 'calib': b.calib,
+              'aug_param': b.aug_param}
+        out = model(bd)
+        loss = out['encoded_spconv_tensor'].features.mean()
+        for t in out['multi_scale_3d_features'].values():
+            loss = loss + t.features.mean()
+        loss.backward()
+        if world > 1:
+            dist.all_reduce(flat)          # gradient all-reduce (SUM; /world folded into the lr by convention)
+        return float(loss) if sync_loss else loss
+
+    def timed(n_steps, from_host):
+        evs = []
+        for s in range(n_steps):
+            flush_buf.zero_()
+            a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            if from_host:
+                hv, hc, b = host[s % POOL]
+                step(hv.to(dev, non_blocking=True), hc.to(dev, non_blocking=True), b, True)
+            else:
+                vf, vc, b = devb[s % POOL]
+                step(vf, vc, b, False)
+            e.record()
+            evs.append((a, e))
+        torch.cuda.synchronize()
+        return [a.elapsed_time(e) for a, e in evs]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if args.ncu_step:
+        timed(max(args.warmup, 1), False)
+        torch.cuda.profiler.start()
+        timed(1, False)
+        torch.cuda.profiler.stop()
+        return
+    timed(max(args.warmup, 3), False)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = lib.vc_launch_count()
+    t_wall = time.time()
+    ms_list = timed(args.steps, False)
+    barrier()
+    wall = time.time() - t_wall
+    launches = (lib.vc_launch_count() - l0) / max(args.steps, 1)
+    timed(2, True)
+    barrier()
+    e2e_list = timed(args.steps, True)
+    barrier()
+    clocks = sampler.stop() if sampler else None
+
+    tot = torch.tensor([sum(ms_list), sum(e2e_list)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    ms_step = float(tot[0]) / args.steps
+    ms_e2e = float(tot[1]) / args.steps
+    scenes_per_step = SCENES_PER_GPU * world
+
+    # roofline pass: the same step with CUDA events around every conv C-ABI call (not part of the timed loops)
+    roof, kern = None, {}
+    if rank == 0:
+        ops.TIMER = ops.KernelTimer()
+        nprof = 3
+        for s in range(nprof):
+            flush_buf.zero_()
+            vf, vc, b = devb[s % POOL]
+            step(vf, vc, b, False)
+        kern = ops.TIMER.summary()
+        ops.TIMER = None
+        peak, how = peaks()
+        g_calls = sum(kern[k][0] for k in ('conv_fwd', 'conv_dgrad') if k in kern)
+        g_ms = sum(kern[k][1] for k in ('conv_fwd', 'conv_dgrad') if k in kern)
+        g_bytes = sum(kern[k][2] for k in ('conv_fwd', 'conv_dgrad') if k in kern)
+        g_flops = sum(kern[k][3] for k in ('conv_fwd', 'conv_dgrad') if k in kern)
+        all_ms = sum(v[1] for v in kern.values())
+        ach = g_bytes / (g_ms * 1e-3) / 1e9 if g_ms > 0 else 0.0
+        roof = {'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'traffic': None,
+                'kernel': 'gather_gemm_kernel<CI,CO> (conv forward + dgrad), prep_weights included',
+                'peak_source': how, 'launches_per_step': g_calls / nprof,
+                'avg_launch_ms': g_ms / max(g_calls, 1), 'alg_bytes_per_launch': g_bytes / max(g_calls, 1),
+                'achieved_tflops_fp32': g_flops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0,
+                'share_of_conv_kernel_time': g_ms / all_ms if all_ms > 0 else None,
+                'per_step_ms': {k: v[1] / nprof for k, v in kern.items()},
+                'note': 'fp32 CUDA-core parity path: FP32-FMA bound today, HBM is the bound it is designed toward'}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cpu_base = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        cm = make_cpu_model()
+        b = host[0][2]
+        t = time.time()
+        cpu_step(cm, b)
+        dt = time.time() - t
+        cpu_base = {'value': SCENES_PER_GPU / dt, 'unit': 'scenes/s', 'cores': cores, 'kind': 'port',
+                    'sample': f'1 fwd+bwd step of one batch of {SCENES_PER_GPU} scenes of the same workload ({dt:.1f} s), '
+                              'restated reference algorithm (oracle/), no warm-up'}
+
+    line = {'metric': 'VirConv-L scenes/sec (fwd+bwd)', 'value': scenes_per_step / (ms_step * 1e-3), 'unit': 'scenes/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_step,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'scenes_per_step': scenes_per_step, 'parallelism': f'dp{world}',
+                       'l2': 'flushed between timed steps (256 MiB write)', 'timing': 'per-step CUDA events, max over ranks',
+                       'precision': 'fp32 storage, fp32 accumulate (parity path)'},
+            'e2e': {'value': scenes_per_step / (ms_e2e * 1e-3), 'unit': 'scenes/s', 'ms_per_step': ms_e2e,
+                    'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': 4 + 4 * 4},
+            'gpu_launches': launches, 'wall_s_timed_region': wall, 'clocks': clocks, 'roofline': roof,
+            'cpu_baseline': cpu_base}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    a = parse()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_ours(a)

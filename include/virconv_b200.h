@@ -45,6 +45,8 @@ typedef void* vc_stream_t;       /* cudaStream_t */
 
 int vc_version(void);
 const char* vc_last_error(void);
+/* number of kernels this library has launched so far in this process (bench.py's gpu_launches) */
+long long vc_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Rulebooks.  Replaces spconv `ops.get_indice_pairs`, reached from every conv call site:

@@ -25,6 +25,17 @@ import torch.nn as nn
 
 from . import rulebook as rb
 
+# 'numpy' = oracle/rulebook.py (the canonical definition); 'c' = oracle/csrc/rulebook_ref.c (sequential
+# hash map like spconv's CPU indexing; identical tables, used for the timed CPU baseline)
+RULEBOOK_BACKEND = 'numpy'
+
+
+def _rulebook_impl():
+    if RULEBOOK_BACKEND == 'c':
+        from . import crulebook
+        return crulebook
+    return rb
+
 
 class SparseConvTensor:
     def __init__(self, features, indices, spatial_shape, batch_size, grid=None, indice_dict=None):
@@ -79,7 +90,7 @@ def native_conv(features, weight, nbr, n_out, subm):
         if o.numel() == 0:
             continue
         i = nbr[k].index_select(0, o)
-        out = out.index_add(0, o, features.index_select(0, i) @ weight[:, k, :].t())
+        out.index_add_(0, o, features.index_select(0, i) @ weight[:, k, :].t())   # scatter-add in place, like spconv Native
     return out
 
 
@@ -103,7 +114,7 @@ class SparseConvolution(SparseModule):
         idx_np = x.indices.detach().cpu().numpy()
         if self.subm:
             if cached is None:
-                nbr = rb.subm_rulebook(idx_np, x.spatial_shape, self.kernel_size, self.dilation)
+                nbr = _rulebook_impl().subm_rulebook(idx_np, x.spatial_shape, self.kernel_size, self.dilation)
                 cached = dict(nbr=torch.from_numpy(nbr).long(), nbr_np=nbr, out_indices=x.indices,
                               out_shape=x.spatial_shape)
                 if key is not None:
@@ -111,7 +122,7 @@ class SparseConvolution(SparseModule):
             out_indices, out_shape = x.indices, x.spatial_shape
         else:
             if cached is None:
-                oi, osh, nf, nb = rb.conv_rulebook(idx_np, x.spatial_shape, self.kernel_size, self.stride,
+                oi, osh, nf, nb = _rulebook_impl().conv_rulebook(idx_np, x.spatial_shape, self.kernel_size, self.stride,
                                                    self.padding, self.dilation)
                 cached = dict(nbr=torch.from_numpy(nf).long(), nbr_np=nf, nbr_bwd_np=nb,
                               out_indices=torch.from_numpy(oi).to(x.indices.dtype), out_shape=osh)
@@ -159,6 +170,9 @@ class SparseSequential(SparseModule):
         super().__init__()
         for i, m in enumerate(mods):
             self.add_module(str(i), m)
+
+    def __getitem__(self, idx):
+        return list(self._modules.values())[idx]
 
     def forward(self, x):
         for m in self._modules.values():

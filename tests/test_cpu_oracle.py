@@ -1,0 +1,158 @@
+"""CPU tests (no GPU): the oracle against the golden vectors made from the reference's own Python, and
+against brute-force dense convolution (the only ground truth for the spconv internals)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import index2uv as ouv
+from oracle import rulebook as orb
+from oracle import spconv_cpu as osp
+from oracle.backbone import VirConvL8x as OracleL
+from oracle.testing import fill_module, rel_err
+from virconv_b200 import scenes
+
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+
+
+def _coords(rng, n, batch, shape, unique=True):
+    c = np.stack([rng.integers(0, batch, n)] + [rng.integers(0, s, n) for s in shape], 1).astype(np.int32)
+    if unique:
+        c = np.unique(c, axis=0)
+        rng.shuffle(c)
+    return c
+
+
+def test_index2uv_matches_reference_golden():
+    g = np.load(os.path.join(GOLD, 'index2uv.npz'))
+    for ci in range(int(g['n_cases'])):
+        aug = g[f'aug{ci}']
+        uv = ouv.index2uv(g[f'idx{ci}'], 2, [scenes.Calib(), scenes.Calib()], int(g[f'stride{ci}']),
+                          aug if aug.shape[0] else None)
+        assert np.array_equal(uv, g[f'uv{ci}'])
+
+
+def test_mean_vfe_matches_reference_golden():
+    g = np.load(os.path.join(GOLD, 'mean_vfe.npz'))
+    assert np.array_equal(scenes.mean_vfe(g['voxels'], g['num'], 'max'), g['features'])
+
+
+def test_voxelizer_first_come_semantics():
+    rng = np.random.default_rng(0)
+    pts = rng.uniform([0, -40, -3, 0, 0, 0, 0, 1], [70.4, 40, 1, 1, 1, 1, 1, 2], size=(5000, 8)).astype(np.float32)
+    pts[::7] = pts[3]                      # repeated points fill one voxel past its 5 slots
+    vox, coords, num = scenes.voxelize_first_come(pts, max_voxels=1000)
+    # sequential restatement
+    seen, order, cnt = {}, [], []
+    for p in pts:
+        c = tuple(np.floor((p[:3] - scenes.POINT_CLOUD_RANGE[:3]) / np.float32(0.05)).astype(int))
+        if not all(0 <= c[i] < (1408, 1600, 80)[i] for i in range(3)):
+            continue
+        if c not in seen:
+            if len(order) >= 1000:
+                continue
+            seen[c] = len(order)
+            order.append(c)
+            cnt.append(0)
+        cnt[seen[c]] += 1
+    assert coords.shape[0] == len(order) == 1000
+    assert np.array_equal(coords, np.array([(c[2], c[1], c[0]) for c in order], dtype=np.int32))
+    assert np.array_equal(num, np.minimum(cnt, 5))
+    assert vox.shape == (1000, 5, 8) and np.all(vox[num == 1][:, 1:] == 0)
+
+
+@pytest.mark.parametrize('mode', ['eval', 'train'])
+def test_oracle_backbone_matches_reference_flow_golden(mode):
+    """The restated VirConvL8x flow == the reference's classes run over the same oracle operators."""
+    g = np.load(os.path.join(GOLD, 'virconv_l_small.npz'))
+    m = OracleL()
+    fill_module(m, int(g['seed']))
+    m.train(mode == 'train')
+    with torch.no_grad():
+        o = m(torch.from_numpy(g['voxel_features'].copy()), torch.from_numpy(g['voxel_coords'].copy()), 2,
+              [scenes.Calib(), scenes.Calib()], g['aug_param'])
+    for k in ('x_conv1', 'x_conv2', 'x_conv3', 'x_conv4', 'out'):
+        assert np.array_equal(o[k].indices.numpy(), g[f'{mode}_{k}_indices'])
+        assert np.array_equal(o[k].features.numpy(), g[f'{mode}_{k}_features'])
+
+
+def test_scene_generator_is_deterministic_and_kitti_shaped():
+    a, b = scenes.make_batch([0]), scenes.make_batch([0])
+    assert np.array_equal(a.voxel_features, b.voxel_features) and np.array_equal(a.voxel_coords, b.voxel_coords)
+    assert a.voxel_features.shape == (40000, 8) and a.sparse_shape() == [81, 1600, 1408]
+    c = a.voxel_coords
+    assert c[:, 1].max() < 81 and c[:, 2].max() < 1600 and c[:, 3].max() < 1408 and c.min() >= 0
+    assert set(np.unique(a.voxel_features[:, 7])) <= {1.0, 2.0}        # 'max' VFE keeps the indicator integral
+
+
+# ------------------------------------------------------------------------------------------------
+# sparse-conv semantics pinned by dense convolution
+# ------------------------------------------------------------------------------------------------
+GEOS = [dict(kernel_size=3, stride=2, padding=1), dict(kernel_size=3, stride=2, padding=(0, 1, 1)),
+        dict(kernel_size=(3, 1, 1), stride=(2, 1, 1), padding=0), dict(kernel_size=2, stride=2, padding=0)]
+
+
+@pytest.mark.parametrize('seed', [0, 1, 2])
+def test_subm_and_strided_conv_equal_dense_conv3d(seed):
+    rng = np.random.default_rng(seed)
+    B, shape = 2, [9, 10, 11]
+    c = _coords(rng, 400, B, shape)
+    feats = torch.randn(c.shape[0], 5)
+    x = osp.SparseConvTensor(feats, torch.from_numpy(c), shape, B)
+    dense_in = x.dense()
+    m = osp.SubMConv3d(5, 7, 3, bias=False)
+    ref = F.conv3d(dense_in, m.weight.detach().permute(0, 4, 1, 2, 3), padding=1)
+    assert rel_err(m(x).features.detach(), ref[c[:, 0], :, c[:, 1], c[:, 2], c[:, 3]]) < 1e-5
+    for geo in GEOS:
+        m = osp.SparseConv3d(5, 7, bias=False, **geo)
+        y = m(x)
+        ref = F.conv3d(dense_in, m.weight.detach().permute(0, 4, 1, 2, 3), stride=geo['stride'], padding=geo['padding'])
+        assert list(y.dense().shape) == list(ref.shape)
+        assert rel_err(y.dense().detach(), ref) < 1e-5
+        # output set = exactly the cells whose receptive field holds an active input
+        occ = F.conv3d((dense_in.abs().sum(1, keepdim=True) > 0).float(), torch.ones(1, 1, *m.kernel_size),
+                       stride=geo['stride'], padding=geo['padding'])
+        assert int((occ > 0).sum()) == y.indices.shape[0]
+        lin = orb.linearize(y.indices.numpy(), y.spatial_shape)
+        assert np.all(np.diff(lin) > 0)
+
+
+def test_subm2d_duplicates_lowest_row_wins():
+    rng = np.random.default_rng(0)
+    c = _coords(rng, 300, 2, [12, 9], unique=False)
+    assert np.unique(c, axis=0).shape[0] < c.shape[0]
+    a = orb.subm_rulebook(c, [12, 9], 3)
+    assert np.array_equal(a, orb.subm_rulebook_sequential(c, [12, 9], 3))
+    assert np.array_equal(a[4], np.arange(c.shape[0]))               # centre = identity
+    # conv value: centre from the row itself, neighbours from the lowest row of each neighbouring pixel
+    feats = torch.randn(c.shape[0], 3)
+    m = osp.SubMConv2d(3, 4, 3, bias=False)
+    y = m(osp.SparseConvTensor(feats, torch.from_numpy(c), [12, 9], 2)).features.detach()
+    w = m.weight.detach()
+    lut = {}
+    for r in range(c.shape[0]):
+        lut.setdefault(tuple(c[r]), r)
+    for r in rng.integers(0, c.shape[0], 25):
+        acc = torch.zeros(4)
+        for ku in range(3):
+            for kv in range(3):
+                if (ku, kv) == (1, 1):
+                    src = r
+                else:
+                    src = lut.get((c[r, 0], c[r, 1] + ku - 1, c[r, 2] + kv - 1))
+                if src is not None:
+                    acc += w[:, ku, kv, :] @ feats[src]
+        assert torch.allclose(acc, y[r], atol=1e-5)
+
+
+def test_pairs_from_nbr_canonical_order():
+    rng = np.random.default_rng(1)
+    c = _coords(rng, 200, 1, [6, 6, 6])
+    nbr = orb.subm_rulebook(c, [6, 6, 6], 3)
+    pairs, num = orb.pairs_from_nbr(nbr)
+    for k in range(27):
+        o = pairs[1, k, :num[k]]
+        assert np.all(np.diff(o) > 0) and np.array_equal(nbr[k, o], pairs[0, k, :num[k]])
+        assert np.all(pairs[:, k, num[k]:] == -1)

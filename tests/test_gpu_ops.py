@@ -234,17 +234,21 @@ def test_conv_bn_relu_fused(lib_built, training, cin, cout):
     bn.train(training)
     import copy
     bn_g = copy.deepcopy(bn).to(_dev())
+    fr = feats.clone().requires_grad_(True)
+    wr = weight.clone().requires_grad_(True)
+    xr = osp.native_conv(fr, wr.reshape(cout, 27, cin), torch.from_numpy(orb.subm_rulebook(c, shape, 3)).long(), n, True)
+    pre = bn(xr)
+    yr = torch.relu(pre)
+    # a pre-activation within rounding distance of 0 may take the other ReLU branch on the GPU; keep those
+    # (a handful of) elements out of the gradient comparison instead of loosening the tolerance
+    dy = dy * (pre.detach().abs() > 1e-4)
+    yr.backward(dy)
     rb = ops.build_subm_rulebook(torch.from_numpy(c).to(_dev()), 2, shape, 3)
     f = feats.to(_dev()).requires_grad_(True)
     w = weight.to(_dev()).requires_grad_(True)
     y = ops.ConvBNReLUFn.apply(f, w, bn_g.weight, bn_g.bias, bn_g.running_mean, bn_g.running_var, rb, training, 1e-3,
                                0.01)
     y.backward(dy.to(_dev()))
-    fr = feats.clone().requires_grad_(True)
-    wr = weight.clone().requires_grad_(True)
-    xr = osp.native_conv(fr, wr.reshape(cout, 27, cin), torch.from_numpy(orb.subm_rulebook(c, shape, 3)).long(), n, True)
-    yr = torch.relu(bn(xr))
-    yr.backward(dy)
     assert rel_err(y.detach().cpu(), yr.detach()) < TOL
     assert rel_err(f.grad.cpu(), fr.grad) < 5e-4
     assert rel_err(w.grad.cpu(), wr.grad) < 5e-4

@@ -23,6 +23,7 @@ _HOSTF = ctypes.POINTER(c_float)
 SIGNATURES = {
     'vc_version': (_I, []),
     'vc_last_error': (c_char_p, []),
+    'vc_launch_count': (ctypes.c_longlong, []),
     'vc_subm_rulebook_ws_bytes': (_Z, [_I]),
     'vc_subm_rulebook': (_I, [_P, _I, _I, _I, _HOST, _HOST, _HOST, _P, _P, _P, _Z, _P]),
     'vc_conv_rulebook_ws_bytes': (_Z, [_I, _I, _HOST]),

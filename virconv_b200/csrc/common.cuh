@@ -10,6 +10,7 @@
 namespace vc {
 
 void set_error(const char* fmt, ...);
+void count_launch();  // bumps the counter behind vc_launch_count()
 
 #define VC_CHECK_ARG(cond, ...)                 \
     do {                                        \
@@ -28,7 +29,11 @@ void set_error(const char* fmt, ...);
         }                                                                                      \
     } while (0)
 
-#define VC_LAUNCH_CHECK() VC_CUDA(cudaGetLastError())
+#define VC_LAUNCH_CHECK()          \
+    do {                           \
+        vc::count_launch();        \
+        VC_CUDA(cudaGetLastError()); \
+    } while (0)
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 

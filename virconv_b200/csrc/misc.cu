@@ -6,6 +6,8 @@
 namespace vc {
 
 static thread_local char g_err[512] = "";
+static long long g_launches = 0;
+void count_launch() { ++g_launches; }
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -109,6 +111,7 @@ using namespace vc;
 
 extern "C" int vc_version(void) { return 100; }
 extern "C" const char* vc_last_error(void) { return g_err; }
+extern "C" long long vc_launch_count(void) { return g_launches; }
 
 extern "C" int vc_index2uv(const int32_t* indices, int n, int batch_size, const float* params, const float* grid,
                            int stride, int u_max, int v_max, int32_t* uv_out, vc_stream_t stream_) {

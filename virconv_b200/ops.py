@@ -44,6 +44,44 @@ def _ws(nbytes, device):
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
 
+class KernelTimer:
+    """Optional per-call CUDA-event timing of the C-ABI calls (bench.py's roofline pass).  Off by default:
+    `ops.TIMER = KernelTimer()` turns it on, `ops.TIMER = None` off.  Events are recorded on the launching
+    stream; `summary()` synchronises once and returns {name: (calls, total_ms, alg_bytes, flops)}."""
+
+    def __init__(self):
+        self.records = []
+
+    def run(self, name, alg_bytes, flops, fn):
+        a = torch.cuda.Event(enable_timing=True)
+        b = torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = fn()
+        b.record()
+        self.records.append((name, a, b, alg_bytes, flops))
+        return out
+
+    def summary(self):
+        torch.cuda.synchronize()
+        agg = {}
+        for name, a, b, by, fl in self.records:
+            c = agg.setdefault(name, [0, 0.0, 0, 0])
+            c[0] += 1
+            c[1] += a.elapsed_time(b)
+            c[2] += by() if callable(by) else by
+            c[3] += fl() if callable(fl) else fl
+        return {k: tuple(v) for k, v in agg.items()}
+
+
+TIMER = None
+
+
+def _timed(name, alg_bytes, flops, fn):
+    if TIMER is None:
+        return fn()
+    return TIMER.run(name, alg_bytes, flops, fn)
+
+
 # ------------------------------------------------------------------------------------------------
 # rulebooks
 # ------------------------------------------------------------------------------------------------
@@ -62,6 +100,12 @@ class Rulebook:
     out_shape: list
     unique_coords: bool = True             # False: many-to-one table (image branch) -> scatter dgrad
     _pairs: tuple | None = field(default=None, repr=False)
+
+    def n_pairs(self):
+        """total rulebook entries P (host read; only the bench's roofline accounting calls this)."""
+        if getattr(self, '_np', None) is None:
+            self._np = int(self.pair_num.sum().item())
+        return self._np
 
     def indice_pairs(self):
         """spconv-style (indice_pairs [2,K,n_out], indice_pair_num [K]); built on demand."""
@@ -133,8 +177,12 @@ def conv_forward(feats, weight, rb: Rulebook, want_bn_partial=False):
     n_tiles = (rb.n_out + TILE_ROWS - 1) // TILE_ROWS
     partial = torch.empty((n_tiles, 2, cout), dtype=torch.float32, device=feats.device) if want_bn_partial else None
     ws = _ws(lib.vc_conv_ws_bytes(cin, cout, rb.K), feats.device)
-    check(lib.vc_conv_fwd_f32(_p(feats), _p(weight), _p(rb.nbr), _p(out), rb.n_out, cin, cout, rb.K, _p(partial),
-                              _p(ws), ws.numel(), _stream()), 'vc_conv_fwd_f32')
+    n_in = feats.shape[0]
+    _timed('conv_fwd',
+           lambda: (n_in * cin + rb.n_out * cout + rb.K * cin * cout) * 4 + rb.n_pairs() * 8,
+           lambda: 2 * rb.n_pairs() * cin * cout,
+           lambda: check(lib.vc_conv_fwd_f32(_p(feats), _p(weight), _p(rb.nbr), _p(out), rb.n_out, cin, cout, rb.K,
+                                             _p(partial), _p(ws), ws.numel(), _stream()), 'vc_conv_fwd_f32'))
     return out, partial
 
 
@@ -147,13 +195,20 @@ def conv_dgrad(dout, weight, rb: Rulebook):
     ws = _ws(lib.vc_conv_ws_bytes(cin, cout, rb.K), dout.device)
     if rb.subm and not rb.unique_coords:
         din = torch.zeros((rb.n_in, cin), dtype=torch.float32, device=dout.device)
-        check(lib.vc_conv_dgrad_scatter_f32(_p(dout), _p(weight), _p(rb.nbr), _p(din), rb.n_out, cin, cout, rb.K,
-                                            _p(ws), ws.numel(), _stream()), 'vc_conv_dgrad_scatter_f32')
+        _timed('conv_dgrad_scatter',
+               lambda: (rb.n_in * cin + rb.n_out * cout + rb.K * cin * cout) * 4 + rb.n_pairs() * 8,
+               lambda: 2 * rb.n_pairs() * cin * cout,
+               lambda: check(lib.vc_conv_dgrad_scatter_f32(_p(dout), _p(weight), _p(rb.nbr), _p(din), rb.n_out, cin,
+                                                           cout, rb.K, _p(ws), ws.numel(), _stream()),
+                             'vc_conv_dgrad_scatter_f32'))
         return din
     din = torch.empty((rb.n_in, cin), dtype=torch.float32, device=dout.device)
     table, mirror = (rb.nbr, 1) if rb.subm else (rb.nbr_bwd, 0)
-    check(lib.vc_conv_dgrad_f32(_p(dout), _p(weight), _p(table), _p(din), rb.n_in, cin, cout, rb.K, mirror, _p(ws),
-                                ws.numel(), _stream()), 'vc_conv_dgrad_f32')
+    _timed('conv_dgrad',
+           lambda: (rb.n_in * cin + rb.n_out * cout + rb.K * cin * cout) * 4 + rb.n_pairs() * 8,
+           lambda: 2 * rb.n_pairs() * cin * cout,
+           lambda: check(lib.vc_conv_dgrad_f32(_p(dout), _p(weight), _p(table), _p(din), rb.n_in, cin, cout, rb.K, mirror,
+                                               _p(ws), ws.numel(), _stream()), 'vc_conv_dgrad_f32'))
     return din
 
 
@@ -165,8 +220,12 @@ def conv_wgrad(feats, dout, weight_shape, rb: Rulebook):
     dout = dout.contiguous()
     dw = torch.empty(tuple(weight_shape), dtype=torch.float32, device=feats.device)
     ws = _ws(lib.vc_conv_wgrad_ws_bytes(rb.n_out, cin, cout, rb.K), feats.device)
-    check(lib.vc_conv_wgrad_f32(_p(feats), _p(dout), _p(rb.nbr), _p(dw), rb.n_out, cin, cout, rb.K, _p(ws), ws.numel(),
-                                _stream()), 'vc_conv_wgrad_f32')
+    n_in = feats.shape[0]
+    _timed('conv_wgrad',
+           lambda: (n_in * cin + rb.n_out * cout + rb.K * cin * cout) * 4 + rb.n_pairs() * 8,
+           lambda: 2 * rb.n_pairs() * cin * cout,
+           lambda: check(lib.vc_conv_wgrad_f32(_p(feats), _p(dout), _p(rb.nbr), _p(dw), rb.n_out, cin, cout, rb.K, _p(ws),
+                                               ws.numel(), _stream()), 'vc_conv_wgrad_f32'))
     return dw
 
 
