@@ -48,6 +48,7 @@ def parse():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--ref-budget-s', type=float, default=150.0)
+    ap.add_argument('--cpu-worker', action='store_true', help=argparse.SUPPRESS)
     ap.add_argument('--ncu-step', action='store_true',
                     help='profiling aid: W warm-up steps, then exactly one step between cudaProfilerStart/Stop; no JSON')
     return ap.parse_args()
@@ -120,6 +121,27 @@ def cpu_step(model, batch):
     return float(loss.detach())
 
 
+def cpu_threads():
+    """Threads for the CPU legs: the per-offset mm / index_add_ of the Native algorithm stop scaling (and then slow
+    down) beyond a few tens of threads, so 'all the threads it can use' is capped at 32."""
+    return max(1, min(os.cpu_count() or 1, 32))
+
+
+def run_cpu_worker():
+    from virconv_b200 import scenes
+    cores = cpu_threads()
+    torch.set_num_threads(cores)
+    cm = make_cpu_model()
+    b = scenes.make_batch([0, 1], N_LIDAR, N_VIRTUAL, MAX_VOXELS, training=True)
+    t = time.time()
+    cpu_step(cm, b)
+    dt = time.time() - t
+    print(json.dumps({'value': SCENES_PER_GPU / dt, 'unit': 'scenes/s', 'cores': cores, 'kind': 'port',
+                      'sample': f'1 fwd+bwd step of one batch of {SCENES_PER_GPU} scenes of the same workload ({dt:.1f} s), '
+                                f'restated reference algorithm (oracle/), {cores} threads of {os.cpu_count()} host cores, '
+                                'no warm-up'}), flush=True)
+
+
 def make_cpu_model():
     from oracle import spconv_cpu
     from oracle.backbone import VirConvL8x as OracleL
@@ -135,7 +157,7 @@ def run_reference(args):
     if rank != 0:
         return
     from virconv_b200 import scenes
-    cores = os.cpu_count() or 1
+    cores = cpu_threads()
     torch.set_num_threads(cores)
     model = make_cpu_model()
     batches = [scenes.make_batch([2 * i, 2 * i + 1], N_LIDAR, N_VIRTUAL, MAX_VOXELS, training=True) for i in range(2)]
@@ -222,7 +244,7 @@ def run_ours(args):
         loss.backward()
         if world > 1:
             dist.all_reduce(flat)          # gradient all-reduce (SUM; /world folded into the lr by convention)
-        return float(loss) if sync_loss else loss
+        return float(loss.detach()) if sync_loss else loss
 
     def timed(n_steps, from_host):
         evs = []
@@ -308,16 +330,14 @@ def run_ours(args):
 
     cpu_base = None
     if world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        torch.set_num_threads(cores)
-        cm = make_cpu_model()
-        b = host[0][2]
-        t = time.time()
-        cpu_step(cm, b)
-        dt = time.time() - t
-        cpu_base = {'value': SCENES_PER_GPU / dt, 'unit': 'scenes/s', 'cores': cores, 'kind': 'port',
-                    'sample': f'1 fwd+bwd step of one batch of {SCENES_PER_GPU} scenes of the same workload ({dt:.1f} s), '
-                              'restated reference algorithm (oracle/), no warm-up'}
+        # bounded sample in a child process (so a slow host cannot take the bench line down with it)
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), '--cpu-worker'], capture_output=True, text=True,
+                               timeout=240)
+            cpu_base = json.loads(r.stdout.strip().splitlines()[-1])
+        except Exception as ex:          # noqa: BLE001
+            cpu_base = {'value': None, 'unit': 'scenes/s', 'cores': cpu_threads(), 'kind': 'port',
+                        'sample': f'CPU baseline did not finish inside its 240 s bound ({type(ex).__name__})'}
 
     line = {'metric': 'VirConv-L scenes/sec (fwd+bwd)', 'value': scenes_per_step / (ms_step * 1e-3), 'unit': 'scenes/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_step,
@@ -336,7 +356,9 @@ def run_ours(args):
 
 if __name__ == '__main__':
     a = parse()
-    if a.impl == 'reference':
+    if a.cpu_worker:
+        run_cpu_worker()
+    elif a.impl == 'reference':
         run_reference(a)
     else:
         run_ours(a)

@@ -113,18 +113,27 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float4* __rest
     }
 }
 
-// pass 2 (one block): dgamma, dbeta, and the per-channel coefficients a, b, d with dx = a*g + b*xhat... folded:
+// pass 2 (one block, lanes x c threads): dgamma, dbeta and the per-channel coefficients of
 //   dx = coef[0]*g + coef[1]*x + coef[2]
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int blocks, int n, int c,
-                                       const float* __restrict__ gamma, const float* __restrict__ mean,
-                                       const float* __restrict__ invstd, int training, float* dgamma, float* dbeta,
-                                       float* __restrict__ coef) {
-    int ch = threadIdx.x;
-    if (ch >= c) return;
+__global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __restrict__ partial, int blocks, int n, int c,
+                                                                const float* __restrict__ gamma,
+                                                                const float* __restrict__ mean,
+                                                                const float* __restrict__ invstd, int training,
+                                                                float* dgamma, float* dbeta, float* __restrict__ coef) {
+    extern __shared__ double shd[];  // [lanes][2][c]
+    int ch = threadIdx.x % c, j = threadIdx.x / c, lanes = blockDim.x / c;
     double s = 0.0, q = 0.0;
-    for (int b = 0; b < blocks; ++b) {
+    for (int b = j; b < blocks; b += lanes) {
         s += (double)partial[((size_t)b * 2 + 0) * c + ch];
         q += (double)partial[((size_t)b * 2 + 1) * c + ch];
+    }
+    shd[(j * 2 + 0) * c + ch] = s;
+    shd[(j * 2 + 1) * c + ch] = q;
+    __syncthreads();
+    if (j != 0) return;
+    for (int l = 1; l < lanes; ++l) {
+        s += shd[(l * 2 + 0) * c + ch];
+        q += shd[(l * 2 + 1) * c + ch];
     }
     dbeta[ch] = (float)s;
     dgamma[ch] = (float)q;
@@ -177,7 +186,7 @@ extern "C" int vc_bn_train_finalize(const float* bn_partial, int n_tiles, int n_
     VC_CHECK_ARG(bn_partial && gamma && beta && running_mean && running_var && scale && shift && save_mean && save_invstd,
                  "null pointer");
     int lanes = 1024 / c;
-    if (lanes > 16) lanes = 16;
+    if (lanes > 32) lanes = 32;
     size_t smem = (size_t)lanes * 2 * c * sizeof(double);
     bn_train_finalize_kernel<<<1, lanes * c, smem, stream>>>(bn_partial, n_tiles, n_rows, c, gamma, beta, running_mean,
                                                               running_var, momentum, eps, scale, shift, save_mean,
@@ -238,8 +247,10 @@ extern "C" int vc_bn_relu_bwd_f32(const float* dy, const float* x, const float* 
     bn_bwd_reduce_kernel<<<blocks, 256, smem, stream>>>((const float4*)dy, (const float4*)x, (const float4*)y, save_mean,
                                                         save_invstd, n, c, partial);
     VC_LAUNCH_CHECK();
-    bn_bwd_finalize_kernel<<<1, 256, 0, stream>>>(partial, blocks, n, c, gamma, save_mean, save_invstd, training, dgamma,
-                                                  dbeta, coef);
+    int flanes = 1024 / c;
+    if (flanes > 32) flanes = 32;
+    bn_bwd_finalize_kernel<<<1, flanes * c, (size_t)flanes * 2 * c * sizeof(double), stream>>>(
+        partial, blocks, n, c, gamma, save_mean, save_invstd, training, dgamma, dbeta, coef);
     VC_LAUNCH_CHECK();
     size_t n4 = (size_t)n * c4;
     int ablocks = (int)((n4 + 255) / 256);
