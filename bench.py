@@ -47,6 +47,8 @@ def parse():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--precision', default=os.environ.get('VIRCONV_PRECISION', 'bf16'), choices=['fp32', 'bf16'],
+                    help='bf16 = tcgen05 tensor-core contractions (BASELINE configs[1] dtype); fp32 = 1e-4 parity kernels')
     ap.add_argument('--ref-budget-s', type=float, default=150.0)
     ap.add_argument('--cpu-worker', action='store_true', help=argparse.SUPPRESS)
     ap.add_argument('--ncu-step', action='store_true',
@@ -209,7 +211,7 @@ def run_ours(args):
     lib = _lib.load()
 
     torch.manual_seed(666)
-    model = VirConvL8x(CFG, 8, [1408, 1600, 80]).to(dev).train()
+    model = VirConvL8x(CFG, 8, [1408, 1600, 80], precision=args.precision).to(dev).train()
     params = [p for p in model.parameters()]
     # one flat gradient bucket: .grad of every parameter is a view into it -> one all-reduce per step
     flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=dev)
@@ -308,20 +310,25 @@ def run_ours(args):
         kern = ops.TIMER.summary()
         ops.TIMER = None
         peak, how = peaks()
-        g_calls = sum(kern[k][0] for k in ('conv_fwd', 'conv_dgrad') if k in kern)
-        g_ms = sum(kern[k][1] for k in ('conv_fwd', 'conv_dgrad') if k in kern)
-        g_bytes = sum(kern[k][2] for k in ('conv_fwd', 'conv_dgrad') if k in kern)
-        g_flops = sum(kern[k][3] for k in ('conv_fwd', 'conv_dgrad') if k in kern)
+        dom = ('conv_fwd_tc', 'conv_dgrad_tc') if args.precision == 'bf16' else ('conv_fwd', 'conv_dgrad')
+        g_calls = sum(kern[k][0] for k in dom if k in kern)
+        g_ms = sum(kern[k][1] for k in dom if k in kern)
+        g_bytes = sum(kern[k][2] for k in dom if k in kern)
+        g_flops = sum(kern[k][3] for k in dom if k in kern)
         all_ms = sum(v[1] for v in kern.values())
         ach = g_bytes / (g_ms * 1e-3) / 1e9 if g_ms > 0 else 0.0
         roof = {'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'traffic': None,
-                'kernel': 'gather_gemm_kernel<CI,CO> (conv forward + dgrad), prep_weights included',
+                'kernel': ('tc_gather_gemm_kernel<KC,NR> (tcgen05 conv forward + dgrad), weight-image prep included'
+                           if args.precision == 'bf16' else
+                           'gather_gemm_kernel<CI,CO> (fp32 conv forward + dgrad), prep_weights included'),
                 'peak_source': how, 'launches_per_step': g_calls / nprof,
                 'avg_launch_ms': g_ms / max(g_calls, 1), 'alg_bytes_per_launch': g_bytes / max(g_calls, 1),
-                'achieved_tflops_fp32': g_flops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0,
+                'achieved_tflops': g_flops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0,
                 'share_of_conv_kernel_time': g_ms / all_ms if all_ms > 0 else None,
                 'per_step_ms': {k: v[1] / nprof for k, v in kern.items()},
-                'note': 'fp32 CUDA-core parity path: FP32-FMA bound today, HBM is the bound it is designed toward'}
+                'note': ('tcgen05 bf16 operands / fp32 TMEM accumulators; bytes = bf16 gathered operand + fp32 output + P*8 '
+                         '+ bf16 weights' if args.precision == 'bf16' else
+                         'fp32 CUDA-core parity path: FP32-FMA bound, HBM is the bound it is designed toward')}
 
     if rank != 0:
         if world > 1:
@@ -341,10 +348,11 @@ def run_ours(args):
 
     line = {'metric': 'VirConv-L scenes/sec (fwd+bwd)', 'value': scenes_per_step / (ms_step * 1e-3), 'unit': 'scenes/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_step,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'scenes_per_step': scenes_per_step, 'parallelism': f'dp{world}',
                        'l2': 'flushed between timed steps (256 MiB write)', 'timing': 'per-step CUDA events, max over ranks',
-                       'precision': 'fp32 storage, fp32 accumulate (parity path)'},
+                       'precision': ('bf16 operands on tcgen05 for conv forward/dgrad (C>=16), fp32 accumulate, fp32 features, '
+                                     'fp32 wgrad/BN' if args.precision == 'bf16' else 'fp32 storage, fp32 accumulate (parity path)')},
             'e2e': {'value': scenes_per_step / (ms_e2e * 1e-3), 'unit': 'scenes/s', 'ms_per_step': ms_e2e,
                     'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': 4 + 4 * 4},
             'gpu_launches': launches, 'wall_s_timed_region': wall, 'clocks': clocks, 'roofline': roof,

@@ -124,6 +124,20 @@ int vc_conv_wgrad_f32(const float* in, const float* dout, const int32_t* nbr, fl
                       int cout, int K, void* ws, size_t ws_bytes, vc_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * bf16 tensor-core variants of forward / dgrad (tcgen05.mma, fp32 accumulators in TMEM).  Same tables,
+ * same tiling, fp32 weights (converted per call) and fp32 outputs; the GATHERED operand (input features for
+ * forward, output gradients for dgrad) is bf16 [N, C] row major — vc_cast_f32_bf16 makes it.
+ * cin, cout in {16,32,64}.  ws >= vc_conv_tc_ws_bytes(cin, cout, K).  err_flag (device int32, may be NULL)
+ * is set to 1 if a pipeline wait ever times out (bounded spin instead of a hang); results are then invalid.
+ * ---------------------------------------------------------------------------------------------- */
+int vc_cast_f32_bf16(const float* in, void* out_bf16, long long n_elements /* multiple of 4 */, vc_stream_t stream);
+size_t vc_conv_tc_ws_bytes(int cin, int cout, int K);
+int vc_conv_fwd_tc(const void* in_bf16, const float* w, const int32_t* nbr, float* out, int n_out, int cin, int cout,
+                   int K, float* bn_partial, void* ws, size_t ws_bytes, int32_t* err_flag, vc_stream_t stream);
+int vc_conv_dgrad_tc(const void* dout_bf16, const float* w, const int32_t* nbr_t, float* din, int n_in, int cin,
+                     int cout, int K, int mirror, void* ws, size_t ws_bytes, int32_t* err_flag, vc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * BatchNorm1d(eps, momentum) + ReLU over the active rows.  Replaces the `norm_fn(out_channels)`,
  * `nn.ReLU()` members of every `spconv.SparseSequential` (spconv_backbone.py:101-105, :160, :561-567).
  * ---------------------------------------------------------------------------------------------- */

@@ -308,3 +308,119 @@ def test_dense_and_gather(lib_built):
     assert torch.equal(ops.gather_rows(feats.to(_dev()), rows).cpu(), feats[rows.cpu().long()])
     idx = torch.from_numpy(c).to(_dev())
     assert torch.equal(ops.gather_rows(idx, rows).cpu(), torch.from_numpy(c)[rows.cpu().long()])
+
+
+# ---------------------------------------------------------------------------------------------- tensor cores
+def _bf(t):
+    return t.bfloat16().float()
+
+
+@pytest.mark.parametrize('cin,cout', [(16, 16), (32, 16), (16, 32), (32, 32), (64, 32), (32, 64), (64, 64), (16, 64), (64, 16)])
+def test_tc_subm3d_conv_fwd_dgrad(lib_built, cin, cout):
+    """tcgen05 path: exact-operand check (oracle fed the same bf16-rounded operands, fp32 accumulate) at 1e-4, and
+    the bf16-precision check against the full-fp32 oracle at 2e-2; pipeline-timeout flag must stay 0."""
+    from virconv_b200 import ops
+    rng = np.random.default_rng(cin * 100 + cout)
+    shape = [12, 40, 40]
+    c = _coords(rng, 9000, 2, shape)
+    n = c.shape[0]
+    torch.manual_seed(cin + cout)
+    feats, weight, dout = torch.randn(n, cin), torch.randn(cout, 3, 3, 3, cin) * 0.1, torch.randn(n, cout)
+    rb = ops.build_subm_rulebook(torch.from_numpy(c).to(_dev()), 2, shape, 3)
+    f = feats.to(_dev()).requires_grad_(True)
+    w = weight.to(_dev()).requires_grad_(True)
+    out = ops.SparseConvFn.apply(f, w, rb, 'bf16')
+    out.backward(dout.to(_dev()))
+    torch.cuda.synchronize()
+    assert int(ops.tc_error_flag(_dev()).item()) == 0
+    nbr = orb.subm_rulebook(c, shape, 3)
+    ro, _, _ = _oracle_conv(_bf(feats), _bf(weight), nbr, n, True, dout)
+    assert rel_err(out.detach().cpu(), ro) < TOL
+    _, rdf, _ = _oracle_conv(feats, _bf(weight), nbr, n, True, _bf(dout))       # dgrad gathers bf16(dout)
+    assert rel_err(f.grad.cpu(), rdf) < TOL
+    ro32, rdf32, rdw32 = _oracle_conv(feats, weight, nbr, n, True, dout)
+    assert rel_err(out.detach().cpu(), ro32) < 2e-2
+    assert rel_err(f.grad.cpu(), rdf32) < 2e-2
+    assert rel_err(w.grad.cpu(), rdw32) < TOL                                    # wgrad stays fp32
+
+
+@pytest.mark.parametrize('cin,cout', [(16, 32), (32, 64), (64, 64)])
+@pytest.mark.parametrize('geo', GEOS[:3])
+def test_tc_strided_conv_fwd_dgrad(lib_built, cin, cout, geo):
+    from virconv_b200 import ops
+    rng = np.random.default_rng(cin + cout)
+    shape = [21, 40, 36]
+    c = _coords(rng, 5000, 2, shape)
+    n = c.shape[0]
+    torch.manual_seed(1)
+    ks = geo['ksize'] if isinstance(geo['ksize'], tuple) else (geo['ksize'],) * 3
+    feats, weight = torch.randn(n, cin), torch.randn(cout, *ks, cin) * 0.1
+    rb = ops.build_conv_rulebook(torch.from_numpy(c).to(_dev()), 2, shape, geo['ksize'], geo['stride'], geo['padding'])
+    oi, osh, nf, nb = orb.conv_rulebook(c, shape, geo['ksize'], geo['stride'], geo['padding'])
+    dout = torch.randn(oi.shape[0], cout)
+    f = feats.to(_dev()).requires_grad_(True)
+    w = weight.to(_dev()).requires_grad_(True)
+    out = ops.SparseConvFn.apply(f, w, rb, 'bf16')
+    out.backward(dout.to(_dev()))
+    torch.cuda.synchronize()
+    assert int(ops.tc_error_flag(_dev()).item()) == 0
+    ro, _, _ = _oracle_conv(_bf(feats), _bf(weight), nf, oi.shape[0], False, dout)
+    assert rel_err(out.detach().cpu(), ro) < TOL
+    _, rdf, _ = _oracle_conv(feats, _bf(weight), nf, oi.shape[0], False, _bf(dout))
+    assert rel_err(f.grad.cpu(), rdf) < TOL
+
+
+def test_tc_subm2d_duplicates_and_tails(lib_built):
+    """image-branch table (forward on tensor cores, dgrad falls back to the fp32 scatter kernel) + ragged tiles"""
+    from virconv_b200 import ops
+    for n_req, cch in ((1, 16), (127, 32), (129, 32), (5000, 32)):
+        rng = np.random.default_rng(n_req)
+        shape = [60, 40]
+        co = _coords(rng, n_req, 2, shape, unique=False)
+        n = co.shape[0]
+        torch.manual_seed(n_req)
+        feats, weight, dout = torch.randn(n, cch), torch.randn(cch, 3, 3, cch) * 0.1, torch.randn(n, cch)
+        rb = ops.build_subm_rulebook(torch.from_numpy(co).to(_dev()), 2, shape, 3)
+        f = feats.to(_dev()).requires_grad_(True)
+        w = weight.to(_dev()).requires_grad_(True)
+        out = ops.SparseConvFn.apply(f, w, rb, 'bf16')
+        out.backward(dout.to(_dev()))
+        torch.cuda.synchronize()
+        assert int(ops.tc_error_flag(_dev()).item()) == 0
+        nbr = orb.subm_rulebook(co, shape, 3)
+        ro, _, _ = _oracle_conv(_bf(feats), _bf(weight), nbr, n, True, dout)
+        assert rel_err(out.detach().cpu(), ro) < TOL
+        _, rdf, _ = _oracle_conv(feats, weight, nbr, n, True, dout)
+        assert rel_err(f.grad.cpu(), rdf) < TOL
+
+
+def test_tc_backbone_bf16_vs_fp32_oracle(lib_built):
+    """whole VirConv-L backbone in bf16 tensor-core mode against the fp32 oracle at a bf16 tolerance"""
+    from virconv_b200 import scenes, ops
+    from virconv_b200.backbone import VirConvL8x
+    from oracle.backbone import VirConvL8x as OracleL
+    from oracle.testing import fill_module
+    cfg = dict(RETURN_NUM_FEATURES_AS_DICT=True, OUT_FEATURES=64, LAYER_DISCARD_RATE=0.1, NUM_FILTERS=[16, 32, 64, 64])
+    batch = scenes.make_batch([0, 5], n_lidar=4096, n_virtual=6000, max_voxels=6000, training=True)
+    m = VirConvL8x(cfg, 8, [1408, 1600, 80], precision='bf16')
+    fill_module(m, 666)
+    ref = OracleL()
+    ref.load_state_dict(m.state_dict())
+    m.to(_dev()).train()
+    ref.train()
+    bd = {'voxel_features': torch.from_numpy(batch.voxel_features.copy()).to(_dev()),
+          'voxel_coords': torch.from_numpy(batch.voxel_coords.copy()).to(_dev()), 'batch_size': 2, 'calib': batch.calib,
+          'aug_param': batch.aug_param}
+    out = m(bd)
+    o = ref(torch.from_numpy(batch.voxel_features.copy()), torch.from_numpy(batch.voxel_coords.copy()), 2, batch.calib,
+            batch.aug_param)
+    named = dict(out['multi_scale_3d_features'])
+    named['out'] = out['encoded_spconv_tensor']
+    for k, t in named.items():
+        assert np.array_equal(t.indices.cpu().numpy(), o[k].indices.numpy()), k     # index work stays bit exact
+        e = rel_err(t.features.detach().cpu(), o[k].features.detach())
+        assert e < 5e-2, (k, e)
+    sum(t.features.mean() for t in named.values()).backward()
+    torch.cuda.synchronize()
+    assert int(ops.tc_error_flag(_dev()).item()) == 0
+    assert all(torch.isfinite(p.grad).all() for p in m.parameters())

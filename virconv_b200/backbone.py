@@ -92,7 +92,8 @@ def discard_rows(t, keep_rows):
 class VirConvL8x(nn.Module):
     """VirConv-L backbone (fused LiDAR + virtual stream), spconv_backbone.py:538-699."""
 
-    def __init__(self, model_cfg, input_channels, grid_size, discard_mode='spconv2_compat', **kwargs):
+    def __init__(self, model_cfg, input_channels, grid_size, discard_mode='spconv2_compat', precision='fp32',
+                 **kwargs):
         super().__init__()
         self.model_cfg = model_cfg
         self.return_num_features_as_dict = _cfg_get(model_cfg, 'RETURN_NUM_FEATURES_AS_DICT', False)
@@ -114,6 +115,7 @@ class VirConvL8x(nn.Module):
             spconv.SparseConv3d(num_filters[3], self.out_features, (3, 1, 1), stride=(2, 1, 1), padding=last_pad,
                                 bias=False, indice_key='spconv_down2'),
             norm_fn(self.out_features), nn.ReLU())
+        spconv.set_precision(self, precision)
         self.num_point_features = self.out_features
         if self.return_num_features_as_dict:
             self.num_point_features = {'x_conv%d' % (i + 1): num_filters[i] for i in range(4)}

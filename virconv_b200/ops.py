@@ -83,6 +83,36 @@ def _timed(name, alg_bytes, flops, fn):
 
 
 # ------------------------------------------------------------------------------------------------
+# precision: 'fp32' = CUDA-core fp32 kernels (1e-4 parity path); 'bf16' = tcgen05 tensor-core kernels for the
+# gathered contractions (bf16 operands, fp32 accumulation in TMEM, fp32 outputs) where the channel counts allow
+# ------------------------------------------------------------------------------------------------
+_TC_ERR = {}
+
+
+def tc_error_flag(device):
+    """Persistent device int32 the tensor-core kernels raise if a pipeline wait times out (never expected)."""
+    key = (device.type, device.index)
+    if key not in _TC_ERR:
+        _TC_ERR[key] = torch.zeros(1, dtype=torch.int32, device=device)
+    return _TC_ERR[key]
+
+
+def tc_supported(cin, cout):
+    return cin in (16, 32, 64) and cout in (16, 32, 64)
+
+
+def cast_bf16(t):
+    """fp32 [N, C] -> bf16 copy (the gathered operand of the tensor-core kernels)."""
+    _require_cuda(t)
+    lib = _lib.load()
+    t = t.contiguous()
+    out = torch.empty(t.shape, dtype=torch.bfloat16, device=t.device)
+    _timed('cast_bf16', t.numel() * 6, 0,
+           lambda: check(lib.vc_cast_f32_bf16(_p(t), _p(out), t.numel(), _stream()), 'vc_cast_f32_bf16'))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # rulebooks
 # ------------------------------------------------------------------------------------------------
 @dataclass
@@ -166,7 +196,7 @@ def build_conv_rulebook(indices, batch_size, spatial_shape, ksize, stride, paddi
 # ------------------------------------------------------------------------------------------------
 # raw kernels
 # ------------------------------------------------------------------------------------------------
-def conv_forward(feats, weight, rb: Rulebook, want_bn_partial=False):
+def conv_forward(feats, weight, rb: Rulebook, want_bn_partial=False, precision='fp32'):
     """feats [n_in, C_in] f32, weight [C_out, *k, C_in] f32 -> out [n_out, C_out] (+ per-tile BN partial sums)."""
     _require_cuda(feats, weight)
     lib = _lib.load()
@@ -176,6 +206,17 @@ def conv_forward(feats, weight, rb: Rulebook, want_bn_partial=False):
     out = torch.empty((rb.n_out, cout), dtype=torch.float32, device=feats.device)
     n_tiles = (rb.n_out + TILE_ROWS - 1) // TILE_ROWS
     partial = torch.empty((n_tiles, 2, cout), dtype=torch.float32, device=feats.device) if want_bn_partial else None
+    if precision == 'bf16' and tc_supported(cin, cout) and rb.n_out > 0:
+        fb = cast_bf16(feats)
+        ws = _ws(lib.vc_conv_tc_ws_bytes(cin, cout, rb.K), feats.device)
+        n_in = feats.shape[0]
+        _timed('conv_fwd_tc',
+               lambda: n_in * cin * 2 + rb.n_out * cout * 4 + rb.K * cin * cout * 2 + rb.n_pairs() * 8,
+               lambda: 2 * rb.n_pairs() * cin * cout,
+               lambda: check(lib.vc_conv_fwd_tc(_p(fb), _p(weight), _p(rb.nbr), _p(out), rb.n_out, cin, cout, rb.K,
+                                                _p(partial), _p(ws), ws.numel(), _p(tc_error_flag(feats.device)),
+                                                _stream()), 'vc_conv_fwd_tc'))
+        return out, partial
     ws = _ws(lib.vc_conv_ws_bytes(cin, cout, rb.K), feats.device)
     n_in = feats.shape[0]
     _timed('conv_fwd',
@@ -186,12 +227,24 @@ def conv_forward(feats, weight, rb: Rulebook, want_bn_partial=False):
     return out, partial
 
 
-def conv_dgrad(dout, weight, rb: Rulebook):
+def conv_dgrad(dout, weight, rb: Rulebook, precision='fp32'):
     _require_cuda(dout, weight)
     lib = _lib.load()
     cout, cin = weight.shape[0], weight.shape[-1]
     dout = dout.contiguous()
     weight = weight.contiguous()
+    if precision == 'bf16' and tc_supported(cin, cout) and rb.n_in > 0 and not (rb.subm and not rb.unique_coords):
+        db = cast_bf16(dout)
+        din = torch.empty((rb.n_in, cin), dtype=torch.float32, device=dout.device)
+        table, mirror = (rb.nbr, 1) if rb.subm else (rb.nbr_bwd, 0)
+        ws = _ws(lib.vc_conv_tc_ws_bytes(cin, cout, rb.K), dout.device)
+        _timed('conv_dgrad_tc',
+               lambda: rb.n_out * cout * 2 + rb.n_in * cin * 4 + rb.K * cin * cout * 2 + rb.n_pairs() * 8,
+               lambda: 2 * rb.n_pairs() * cin * cout,
+               lambda: check(lib.vc_conv_dgrad_tc(_p(db), _p(weight), _p(table), _p(din), rb.n_in, cin, cout, rb.K, mirror,
+                                                  _p(ws), ws.numel(), _p(tc_error_flag(dout.device)), _stream()),
+                             'vc_conv_dgrad_tc'))
+        return din
     ws = _ws(lib.vc_conv_ws_bytes(cin, cout, rb.K), dout.device)
     if rb.subm and not rb.unique_coords:
         din = torch.zeros((rb.n_in, cin), dtype=torch.float32, device=dout.device)
@@ -233,9 +286,9 @@ class SparseConvFn(torch.autograd.Function):
     """Plain sparse convolution (no norm): out = conv(feats, weight) through a rulebook."""
 
     @staticmethod
-    def forward(ctx, feats, weight, rb):
-        out, _ = conv_forward(feats, weight, rb, False)
-        ctx.rb = rb
+    def forward(ctx, feats, weight, rb, precision='fp32'):
+        out, _ = conv_forward(feats, weight, rb, False, precision)
+        ctx.rb, ctx.precision = rb, precision
         ctx.save_for_backward(feats, weight)
         return out
 
@@ -244,9 +297,9 @@ class SparseConvFn(torch.autograd.Function):
         feats, weight = ctx.saved_tensors
         rb = ctx.rb
         dout = dout.contiguous()
-        din = conv_dgrad(dout, weight, rb) if ctx.needs_input_grad[0] else None
+        din = conv_dgrad(dout, weight, rb, ctx.precision) if ctx.needs_input_grad[0] else None
         dw = conv_wgrad(feats, dout, weight.shape, rb) if ctx.needs_input_grad[1] else None
-        return din, dw, None
+        return din, dw, None, None
 
 
 class ConvBNReLUFn(torch.autograd.Function):
@@ -255,11 +308,12 @@ class ConvBNReLUFn(torch.autograd.Function):
     dgrad + wgrad."""
 
     @staticmethod
-    def forward(ctx, feats, weight, gamma, beta, running_mean, running_var, rb, training, eps, momentum):
+    def forward(ctx, feats, weight, gamma, beta, running_mean, running_var, rb, training, eps, momentum,
+                precision='fp32'):
         lib = _lib.load()
         dev = feats.device
         cout = weight.shape[0]
-        x, partial = conv_forward(feats, weight, rb, want_bn_partial=training)
+        x, partial = conv_forward(feats, weight, rb, want_bn_partial=training, precision=precision)
         stats = torch.empty((4, cout), dtype=torch.float32, device=dev)  # scale, shift, mean, invstd
         scale, shift, mean, invstd = stats[0], stats[1], stats[2], stats[3]
         if training:
@@ -272,7 +326,7 @@ class ConvBNReLUFn(torch.autograd.Function):
         y = torch.empty_like(x)
         check(lib.vc_affine_relu_f32(_p(x), _p(scale), _p(shift), _p(y), rb.n_out, cout, 1, _stream()),
               'vc_affine_relu_f32')
-        ctx.rb, ctx.training = rb, training
+        ctx.rb, ctx.training, ctx.precision = rb, training, precision
         ctx.save_for_backward(feats, weight, gamma, x, y, stats)
         return y
 
@@ -290,9 +344,9 @@ class ConvBNReLUFn(torch.autograd.Function):
         check(lib.vc_bn_relu_bwd_f32(_p(dy), _p(x), _p(y), _p(gamma), _p(stats[2]), _p(stats[3]), _p(dx), _p(dgamma),
                                      _p(dbeta), rb.n_out, cout, int(ctx.training), _p(ws), ws.numel(), _stream()),
               'vc_bn_relu_bwd_f32')
-        din = conv_dgrad(dx, weight, rb) if ctx.needs_input_grad[0] else None
+        din = conv_dgrad(dx, weight, rb, ctx.precision) if ctx.needs_input_grad[0] else None
         dw = conv_wgrad(feats, dx, weight.shape, rb) if ctx.needs_input_grad[1] else None
-        return din, dw, dgamma, dbeta, None, None, None, None, None, None
+        return din, dw, dgamma, dbeta, None, None, None, None, None, None, None
 
 
 # ------------------------------------------------------------------------------------------------

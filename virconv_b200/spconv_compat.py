@@ -95,6 +95,7 @@ class SparseConvolution(SparseModule):
         self.conv1x1 = all(k == 1 for k in self.kernel_size)
         self.subm, self.indice_key = subm, indice_key
         self.groups = groups
+        self.precision = 'fp32'      # 'bf16' -> tcgen05 tensor-core kernels (see ops.py); set via set_precision()
         self.weight = nn.Parameter(torch.empty(out_channels, *self.kernel_size, in_channels))
         if bias:
             self.bias = nn.Parameter(torch.empty(out_channels))
@@ -149,7 +150,7 @@ class SparseConvolution(SparseModule):
     def forward(self, x: SparseConvTensor):
         assert isinstance(x, SparseConvTensor)
         rb = self.rulebook(x)
-        out = ops.SparseConvFn.apply(x.features, self.weight, rb)
+        out = ops.SparseConvFn.apply(x.features, self.weight, rb, self.precision)
         if self.bias is not None:
             out = out + self.bias
         return self._out_tensor(x, out, rb)
@@ -162,8 +163,17 @@ class SparseConvolution(SparseModule):
         if training and bn.track_running_stats and bn.num_batches_tracked is not None:
             bn.num_batches_tracked.add_(1)
         y = ops.ConvBNReLUFn.apply(x.features, self.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, rb,
-                                   training, bn.eps, momentum)
+                                   training, bn.eps, momentum, self.precision)
         return self._out_tensor(x, y, rb)
+
+
+def set_precision(module: nn.Module, precision: str):
+    """Select 'fp32' (parity) or 'bf16' (tensor-core) kernels for every sparse conv under `module`."""
+    assert precision in ('fp32', 'bf16')
+    for m in module.modules():
+        if isinstance(m, SparseConvolution):
+            m.precision = precision
+    return module
 
 
 def _make(ndim, subm):
@@ -229,7 +239,7 @@ class SparseSequential(SparseModule):
         i = 0
         while i < len(mods):
             m = mods[i]
-            if (isinstance(m, SparseConvolution) and m.bias is None and i + 2 < len(mods) + 0
+            if (isinstance(m, SparseConvolution) and m.bias is None and i + 2 < len(mods)
                     and isinstance(mods[i + 1], nn.BatchNorm1d) and mods[i + 1].affine
                     and mods[i + 1].track_running_stats and isinstance(mods[i + 2], nn.ReLU)
                     and isinstance(x, SparseConvTensor) and x.indices.shape[0] > 0):
