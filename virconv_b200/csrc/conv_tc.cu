@@ -9,7 +9,7 @@
 //     offset is a pre-formatted image copied linearly — no register staging, no re-layout pass;
 //   * one elected thread issues C_in/16 `tcgen05.mma.cta_group::1.kind::f16` (M=128, N=C_out, K=16) per offset,
 //     accumulating all offsets of the tile in TMEM (fp32, C_out columns); `tcgen05.commit` onto an mbarrier
-//     frees the operand stage; a 4-deep ring keeps 3 gathers in flight behind the MMA;
+//     frees the operand stage; a 3-deep ring keeps 2 gathers in flight behind the MMA;
 //   * epilogue: `tcgen05.ld` 32x32b (thread = output row) -> smem -> coalesced fp32 stores + per-tile BN sums.
 // Replaces spconv `ops.indice_conv` behind spconv_backbone.py:89,92-93,113,563-564 in the bf16 (benchmark)
 // precision mode; the fp32 kernels in conv_f32.cu stay the 1e-4 parity path.
@@ -23,7 +23,7 @@ namespace vc {
 
 static constexpr int TCM = 128;        // rows per tile == UMMA M
 static constexpr int TC_THREADS = 128; // 4 warps: warp w owns TMEM lanes [32w, 32w+32)
-static constexpr int TC_STAGES = 4;
+static constexpr int TC_STAGES = 3;
 static constexpr int MAXK_TC = 32;
 static constexpr unsigned SPIN_LIMIT = 1u << 24;
 
@@ -97,7 +97,7 @@ struct TcCfg {
     static constexpr int TMEM_COLS = NR < 32 ? 32 : NR;      // power of two >= 32
     static constexpr int EPI_BYTES = TCM * (NR + 1) * 4;     // epilogue staging, aliases the stage ring
     static constexpr int RING_BYTES = TC_STAGES * STAGE_BYTES > EPI_BYTES ? TC_STAGES * STAGE_BYTES : EPI_BYTES;
-    static constexpr size_t smem(int K) { return (size_t)RING_BYTES + (size_t)K * TCM * 4 + 1024; }
+    static constexpr size_t smem(int K) { return (size_t)RING_BYTES + (size_t)K * TCM * 4; }
 };
 
 // f32 -> bf16 cast of a feature matrix (the gathered operand)
