@@ -136,6 +136,12 @@ int vc_conv_fwd_tc(const void* in_bf16, const float* w, const int32_t* nbr, floa
                    int K, float* bn_partial, void* ws, size_t ws_bytes, int32_t* err_flag, vc_stream_t stream);
 int vc_conv_dgrad_tc(const void* dout_bf16, const float* w, const int32_t* nbr_t, float* din, int n_in, int cin,
                      int cout, int K, int mirror, void* ws, size_t ws_bytes, int32_t* err_flag, vc_stream_t stream);
+/* dw[co,k,ci] = sum_o in[nbr[k,o],ci] * dout[o,co] on tensor cores: both operands bf16 (MN-major UMMA), 128/cin
+ * kernel offsets stacked along the MMA M dimension, accumulators resident in TMEM across all tiles of a
+ * persistent CTA, fixed-order reduction of the per-CTA partials.  ws >= vc_conv_wgrad_tc_ws_bytes(...). */
+size_t vc_conv_wgrad_tc_ws_bytes(int n_out, int cin, int cout, int K);
+int vc_conv_wgrad_tc(const void* in_bf16, const void* dout_bf16, const int32_t* nbr, float* dw, int n_out, int cin,
+                     int cout, int K, void* ws, size_t ws_bytes, int32_t* err_flag, vc_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * BatchNorm1d(eps, momentum) + ReLU over the active rows.  Replaces the `norm_fn(out_channels)`,

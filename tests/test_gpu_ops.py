@@ -338,10 +338,12 @@ def test_tc_subm3d_conv_fwd_dgrad(lib_built, cin, cout):
     assert rel_err(out.detach().cpu(), ro) < TOL
     _, rdf, _ = _oracle_conv(feats, _bf(weight), nbr, n, True, _bf(dout))       # dgrad gathers bf16(dout)
     assert rel_err(f.grad.cpu(), rdf) < TOL
+    _, _, rdw = _oracle_conv(_bf(feats), weight, nbr, n, True, _bf(dout))        # wgrad: both operands bf16
+    assert rel_err(w.grad.cpu(), rdw) < TOL
     ro32, rdf32, rdw32 = _oracle_conv(feats, weight, nbr, n, True, dout)
     assert rel_err(out.detach().cpu(), ro32) < 2e-2
     assert rel_err(f.grad.cpu(), rdf32) < 2e-2
-    assert rel_err(w.grad.cpu(), rdw32) < TOL                                    # wgrad stays fp32
+    assert rel_err(w.grad.cpu(), rdw32) < 2e-2
 
 
 @pytest.mark.parametrize('cin,cout', [(16, 32), (32, 64), (64, 64)])
@@ -368,6 +370,8 @@ def test_tc_strided_conv_fwd_dgrad(lib_built, cin, cout, geo):
     assert rel_err(out.detach().cpu(), ro) < TOL
     _, rdf, _ = _oracle_conv(feats, _bf(weight), nf, oi.shape[0], False, _bf(dout))
     assert rel_err(f.grad.cpu(), rdf) < TOL
+    _, _, rdw = _oracle_conv(_bf(feats), weight, nf, oi.shape[0], False, _bf(dout))
+    assert rel_err(w.grad.cpu(), rdw) < TOL
 
 
 def test_tc_subm2d_duplicates_and_tails(lib_built):
@@ -392,6 +396,8 @@ def test_tc_subm2d_duplicates_and_tails(lib_built):
         assert rel_err(out.detach().cpu(), ro) < TOL
         _, rdf, _ = _oracle_conv(feats, weight, nbr, n, True, dout)
         assert rel_err(f.grad.cpu(), rdf) < TOL
+        _, _, rdw = _oracle_conv(_bf(feats), weight, nbr, n, True, _bf(dout))
+        assert rel_err(w.grad.cpu(), rdw) < TOL
 
 
 def test_tc_backbone_bf16_vs_fp32_oracle(lib_built):

@@ -382,3 +382,294 @@ extern "C" int vc_conv_dgrad_tc(const void* dout_bf16, const float* w, const int
     return tc_common(dout_bf16, w, nbr_t, din, n_in, cin, cout, K, 1, mirror, nullptr, ws, ws_bytes, err_flag,
                      (cudaStream_t)stream_);
 }
+
+// ================================================================================================
+// wgrad on tensor cores.
+//   dW[k] (C_in x C_out) = sum over output rows o of  in[nbr[k,o], :]^T  (x)  dout[o, :]
+// Output-stationary again: for one tile of 128 output rows the dout tile B [128 x C_out] is the SAME operand
+// for every kernel offset, and the gathered tile A_k [128 x C_in] is exactly the forward kernel's operand.
+// Both are used MN-major (the reduction runs over the 128 rows), which is the same core-matrix image as the
+// forward K-major gather — so no transpose anywhere.  G = 128/C_in offsets are stacked along the UMMA M
+// dimension (rows of D = (offset j, channel ci)), 8 MMAs (K=16 rows each) per group and tile; every CTA keeps
+// all its offsets' accumulators resident in TMEM (<= 512 columns) across ALL the tiles it owns (persistent
+// CTAs, one per SM) and writes one fp32 partial at the end; partials are summed in a fixed order.
+// ================================================================================================
+namespace vc {
+
+__host__ __device__ constexpr uint32_t umma_idesc_mn(int m, int n) {   // both operands MN-major (bits 15, 16)
+    return umma_idesc(m, n) | (1u << 15) | (1u << 16);
+}
+
+template <int CI, int CO>
+struct WgTc {
+    static constexpr int CPR = CI / 8, CPO = CO / 8;
+    static constexpr int G = 128 / CI;                 // offsets stacked along M
+    static constexpr int A_STAGE = 16 * 2048;          // [16 row groups][16 slots][8 rows][16 B]
+    static constexpr int B_BYTES = TCM * CO * 2;
+    static constexpr int STAGES = 3;
+    static constexpr int MAX_GROUPS = 512 / CO;        // TMEM budget per CTA
+    static constexpr size_t smem(int kcount) { return (size_t)STAGES * A_STAGE + B_BYTES + (size_t)kcount * TCM * 4; }
+};
+
+template <int CI, int CO>
+__global__ void __launch_bounds__(TC_THREADS)
+tc_wgrad_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __restrict__ dout,
+                const int32_t* __restrict__ nbr, float* __restrict__ partial, int n_out, int K, int groups_per_pass,
+                int tmem_cols, int* __restrict__ err) {
+    using C = WgTc<CI, CO>;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* ring = smem_raw;
+    unsigned char* Bt = smem_raw + C::STAGES * C::A_STAGE;
+    int* nbr_s = reinterpret_cast<int*>(Bt + C::B_BYTES);
+    __shared__ __align__(8) uint64_t stage_done[C::STAGES];
+    __shared__ __align__(8) uint64_t tile_done;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ unsigned gmask_s, started_s;
+    __shared__ int glist[32];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_groups_total = (K + C::G - 1) / C::G;
+    const int g_begin = blockIdx.y * groups_per_pass;
+    const int g_count = min(groups_per_pass, n_groups_total - g_begin);
+    const int k_begin = g_begin * C::G;
+    const int k_count = min(g_count * C::G, K - k_begin);
+    const int n_tiles = (n_out + TCM - 1) / TCM;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                     "r"((uint32_t)tmem_cols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    if (tid == 0) {
+        for (int s = 0; s < C::STAGES; ++s) mbar_init(&stage_done[s], 1);
+        mbar_init(&tile_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        started_s = 0u;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    const int rl = lane & 7, xq = lane >> 3;   // 8 rows x 4 consecutive slots per warp instruction
+    unsigned it = 0;          // stage uses so far (ring position; same value in every thread)
+    unsigned tiles_done = 0;  // tiles that issued at least one MMA group
+    unsigned started = 0;     // thread 0: groups that already hold an accumulator
+    bool ok = true;
+    constexpr uint32_t IDESC = umma_idesc_mn(TCM, CO);
+
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int base = tile * TCM;
+        // previous tile's MMAs still read Bt / were steered by nbr_s: wait for them before overwriting
+        if (tiles_done > 0) ok &= mbar_wait(&tile_done, (tiles_done - 1) & 1u, err);
+        if (tid == 0) gmask_s = 0u;
+        for (int i = tid; i < k_count * TCM; i += TC_THREADS) {
+            int kk = i / TCM, r = i % TCM, row = base + r;
+            nbr_s[i] = (row < n_out) ? __ldg(nbr + (size_t)(k_begin + kk) * n_out + row) : -1;
+        }
+        // dout tile, image [r/8][CPO][r%8][16 B]
+        for (int q = tid; q < TCM * C::CPO; q += TC_THREADS) {
+            int r = (q / (8 * C::CPO)) * 8 + (q & 7), c = (q >> 3) % C::CPO;
+            bool v = base + r < n_out;
+            cp_async16(Bt + ((r >> 3) * C::CPO + c) * 128 + (r & 7) * 16, dout + (size_t)(v ? base + r : 0) * CO + c * 8, v);
+        }
+        cp_async_commit();
+        __syncthreads();
+        for (int g = warp; g < g_count; g += TC_THREADS / 32) {
+            bool any = false;
+            for (int j = 0; j < C::G; ++j) {
+                int kk = g * C::G + j;
+                if (kk < k_count) {
+#pragma unroll
+                    for (int q = 0; q < TCM / 32; ++q) any |= nbr_s[kk * TCM + q * 32 + lane] >= 0;
+                }
+            }
+            if (__any_sync(0xffffffffu, any) && lane == 0) atomicOr(&gmask_s, 1u << g);
+        }
+        __syncthreads();
+        const unsigned gm = gmask_s;
+        const int ng = __popc(gm);
+        if (tid == 0) {
+            int c = 0;
+            for (int g = 0; g < g_count; ++g)
+                if (gm >> g & 1u) glist[c++] = g;
+        }
+        __syncthreads();
+        if (ng == 0) {
+            cp_async_wait<0>();
+            __syncthreads();
+            continue;
+        }
+
+        auto issue_group = [&](int t, unsigned use) {
+            const int g = glist[t];
+            unsigned char* A = ring + (use % C::STAGES) * C::A_STAGE;
+#pragma unroll
+            for (int itr = 0; itr < 4; ++itr) {                 // 4 x 8 rows per warp
+                const int r = warp * 32 + itr * 8 + rl;
+#pragma unroll
+                for (int sg = 0; sg < 4; ++sg) {                // 16 slots = 4 x 4
+                    const int slot = sg * 4 + xq;
+                    const int j = slot / C::CPR, c = slot % C::CPR;
+                    const int kk = g * C::G + j;
+                    const int src = (kk < k_count) ? nbr_s[kk * TCM + r] : -1;
+                    cp_async16(A + ((r >> 3) * 16 + slot) * 128 + (r & 7) * 16,
+                               in + (size_t)(src < 0 ? 0 : src) * CI + c * 8, src >= 0);
+                }
+            }
+        };
+
+        // software pipeline over the active groups of this tile (ring positions continue across tiles)
+        const unsigned it0 = it;
+        for (int t = 0; t < C::STAGES - 1; ++t) {
+            if (t < ng) {
+                unsigned use = it0 + t;
+                if (use >= (unsigned)C::STAGES) ok &= mbar_wait(&stage_done[use % C::STAGES], ((use / C::STAGES) - 1) & 1u, err);
+                issue_group(t, use);
+            }
+            cp_async_commit();
+        }
+        for (int t = 0; t < ng; ++t) {
+            const int tn = t + C::STAGES - 1;
+            if (tn < ng) {
+                unsigned use = it0 + tn;
+                if (use >= (unsigned)C::STAGES) ok &= mbar_wait(&stage_done[use % C::STAGES], ((use / C::STAGES) - 1) & 1u, err);
+                issue_group(tn, use);
+            }
+            cp_async_commit();
+            cp_async_wait<C::STAGES - 1>();      // group t (and, on t == 0, the dout tile) has landed
+            fence_async_smem();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after();
+                const unsigned use = it0 + t;
+                const int g = glist[t];
+                const uint32_t a0 = smem_u32(ring + (use % C::STAGES) * C::A_STAGE);
+                const uint32_t b0 = smem_u32(Bt);
+                const bool first = !(started >> g & 1u);
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {   // 16 rows (two 8-row groups) per MMA
+                    const uint64_t ad = umma_desc(a0 + s * 2 * 2048, 2048, 128);
+                    const uint64_t bd = umma_desc(b0 + s * 2 * C::CPO * 128, C::CPO * 128, 128);
+                    umma_f16(tmem_base + (uint32_t)(g * CO), ad, bd, IDESC, (first && s == 0) ? 0u : 1u);
+                }
+                started |= 1u << g;
+                umma_commit(&stage_done[use % C::STAGES]);
+                if (t == ng - 1) umma_commit(&tile_done);
+            }
+        }
+        it = it0 + ng;
+        ++tiles_done;
+    }
+    if (tiles_done > 0) ok &= mbar_wait(&tile_done, (tiles_done - 1) & 1u, err);
+    cp_async_wait<0>();
+    if (tid == 0) started_s = started;
+    tc_fence_after();
+    __syncthreads();
+    const unsigned st = started_s;
+    // epilogue: TMEM lane = (offset j, channel ci) of the group, columns = C_out
+    float* mine = partial + (size_t)blockIdx.x * K * CI * CO;
+    const int row = warp * 32 + lane;
+    const int j = row / CI, ci = row % CI;
+    for (int g = 0; g < g_count; ++g) {
+        const int kk = g * C::G + j;
+        const bool live = (st >> g & 1u) != 0;
+#pragma unroll
+        for (int c0 = 0; c0 < CO; c0 += 16) {
+            float v[16];
+            if (live) {
+                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(g * CO + c0), v);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = 0.f;
+            }
+            if (kk < k_count) {
+                float* dst = mine + ((size_t)(k_begin + kk) * CI + ci) * CO + c0;
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tmem_cols));
+    }
+    (void)ok;
+}
+
+__global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int R, int K, int cin,
+                                       int cout) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;  // index into dw [co][k][ci]
+    int total = K * cin * cout;
+    if (i >= total) return;
+    int ci = i % cin, k = (i / cin) % K, co = i / (cin * K);
+    float v = 0.f;
+    for (int r = 0; r < R; ++r) v += partial[(((size_t)r * K + k) * cin + ci) * cout + co];
+    dw[i] = v;
+}
+
+static int wgrad_tc_grid(int n_out) {
+    int tiles = (n_out + TCM - 1) / TCM;
+    return tiles < 148 ? (tiles < 1 ? 1 : tiles) : 148;
+}
+
+template <int CI, int CO>
+static int launch_wgrad_tc(const __nv_bfloat16* in, const __nv_bfloat16* dout, const int32_t* nbr, float* partial, int n_out,
+                           int K, int* err, cudaStream_t stream) {
+    using C = WgTc<CI, CO>;
+    int n_groups = (K + C::G - 1) / C::G;
+    int gpp = n_groups < C::MAX_GROUPS ? n_groups : C::MAX_GROUPS;
+    int passes = (n_groups + gpp - 1) / gpp;
+    gpp = (n_groups + passes - 1) / passes;       // balance the passes
+    int cols = 32;
+    while (cols < gpp * CO) cols <<= 1;
+    int kcount = gpp * C::G < K ? gpp * C::G : K;
+    size_t smem = C::smem(kcount);
+    auto kern = tc_wgrad_kernel<CI, CO>;
+    VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3(wgrad_tc_grid(n_out), passes), TC_THREADS, smem, stream>>>(in, dout, nbr, partial, n_out, K, gpp, cols, err);
+    VC_LAUNCH_CHECK();
+    return VC_OK;
+}
+
+}  // namespace vc
+
+extern "C" size_t vc_conv_wgrad_tc_ws_bytes(int n_out, int cin, int cout, int K) {
+    return (size_t)vc::wgrad_tc_grid(n_out) * K * cin * cout * sizeof(float);
+}
+
+extern "C" int vc_conv_wgrad_tc(const void* in_bf16, const void* dout_bf16, const int32_t* nbr, float* dw, int n_out,
+                                int cin, int cout, int K, void* ws, size_t ws_bytes, int32_t* err_flag,
+                                vc_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    VC_CHECK_ARG(n_out >= 0 && K >= 1 && K <= MAXK_TC && dw, "bad arguments");
+    if (!tc_ch_ok(cin) || !tc_ch_ok(cout)) {
+        set_error("tensor-core wgrad: unsupported channels cin=%d cout=%d (need 16/32/64)", cin, cout);
+        return VC_ERR_UNSUPPORTED;
+    }
+    if (n_out == 0) {
+        VC_CUDA(cudaMemsetAsync(dw, 0, (size_t)K * cin * cout * 4, stream));
+        return VC_OK;
+    }
+    VC_CHECK_ARG(in_bf16 && dout_bf16 && nbr && ws, "null pointer");
+    if (ws_bytes < vc_conv_wgrad_tc_ws_bytes(n_out, cin, cout, K)) {
+        set_error("tensor-core wgrad workspace %zu < %zu", ws_bytes, vc_conv_wgrad_tc_ws_bytes(n_out, cin, cout, K));
+        return VC_ERR_WORKSPACE;
+    }
+    float* partial = (float*)ws;
+    const __nv_bfloat16* a = (const __nv_bfloat16*)in_bf16;
+    const __nv_bfloat16* b = (const __nv_bfloat16*)dout_bf16;
+    int rc = VC_ERR_UNSUPPORTED;
+#define VC_WG_CASE(A, B) \
+    if (cin == A && cout == B) rc = launch_wgrad_tc<A, B>(a, b, nbr, partial, n_out, K, err_flag, stream);
+    VC_WG_CASE(16, 16) VC_WG_CASE(16, 32) VC_WG_CASE(16, 64)
+    VC_WG_CASE(32, 16) VC_WG_CASE(32, 32) VC_WG_CASE(32, 64)
+    VC_WG_CASE(64, 16) VC_WG_CASE(64, 32) VC_WG_CASE(64, 64)
+#undef VC_WG_CASE
+    if (rc) return rc;
+    int total = K * cin * cout;
+    wgrad_tc_reduce_kernel<<<cdiv(total, 256), 256, 0, stream>>>(partial, dw, wgrad_tc_grid(n_out), K, cin, cout);
+    VC_LAUNCH_CHECK();
+    return VC_OK;
+}

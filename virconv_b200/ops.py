@@ -196,7 +196,7 @@ def build_conv_rulebook(indices, batch_size, spatial_shape, ksize, stride, paddi
 # ------------------------------------------------------------------------------------------------
 # raw kernels
 # ------------------------------------------------------------------------------------------------
-def conv_forward(feats, weight, rb: Rulebook, want_bn_partial=False, precision='fp32'):
+def conv_forward(feats, weight, rb: Rulebook, want_bn_partial=False, precision='fp32', feats_bf16=None, keep=None):
     """feats [n_in, C_in] f32, weight [C_out, *k, C_in] f32 -> out [n_out, C_out] (+ per-tile BN partial sums)."""
     _require_cuda(feats, weight)
     lib = _lib.load()
@@ -207,7 +207,9 @@ def conv_forward(feats, weight, rb: Rulebook, want_bn_partial=False, precision='
     n_tiles = (rb.n_out + TILE_ROWS - 1) // TILE_ROWS
     partial = torch.empty((n_tiles, 2, cout), dtype=torch.float32, device=feats.device) if want_bn_partial else None
     if precision == 'bf16' and tc_supported(cin, cout) and rb.n_out > 0:
-        fb = cast_bf16(feats)
+        fb = feats_bf16 if feats_bf16 is not None else cast_bf16(feats)
+        if keep is not None:
+            keep['feats_bf16'] = fb
         ws = _ws(lib.vc_conv_tc_ws_bytes(cin, cout, rb.K), feats.device)
         n_in = feats.shape[0]
         _timed('conv_fwd_tc',
@@ -227,14 +229,14 @@ def conv_forward(feats, weight, rb: Rulebook, want_bn_partial=False, precision='
     return out, partial
 
 
-def conv_dgrad(dout, weight, rb: Rulebook, precision='fp32'):
+def conv_dgrad(dout, weight, rb: Rulebook, precision='fp32', dout_bf16=None):
     _require_cuda(dout, weight)
     lib = _lib.load()
     cout, cin = weight.shape[0], weight.shape[-1]
     dout = dout.contiguous()
     weight = weight.contiguous()
     if precision == 'bf16' and tc_supported(cin, cout) and rb.n_in > 0 and not (rb.subm and not rb.unique_coords):
-        db = cast_bf16(dout)
+        db = dout_bf16 if dout_bf16 is not None else cast_bf16(dout)
         din = torch.empty((rb.n_in, cin), dtype=torch.float32, device=dout.device)
         table, mirror = (rb.nbr, 1) if rb.subm else (rb.nbr_bwd, 0)
         ws = _ws(lib.vc_conv_tc_ws_bytes(cin, cout, rb.K), dout.device)
@@ -265,13 +267,25 @@ def conv_dgrad(dout, weight, rb: Rulebook, precision='fp32'):
     return din
 
 
-def conv_wgrad(feats, dout, weight_shape, rb: Rulebook):
+def conv_wgrad(feats, dout, weight_shape, rb: Rulebook, precision='fp32', feats_bf16=None, dout_bf16=None):
     _require_cuda(feats, dout)
     lib = _lib.load()
     cout, cin = weight_shape[0], weight_shape[-1]
     feats = feats.contiguous()
     dout = dout.contiguous()
     dw = torch.empty(tuple(weight_shape), dtype=torch.float32, device=feats.device)
+    if precision == 'bf16' and tc_supported(cin, cout) and rb.n_out > 0:
+        fb = feats_bf16 if feats_bf16 is not None else cast_bf16(feats)
+        db = dout_bf16 if dout_bf16 is not None else cast_bf16(dout)
+        ws = _ws(lib.vc_conv_wgrad_tc_ws_bytes(rb.n_out, cin, cout, rb.K), feats.device)
+        n_in = feats.shape[0]
+        _timed('conv_wgrad_tc',
+               lambda: (n_in * cin + rb.n_out * cout) * 2 + rb.K * cin * cout * 4 + rb.n_pairs() * 8,
+               lambda: 2 * rb.n_pairs() * cin * cout,
+               lambda: check(lib.vc_conv_wgrad_tc(_p(fb), _p(db), _p(rb.nbr), _p(dw), rb.n_out, cin, cout, rb.K, _p(ws),
+                                                  ws.numel(), _p(tc_error_flag(feats.device)), _stream()),
+                             'vc_conv_wgrad_tc'))
+        return dw
     ws = _ws(lib.vc_conv_wgrad_ws_bytes(rb.n_out, cin, cout, rb.K), feats.device)
     n_in = feats.shape[0]
     _timed('conv_wgrad',
@@ -287,8 +301,10 @@ class SparseConvFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, feats, weight, rb, precision='fp32'):
-        out, _ = conv_forward(feats, weight, rb, False, precision)
+        keep = {}
+        out, _ = conv_forward(feats, weight, rb, False, precision, keep=keep)
         ctx.rb, ctx.precision = rb, precision
+        ctx.fb = keep.get('feats_bf16')
         ctx.save_for_backward(feats, weight)
         return out
 
@@ -297,8 +313,10 @@ class SparseConvFn(torch.autograd.Function):
         feats, weight = ctx.saved_tensors
         rb = ctx.rb
         dout = dout.contiguous()
-        din = conv_dgrad(dout, weight, rb, ctx.precision) if ctx.needs_input_grad[0] else None
-        dw = conv_wgrad(feats, dout, weight.shape, rb) if ctx.needs_input_grad[1] else None
+        cout, cin = weight.shape[0], weight.shape[-1]
+        db = cast_bf16(dout) if (ctx.precision == 'bf16' and tc_supported(cin, cout) and rb.n_out > 0) else None
+        din = conv_dgrad(dout, weight, rb, ctx.precision, db) if ctx.needs_input_grad[0] else None
+        dw = conv_wgrad(feats, dout, weight.shape, rb, ctx.precision, ctx.fb, db) if ctx.needs_input_grad[1] else None
         return din, dw, None, None
 
 
@@ -313,7 +331,9 @@ class ConvBNReLUFn(torch.autograd.Function):
         lib = _lib.load()
         dev = feats.device
         cout = weight.shape[0]
-        x, partial = conv_forward(feats, weight, rb, want_bn_partial=training, precision=precision)
+        keep = {}
+        x, partial = conv_forward(feats, weight, rb, want_bn_partial=training, precision=precision, keep=keep)
+        ctx.fb = keep.get('feats_bf16')
         stats = torch.empty((4, cout), dtype=torch.float32, device=dev)  # scale, shift, mean, invstd
         scale, shift, mean, invstd = stats[0], stats[1], stats[2], stats[3]
         if training:
@@ -344,8 +364,10 @@ class ConvBNReLUFn(torch.autograd.Function):
         check(lib.vc_bn_relu_bwd_f32(_p(dy), _p(x), _p(y), _p(gamma), _p(stats[2]), _p(stats[3]), _p(dx), _p(dgamma),
                                      _p(dbeta), rb.n_out, cout, int(ctx.training), _p(ws), ws.numel(), _stream()),
               'vc_bn_relu_bwd_f32')
-        din = conv_dgrad(dx, weight, rb, ctx.precision) if ctx.needs_input_grad[0] else None
-        dw = conv_wgrad(feats, dx, weight.shape, rb) if ctx.needs_input_grad[1] else None
+        cin = weight.shape[-1]
+        db = cast_bf16(dx) if (ctx.precision == 'bf16' and tc_supported(cin, cout) and rb.n_out > 0) else None
+        din = conv_dgrad(dx, weight, rb, ctx.precision, db) if ctx.needs_input_grad[0] else None
+        dw = conv_wgrad(feats, dx, weight.shape, rb, ctx.precision, ctx.fb, db) if ctx.needs_input_grad[1] else None
         return din, dw, dgamma, dbeta, None, None, None, None, None, None, None
 
 
