@@ -213,12 +213,6 @@ def run_ours(args):
     torch.manual_seed(666)
     model = VirConvL8x(CFG, 8, [1408, 1600, 80], precision=args.precision).to(dev).train()
     params = [p for p in model.parameters()]
-    # one flat gradient bucket: .grad of every parameter is a view into it -> one all-reduce per step
-    flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=dev)
-    off = 0
-    for p in params:
-        p.grad = flat[off:off + p.numel()].view_as(p)
-        off += p.numel()
     if world > 1:
         for p in params:
             dist.broadcast(p.data, 0)
@@ -236,7 +230,8 @@ def run_ours(args):
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     def step(vf, vc, b, sync_loss):
-        flat.zero_()
+        for p in params:
+            p.grad = None
         bd = {'voxel_features': vf, 'voxel_coords': vc, 'batch_size': b.batch_size, 'calib': b.calib,
               'aug_param': b.aug_param}
         out = model(bd)
@@ -245,7 +240,11 @@ def run_ours(args):
             loss = loss + t.features.mean()
         loss.backward()
         if world > 1:
-            dist.all_reduce(flat)          # gradient all-reduce (SUM; /world folded into the lr by convention)
+            # ONE gradient all-reduce per step: flatten (1 kernel) -> NCCL all-reduce over NVLink -> scatter back
+            grads = [p.grad for p in params]
+            flat = torch.cat([g.reshape(-1) for g in grads])
+            dist.all_reduce(flat)
+            torch._foreach_copy_(grads, [v.view_as(g) for v, g in zip(flat.split([g.numel() for g in grads]), grads)])
         return float(loss.detach()) if sync_loss else loss
 
     def timed(n_steps, from_host):
