@@ -158,17 +158,19 @@ int vc_bn_train_finalize(const float* bn_partial, int n_tiles, int n_rows, int c
 int vc_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean,
                       const float* running_var, float eps, int c, float* scale, float* shift,
                       float* save_mean, float* save_invstd, vc_stream_t stream);
-/* y = max(x*scale + shift, 0) (relu != 0) — in place allowed. */
-int vc_affine_relu_f32(const float* x, const float* scale, const float* shift, float* y, int n, int c, int relu,
-                       vc_stream_t stream);
+/* y = max(x*scale + shift, 0) (relu != 0) — in place allowed.  y_bf16 (may be NULL): bf16 shadow copy of y, the
+ * gathered operand of the next layer's tensor-core conv (saves a separate cast pass). */
+int vc_affine_relu_f32(const float* x, const float* scale, const float* shift, float* y, void* y_bf16, int n, int c,
+                       int relu, vc_stream_t stream);
 /* Backward of y = relu(gamma*(x-mean)*invstd + beta):
  *   g = dy * (y > 0); dbeta = sum g; dgamma = sum g*xhat;
  *   train: dx = gamma*invstd*(g - dbeta/n - xhat*dgamma/n);   eval: dx = gamma*invstd*g.
  * ws >= vc_bn_bwd_ws_bytes(n, c). */
 size_t vc_bn_bwd_ws_bytes(int n, int c);
 int vc_bn_relu_bwd_f32(const float* dy, const float* x, const float* y, const float* gamma,
-                       const float* save_mean, const float* save_invstd, float* dx, float* dgamma, float* dbeta,
-                       int n, int c, int training, void* ws, size_t ws_bytes, vc_stream_t stream);
+                       const float* save_mean, const float* save_invstd, float* dx, void* dx_bf16 /*may be NULL*/,
+                       float* dgamma, float* dbeta, int n, int c, int training, void* ws, size_t ws_bytes,
+                       vc_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Voxel index -> image pixel index.  Replaces `index2uv` + `index2points` + the per-sample
@@ -190,6 +192,10 @@ int vc_dense_f32(const float* features, const int32_t* indices, int n, int c, in
 /* Gradient of dense(): dfeatures[n, c] = dout[b, c, coords]. */
 int vc_dense_bwd_f32(const float* dout, const int32_t* indices, int n, int c, int ndim, int batch_size,
                      const int32_t* spatial_shape, float* dfeatures, vc_stream_t stream);
+
+/* NRConv channel concat (spconv_backbone.py:227): out[:, :ca] = a, out[:, ca:] = b, plus an optional bf16 shadow. */
+int vc_cat2_f32(const float* a, const float* b, float* out, void* out_bf16 /*may be NULL*/, int n, int ca, int cb,
+                vc_stream_t stream);
 
 /* Row gather for StVD layer discard (spconv_backbone.py:134-147): out[r] = in[rows[r]]. */
 int vc_gather_rows(const void* in, const int32_t* rows, void* out, int n_rows, int row_bytes, vc_stream_t stream);

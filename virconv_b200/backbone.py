@@ -71,8 +71,14 @@ class NRConvBlock(nn.Module):
         d3 = self.d3_conv2(self.d3_conv1(sp_tensor))
         uv = ops.index2uv(spconv._as_i32(d3.indices), batch_size, proj_params, stride)
         img = spconv.SparseConvTensor(d3.features, uv, [1600, 600], batch_size)
+        img.features_bf16 = d3.features_bf16
         d2 = self.d2_conv2(self.d2_conv1(img))
-        return d3.replace_feature(torch.cat([d3.features, d2.features], -1))
+        cat = ops.Cat2Fn.apply(d3.features, d2.features, d3.features_bf16 is not None)
+        if isinstance(cat, tuple):
+            out = d3.replace_feature(cat[0])
+            out.features_bf16 = cat[1]
+            return out
+        return d3.replace_feature(cat)
 
 
 def stvd_keep_rows(n, rate, rng=np.random):

@@ -4,9 +4,19 @@
 // (spconv_backbone.py:101-105, :160 eps=1e-3 momentum=0.01, :561-567).  HBM-bound elementwise work:
 // forward apply reads N*C*4 and writes N*C*4 bytes; the channel statistics come for free from the conv
 // epilogue (per-tile partial sums) and are reduced here in a fixed order (deterministic).
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace vc {
+
+__device__ __forceinline__ uint2 pack_bf16x4(float4 v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&a);
+    o.y = *reinterpret_cast<uint32_t*>(&b);
+    return o;
+}
 
 // one block; thread (j, ch): j strides over tiles.  double accumulation of the fp32 tile partials.
 __global__ void __launch_bounds__(1024) bn_train_finalize_kernel(
@@ -16,11 +26,20 @@ __global__ void __launch_bounds__(1024) bn_train_finalize_kernel(
     float* __restrict__ save_invstd) {
     extern __shared__ double sh[];  // [lanes][2][c]
     int ch = threadIdx.x % c, j = threadIdx.x / c, lanes = blockDim.x / c;
-    double s = 0.0, q = 0.0;
-    for (int t = j; t < n_tiles; t += lanes) {
-        s += (double)partial[((size_t)t * 2 + 0) * c + ch];
-        q += (double)partial[((size_t)t * 2 + 1) * c + ch];
+    double s = 0.0, q = 0.0, s1 = 0.0, q1 = 0.0;
+    int t = j;
+    for (; t + lanes < n_tiles; t += 2 * lanes) {     // two independent chains: loads of both are in flight together
+        s += (double)__ldg(partial + ((size_t)t * 2 + 0) * c + ch);
+        q += (double)__ldg(partial + ((size_t)t * 2 + 1) * c + ch);
+        s1 += (double)__ldg(partial + ((size_t)(t + lanes) * 2 + 0) * c + ch);
+        q1 += (double)__ldg(partial + ((size_t)(t + lanes) * 2 + 1) * c + ch);
     }
+    for (; t < n_tiles; t += lanes) {
+        s += (double)__ldg(partial + ((size_t)t * 2 + 0) * c + ch);
+        q += (double)__ldg(partial + ((size_t)t * 2 + 1) * c + ch);
+    }
+    s += s1;
+    q += q1;
     sh[(j * 2 + 0) * c + ch] = s;
     sh[(j * 2 + 1) * c + ch] = q;
     __syncthreads();
@@ -60,7 +79,7 @@ __global__ void bn_eval_affine_kernel(const float* __restrict__ gamma, const flo
 
 __global__ void __launch_bounds__(256) affine_relu_kernel(const float4* __restrict__ x, const float* __restrict__ scale,
                                                           const float* __restrict__ shift, float4* __restrict__ y,
-                                                          size_t n4, int c4, int relu) {
+                                                          uint2* __restrict__ y_bf16, size_t n4, int c4, int relu) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
     for (; i < n4; i += stride) {
@@ -74,6 +93,7 @@ __global__ void __launch_bounds__(256) affine_relu_kernel(const float4* __restri
             v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
         }
         y[i] = v;
+        if (y_bf16 != nullptr) y_bf16[i] = pack_bf16x4(v);   // shadow copy: the next conv's tensor-core operand
     }
 }
 
@@ -153,7 +173,8 @@ __global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __re
 
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float4* __restrict__ dy, const float4* __restrict__ x,
                                                            const float4* __restrict__ y, const float* __restrict__ coef,
-                                                           float4* __restrict__ dx, size_t n4, int c) {
+                                                           float4* __restrict__ dx, uint2* __restrict__ dx_bf16, size_t n4,
+                                                           int c) {
     int c4 = c / 4;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -168,6 +189,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float4* __restr
         r.x = fmaf(a.x, g.x, fmaf(b.x, xx.x, d.x)); r.y = fmaf(a.y, g.y, fmaf(b.y, xx.y, d.y));
         r.z = fmaf(a.z, g.z, fmaf(b.z, xx.z, d.z)); r.w = fmaf(a.w, g.w, fmaf(b.w, xx.w, d.w));
         dx[i] = r;
+        if (dx_bf16 != nullptr) dx_bf16[i] = pack_bf16x4(r);
     }
 }
 
@@ -206,15 +228,16 @@ extern "C" int vc_bn_eval_affine(const float* gamma, const float* beta, const fl
     return VC_OK;
 }
 
-extern "C" int vc_affine_relu_f32(const float* x, const float* scale, const float* shift, float* y, int n, int c,
-                                  int relu, vc_stream_t stream_) {
+extern "C" int vc_affine_relu_f32(const float* x, const float* scale, const float* shift, float* y, void* y_bf16, int n,
+                                  int c, int relu, vc_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     VC_CHECK_ARG(c_ok(c) && n >= 0, "bad args n=%d c=%d", n, c);
     if (n == 0) return VC_OK;
     size_t n4 = (size_t)n * c / 4;
     int blocks = (int)((n4 + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
-    affine_relu_kernel<<<blocks, 256, 0, stream>>>((const float4*)x, scale, shift, (float4*)y, n4, c / 4, relu);
+    affine_relu_kernel<<<blocks, 256, 0, stream>>>((const float4*)x, scale, shift, (float4*)y, (uint2*)y_bf16, n4, c / 4,
+                                                   relu);
     VC_LAUNCH_CHECK();
     return VC_OK;
 }
@@ -222,8 +245,8 @@ extern "C" int vc_affine_relu_f32(const float* x, const float* scale, const floa
 extern "C" size_t vc_bn_bwd_ws_bytes(int n, int c) { return ((size_t)BWD_BLOCKS * 2 * c + 3 * c) * sizeof(float); }
 
 extern "C" int vc_bn_relu_bwd_f32(const float* dy, const float* x, const float* y, const float* gamma,
-                                  const float* save_mean, const float* save_invstd, float* dx, float* dgamma,
-                                  float* dbeta, int n, int c, int training, void* ws, size_t ws_bytes,
+                                  const float* save_mean, const float* save_invstd, float* dx, void* dx_bf16,
+                                  float* dgamma, float* dbeta, int n, int c, int training, void* ws, size_t ws_bytes,
                                   vc_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     VC_CHECK_ARG(c_ok(c) && n >= 0 && c <= 64 * 4, "bad args n=%d c=%d", n, c);
@@ -256,7 +279,7 @@ extern "C" int vc_bn_relu_bwd_f32(const float* dy, const float* x, const float* 
     int ablocks = (int)((n4 + 255) / 256);
     if (ablocks > 148 * 16) ablocks = 148 * 16;
     bn_bwd_apply_kernel<<<ablocks, 256, 0, stream>>>((const float4*)dy, (const float4*)x, (const float4*)y, coef,
-                                                     (float4*)dx, n4, c);
+                                                     (float4*)dx, (uint2*)dx_bf16, n4, c);
     VC_LAUNCH_CHECK();
     return VC_OK;
 }

@@ -278,7 +278,8 @@ static constexpr int WG_WIN = 256;  // candidate rows per window (one per thread
 template <int CI, int CO>
 struct WCfg {
     static constexpr int NCG = CO / 4;
-    static constexpr int ACTIVE = (CI * NCG < NTHREADS) ? CI * NCG : NTHREADS;  // threads that own outputs
+    static constexpr int ACTIVE = (CI * NCG < NTHREADS) ? CI * NCG : NTHREADS;  // threads covering one [CI, CO] tile
+    static constexpr int REP = NTHREADS / ACTIVE;  // replicas: each takes every REP-th pair (small channel counts)
     static constexpr int NIG = ACTIVE / NCG;       // ci groups
     static constexpr int RI = CI / NIG;            // ci rows per thread (1,2,4)
     static constexpr size_t smem = (size_t)WG_WIN * (CI + CO) * 4 + 2 * WG_WIN * 4;
@@ -299,8 +300,8 @@ wgrad_kernel(const float* __restrict__ in, const float* __restrict__ dout, const
     const int k = blockIdx.x, chunk = blockIdx.y;
     const int begin = chunk * rows_per_chunk;
     const int end = min(n_out, begin + rows_per_chunk);
-    const int tx = threadIdx.x % W::NCG, ti = threadIdx.x / W::NCG;
-    const bool active = threadIdx.x < W::ACTIVE;
+    const int rep = threadIdx.x / W::ACTIVE, tl = threadIdx.x % W::ACTIVE;
+    const int tx = tl % W::NCG, ti = tl / W::NCG;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float acc[W::RI][4];
 #pragma unroll
@@ -336,26 +337,38 @@ wgrad_kernel(const float* __restrict__ in, const float* __restrict__ dout, const
         cp_async_commit();
         cp_async_wait<0>();
         __syncthreads();
-        if (active) {
 #pragma unroll 4
-            for (int p = 0; p < total; ++p) {
-                float4 b = *reinterpret_cast<const float4*>(Bs + p * CO + tx * 4);
+        for (int p = rep; p < total; p += W::REP) {
+            float4 b = *reinterpret_cast<const float4*>(Bs + p * CO + tx * 4);
 #pragma unroll
-                for (int r = 0; r < W::RI; ++r) {
-                    float a = As[p * CI + ti * W::RI + r];
-                    acc[r][0] = fmaf(a, b.x, acc[r][0]);
-                    acc[r][1] = fmaf(a, b.y, acc[r][1]);
-                    acc[r][2] = fmaf(a, b.z, acc[r][2]);
-                    acc[r][3] = fmaf(a, b.w, acc[r][3]);
-                }
+            for (int r = 0; r < W::RI; ++r) {
+                float a = As[p * CI + ti * W::RI + r];
+                acc[r][0] = fmaf(a, b.x, acc[r][0]);
+                acc[r][1] = fmaf(a, b.y, acc[r][1]);
+                acc[r][2] = fmaf(a, b.z, acc[r][2]);
+                acc[r][3] = fmaf(a, b.w, acc[r][3]);
             }
         }
     }
-    if (active) {
-        float* dst = partial + ((size_t)chunk * K + k) * CI * CO;
+    float* dst = partial + ((size_t)chunk * K + k) * CI * CO;
+    if constexpr (W::REP == 1) {
 #pragma unroll
         for (int r = 0; r < W::RI; ++r)
             *reinterpret_cast<float4*>(dst + (ti * W::RI + r) * CO + tx * 4) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+    } else {
+        // fold the replicas through shared memory in replica order (deterministic)
+        __syncthreads();
+        float* red = As;   // REP * CI * CO floats <= WG_WIN * CI
+#pragma unroll
+        for (int r = 0; r < W::RI; ++r)
+            *reinterpret_cast<float4*>(red + ((size_t)rep * CI + ti * W::RI + r) * CO + tx * 4) =
+                make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+        __syncthreads();
+        for (int e = threadIdx.x; e < CI * CO; e += NTHREADS) {
+            float v = 0.f;
+            for (int q = 0; q < W::REP; ++q) v += red[(size_t)q * CI * CO + e];
+            dst[e] = v;
+        }
     }
 }
 

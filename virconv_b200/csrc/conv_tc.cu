@@ -598,15 +598,24 @@ tc_wgrad_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __res
     (void)ok;
 }
 
-__global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int R, int K, int cin,
-                                       int cout) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;  // index into dw [co][k][ci]
+// fixed-order sum of the per-CTA partials; threads index the PARTIAL layout [k][ci][co] so every one of the R reads
+// is coalesced, the single (transposing) write goes to the parameter layout [co][k][ci]
+__global__ void __launch_bounds__(256) wgrad_tc_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw,
+                                                              int R, int K, int cin, int cout) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
     int total = K * cin * cout;
     if (i >= total) return;
-    int ci = i % cin, k = (i / cin) % K, co = i / (cin * K);
-    float v = 0.f;
-    for (int r = 0; r < R; ++r) v += partial[(((size_t)r * K + k) * cin + ci) * cout + co];
-    dw[i] = v;
+    int co = i % cout, ci = (i / cout) % cin, k = i / (cout * cin);
+    float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+    int r = 0;
+    for (; r + 4 <= R; r += 4) {
+        v0 += __ldg(partial + (size_t)(r + 0) * total + i);
+        v1 += __ldg(partial + (size_t)(r + 1) * total + i);
+        v2 += __ldg(partial + (size_t)(r + 2) * total + i);
+        v3 += __ldg(partial + (size_t)(r + 3) * total + i);
+    }
+    for (; r < R; ++r) v0 += __ldg(partial + (size_t)r * total + i);
+    dw[((size_t)co * K + k) * cin + ci] = (v0 + v1) + (v2 + v3);
 }
 
 static int wgrad_tc_grid(int n_out) {

@@ -1,4 +1,5 @@
 // index2uv, dense(), row gather, error plumbing — sm_100a.
+#include <cuda_bf16.h>
 #include <stdarg.h>
 
 #include "common.cuh"
@@ -105,9 +106,40 @@ __global__ void gather_rows4_kernel(const uint32_t* __restrict__ in, const int32
     out[t] = in[(size_t)rows[r] * words + c];
 }
 
+// out[:, :ca] = a, out[:, ca:] = b (fp32) plus an optional bf16 shadow of the same matrix; float4 granularity
+__global__ void cat2_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float4* __restrict__ out,
+                            uint2* __restrict__ out_bf16, int n, int ca4, int cb4) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int w = ca4 + cb4;
+    if (t >= (long long)n * w) return;
+    int r = (int)(t / w), c = (int)(t % w);
+    float4 v = c < ca4 ? a[(size_t)r * ca4 + c] : b[(size_t)r * cb4 + (c - ca4)];
+    out[t] = v;
+    if (out_bf16 != nullptr) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+        uint2 o;
+        o.x = *reinterpret_cast<uint32_t*>(&lo);
+        o.y = *reinterpret_cast<uint32_t*>(&hi);
+        out_bf16[t] = o;
+    }
+}
+
 }  // namespace vc
 
 using namespace vc;
+
+extern "C" int vc_cat2_f32(const float* a, const float* b, float* out, void* out_bf16, int n, int ca, int cb,
+                           vc_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    VC_CHECK_ARG(n >= 0 && ca > 0 && cb > 0 && ca % 4 == 0 && cb % 4 == 0, "bad cat2 arguments");
+    if (n == 0) return VC_OK;
+    VC_CHECK_ARG(a && b && out, "null pointer");
+    long long total = (long long)n * (ca + cb) / 4;
+    cat2_kernel<<<cdiv(total, 256), 256, 0, stream>>>((const float4*)a, (const float4*)b, (float4*)out, (uint2*)out_bf16, n,
+                                                      ca / 4, cb / 4);
+    VC_LAUNCH_CHECK();
+    return VC_OK;
+}
 
 extern "C" int vc_version(void) { return 100; }
 extern "C" const char* vc_last_error(void) { return g_err; }

@@ -75,45 +75,44 @@ __device__ __forceinline__ int hash_lookup(const unsigned long long* __restrict_
     }
 }
 
-// One thread per output row, loop over the K offsets: nbr[k, o] writes are coalesced per k.
-// Pair counts: warp ballot -> shared-memory histogram -> one global atomic per (block, offset).
+// One thread per (output row, kernel offset): grid (ceil(n/256), K).  Every probe chain is independent, so the
+// hash look-ups of all K offsets are in flight together (the per-row loop this replaced was latency bound);
+// nbr[k, row] writes stay fully coalesced.  Pair counts: warp ballot -> shared counter -> one atomic per block.
 __global__ void __launch_bounds__(256) subm_probe_kernel(const int32_t* __restrict__ idx, int n, Geom g,
                                                          const unsigned long long* __restrict__ table,
                                                          uint32_t mask, int32_t* __restrict__ nbr,
                                                          int32_t* __restrict__ pair_num) {
-    __shared__ int hist[MAXK];
-    if (threadIdx.x < MAXK) hist[threadIdx.x] = 0;
+    __shared__ int cnt;
+    if (threadIdx.x == 0) cnt = 0;
     __syncthreads();
-    int row = blockIdx.x * blockDim.x + threadIdx.x;
-    bool live = row < n;
-    int b = 0, c[VC_MAX_NDIM] = {0, 0, 0};
-    if (live) load_index(idx, row, g.ndim, b, c);
-    int centre = 0;
-    for (int d = 0; d < g.ndim; ++d) centre = centre * g.ksize[d] + g.ksize[d] / 2;
-    for (int k = 0; k < g.K; ++k) {
-        int res = -1;
-        if (live) {
-            if (k == centre) {
-                res = row;  // identity (spconv Native: out = features @ W[centre])
-            } else {
-                int off[VC_MAX_NDIM];
-                decode_k(g, k, off);
-                bool ok = true;
-                unsigned long long key = (unsigned long long)b;
-                for (int d = 0; d < g.ndim; ++d) {
-                    int v = c[d] + (off[d] - g.ksize[d] / 2) * g.dil[d];
-                    ok &= (v >= 0) & (v < g.shape[d]);
-                    key = key * (unsigned long long)g.shape[d] + (unsigned long long)v;
-                }
-                if (ok) res = hash_lookup(table, mask, key);
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y;
+    int res = -1;
+    if (row < n) {
+        int centre = 0;
+        for (int d = 0; d < g.ndim; ++d) centre = centre * g.ksize[d] + g.ksize[d] / 2;
+        if (k == centre) {
+            res = row;  // identity (spconv Native: out = features @ W[centre])
+        } else {
+            int b, c[VC_MAX_NDIM];
+            load_index(idx, row, g.ndim, b, c);
+            int off[VC_MAX_NDIM];
+            decode_k(g, k, off);
+            bool ok = true;
+            unsigned long long key = (unsigned long long)b;
+            for (int d = 0; d < g.ndim; ++d) {
+                int v = c[d] + (off[d] - g.ksize[d] / 2) * g.dil[d];
+                ok &= (v >= 0) & (v < g.shape[d]);
+                key = key * (unsigned long long)g.shape[d] + (unsigned long long)v;
             }
-            nbr[(size_t)k * n + row] = res;
+            if (ok) res = hash_lookup(table, mask, key);
         }
-        unsigned m = __ballot_sync(0xffffffffu, res >= 0);
-        if ((threadIdx.x & 31) == 0 && m) atomicAdd(&hist[k], __popc(m));
+        nbr[(size_t)k * n + row] = res;
     }
+    unsigned m = __ballot_sync(0xffffffffu, res >= 0);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&cnt, __popc(m));
     __syncthreads();
-    if (pair_num != nullptr && threadIdx.x < g.K && hist[threadIdx.x]) atomicAdd(&pair_num[threadIdx.x], hist[threadIdx.x]);
+    if (pair_num != nullptr && threadIdx.x == 0 && cnt) atomicAdd(&pair_num[k], cnt);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -136,18 +135,16 @@ __device__ __forceinline__ long long out_cell(const Geom& g, int b, const int* c
     return lin;
 }
 
-__global__ void conv_mark_kernel(const int32_t* __restrict__ idx, int n, Geom g, uint32_t* bitmap) {
+__global__ void conv_mark_kernel(const int32_t* __restrict__ idx, int n, Geom g, uint32_t* bitmap) {   // grid (rows, K)
     int row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= n) return;
     int b, c[VC_MAX_NDIM];
     load_index(idx, row, g.ndim, b, c);
-    for (int k = 0; k < g.K; ++k) {
-        long long lin = out_cell(g, b, c, k);
-        if (lin < 0) continue;
-        uint32_t bit = 1u << (lin & 31);
-        uint32_t* w = bitmap + (lin >> 5);
-        if (!(*w & bit)) atomicOr(w, bit);
-    }
+    long long lin = out_cell(g, b, c, blockIdx.y);
+    if (lin < 0) return;
+    uint32_t bit = 1u << (lin & 31);
+    uint32_t* w = bitmap + (lin >> 5);
+    if (!(*w & bit)) atomicOr(w, bit);
 }
 
 // local exclusive scan of popcounts inside blocks of SCAN_WORDS words; block totals to block_sum
@@ -248,29 +245,27 @@ __global__ void __launch_bounds__(256) conv_tables_kernel(const int32_t* __restr
                                                           const uint32_t* __restrict__ word_rank,
                                                           const uint32_t* __restrict__ block_sum,
                                                           int32_t* __restrict__ nbr_fwd, int32_t* __restrict__ nbr_bwd,
-                                                          int32_t* __restrict__ pair_num) {
-    __shared__ int hist[MAXK];
-    if (threadIdx.x < MAXK) hist[threadIdx.x] = 0;
+                                                          int32_t* __restrict__ pair_num) {   // grid (rows, K)
+    __shared__ int cnt;
+    if (threadIdx.x == 0) cnt = 0;
     __syncthreads();
-    int row = blockIdx.x * blockDim.x + threadIdx.x;
-    bool live = row < n;
-    int b = 0, c[VC_MAX_NDIM] = {0, 0, 0};
-    if (live) load_index(idx, row, g.ndim, b, c);
-    for (int k = 0; k < g.K; ++k) {
-        int orow = -1;
-        if (live) {
-            long long lin = out_cell(g, b, c, k);
-            if (lin >= 0) {
-                orow = cell_rank(bitmap, word_rank, block_sum, lin);
-                nbr_fwd[(size_t)k * n_out + orow] = row;  // unique writer: (o,k) determines the input cell
-            }
-            nbr_bwd[(size_t)k * n + row] = orow;
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y;
+    int orow = -1;
+    if (row < n) {
+        int b, c[VC_MAX_NDIM];
+        load_index(idx, row, g.ndim, b, c);
+        long long lin = out_cell(g, b, c, k);
+        if (lin >= 0) {
+            orow = cell_rank(bitmap, word_rank, block_sum, lin);
+            nbr_fwd[(size_t)k * n_out + orow] = row;  // unique writer: (o,k) determines the input cell
         }
-        unsigned m = __ballot_sync(0xffffffffu, orow >= 0);
-        if ((threadIdx.x & 31) == 0 && m) atomicAdd(&hist[k], __popc(m));
+        nbr_bwd[(size_t)k * n + row] = orow;
     }
+    unsigned m = __ballot_sync(0xffffffffu, orow >= 0);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&cnt, __popc(m));
     __syncthreads();
-    if (pair_num != nullptr && threadIdx.x < g.K && hist[threadIdx.x]) atomicAdd(&pair_num[threadIdx.x], hist[threadIdx.x]);
+    if (pair_num != nullptr && threadIdx.x == 0 && cnt) atomicAdd(&pair_num[k], cnt);
 }
 
 // one block per offset: order-preserving compaction of nbr[k, :] into spconv-style pairs
@@ -369,7 +364,7 @@ extern "C" int vc_subm_rulebook(const int32_t* indices, int n, int ndim, int bat
     VC_CUDA(cudaMemsetAsync(table, 0xFF, (size_t)slots * 8, stream));
     hash_insert_kernel<<<cdiv(n, 256), 256, 0, stream>>>(indices, n, g, table, slots - 1);
     VC_LAUNCH_CHECK();
-    subm_probe_kernel<<<cdiv(n, 256), 256, 0, stream>>>(indices, n, g, table, slots - 1, nbr, pair_num);
+    subm_probe_kernel<<<dim3(cdiv(n, 256), g.K), 256, 0, stream>>>(indices, n, g, table, slots - 1, nbr, pair_num);
     VC_LAUNCH_CHECK();
     return VC_OK;
 }
@@ -428,7 +423,7 @@ extern "C" int vc_conv_rulebook_count(const int32_t* indices, int n, int ndim, i
     }
     VC_CUDA(cudaMemsetAsync(w.bitmap, 0, (size_t)w.n_words * 4, stream));
     if (n > 0) {
-        conv_mark_kernel<<<cdiv(n, 256), 256, 0, stream>>>(indices, n, g, w.bitmap);
+        conv_mark_kernel<<<dim3(cdiv(n, 256), g.K), 256, 0, stream>>>(indices, n, g, w.bitmap);
         VC_LAUNCH_CHECK();
     }
     scan_local_kernel<<<w.n_blocks, 256, 0, stream>>>(w.bitmap, w.n_words, w.word_rank, w.block_sum);
@@ -462,7 +457,7 @@ extern "C" int vc_conv_rulebook_fill(const int32_t* indices, int n, int ndim, in
     }
     if (n > 0) {
         VC_CHECK_ARG(nbr_bwd, "null nbr_bwd");
-        conv_tables_kernel<<<cdiv(n, 256), 256, 0, stream>>>(indices, n, n_out, g, w.bitmap, w.word_rank, w.block_sum,
+        conv_tables_kernel<<<dim3(cdiv(n, 256), g.K), 256, 0, stream>>>(indices, n, n_out, g, w.bitmap, w.word_rank, w.block_sum,
                                                              nbr_fwd, nbr_bwd, pair_num);
         VC_LAUNCH_CHECK();
     }

@@ -26,7 +26,8 @@ def _require_cuda(*tensors):
 
 
 def _stream():
-    return torch.cuda.current_stream().cuda_stream
+    # raw cudaStream_t of torch's current stream (torch.cuda.current_stream() costs ~10 us per call)
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
 
 
 def _p(t):
@@ -40,8 +41,21 @@ def _tup(v, nd):
     return (int(v),) * nd
 
 
+_WS = {}
+
+
 def _ws(nbytes, device):
-    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+    """Scratch for one C-ABI call.  One persistent, geometrically grown buffer per device: every user is a kernel
+    sequence enqueued on the current stream by a single call (or the count/fill pair of the strided rulebook, which
+    has no other call in between), so stream order makes reuse safe."""
+    nbytes = max(int(nbytes), 256)
+    key = (device.type, device.index)
+    buf = _WS.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 2 * (buf.numel() if buf is not None else 0), 1 << 24), dtype=torch.uint8,
+                          device=device)
+        _WS[key] = buf
+    return buf
 
 
 class KernelTimer:
@@ -323,16 +337,18 @@ class SparseConvFn(torch.autograd.Function):
 class ConvBNReLUFn(torch.autograd.Function):
     """conv -> BatchNorm1d (batch or running statistics) -> ReLU, the unit every VirConv layer is built from
     (spconv_backbone.py:86-131).  BN statistics ride on the conv epilogue; backward = BN/ReLU backward ->
-    dgrad + wgrad."""
+    dgrad + wgrad.  In 'bf16' precision the op also returns a bf16 shadow of its output (non-differentiable) that
+    the next layer gathers from, and accepts the shadow of its own input (`feats_bf16`)."""
 
     @staticmethod
     def forward(ctx, feats, weight, gamma, beta, running_mean, running_var, rb, training, eps, momentum,
-                precision='fp32'):
+                precision='fp32', feats_bf16=None):
         lib = _lib.load()
         dev = feats.device
         cout = weight.shape[0]
         keep = {}
-        x, partial = conv_forward(feats, weight, rb, want_bn_partial=training, precision=precision, keep=keep)
+        x, partial = conv_forward(feats, weight, rb, want_bn_partial=training, precision=precision,
+                                  feats_bf16=feats_bf16, keep=keep)
         ctx.fb = keep.get('feats_bf16')
         stats = torch.empty((4, cout), dtype=torch.float32, device=dev)  # scale, shift, mean, invstd
         scale, shift, mean, invstd = stats[0], stats[1], stats[2], stats[3]
@@ -344,31 +360,59 @@ class ConvBNReLUFn(torch.autograd.Function):
             check(lib.vc_bn_eval_affine(_p(gamma), _p(beta), _p(running_mean), _p(running_var), float(eps), cout,
                                         _p(scale), _p(shift), _p(mean), _p(invstd), _stream()), 'vc_bn_eval_affine')
         y = torch.empty_like(x)
-        check(lib.vc_affine_relu_f32(_p(x), _p(scale), _p(shift), _p(y), rb.n_out, cout, 1, _stream()),
+        yb = torch.empty(x.shape, dtype=torch.bfloat16, device=dev) if precision == 'bf16' else None
+        check(lib.vc_affine_relu_f32(_p(x), _p(scale), _p(shift), _p(y), _p(yb), rb.n_out, cout, 1, _stream()),
               'vc_affine_relu_f32')
         ctx.rb, ctx.training, ctx.precision = rb, training, precision
         ctx.save_for_backward(feats, weight, gamma, x, y, stats)
-        return y
+        if yb is None:
+            return y
+        ctx.mark_non_differentiable(yb)
+        return y, yb
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, *unused):
         lib = _lib.load()
         feats, weight, gamma, x, y, stats = ctx.saved_tensors
         rb = ctx.rb
-        cout = weight.shape[0]
+        cout, cin = weight.shape[0], weight.shape[-1]
         dy = dy.contiguous()
         dx = torch.empty_like(x)
+        use_tc = ctx.precision == 'bf16' and tc_supported(cin, cout) and rb.n_out > 0
+        db = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device) if use_tc else None
         dgamma = torch.empty_like(gamma)
         dbeta = torch.empty_like(gamma)
         ws = _ws(lib.vc_bn_bwd_ws_bytes(rb.n_out, cout), dy.device)
-        check(lib.vc_bn_relu_bwd_f32(_p(dy), _p(x), _p(y), _p(gamma), _p(stats[2]), _p(stats[3]), _p(dx), _p(dgamma),
-                                     _p(dbeta), rb.n_out, cout, int(ctx.training), _p(ws), ws.numel(), _stream()),
-              'vc_bn_relu_bwd_f32')
-        cin = weight.shape[-1]
-        db = cast_bf16(dx) if (ctx.precision == 'bf16' and tc_supported(cin, cout) and rb.n_out > 0) else None
+        check(lib.vc_bn_relu_bwd_f32(_p(dy), _p(x), _p(y), _p(gamma), _p(stats[2]), _p(stats[3]), _p(dx), _p(db),
+                                     _p(dgamma), _p(dbeta), rb.n_out, cout, int(ctx.training), _p(ws), ws.numel(),
+                                     _stream()), 'vc_bn_relu_bwd_f32')
         din = conv_dgrad(dx, weight, rb, ctx.precision, db) if ctx.needs_input_grad[0] else None
         dw = conv_wgrad(feats, dx, weight.shape, rb, ctx.precision, ctx.fb, db) if ctx.needs_input_grad[1] else None
-        return din, dw, dgamma, dbeta, None, None, None, None, None, None, None
+        return din, dw, dgamma, dbeta, None, None, None, None, None, None, None, None
+
+
+class Cat2Fn(torch.autograd.Function):
+    """Channel concat of the 3-D and 2-D branch outputs of an NRConv block (spconv_backbone.py:227), optionally with
+    the bf16 shadow of the result (the next strided conv's tensor-core operand)."""
+
+    @staticmethod
+    def forward(ctx, a, b, want_bf16):
+        _require_cuda(a, b)
+        lib = _lib.load()
+        a, b = a.contiguous(), b.contiguous()
+        n, ca, cb = a.shape[0], a.shape[1], b.shape[1]
+        out = torch.empty((n, ca + cb), dtype=torch.float32, device=a.device)
+        ob = torch.empty((n, ca + cb), dtype=torch.bfloat16, device=a.device) if want_bf16 else None
+        check(lib.vc_cat2_f32(_p(a), _p(b), _p(out), _p(ob), n, ca, cb, _stream()), 'vc_cat2_f32')
+        ctx.ca = ca
+        if ob is None:
+            return out
+        ctx.mark_non_differentiable(ob)
+        return out, ob
+
+    @staticmethod
+    def backward(ctx, dout, *unused):
+        return dout[:, :ctx.ca], dout[:, ctx.ca:], None
 
 
 # ------------------------------------------------------------------------------------------------

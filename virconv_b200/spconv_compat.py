@@ -37,6 +37,7 @@ class SparseConvTensor:
         self.grid = grid
         self.voxel_num = voxel_num
         self.benchmark = benchmark
+        self.features_bf16 = None            # optional bf16 shadow of `features` (tensor-core operand), see ops.py
 
     @property
     def features(self):
@@ -162,9 +163,13 @@ class SparseConvolution(SparseModule):
         momentum = 0.0 if bn.momentum is None else bn.momentum
         if training and bn.track_running_stats and bn.num_batches_tracked is not None:
             bn.num_batches_tracked.add_(1)
-        y = ops.ConvBNReLUFn.apply(x.features, self.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, rb,
-                                   training, bn.eps, momentum, self.precision)
-        return self._out_tensor(x, y, rb)
+        res = ops.ConvBNReLUFn.apply(x.features, self.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, rb,
+                                     training, bn.eps, momentum, self.precision, x.features_bf16)
+        if isinstance(res, tuple):
+            out = self._out_tensor(x, res[0], rb)
+            out.features_bf16 = res[1]
+            return out
+        return self._out_tensor(x, res, rb)
 
 
 def set_precision(module: nn.Module, precision: str):
