@@ -101,10 +101,10 @@ int vc_pairs_from_nbr(const int32_t* nbr, int K, int n, int32_t* pairs /*[2,K,n]
 size_t vc_conv_ws_bytes(int cin, int cout, int K);
 
 /* out[o, co] = sum_k sum_ci in[nbr[k,o], ci] * w[co, k, ci].
- * bn_partial (may be NULL): [ceil(n_out/VC_TILE_ROWS), 2, cout] per-tile channel sums (sum x, sum x^2)
- * of the output, for the BatchNorm1d that follows every conv (spconv_backbone.py:101-105). */
+ * bn_sums (may be NULL): [2, cout] float64 accumulator the kernel ADDS the output's channel sums (sum x,
+ * sum x^2) to, for the BatchNorm1d that follows every conv (spconv_backbone.py:101-105); caller zeroes it. */
 int vc_conv_fwd_f32(const float* in, const float* w, const int32_t* nbr, float* out, int n_out, int cin,
-                    int cout, int K, float* bn_partial, void* ws, size_t ws_bytes, vc_stream_t stream);
+                    int cout, int K, double* bn_sums, void* ws, size_t ws_bytes, vc_stream_t stream);
 
 /* din[i, ci] = sum_k sum_co dout[nbr_t[k,i], co] * w[co, kk, ci],  kk = mirror ? K-1-k : k.
  * nbr_t is the table indexed by INPUT row: the rulebook's nbr_bwd for a regular conv, or the
@@ -133,7 +133,7 @@ int vc_conv_wgrad_f32(const float* in, const float* dout, const int32_t* nbr, fl
 int vc_cast_f32_bf16(const float* in, void* out_bf16, long long n_elements /* multiple of 4 */, vc_stream_t stream);
 size_t vc_conv_tc_ws_bytes(int cin, int cout, int K);
 int vc_conv_fwd_tc(const void* in_bf16, const float* w, const int32_t* nbr, float* out, int n_out, int cin, int cout,
-                   int K, float* bn_partial, void* ws, size_t ws_bytes, int32_t* err_flag, vc_stream_t stream);
+                   int K, double* bn_sums, void* ws, size_t ws_bytes, int32_t* err_flag, vc_stream_t stream);
 int vc_conv_dgrad_tc(const void* dout_bf16, const float* w, const int32_t* nbr_t, float* din, int n_in, int cin,
                      int cout, int K, int mirror, void* ws, size_t ws_bytes, int32_t* err_flag, vc_stream_t stream);
 /* dw[co,k,ci] = sum_o in[nbr[k,o],ci] * dout[o,co] on tensor cores: both operands bf16 (MN-major UMMA), 128/cin
@@ -148,29 +148,22 @@ int vc_conv_wgrad_tc(const void* in_bf16, const void* dout_bf16, const int32_t* 
  * `nn.ReLU()` members of every `spconv.SparseSequential` (spconv_backbone.py:101-105, :160, :561-567).
  * ---------------------------------------------------------------------------------------------- */
 
-/* Train mode: reduce conv partials -> batch mean / biased var; scale = gamma*invstd,
- * shift = beta - mean*scale; running stats updated in place with the unbiased variance
- * (torch.nn.BatchNorm1d semantics).  save_mean/save_invstd [c] are kept for backward. */
-int vc_bn_train_finalize(const float* bn_partial, int n_tiles, int n_rows, int c, const float* gamma,
-                         const float* beta, float* running_mean, float* running_var, float momentum, float eps,
-                         float* scale, float* shift, float* save_mean, float* save_invstd, vc_stream_t stream);
-/* Eval mode: scale/shift from the running statistics. */
-int vc_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean,
-                      const float* running_var, float eps, int c, float* scale, float* shift,
-                      float* save_mean, float* save_invstd, vc_stream_t stream);
-/* y = max(x*scale + shift, 0) (relu != 0) — in place allowed.  y_bf16 (may be NULL): bf16 shadow copy of y, the
- * gathered operand of the next layer's tensor-core conv (saves a separate cast pass). */
-int vc_affine_relu_f32(const float* x, const float* scale, const float* shift, float* y, void* y_bf16, int n, int c,
-                       int relu, vc_stream_t stream);
-/* Backward of y = relu(gamma*(x-mean)*invstd + beta):
+/* y = relu(BN(x)) in one pass.  training != 0: batch statistics from `sums` (the [2,c] float64 accumulator the conv
+ * filled): mean, biased var -> scale = gamma*invstd, shift = beta - mean*scale; running_mean / running_var updated in
+ * place with the unbiased variance and *num_batches_tracked (int64, may be NULL) incremented — torch.nn.BatchNorm1d
+ * semantics.  training == 0: statistics from the running buffers.  stats_out [4,c] = scale, shift, mean, invstd is
+ * kept for backward.  y_bf16 (may be NULL): bf16 shadow of y = the next conv's tensor-core operand.  In place
+ * (y == x) allowed. */
+int vc_bn_apply_relu_f32(const float* x, const double* sums, int n_rows, int c, const float* gamma, const float* beta,
+                         float* running_mean, float* running_var, long long* num_batches_tracked, float momentum,
+                         float eps, int training, float* y, void* y_bf16, float* stats_out, int relu, vc_stream_t stream);
+/* Backward of y = relu(gamma*(x-mean)*invstd + beta), stats = the forward's stats_out:
  *   g = dy * (y > 0); dbeta = sum g; dgamma = sum g*xhat;
  *   train: dx = gamma*invstd*(g - dbeta/n - xhat*dgamma/n);   eval: dx = gamma*invstd*g.
- * ws >= vc_bn_bwd_ws_bytes(n, c). */
-size_t vc_bn_bwd_ws_bytes(int n, int c);
-int vc_bn_relu_bwd_f32(const float* dy, const float* x, const float* y, const float* gamma,
-                       const float* save_mean, const float* save_invstd, float* dx, void* dx_bf16 /*may be NULL*/,
-                       float* dgamma, float* dbeta, int n, int c, int training, void* ws, size_t ws_bytes,
-                       vc_stream_t stream);
+ * bsums: [2,c] float64 scratch accumulator, zeroed by the caller.  dx_bf16 (may be NULL): bf16 shadow of dx. */
+int vc_bn_relu_bwd_f32(const float* dy, const float* x, const float* y, const float* gamma, const float* stats,
+                       float* dx, void* dx_bf16, float* dgamma, float* dbeta, int n, int c, int training,
+                       double* bsums, vc_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Voxel index -> image pixel index.  Replaces `index2uv` + `index2points` + the per-sample

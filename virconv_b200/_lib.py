@@ -43,11 +43,8 @@ SIGNATURES = {
     'vc_conv_dgrad_tc': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _Z, _P, _P]),
     'vc_conv_wgrad_tc_ws_bytes': (_Z, [_I, _I, _I, _I]),
     'vc_conv_wgrad_tc': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _Z, _P, _P]),
-    'vc_bn_train_finalize': (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P]),
-    'vc_bn_eval_affine': (_I, [_P, _P, _P, _P, _F, _I, _P, _P, _P, _P, _P]),
-    'vc_affine_relu_f32': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
-    'vc_bn_bwd_ws_bytes': (_Z, [_I, _I]),
-    'vc_bn_relu_bwd_f32': (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _Z, _P]),
+    'vc_bn_apply_relu_f32': (_I, [_P, _P, _I, _I, _P, _P, _P, _P, _P, _F, _F, _I, _P, _P, _P, _I, _P]),
+    'vc_bn_relu_bwd_f32': (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P]),
     'vc_index2uv': (_I, [_P, _I, _I, _P, _HOSTF, _I, _I, _I, _P, _P]),
     'vc_dense_f32': (_I, [_P, _P, _I, _I, _I, _I, _HOST, _P, _P]),
     'vc_dense_bwd_f32': (_I, [_P, _P, _I, _I, _I, _I, _HOST, _P, _P]),

@@ -137,6 +137,7 @@ class VirConvL8x(nn.Module):
         rot_num = batch_dict['transform_param'].shape[1] if 'transform_param' in batch_dict else 1
         batch_size = batch_dict['batch_size']
         calib = batch_dict['calib']
+        ops.stats_arena(batch_dict['voxel_features'].device).reset()    # one memset for all BN accumulators of this pass
         for i in range(rot_num):
             rid = '' if i == 0 else str(i)
             feats, coords = batch_dict['voxel_features' + rid], batch_dict['voxel_coords' + rid]

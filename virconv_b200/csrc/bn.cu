@@ -1,9 +1,14 @@
 // BatchNorm1d(eps, momentum) + ReLU over the active rows of a sparse tensor — sm_100a.
 //
 // Replaces the `norm_fn(out_channels)` / `nn.ReLU()` members of every spconv.SparseSequential
-// (spconv_backbone.py:101-105, :160 eps=1e-3 momentum=0.01, :561-567).  HBM-bound elementwise work:
-// forward apply reads N*C*4 and writes N*C*4 bytes; the channel statistics come for free from the conv
-// epilogue (per-tile partial sums) and are reduced here in a fixed order (deterministic).
+// (spconv_backbone.py:101-105, :160 eps=1e-3 momentum=0.01, :561-567).  HBM-bound elementwise work.
+//
+// Statistics never get their own pass: the conv epilogue adds each tile's channel sums (sum x, sum x^2) into a
+// [2, C] float64 accumulator with atomics, and the apply kernel below derives mean / invstd / scale / shift from
+// it per thread (block 0 also publishes them for backward and updates the running statistics).  Backward is two
+// kernels: a reduce that accumulates (sum g, sum g*xhat) the same way, and an apply that derives its per-channel
+// coefficients from those sums.  The float64 accumulators make the fp32-rounded results independent of the
+// atomic arrival order for all practical purposes (each addend is an fp32 tile partial, < 2^12 of them).
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -18,77 +23,55 @@ __device__ __forceinline__ uint2 pack_bf16x4(float4 v) {
     return o;
 }
 
-// one block; thread (j, ch): j strides over tiles.  double accumulation of the fp32 tile partials.
-__global__ void __launch_bounds__(1024) bn_train_finalize_kernel(
-    const float* __restrict__ partial, int n_tiles, int n_rows, int c, const float* __restrict__ gamma,
-    const float* __restrict__ beta, float* running_mean, float* running_var, float momentum, float eps,
-    float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ save_mean,
-    float* __restrict__ save_invstd) {
-    extern __shared__ double sh[];  // [lanes][2][c]
-    int ch = threadIdx.x % c, j = threadIdx.x / c, lanes = blockDim.x / c;
-    double s = 0.0, q = 0.0, s1 = 0.0, q1 = 0.0;
-    int t = j;
-    for (; t + lanes < n_tiles; t += 2 * lanes) {     // two independent chains: loads of both are in flight together
-        s += (double)__ldg(partial + ((size_t)t * 2 + 0) * c + ch);
-        q += (double)__ldg(partial + ((size_t)t * 2 + 1) * c + ch);
-        s1 += (double)__ldg(partial + ((size_t)(t + lanes) * 2 + 0) * c + ch);
-        q1 += (double)__ldg(partial + ((size_t)(t + lanes) * 2 + 1) * c + ch);
-    }
-    for (; t < n_tiles; t += lanes) {
-        s += (double)__ldg(partial + ((size_t)t * 2 + 0) * c + ch);
-        q += (double)__ldg(partial + ((size_t)t * 2 + 1) * c + ch);
-    }
-    s += s1;
-    q += q1;
-    sh[(j * 2 + 0) * c + ch] = s;
-    sh[(j * 2 + 1) * c + ch] = q;
-    __syncthreads();
-    if (j == 0) {
-        for (int l = 1; l < lanes; ++l) {
-            s += sh[(l * 2 + 0) * c + ch];
-            q += sh[(l * 2 + 1) * c + ch];
+// y = relu(x*scale + shift); train: statistics from `sums`, eval: from the running buffers.
+// stats_out [4, c] = scale, shift, mean, invstd (block 0).  grid-stride over float4 with stride % (c/4) == 0.
+__global__ void __launch_bounds__(256) bn_apply_relu_kernel(
+    const float4* __restrict__ x, const double* __restrict__ sums, int n_rows, int c, const float* __restrict__ gamma,
+    const float* __restrict__ beta, float* running_mean, float* running_var, long long* num_batches_tracked,
+    float momentum, float eps, int training, float4* __restrict__ y, uint2* __restrict__ y_bf16,
+    float* __restrict__ stats_out, int relu) {
+    const int c4 = c / 4;
+    const size_t n4 = (size_t)n_rows * c4;
+    const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const int cg = (int)(i0 % c4);
+    float sc[4], sh[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int ch = cg * 4 + j;
+        float mean, invstd;
+        double var = 0.0;
+        if (training) {
+            const double n = (double)n_rows;
+            const double m = sums[ch] / n;
+            var = sums[c + ch] / n - m * m;
+            if (var < 0.0) var = 0.0;
+            mean = (float)m;
+            invstd = (float)(1.0 / sqrt(var + (double)eps));
+        } else {
+            mean = running_mean[ch];
+            invstd = 1.f / sqrtf(running_var[ch] + eps);
         }
-        double n = (double)n_rows;
-        double mean = s / n;
-        double var = q / n - mean * mean;
-        if (var < 0.0) var = 0.0;
-        float invstd = (float)(1.0 / sqrt(var + (double)eps));
-        float sc = gamma[ch] * invstd;
-        scale[ch] = sc;
-        shift[ch] = beta[ch] - (float)mean * sc;
-        save_mean[ch] = (float)mean;
-        save_invstd[ch] = invstd;
-        double unbiased = n_rows > 1 ? var * n / (n - 1.0) : var;
-        running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * (float)mean;
-        running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * (float)unbiased;
+        sc[j] = gamma[ch] * invstd;
+        sh[j] = beta[ch] - mean * sc[j];
+        if (blockIdx.x == 0 && threadIdx.x < c4) {   // one writer per channel
+            stats_out[ch] = sc[j];
+            stats_out[c + ch] = sh[j];
+            stats_out[2 * c + ch] = mean;
+            stats_out[3 * c + ch] = invstd;
+            if (training) {
+                const double n = (double)n_rows;
+                const double unbiased = n_rows > 1 ? var * n / (n - 1.0) : var;
+                running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * mean;
+                running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * (float)unbiased;
+            }
+        }
     }
-}
-
-__global__ void bn_eval_affine_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
-                                      const float* __restrict__ rm, const float* __restrict__ rv, float eps, int c,
-                                      float* scale, float* shift, float* save_mean, float* save_invstd) {
-    int ch = threadIdx.x;
-    if (ch >= c) return;
-    float invstd = 1.f / sqrtf(rv[ch] + eps);
-    float sc = gamma[ch] * invstd;
-    scale[ch] = sc;
-    shift[ch] = beta[ch] - rm[ch] * sc;
-    save_mean[ch] = rm[ch];
-    save_invstd[ch] = invstd;
-}
-
-__global__ void __launch_bounds__(256) affine_relu_kernel(const float4* __restrict__ x, const float* __restrict__ scale,
-                                                          const float* __restrict__ shift, float4* __restrict__ y,
-                                                          uint2* __restrict__ y_bf16, size_t n4, int c4, int relu) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (; i < n4; i += stride) {
-        int cg = (int)(i % c4);
+    if (training && blockIdx.x == 0 && threadIdx.x == 0 && num_batches_tracked != nullptr) *num_batches_tracked += 1;
+    for (size_t i = i0; i < n4; i += stride) {
         float4 v = x[i];
-        float4 sc = reinterpret_cast<const float4*>(scale)[cg];
-        float4 sh = reinterpret_cast<const float4*>(shift)[cg];
-        v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
-        v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+        v.x = fmaf(v.x, sc[0], sh[0]); v.y = fmaf(v.y, sc[1], sh[1]);
+        v.z = fmaf(v.z, sc[2], sh[2]); v.w = fmaf(v.w, sc[3], sh[3]);
         if (relu) {
             v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
         }
@@ -97,18 +80,16 @@ __global__ void __launch_bounds__(256) affine_relu_kernel(const float4* __restri
     }
 }
 
-// backward pass 1: per-block partial sums of g = dy*(y>0) and g*xhat      partial [blocks][2][c]
-static constexpr int BWD_BLOCKS = 296;
+// backward pass 1: sum g and sum g*xhat over rows, g = dy*(y>0); block partial -> float64 atomics on bsums [2, c]
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float4* __restrict__ dy, const float4* __restrict__ x,
                                                             const float4* __restrict__ y,
-                                                            const float* __restrict__ mean,
-                                                            const float* __restrict__ invstd, int n, int c,
-                                                            float* __restrict__ partial) {
+                                                            const float* __restrict__ stats, int n, int c,
+                                                            double* __restrict__ bsums) {
     extern __shared__ float shf[];  // [rowlanes][2][c]
-    int c4 = c / 4;
-    int cg = threadIdx.x % c4, rl = threadIdx.x / c4, rowlanes = blockDim.x / c4;
-    float4 m = reinterpret_cast<const float4*>(mean)[cg];
-    float4 is = reinterpret_cast<const float4*>(invstd)[cg];
+    const int c4 = c / 4;
+    const int cg = threadIdx.x % c4, rl = threadIdx.x / c4, rowlanes = blockDim.x / c4;
+    const float4 m = reinterpret_cast<const float4*>(stats + 2 * c)[cg];
+    const float4 is = reinterpret_cast<const float4*>(stats + 3 * c)[cg];
     float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
     for (int row = blockIdx.x * rowlanes + rl; row < n; row += gridDim.x * rowlanes) {
         size_t i = (size_t)row * c4 + cg;
@@ -129,157 +110,104 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float4* __rest
         int which = threadIdx.x / c, ch = threadIdx.x % c;
         float v = 0.f;
         for (int l = 0; l < rowlanes; ++l) v += shf[(l * 2 + which) * c + ch];
-        partial[((size_t)blockIdx.x * 2 + which) * c + ch] = v;
+        atomicAdd(bsums + which * c + ch, (double)v);
     }
 }
 
-// pass 2 (one block, lanes x c threads): dgamma, dbeta and the per-channel coefficients of
-//   dx = coef[0]*g + coef[1]*x + coef[2]
-__global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __restrict__ partial, int blocks, int n, int c,
-                                                                const float* __restrict__ gamma,
-                                                                const float* __restrict__ mean,
-                                                                const float* __restrict__ invstd, int training,
-                                                                float* dgamma, float* dbeta, float* __restrict__ coef) {
-    extern __shared__ double shd[];  // [lanes][2][c]
-    int ch = threadIdx.x % c, j = threadIdx.x / c, lanes = blockDim.x / c;
-    double s = 0.0, q = 0.0;
-    for (int b = j; b < blocks; b += lanes) {
-        s += (double)partial[((size_t)b * 2 + 0) * c + ch];
-        q += (double)partial[((size_t)b * 2 + 1) * c + ch];
-    }
-    shd[(j * 2 + 0) * c + ch] = s;
-    shd[(j * 2 + 1) * c + ch] = q;
-    __syncthreads();
-    if (j != 0) return;
-    for (int l = 1; l < lanes; ++l) {
-        s += shd[(l * 2 + 0) * c + ch];
-        q += shd[(l * 2 + 1) * c + ch];
-    }
-    dbeta[ch] = (float)s;
-    dgamma[ch] = (float)q;
-    float gi = gamma[ch] * invstd[ch];
-    if (training) {
-        // dx = gi*(g - s/n - xhat*q/n),  xhat = (x-mean)*invstd
-        float k1 = (float)(q / (double)n) * invstd[ch];
-        coef[ch] = gi;
-        coef[c + ch] = -gi * k1;
-        coef[2 * c + ch] = gi * (k1 * mean[ch] - (float)(s / (double)n));
-    } else {
-        coef[ch] = gi;
-        coef[c + ch] = 0.f;
-        coef[2 * c + ch] = 0.f;
-    }
-}
-
+// backward pass 2:  train: dx = gi*(g - S/n - xhat*Q/n);  eval: dx = gi*g;   gi = gamma*invstd
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float4* __restrict__ dy, const float4* __restrict__ x,
-                                                           const float4* __restrict__ y, const float* __restrict__ coef,
-                                                           float4* __restrict__ dx, uint2* __restrict__ dx_bf16, size_t n4,
-                                                           int c) {
-    int c4 = c / 4;
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (; i < n4; i += stride) {
-        int cg = (int)(i % c4);
-        float4 a = reinterpret_cast<const float4*>(coef)[cg];
-        float4 b = reinterpret_cast<const float4*>(coef + c)[cg];
-        float4 d = reinterpret_cast<const float4*>(coef + 2 * c)[cg];
+                                                           const float4* __restrict__ y, const float* __restrict__ gamma,
+                                                           const float* __restrict__ stats,
+                                                           const double* __restrict__ bsums, int n_rows, int c, int training,
+                                                           float4* __restrict__ dx, uint2* __restrict__ dx_bf16,
+                                                           float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    const int c4 = c / 4;
+    const size_t n4 = (size_t)n_rows * c4;
+    const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const int cg = (int)(i0 % c4);
+    float a[4], b[4], d[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int ch = cg * 4 + j;
+        const double S = bsums[ch], Q = bsums[c + ch];
+        const float mean = stats[2 * c + ch], invstd = stats[3 * c + ch];
+        const float gi = gamma[ch] * invstd;
+        if (training) {
+            const float k1 = (float)(Q / (double)n_rows) * invstd;
+            a[j] = gi;
+            b[j] = -gi * k1;
+            d[j] = gi * (k1 * mean - (float)(S / (double)n_rows));
+        } else {
+            a[j] = gi;
+            b[j] = 0.f;
+            d[j] = 0.f;
+        }
+        if (blockIdx.x == 0 && threadIdx.x < c4) {
+            dbeta[ch] = (float)S;
+            dgamma[ch] = (float)Q;
+        }
+    }
+    for (size_t i = i0; i < n4; i += stride) {
         float4 g = dy[i], yy = y[i], xx = x[i], r;
         g.x = yy.x > 0.f ? g.x : 0.f; g.y = yy.y > 0.f ? g.y : 0.f;
         g.z = yy.z > 0.f ? g.z : 0.f; g.w = yy.w > 0.f ? g.w : 0.f;
-        r.x = fmaf(a.x, g.x, fmaf(b.x, xx.x, d.x)); r.y = fmaf(a.y, g.y, fmaf(b.y, xx.y, d.y));
-        r.z = fmaf(a.z, g.z, fmaf(b.z, xx.z, d.z)); r.w = fmaf(a.w, g.w, fmaf(b.w, xx.w, d.w));
+        r.x = fmaf(a[0], g.x, fmaf(b[0], xx.x, d[0])); r.y = fmaf(a[1], g.y, fmaf(b[1], xx.y, d[1]));
+        r.z = fmaf(a[2], g.z, fmaf(b[2], xx.z, d[2])); r.w = fmaf(a[3], g.w, fmaf(b[3], xx.w, d[3]));
         dx[i] = r;
         if (dx_bf16 != nullptr) dx_bf16[i] = pack_bf16x4(r);
     }
 }
 
-static bool c_ok(int c) { return c > 0 && c % 4 == 0 && c <= 256; }
+static bool c_ok(int c) { return c > 0 && c % 4 == 0 && c <= 128; }
+
+static int ew_blocks(size_t n4) {
+    size_t b = (n4 + 255) / 256;
+    if (b > 148 * 16) b = 148 * 16;
+    return (int)(b < 1 ? 1 : b);
+}
 
 }  // namespace vc
 
 using namespace vc;
 
-extern "C" int vc_bn_train_finalize(const float* bn_partial, int n_tiles, int n_rows, int c, const float* gamma,
-                                    const float* beta, float* running_mean, float* running_var, float momentum,
-                                    float eps, float* scale, float* shift, float* save_mean, float* save_invstd,
-                                    vc_stream_t stream_) {
+extern "C" int vc_bn_apply_relu_f32(const float* x, const double* sums, int n_rows, int c, const float* gamma,
+                                    const float* beta, float* running_mean, float* running_var,
+                                    long long* num_batches_tracked, float momentum, float eps, int training, float* y,
+                                    void* y_bf16, float* stats_out, int relu, vc_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    VC_CHECK_ARG(c_ok(c) && n_tiles >= 0 && n_rows > 0, "bad bn args c=%d tiles=%d rows=%d", c, n_tiles, n_rows);
-    VC_CHECK_ARG(bn_partial && gamma && beta && running_mean && running_var && scale && shift && save_mean && save_invstd,
-                 "null pointer");
-    int lanes = 1024 / c;
-    if (lanes > 32) lanes = 32;
-    size_t smem = (size_t)lanes * 2 * c * sizeof(double);
-    bn_train_finalize_kernel<<<1, lanes * c, smem, stream>>>(bn_partial, n_tiles, n_rows, c, gamma, beta, running_mean,
-                                                              running_var, momentum, eps, scale, shift, save_mean,
-                                                              save_invstd);
+    VC_CHECK_ARG(c_ok(c) && n_rows >= 0, "bad bn args c=%d rows=%d", c, n_rows);
+    VC_CHECK_ARG(gamma && beta && running_mean && running_var && stats_out, "null pointer");
+    VC_CHECK_ARG(!training || sums, "training-mode BN needs the conv's channel sums");
+    VC_CHECK_ARG(!training || n_rows > 0, "training-mode BN over zero rows");
+    VC_CHECK_ARG(n_rows == 0 || (x && y), "null pointer");
+    bn_apply_relu_kernel<<<ew_blocks((size_t)n_rows * c / 4), 256, 0, stream>>>(
+        (const float4*)x, sums, n_rows, c, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps,
+        training, (float4*)y, (uint2*)y_bf16, stats_out, relu);
     VC_LAUNCH_CHECK();
     return VC_OK;
 }
 
-extern "C" int vc_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean,
-                                 const float* running_var, float eps, int c, float* scale, float* shift,
-                                 float* save_mean, float* save_invstd, vc_stream_t stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
-    VC_CHECK_ARG(c_ok(c), "bad channel count %d", c);
-    bn_eval_affine_kernel<<<1, 256, 0, stream>>>(gamma, beta, running_mean, running_var, eps, c, scale, shift,
-                                                  save_mean, save_invstd);
-    VC_LAUNCH_CHECK();
-    return VC_OK;
-}
-
-extern "C" int vc_affine_relu_f32(const float* x, const float* scale, const float* shift, float* y, void* y_bf16, int n,
-                                  int c, int relu, vc_stream_t stream_) {
+extern "C" int vc_bn_relu_bwd_f32(const float* dy, const float* x, const float* y, const float* gamma, const float* stats,
+                                  float* dx, void* dx_bf16, float* dgamma, float* dbeta, int n, int c, int training,
+                                  double* bsums, vc_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     VC_CHECK_ARG(c_ok(c) && n >= 0, "bad args n=%d c=%d", n, c);
-    if (n == 0) return VC_OK;
-    size_t n4 = (size_t)n * c / 4;
-    int blocks = (int)((n4 + 255) / 256);
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    affine_relu_kernel<<<blocks, 256, 0, stream>>>((const float4*)x, scale, shift, (float4*)y, (uint2*)y_bf16, n4, c / 4,
-                                                   relu);
-    VC_LAUNCH_CHECK();
-    return VC_OK;
-}
-
-extern "C" size_t vc_bn_bwd_ws_bytes(int n, int c) { return ((size_t)BWD_BLOCKS * 2 * c + 3 * c) * sizeof(float); }
-
-extern "C" int vc_bn_relu_bwd_f32(const float* dy, const float* x, const float* y, const float* gamma,
-                                  const float* save_mean, const float* save_invstd, float* dx, void* dx_bf16,
-                                  float* dgamma, float* dbeta, int n, int c, int training, void* ws, size_t ws_bytes,
-                                  vc_stream_t stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
-    VC_CHECK_ARG(c_ok(c) && n >= 0 && c <= 64 * 4, "bad args n=%d c=%d", n, c);
-    VC_CHECK_ARG(dgamma && dbeta && ws, "null pointer");
-    if (ws_bytes < vc_bn_bwd_ws_bytes(n, c)) {
-        set_error("bn bwd workspace %zu < %zu", ws_bytes, vc_bn_bwd_ws_bytes(n, c));
-        return VC_ERR_WORKSPACE;
+    VC_CHECK_ARG(dgamma && dbeta && bsums && stats && gamma, "null pointer");
+    if (n > 0) {
+        VC_CHECK_ARG(dy && x && y && dx, "null pointer");
+        int c4 = c / 4;
+        int rowlanes = 256 / c4;
+        int blocks = (n + rowlanes - 1) / rowlanes;
+        if (blocks > 296) blocks = 296;
+        size_t smem = (size_t)rowlanes * 2 * c * sizeof(float);
+        bn_bwd_reduce_kernel<<<blocks, 256, smem, stream>>>((const float4*)dy, (const float4*)x, (const float4*)y, stats, n, c,
+                                                            bsums);
+        VC_LAUNCH_CHECK();
     }
-    if (n == 0) {
-        VC_CUDA(cudaMemsetAsync(dgamma, 0, c * 4, stream));
-        VC_CUDA(cudaMemsetAsync(dbeta, 0, c * 4, stream));
-        return VC_OK;
-    }
-    float* partial = (float*)ws;
-    float* coef = partial + (size_t)BWD_BLOCKS * 2 * c;
-    int c4 = c / 4;
-    int rowlanes = 256 / c4;
-    int blocks = (n + rowlanes - 1) / rowlanes;
-    if (blocks > BWD_BLOCKS) blocks = BWD_BLOCKS;
-    size_t smem = (size_t)rowlanes * 2 * c * sizeof(float);
-    bn_bwd_reduce_kernel<<<blocks, 256, smem, stream>>>((const float4*)dy, (const float4*)x, (const float4*)y, save_mean,
-                                                        save_invstd, n, c, partial);
-    VC_LAUNCH_CHECK();
-    int flanes = 1024 / c;
-    if (flanes > 32) flanes = 32;
-    bn_bwd_finalize_kernel<<<1, flanes * c, (size_t)flanes * 2 * c * sizeof(double), stream>>>(
-        partial, blocks, n, c, gamma, save_mean, save_invstd, training, dgamma, dbeta, coef);
-    VC_LAUNCH_CHECK();
-    size_t n4 = (size_t)n * c4;
-    int ablocks = (int)((n4 + 255) / 256);
-    if (ablocks > 148 * 16) ablocks = 148 * 16;
-    bn_bwd_apply_kernel<<<ablocks, 256, 0, stream>>>((const float4*)dy, (const float4*)x, (const float4*)y, coef,
-                                                     (float4*)dx, (uint2*)dx_bf16, n4, c);
+    bn_bwd_apply_kernel<<<ew_blocks((size_t)n * c / 4), 256, 0, stream>>>((const float4*)dy, (const float4*)x,
+                                                                          (const float4*)y, gamma, stats, bsums, n, c, training,
+                                                                          (float4*)dx, (uint2*)dx_bf16, dgamma, dbeta);
     VC_LAUNCH_CHECK();
     return VC_OK;
 }

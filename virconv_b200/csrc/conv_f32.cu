@@ -129,7 +129,7 @@ __device__ __forceinline__ void tile_mac(const float* As, const float* Ws, int r
 template <int CI, int CO>
 __global__ void __launch_bounds__(NTHREADS, (Cfg<CI, CO>::RT >= 8) ? 2 : 3)
 gather_gemm_kernel(const float* __restrict__ in, const float* __restrict__ wt, const int32_t* __restrict__ nbr,
-                   float* __restrict__ out, int n_out, int K, float* __restrict__ bn_partial) {
+                   float* __restrict__ out, int n_out, int K, double* __restrict__ bn_sums) {
     using C = Cfg<CI, CO>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* As = reinterpret_cast<float*>(smem_raw);         // [2][TM][AS]
@@ -184,7 +184,7 @@ gather_gemm_kernel(const float* __restrict__ in, const float* __restrict__ wt, c
             }
         }
     }
-    if (bn_partial != nullptr) {  // per-tile channel sums for the BatchNorm that follows
+    if (bn_sums != nullptr) {  // tile's channel sums for the BatchNorm that follows -> float64 accumulator [2, CO]
 #pragma unroll
         for (int off = C::NCG; off < 32; off <<= 1) {
 #pragma unroll
@@ -206,7 +206,7 @@ gather_gemm_kernel(const float* __restrict__ in, const float* __restrict__ wt, c
             float v = 0.f;
 #pragma unroll
             for (int w = 0; w < NTHREADS / 32; ++w) v += red[w][which][ch];
-            bn_partial[((size_t)blockIdx.x * 2 + which) * CO + ch] = v;
+            atomicAdd(bn_sums + which * CO + ch, (double)v);
         }
     }
 }
@@ -390,11 +390,11 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
 
 template <int CI, int CO>
 static int launch_gather(const float* in, const float* wt, const int32_t* nbr, float* out, int n_out, int K,
-                         float* bn_partial, cudaStream_t stream) {
+                         double* bn_sums, cudaStream_t stream) {
     size_t smem = Cfg<CI, CO>::smem_gather(K);
     auto kern = gather_gemm_kernel<CI, CO>;
     VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<cdiv(n_out, TM), NTHREADS, smem, stream>>>(in, wt, nbr, out, n_out, K, bn_partial);
+    kern<<<cdiv(n_out, TM), NTHREADS, smem, stream>>>(in, wt, nbr, out, n_out, K, bn_sums);
     VC_LAUNCH_CHECK();
     return VC_OK;
 }
@@ -479,14 +479,14 @@ static int check_conv_args(int n, int cin, int cout, int K, const void* a, const
 }
 
 extern "C" int vc_conv_fwd_f32(const float* in, const float* w, const int32_t* nbr, float* out, int n_out, int cin,
-                               int cout, int K, float* bn_partial, void* ws, size_t ws_bytes, vc_stream_t stream_) {
+                               int cout, int K, double* bn_sums, void* ws, size_t ws_bytes, vc_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     int rc = check_conv_args(n_out, cin, cout, K, in, w, nbr, out, ws, ws_bytes);
     if (rc || n_out == 0) return rc;
     float* wt = (float*)ws;
     if ((rc = prep(w, wt, cin, cout, K, 0, 0, stream))) return rc;
     return dispatch(cin, cout, [&](auto ci, auto co) {
-        return launch_gather<decltype(ci)::value, decltype(co)::value>(in, wt, nbr, out, n_out, K, bn_partial, stream);
+        return launch_gather<decltype(ci)::value, decltype(co)::value>(in, wt, nbr, out, n_out, K, bn_sums, stream);
     });
 }
 

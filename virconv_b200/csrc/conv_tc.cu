@@ -139,7 +139,7 @@ template <int KC, int NR>
 __global__ void __launch_bounds__(TC_THREADS)
 tc_gather_gemm_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __restrict__ wimg,
                       const int32_t* __restrict__ nbr, float* __restrict__ out, int n_out, int K,
-                      float* __restrict__ bn_partial, int* __restrict__ err) {
+                      double* __restrict__ bn_sums, int* __restrict__ err) {
     using C = TcCfg<KC, NR>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* ring = smem_raw;                                          // [stages][A | B]
@@ -277,7 +277,7 @@ tc_gather_gemm_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16*
             *reinterpret_cast<float4*>(out + (size_t)(base + r) * NR + c4 * 4) = make_float4(s[0], s[1], s[2], s[3]);
         }
     }
-    if (bn_partial != nullptr) {
+    if (bn_sums != nullptr) {
         // column sums over the tile's valid rows: thread (ch, quarter) sums 32 rows
         const int rows_valid = min(TCM, n_out - base);
         for (int idx = tid; idx < NR * 4; idx += TC_THREADS) {
@@ -294,8 +294,8 @@ tc_gather_gemm_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16*
         __syncthreads();
         for (int idx = tid; idx < 2 * NR; idx += TC_THREADS) {
             const int which = idx / NR, ch = idx % NR;
-            bn_partial[((size_t)blockIdx.x * 2 + which) * NR + ch] =
-                red[0][which][ch] + red[1][which][ch] + red[2][which][ch] + red[3][which][ch];
+            atomicAdd(bn_sums + which * NR + ch,
+                      (double)(red[0][which][ch] + red[1][which][ch] + red[2][which][ch] + red[3][which][ch]));
         }
     }
     __syncthreads();
@@ -307,11 +307,11 @@ tc_gather_gemm_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16*
 
 template <int KC, int NR>
 static int launch_tc(const __nv_bfloat16* in, const __nv_bfloat16* wimg, const int32_t* nbr, float* out, int n_out, int K,
-                     float* bn_partial, int* err, cudaStream_t stream) {
+                     double* bn_sums, int* err, cudaStream_t stream) {
     size_t smem = TcCfg<KC, NR>::smem(K);
     auto kern = tc_gather_gemm_kernel<KC, NR>;
     VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<cdiv(n_out, TCM), TC_THREADS, smem, stream>>>(in, wimg, nbr, out, n_out, K, bn_partial, err);
+    kern<<<cdiv(n_out, TCM), TC_THREADS, smem, stream>>>(in, wimg, nbr, out, n_out, K, bn_sums, err);
     VC_LAUNCH_CHECK();
     return VC_OK;
 }
@@ -319,9 +319,9 @@ static int launch_tc(const __nv_bfloat16* in, const __nv_bfloat16* wimg, const i
 static bool tc_ch_ok(int c) { return c == 16 || c == 32 || c == 64; }
 
 static int dispatch_tc(int kc, int nr, const __nv_bfloat16* in, const __nv_bfloat16* wimg, const int32_t* nbr, float* out,
-                       int n_out, int K, float* bn_partial, int* err, cudaStream_t stream) {
+                       int n_out, int K, double* bn_sums, int* err, cudaStream_t stream) {
 #define VC_TC_CASE(A, B) \
-    if (kc == A && nr == B) return launch_tc<A, B>(in, wimg, nbr, out, n_out, K, bn_partial, err, stream);
+    if (kc == A && nr == B) return launch_tc<A, B>(in, wimg, nbr, out, n_out, K, bn_sums, err, stream);
     VC_TC_CASE(16, 16) VC_TC_CASE(16, 32) VC_TC_CASE(16, 64)
     VC_TC_CASE(32, 16) VC_TC_CASE(32, 32) VC_TC_CASE(32, 64)
     VC_TC_CASE(64, 16) VC_TC_CASE(64, 32) VC_TC_CASE(64, 64)
@@ -350,7 +350,7 @@ extern "C" int vc_cast_f32_bf16(const float* in, void* out, long long n, vc_stre
 extern "C" size_t vc_conv_tc_ws_bytes(int cin, int cout, int K) { return (size_t)K * cin * cout * 2; }
 
 static int tc_common(const void* feats_bf16, const float* w, const int32_t* nbr, float* out, int n_rows, int cin, int cout,
-                     int K, int mode, int mirror, float* bn_partial, void* ws, size_t ws_bytes, int32_t* err, cudaStream_t stream) {
+                     int K, int mode, int mirror, double* bn_sums, void* ws, size_t ws_bytes, int32_t* err, cudaStream_t stream) {
     VC_CHECK_ARG(n_rows >= 0 && K >= 1 && K <= MAXK_TC, "bad n=%d or K=%d", n_rows, K);
     if (!tc_ch_ok(cin) || !tc_ch_ok(cout)) {
         set_error("tensor-core conv: unsupported channels cin=%d cout=%d (need 16/32/64)", cin, cout);
@@ -367,13 +367,13 @@ static int tc_common(const void* feats_bf16, const float* w, const int32_t* nbr,
     prep_weights_tc_kernel<<<cdiv(total, 256), 256, 0, stream>>>(w, img, cin, cout, K, mode, mirror);
     VC_LAUNCH_CHECK();
     int kc = mode == 0 ? cin : cout, nr = mode == 0 ? cout : cin;
-    return dispatch_tc(kc, nr, (const __nv_bfloat16*)feats_bf16, img, nbr, out, n_rows, K, bn_partial, err, stream);
+    return dispatch_tc(kc, nr, (const __nv_bfloat16*)feats_bf16, img, nbr, out, n_rows, K, bn_sums, err, stream);
 }
 
 extern "C" int vc_conv_fwd_tc(const void* in_bf16, const float* w, const int32_t* nbr, float* out, int n_out, int cin,
-                              int cout, int K, float* bn_partial, void* ws, size_t ws_bytes, int32_t* err_flag,
+                              int cout, int K, double* bn_sums, void* ws, size_t ws_bytes, int32_t* err_flag,
                               vc_stream_t stream_) {
-    return tc_common(in_bf16, w, nbr, out, n_out, cin, cout, K, 0, 0, bn_partial, ws, ws_bytes, err_flag, (cudaStream_t)stream_);
+    return tc_common(in_bf16, w, nbr, out, n_out, cin, cout, K, 0, 0, bn_sums, ws, ws_bytes, err_flag, (cudaStream_t)stream_);
 }
 
 extern "C" int vc_conv_dgrad_tc(const void* dout_bf16, const float* w, const int32_t* nbr_t, float* din, int n_in, int cin,

@@ -58,6 +58,45 @@ def _ws(nbytes, device):
     return buf
 
 
+class StatsArena:
+    """Zeroed float64 scratch for the BatchNorm channel sums (forward [2,C] + backward [2,C] per layer).  One buffer
+    per device; `reset()` (called once per backbone forward) re-zeroes it with a single memset and rewinds the cursor;
+    each conv+BN layer takes a fresh slice, so no per-layer memset is needed.  Past the end (or without a reset
+    between uses) it falls back to a fresh zeros tensor."""
+    SIZE = 16384   # doubles: 64 layers x 4 x 64 channels
+
+    def __init__(self, device):
+        self.buf = torch.zeros(self.SIZE, dtype=torch.float64, device=device)
+        self.cursor = 0
+        self.dirty = False
+        self.generation = 0
+
+    def reset(self):
+        if self.dirty:
+            self.buf.zero_()
+        self.cursor = 0
+        self.dirty = False
+        self.generation += 1
+
+    def take(self, n):
+        if self.cursor + n > self.SIZE:
+            return torch.zeros(n, dtype=torch.float64, device=self.buf.device)
+        out = self.buf[self.cursor:self.cursor + n]
+        self.cursor += n
+        self.dirty = True
+        return out
+
+
+_ARENAS = {}
+
+
+def stats_arena(device) -> StatsArena:
+    key = (device.type, device.index)
+    if key not in _ARENAS:
+        _ARENAS[key] = StatsArena(device)
+    return _ARENAS[key]
+
+
 class KernelTimer:
     """Optional per-call CUDA-event timing of the C-ABI calls (bench.py's roofline pass).  Off by default:
     `ops.TIMER = KernelTimer()` turns it on, `ops.TIMER = None` off.  Events are recorded on the launching
@@ -210,16 +249,15 @@ def build_conv_rulebook(indices, batch_size, spatial_shape, ksize, stride, paddi
 # ------------------------------------------------------------------------------------------------
 # raw kernels
 # ------------------------------------------------------------------------------------------------
-def conv_forward(feats, weight, rb: Rulebook, want_bn_partial=False, precision='fp32', feats_bf16=None, keep=None):
-    """feats [n_in, C_in] f32, weight [C_out, *k, C_in] f32 -> out [n_out, C_out] (+ per-tile BN partial sums)."""
+def conv_forward(feats, weight, rb: Rulebook, bn_sums=None, precision='fp32', feats_bf16=None, keep=None):
+    """feats [n_in, C_in] f32, weight [C_out, *k, C_in] f32 -> out [n_out, C_out]; when `bn_sums` ([2*C_out] float64,
+    zeroed) is given the kernel adds the output's channel sums (sum x, sum x^2) to it."""
     _require_cuda(feats, weight)
     lib = _lib.load()
     cout, cin = weight.shape[0], weight.shape[-1]
     feats = feats.contiguous()
     weight = weight.contiguous()
     out = torch.empty((rb.n_out, cout), dtype=torch.float32, device=feats.device)
-    n_tiles = (rb.n_out + TILE_ROWS - 1) // TILE_ROWS
-    partial = torch.empty((n_tiles, 2, cout), dtype=torch.float32, device=feats.device) if want_bn_partial else None
     if precision == 'bf16' and tc_supported(cin, cout) and rb.n_out > 0:
         fb = feats_bf16 if feats_bf16 is not None else cast_bf16(feats)
         if keep is not None:
@@ -230,17 +268,17 @@ def conv_forward(feats, weight, rb: Rulebook, want_bn_partial=False, precision='
                lambda: n_in * cin * 2 + rb.n_out * cout * 4 + rb.K * cin * cout * 2 + rb.n_pairs() * 8,
                lambda: 2 * rb.n_pairs() * cin * cout,
                lambda: check(lib.vc_conv_fwd_tc(_p(fb), _p(weight), _p(rb.nbr), _p(out), rb.n_out, cin, cout, rb.K,
-                                                _p(partial), _p(ws), ws.numel(), _p(tc_error_flag(feats.device)),
+                                                _p(bn_sums), _p(ws), ws.numel(), _p(tc_error_flag(feats.device)),
                                                 _stream()), 'vc_conv_fwd_tc'))
-        return out, partial
+        return out
     ws = _ws(lib.vc_conv_ws_bytes(cin, cout, rb.K), feats.device)
     n_in = feats.shape[0]
     _timed('conv_fwd',
            lambda: (n_in * cin + rb.n_out * cout + rb.K * cin * cout) * 4 + rb.n_pairs() * 8,
            lambda: 2 * rb.n_pairs() * cin * cout,
            lambda: check(lib.vc_conv_fwd_f32(_p(feats), _p(weight), _p(rb.nbr), _p(out), rb.n_out, cin, cout, rb.K,
-                                             _p(partial), _p(ws), ws.numel(), _stream()), 'vc_conv_fwd_f32'))
-    return out, partial
+                                             _p(bn_sums), _p(ws), ws.numel(), _stream()), 'vc_conv_fwd_f32'))
+    return out
 
 
 def conv_dgrad(dout, weight, rb: Rulebook, precision='fp32', dout_bf16=None):
@@ -316,7 +354,7 @@ class SparseConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, feats, weight, rb, precision='fp32'):
         keep = {}
-        out, _ = conv_forward(feats, weight, rb, False, precision, keep=keep)
+        out = conv_forward(feats, weight, rb, None, precision, keep=keep)
         ctx.rb, ctx.precision = rb, precision
         ctx.fb = keep.get('feats_bf16')
         ctx.save_for_backward(feats, weight)
@@ -342,27 +380,22 @@ class ConvBNReLUFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, feats, weight, gamma, beta, running_mean, running_var, rb, training, eps, momentum,
-                precision='fp32', feats_bf16=None):
+                precision='fp32', feats_bf16=None, num_batches_tracked=None):
         lib = _lib.load()
+        ctx.set_materialize_grads(False)
         dev = feats.device
         cout = weight.shape[0]
         keep = {}
-        x, partial = conv_forward(feats, weight, rb, want_bn_partial=training, precision=precision,
-                                  feats_bf16=feats_bf16, keep=keep)
+        sums = stats_arena(dev).take(4 * cout)      # [0:2C] forward sums, [2C:4C] backward sums (used in backward)
+        x = conv_forward(feats, weight, rb, sums if training else None, precision, feats_bf16=feats_bf16, keep=keep)
         ctx.fb = keep.get('feats_bf16')
         stats = torch.empty((4, cout), dtype=torch.float32, device=dev)  # scale, shift, mean, invstd
-        scale, shift, mean, invstd = stats[0], stats[1], stats[2], stats[3]
-        if training:
-            check(lib.vc_bn_train_finalize(_p(partial), partial.shape[0], rb.n_out, cout, _p(gamma), _p(beta),
-                                           _p(running_mean), _p(running_var), float(momentum), float(eps), _p(scale),
-                                           _p(shift), _p(mean), _p(invstd), _stream()), 'vc_bn_train_finalize')
-        else:
-            check(lib.vc_bn_eval_affine(_p(gamma), _p(beta), _p(running_mean), _p(running_var), float(eps), cout,
-                                        _p(scale), _p(shift), _p(mean), _p(invstd), _stream()), 'vc_bn_eval_affine')
         y = torch.empty_like(x)
         yb = torch.empty(x.shape, dtype=torch.bfloat16, device=dev) if precision == 'bf16' else None
-        check(lib.vc_affine_relu_f32(_p(x), _p(scale), _p(shift), _p(y), _p(yb), rb.n_out, cout, 1, _stream()),
-              'vc_affine_relu_f32')
+        check(lib.vc_bn_apply_relu_f32(_p(x), _p(sums), rb.n_out, cout, _p(gamma), _p(beta), _p(running_mean),
+                                       _p(running_var), _p(num_batches_tracked), float(momentum), float(eps), int(training),
+                                       _p(y), _p(yb), _p(stats), 1, _stream()), 'vc_bn_apply_relu_f32')
+        ctx.bsums, ctx.arena_gen = sums[2 * cout:], stats_arena(dev).generation
         ctx.rb, ctx.training, ctx.precision = rb, training, precision
         ctx.save_for_backward(feats, weight, gamma, x, y, stats)
         if yb is None:
@@ -382,13 +415,14 @@ class ConvBNReLUFn(torch.autograd.Function):
         db = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device) if use_tc else None
         dgamma = torch.empty_like(gamma)
         dbeta = torch.empty_like(gamma)
-        ws = _ws(lib.vc_bn_bwd_ws_bytes(rb.n_out, cout), dy.device)
-        check(lib.vc_bn_relu_bwd_f32(_p(dy), _p(x), _p(y), _p(gamma), _p(stats[2]), _p(stats[3]), _p(dx), _p(db),
-                                     _p(dgamma), _p(dbeta), rb.n_out, cout, int(ctx.training), _p(ws), ws.numel(),
-                                     _stream()), 'vc_bn_relu_bwd_f32')
+        bsums = ctx.bsums
+        if stats_arena(dy.device).generation != ctx.arena_gen:     # another forward re-used the arena since: own zeros
+            bsums = torch.zeros(2 * cout, dtype=torch.float64, device=dy.device)
+        check(lib.vc_bn_relu_bwd_f32(_p(dy), _p(x), _p(y), _p(gamma), _p(stats), _p(dx), _p(db), _p(dgamma), _p(dbeta),
+                                     rb.n_out, cout, int(ctx.training), _p(bsums), _stream()), 'vc_bn_relu_bwd_f32')
         din = conv_dgrad(dx, weight, rb, ctx.precision, db) if ctx.needs_input_grad[0] else None
         dw = conv_wgrad(feats, dx, weight.shape, rb, ctx.precision, ctx.fb, db) if ctx.needs_input_grad[1] else None
-        return din, dw, dgamma, dbeta, None, None, None, None, None, None, None, None
+        return din, dw, dgamma, dbeta, None, None, None, None, None, None, None, None, None
 
 
 class Cat2Fn(torch.autograd.Function):
@@ -399,6 +433,7 @@ class Cat2Fn(torch.autograd.Function):
     def forward(ctx, a, b, want_bf16):
         _require_cuda(a, b)
         lib = _lib.load()
+        ctx.set_materialize_grads(False)
         a, b = a.contiguous(), b.contiguous()
         n, ca, cb = a.shape[0], a.shape[1], b.shape[1]
         out = torch.empty((n, ca + cb), dtype=torch.float32, device=a.device)

@@ -161,10 +161,8 @@ class SparseConvolution(SparseModule):
         rb = self.rulebook(x)
         training = bn.training or (bn.running_mean is None)
         momentum = 0.0 if bn.momentum is None else bn.momentum
-        if training and bn.track_running_stats and bn.num_batches_tracked is not None:
-            bn.num_batches_tracked.add_(1)
         res = ops.ConvBNReLUFn.apply(x.features, self.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, rb,
-                                     training, bn.eps, momentum, self.precision, x.features_bf16)
+                                     training, bn.eps, momentum, self.precision, x.features_bf16, bn.num_batches_tracked)
         if isinstance(res, tuple):
             out = self._out_tensor(x, res[0], rb)
             out.features_bf16 = res[1]
