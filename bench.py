@@ -195,7 +195,7 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch.distributed as dist
-    from virconv_b200 import _lib, ops, scenes
+    from virconv_b200 import _lib, ops, parallel, scenes
     from virconv_b200.backbone import VirConvL8x
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -220,8 +220,8 @@ def run_ours(args):
     host, devb = [], []
     h2d = 0
     for i in range(POOL):
-        sid = 1000 * rank + 2 * i
-        b = scenes.make_batch([sid, sid + 1], N_LIDAR, N_VIRTUAL, MAX_VOXELS, training=True)
+        b = scenes.make_batch(parallel.shard_scene_ids(i, rank, world, SCENES_PER_GPU), N_LIDAR, N_VIRTUAL, MAX_VOXELS,
+                              training=True)
         hv = torch.from_numpy(b.voxel_features).pin_memory()
         hc = torch.from_numpy(b.voxel_coords).pin_memory()
         host.append((hv, hc, b))
@@ -239,12 +239,7 @@ def run_ours(args):
         for t in out['multi_scale_3d_features'].values():
             loss = loss + t.features.mean()
         loss.backward()
-        if world > 1:
-            # ONE gradient all-reduce per step: flatten (1 kernel) -> NCCL all-reduce over NVLink -> scatter back
-            grads = [p.grad for p in params]
-            flat = torch.cat([g.reshape(-1) for g in grads])
-            dist.all_reduce(flat)
-            torch._foreach_copy_(grads, [v.view_as(g) for v, g in zip(flat.split([g.numel() for g in grads]), grads)])
+        parallel.allreduce_gradients(params, average=True)     # one flat fp32 bucket over NCCL/NVLink; no-op at N=1
         return float(loss.detach()) if sync_loss else loss
 
     def timed(n_steps, from_host):

@@ -208,7 +208,7 @@ def test_empty_and_tail_tiles(lib_built):
         c = _coords(rng, n, 1, shape)
         rb = ops.build_subm_rulebook(torch.from_numpy(c).to(_dev()), 1, shape, 3)
         feats, weight = torch.randn(c.shape[0], 8), torch.randn(16, 3, 3, 3, 8)
-        out, _ = ops.conv_forward(feats.to(_dev()), weight.to(_dev()), rb)
+        out = ops.conv_forward(feats.to(_dev()), weight.to(_dev()), rb)
         ro = osp.native_conv(feats, weight.reshape(16, 27, 8), torch.from_numpy(orb.subm_rulebook(c, shape, 3)).long(),
                              c.shape[0], True)
         assert rel_err(out.cpu(), ro) < TOL

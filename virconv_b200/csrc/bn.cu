@@ -35,10 +35,9 @@ __global__ void __launch_bounds__(256) bn_apply_relu_kernel(
     const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const int cg = (int)(i0 % c4);
-    float sc[4], sh[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int ch = cg * 4 + j;
+    __shared__ float sc_s[128], sh_s[128];
+    if (threadIdx.x < c) {   // one thread per channel derives scale / shift (float64 once per block, not per thread)
+        const int ch = threadIdx.x;
         float mean, invstd;
         double var = 0.0;
         if (training) {
@@ -52,11 +51,13 @@ __global__ void __launch_bounds__(256) bn_apply_relu_kernel(
             mean = running_mean[ch];
             invstd = 1.f / sqrtf(running_var[ch] + eps);
         }
-        sc[j] = gamma[ch] * invstd;
-        sh[j] = beta[ch] - mean * sc[j];
-        if (blockIdx.x == 0 && threadIdx.x < c4) {   // one writer per channel
-            stats_out[ch] = sc[j];
-            stats_out[c + ch] = sh[j];
+        const float scv = gamma[ch] * invstd;
+        const float shv = beta[ch] - mean * scv;
+        sc_s[ch] = scv;
+        sh_s[ch] = shv;
+        if (blockIdx.x == 0) {
+            stats_out[ch] = scv;
+            stats_out[c + ch] = shv;
             stats_out[2 * c + ch] = mean;
             stats_out[3 * c + ch] = invstd;
             if (training) {
@@ -68,6 +69,13 @@ __global__ void __launch_bounds__(256) bn_apply_relu_kernel(
         }
     }
     if (training && blockIdx.x == 0 && threadIdx.x == 0 && num_batches_tracked != nullptr) *num_batches_tracked += 1;
+    __syncthreads();
+    float sc[4], sh[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        sc[j] = sc_s[cg * 4 + j];
+        sh[j] = sh_s[cg * 4 + j];
+    }
     for (size_t i = i0; i < n4; i += stride) {
         float4 v = x[i];
         v.x = fmaf(v.x, sc[0], sh[0]); v.y = fmaf(v.y, sc[1], sh[1]);
@@ -126,27 +134,34 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float4* __restr
     const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const int cg = (int)(i0 % c4);
-    float a[4], b[4], d[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int ch = cg * 4 + j;
+    __shared__ float a_s[128], b_s[128], d_s[128];
+    if (threadIdx.x < c) {
+        const int ch = threadIdx.x;
         const double S = bsums[ch], Q = bsums[c + ch];
         const float mean = stats[2 * c + ch], invstd = stats[3 * c + ch];
         const float gi = gamma[ch] * invstd;
         if (training) {
             const float k1 = (float)(Q / (double)n_rows) * invstd;
-            a[j] = gi;
-            b[j] = -gi * k1;
-            d[j] = gi * (k1 * mean - (float)(S / (double)n_rows));
+            a_s[ch] = gi;
+            b_s[ch] = -gi * k1;
+            d_s[ch] = gi * (k1 * mean - (float)(S / (double)n_rows));
         } else {
-            a[j] = gi;
-            b[j] = 0.f;
-            d[j] = 0.f;
+            a_s[ch] = gi;
+            b_s[ch] = 0.f;
+            d_s[ch] = 0.f;
         }
-        if (blockIdx.x == 0 && threadIdx.x < c4) {
+        if (blockIdx.x == 0) {
             dbeta[ch] = (float)S;
             dgamma[ch] = (float)Q;
         }
+    }
+    __syncthreads();
+    float a[4], b[4], d[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        a[j] = a_s[cg * 4 + j];
+        b[j] = b_s[cg * 4 + j];
+        d[j] = d_s[cg * 4 + j];
     }
     for (size_t i = i0; i < n4; i += stride) {
         float4 g = dy[i], yy = y[i], xx = x[i], r;
