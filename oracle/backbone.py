@@ -104,3 +104,101 @@ class VirConvL8x(nn.Module):
             outs['x_conv%d' % (li + 1)] = x
         outs['out'] = self.conv_out(x)
         return outs
+
+
+def decompose_tensor(t, i, batch_size):
+    """spconv_backbone.py:314-337: strict `begin < x < end` (drops the x == begin column), q = shape[2] // 4."""
+    q = t.spatial_shape[2] // 4
+    x = t.indices[:, 3]
+    mask = (i * q < x) & (x < (i + 1) * q)
+    idx = t.indices[mask].clone()
+    idx[:, 3] -= i * q
+    return spconv.SparseConvTensor(t.features[mask], idx.int(), [t.spatial_shape[0], t.spatial_shape[1], q], batch_size)
+
+
+class VirConv8x(nn.Module):
+    """VirConv-T / -S backbone: LiDAR stream (shared rulebooks per stage) + virtual-point stream of NRConv blocks
+    (spconv_backbone.py:232-535)."""
+
+    def __init__(self, num_filters=(16, 32, 64, 64), out_features=64, input_channels=8, grid_size=(1408, 1600, 80),
+                 layer_discard_rate=0.15, last_pad=0, mm=True, discard_mode='spconv2_compat'):
+        super().__init__()
+        norm_fn = partial(nn.BatchNorm1d, eps=1e-3, momentum=0.01)
+        gs = list(grid_size)
+        self.sparse_shape = [gs[2] + 1, gs[1], gs[0]]
+        f = num_filters
+        self.conv_input = spconv.SparseSequential(
+            spconv.SubMConv3d(input_channels, f[0], 3, padding=1, bias=False, indice_key='subm1'), norm_fn(f[0]), nn.ReLU())
+        blk = lambda ci, co, key, **kw: conv_bn_relu(ci, co, 3, 3, kw.pop('conv_type', 'subm'), norm_fn, indice_key=key, **kw)
+        self.conv1 = spconv.SparseSequential(blk(f[0], f[0], 'subm1'))
+        self.conv2 = spconv.SparseSequential(blk(f[0], f[1], 'spconv2', conv_type='spconv', stride=2, padding=1),
+                                             blk(f[1], f[1], 'subm2'), blk(f[1], f[1], 'subm2'))
+        self.conv3 = spconv.SparseSequential(blk(f[1], f[2], 'spconv3', conv_type='spconv', stride=2, padding=1),
+                                             blk(f[2], f[2], 'subm3'), blk(f[2], f[2], 'subm3'))
+        self.conv4 = spconv.SparseSequential(blk(f[2], f[3], 'spconv4', conv_type='spconv', stride=2, padding=(0, 1, 1)),
+                                             blk(f[3], f[3], 'subm4'), blk(f[3], f[3], 'subm4'))
+        self.conv_out = spconv.SparseSequential(
+            spconv.SparseConv3d(f[3], out_features, (3, 1, 1), stride=(2, 1, 1), padding=last_pad, bias=False,
+                                indice_key='spconv_down2'), norm_fn(out_features), nn.ReLU())
+        self.mm = mm
+        if mm:
+            self.vir_conv1 = NRConvBlock(input_channels, f[0], stride=1, indice_key='vir1')
+            self.vir_conv2 = NRConvBlock(f[0], f[1], stride=2, indice_key='vir2')
+            self.vir_conv3 = NRConvBlock(f[1], f[2], stride=2, indice_key='vir3')
+            self.vir_conv4 = NRConvBlock(f[2], f[3], stride=2, padding=(0, 1, 1), indice_key='vir4')
+        self.layer_discard_rate = layer_discard_rate
+        self.discard_mode = discard_mode
+
+    def _lidar(self, feats, coords, shape, batch_size):
+        x = spconv.SparseConvTensor(feats, coords.int(), shape, batch_size)
+        x1 = self.conv1(self.conv_input(x))
+        x2 = self.conv2(x1)
+        x3 = self.conv3(x2)
+        x4 = self.conv4(x3)
+        return x1, x2, x3, x4, self.conv_out(x4)
+
+    def forward(self, arrays, batch_size, calib, aug_param=None, transform_param=None, keep_rows=None):
+        """arrays: dict of torch tensors keyed like batch_dict (voxel_features{,i}, voxel_coords{,i}, *_mm{,i}).
+        Returns a dict with the reference's output keys."""
+        rot_num = 1 if transform_param is None else transform_param.shape[1]
+        sfx = [''] + [str(i) for i in range(1, rot_num)]
+        out = {}
+        if self.training:
+            for s in sfx:
+                x1, x2, x3, x4, o = self._lidar(arrays['voxel_features' + s], arrays['voxel_coords' + s],
+                                                self.sparse_shape, batch_size)
+                out['encoded_spconv_tensor' + s] = o
+                out['multi_scale_3d_features' + s] = dict(x_conv1=x1, x_conv2=x2, x_conv3=x3, x_conv4=x4)
+        else:
+            feats, coords = [], []
+            for i, s in enumerate(sfx):
+                feats.append(arrays['voxel_features' + s])
+                c = arrays['voxel_coords' + s].clone()
+                c[:, 3] += i * self.sparse_shape[2]
+                coords.append(c)
+            big = [self.sparse_shape[0], self.sparse_shape[1], self.sparse_shape[2] * 4]
+            x1, x2, x3, x4, o = self._lidar(torch.cat(feats, 0), torch.cat(coords), big, batch_size)
+            for i, s in enumerate(sfx):
+                out['encoded_spconv_tensor' + s] = decompose_tensor(o, i, batch_size)
+                out['multi_scale_3d_features' + s] = dict(x_conv1=None, x_conv2=None,
+                                                          x_conv3=decompose_tensor(x3, i, batch_size),
+                                                          x_conv4=decompose_tensor(x4, i, batch_size))
+        if self.mm:
+            for i, s in enumerate(sfx):
+                tp = aug_param
+                if transform_param is not None:
+                    tp = transform_param[:, i, :]
+                x = spconv.SparseConvTensor(arrays['voxel_features_mm' + s], arrays['voxel_coords_mm' + s].int(),
+                                            self.sparse_shape, batch_size)
+                paper = self.training and self.discard_mode == 'paper' and keep_rows is not None
+                if paper:
+                    x = discard_rows(x, keep_rows[0])
+                feats = {}
+                blocks = [(self.vir_conv1, 1), (self.vir_conv2, 2), (self.vir_conv3, 4), (self.vir_conv4, 8)]
+                for li, (blk, stride) in enumerate(blocks):
+                    x = blk(x, batch_size, calib, stride, tp)
+                    if paper and li < 3:
+                        x = discard_rows(x, keep_rows[li + 1])
+                    feats['x_conv%d' % (li + 1)] = x
+                out['multi_scale_3d_features_mm' + s] = feats
+        return out

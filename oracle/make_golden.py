@@ -160,6 +160,59 @@ def main():
     np.savez_compressed(os.path.join(OUT, 'virconv_l_small.npz'), voxel_features=batch.voxel_features,
                         voxel_coords=batch.voxel_coords, aug_param=batch.aug_param, seed=np.int32(666), **out)
 
+    # ---- VirConv8x control flow (VirConv-T/S: LiDAR stream + MM stream, train and x-batched eval) ---------
+    from .backbone import VirConv8x as OracleT
+    bb.index2uv = ref_index2uv
+    cfg8 = AttrDict(RETURN_NUM_FEATURES_AS_DICT=True, OUT_FEATURES=64, LAYER_DISCARD_RATE=0.15,
+                    NUM_FILTERS=[16, 32, 64, 64], MM=True)
+    ref8 = bb.VirConv8x(cfg8, 8, np.array([1408, 1600, 80]))
+    fill_module(ref8, 667)
+    ora8 = OracleT()
+    ora8.load_state_dict(ref8.state_dict())
+    gold8 = {}
+    for mode in ('train', 'eval'):
+        training = mode == 'train'
+        for first_scene in range(21, 60, 2):
+            bm = scenes.make_batch_mm([first_scene, first_scene + 1], n_lidar=256, n_virtual=300, max_voxels=110,
+                                      training=training, rot_num=3)
+            fill_module(ref8, 667)                       # train-mode passes move the BN running statistics
+            ora8.load_state_dict(ref8.state_dict())
+            ref8.train(training)
+            ora8.train(training)
+            bd = {k: torch.from_numpy(v.copy()) for k, v in bm.arrays.items()}
+            bd.update(batch_size=bm.batch_size, calib=[calib_mod.Calibration(dict(calib_dict)) for _ in range(bm.batch_size)])
+            if training:
+                bd['aug_param'] = torch.from_numpy(bm.aug_param.copy())
+            else:
+                bd['transform_param'] = torch.from_numpy(bm.transform_param.copy())
+            with torch.no_grad():
+                r = ref8(bd)
+                o = ora8({k: torch.from_numpy(v.copy()) for k, v in bm.arrays.items()}, bm.batch_size, bm.calib,
+                         aug_param=bm.aug_param, transform_param=bm.transform_param)
+            worst, same, tensors = 0.0, True, {}
+            for key in sorted(o.keys()):
+                for name, t in ([('out', o[key])] if not isinstance(o[key], dict) else o[key].items()):
+                    rt = r[key] if not isinstance(o[key], dict) else r[key][name]
+                    if t is None:
+                        assert rt is None
+                        continue
+                    same &= np.array_equal(t.indices.numpy(), rt.indices.numpy())
+                    if same:
+                        worst = max(worst, float((t.features - rt.features).abs().max() / rt.features.abs().max().clamp_min(1e-30)))
+                    tensors[f'{mode}:{key}:{name}:features'] = rt.features.numpy()
+                    tensors[f'{mode}:{key}:{name}:indices'] = rt.indices.numpy().astype(np.int32)
+            if same and worst == 0.0:
+                report.append(f'VirConv8x[{mode}] fixture: scenes ({first_scene},{first_scene + 1}), {len(tensors) // 2} published '
+                              f'tensors, indices identical, restated-vs-reference-flow rel err 0')
+                gold8.update(tensors)
+                for k, v in bm.arrays.items():
+                    gold8[f'{mode}:in:{k}'] = v
+                gold8[f'{mode}:aug'] = bm.aug_param if training else bm.transform_param
+                break
+            report.append(f'VirConv8x[{mode}]: scenes ({first_scene},{first_scene + 1}) skipped (pixel-cell flip or mismatch: '
+                          f'same_idx={same} err={worst:.2e})')
+    np.savez_compressed(os.path.join(OUT, 'virconv_t_small.npz'), seed=np.int32(667), **gold8)
+
     with open(os.path.join(OUT, 'REPORT.txt'), 'w') as f:
         f.write('\n'.join(report) + '\n')
     print('\n'.join(report))

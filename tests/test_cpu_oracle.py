@@ -156,3 +156,28 @@ def test_pairs_from_nbr_canonical_order():
         o = pairs[1, k, :num[k]]
         assert np.all(np.diff(o) > 0) and np.array_equal(nbr[k, o], pairs[0, k, :num[k]])
         assert np.all(pairs[:, k, num[k]:] == -1)
+
+
+@pytest.mark.parametrize('mode', ['train', 'eval'])
+def test_oracle_virconv8x_matches_reference_flow_golden(mode):
+    """VirConv-T/S backbone: restated flow (LiDAR stream with shared rulebooks, MM stream, x-batched eval +
+    decompose_tensor) == the reference's VirConv8x class run over the same oracle operators."""
+    from oracle.backbone import VirConv8x
+    g = np.load(os.path.join(GOLD, 'virconv_t_small.npz'))
+    m = VirConv8x()
+    fill_module(m, int(g['seed']))
+    m.train(mode == 'train')
+    arrays = {k.split(':')[2]: torch.from_numpy(g[k].copy()) for k in g.files if k.startswith(f'{mode}:in:')}
+    kw = dict(aug_param=g[f'{mode}:aug']) if mode == 'train' else dict(transform_param=g[f'{mode}:aug'])
+    with torch.no_grad():
+        o = m(arrays, 2, [scenes.Calib(), scenes.Calib()], **kw)
+    n = 0
+    for k in g.files:
+        parts = k.split(':')
+        if parts[0] != mode or parts[1] == 'in' or parts[1] == 'aug' or parts[3] != 'features':
+            continue
+        t = o[parts[1]] if parts[2] == 'out' else o[parts[1]][parts[2]]
+        assert np.array_equal(t.indices.numpy(), g[f'{mode}:{parts[1]}:{parts[2]}:indices'])
+        assert np.array_equal(t.features.numpy(), g[k])
+        n += 1
+    assert n == (9 if mode == 'train' else 21)

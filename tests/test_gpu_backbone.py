@@ -158,3 +158,72 @@ def test_full_size_properties(lib_built):
     dense = named['out'].dense()
     assert dense.shape == (2, 64, 4, 200, 176)
     assert float(dense.abs().sum()) == pytest.approx(float(named['out'].features.abs().sum()), rel=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ VirConv-T / -S
+CFG8 = dict(RETURN_NUM_FEATURES_AS_DICT=True, OUT_FEATURES=64, LAYER_DISCARD_RATE=0.15, NUM_FILTERS=[16, 32, 64, 64], MM=True)
+
+
+def _published(out_dict, sfx_list):
+    res = {}
+    for s in sfx_list:
+        res[f'encoded_spconv_tensor{s}:out'] = out_dict['encoded_spconv_tensor' + s]
+        for grp in ('multi_scale_3d_features', 'multi_scale_3d_features_mm'):
+            for name, t in out_dict[grp + s].items():
+                if t is not None:
+                    res[f'{grp}{s}:{name}'] = t
+    return res
+
+
+@pytest.mark.parametrize('mode', ['train', 'eval'])
+def test_virconv8x_matches_reference_golden(lib_built, mode):
+    from virconv_b200 import scenes
+    from virconv_b200.backbone import VirConv8x
+    g = np.load(os.path.join(GOLD, 'virconv_t_small.npz'))
+    m = VirConv8x(CFG8, 8, [1408, 1600, 80])
+    fill_module(m, int(g['seed']))
+    m.to('cuda:0').train(mode == 'train')
+    bd = {k.split(':')[2]: torch.from_numpy(g[k].copy()).cuda() for k in g.files if k.startswith(f'{mode}:in:')}
+    bd.update(batch_size=2, calib=[scenes.Calib(), scenes.Calib()])
+    bd['aug_param' if mode == 'train' else 'transform_param'] = torch.from_numpy(g[f'{mode}:aug'].copy())
+    with torch.no_grad():
+        out = m(bd)
+    pub = _published(out, [''] if mode == 'train' else ['', '1', '2'])
+    assert len(pub) == (9 if mode == 'train' else 21)
+    for k, t in pub.items():
+        assert np.array_equal(t.indices.cpu().numpy(), g[f'{mode}:{k}:indices']), k
+        assert rel_err(t.features.cpu(), g[f'{mode}:{k}:features']) < TOL, k
+
+
+def test_virconv8x_forward_backward_vs_oracle(lib_built):
+    from virconv_b200 import scenes
+    from virconv_b200.backbone import VirConv8x
+    from oracle.backbone import VirConv8x as Oracle8
+    batch = scenes.make_batch_mm([2, 7], n_lidar=4096, n_virtual=6000, max_voxels=3000, training=True)
+    m = VirConv8x(CFG8, 8, [1408, 1600, 80])
+    fill_module(m, 667)
+    ref = Oracle8()
+    ref.load_state_dict(m.state_dict())
+    m.to('cuda:0').train()
+    ref.train()
+    bd = {k: torch.from_numpy(v.copy()).cuda() for k, v in batch.arrays.items()}
+    bd.update(batch_size=2, calib=batch.calib, aug_param=torch.from_numpy(batch.aug_param))
+    out = m(bd)
+    o = ref({k: torch.from_numpy(v.copy()) for k, v in batch.arrays.items()}, 2, batch.calib, aug_param=batch.aug_param)
+    pub = _published(out, [''])
+    loss, rloss = 0, 0
+    for k, t in pub.items():
+        grp, name = k.split(':')
+        rt = o[grp] if name == 'out' else o[grp][name]
+        assert np.array_equal(t.indices.cpu().numpy(), rt.indices.numpy()), k
+        assert rel_err(t.features.detach().cpu(), rt.features.detach()) < TOL, k
+        loss = loss + t.features.mean()
+        rloss = rloss + rt.features.mean()
+    loss.backward()
+    rloss.backward()
+    gp = dict(m.named_parameters())
+    for name, p in ref.named_parameters():
+        assert rel_err(gp[name].grad.cpu(), p.grad) < 2e-3, name
+    # shared rulebooks: conv_input / conv1 use one 'subm1' table
+    d = pub['multi_scale_3d_features:x_conv1'].indice_dict
+    assert d['subm1'] is not None and len([k for k in d if isinstance(k, str)]) == 9

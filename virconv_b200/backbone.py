@@ -164,3 +164,126 @@ class VirConvL8x(nn.Module):
                 'multi_scale_3d_strides' + rid: {'x_conv1': 1, 'x_conv2': 2, 'x_conv3': 4, 'x_conv4': 8},
             })
         return batch_dict
+
+
+def decompose_tensor(t, i, batch_size):
+    """Split the i-th transformed copy back out of an x-axis-batched tensor (spconv_backbone.py:314-337):
+    rows with `i*q < x < (i+1)*q` (strict on both sides — the reference drops the x == i*q column), q = W // 4."""
+    q = t.spatial_shape[2] // 4
+    idx = spconv._as_i32(t.indices)
+    x = idx[:, 3]
+    rows = torch.nonzero((x > i * q) & (x < (i + 1) * q)).squeeze(1).to(torch.int32)   # data-dependent size (eval only)
+    feats = ops.gather_rows(t.features, rows)
+    sub = ops.gather_rows(idx, rows)
+    sub[:, 3] -= i * q
+    return spconv.SparseConvTensor(feats, sub, [t.spatial_shape[0], t.spatial_shape[1], q], batch_size)
+
+
+class VirConv8x(nn.Module):
+    """VirConv-T / VirConv-S backbone (spconv_backbone.py:232-535): a LiDAR stream whose submanifold convs share one
+    rulebook per stage (indice_keys 'subm1'..'subm4') plus, when `MM`, the virtual-point stream of NRConv blocks.
+    Eval mode batches the ROT_NUM transformed copies along x into one [D, H, 4W] tensor (:360,:418-432) and splits the
+    published tensors afterwards."""
+
+    def __init__(self, model_cfg, input_channels, grid_size, discard_mode='spconv2_compat', precision='fp32', **kwargs):
+        super().__init__()
+        self.model_cfg = model_cfg
+        self.return_num_features_as_dict = _cfg_get(model_cfg, 'RETURN_NUM_FEATURES_AS_DICT', False)
+        self.out_features = _cfg_get(model_cfg, 'OUT_FEATURES', 64)
+        self.layer_discard_rate = _cfg_get(model_cfg, 'LAYER_DISCARD_RATE', 0.0)
+        f = list(_cfg_get(model_cfg, 'NUM_FILTERS', [16, 32, 64, 64]))
+        self.mm = bool(_cfg_get(model_cfg, 'MM', False))
+        assert discard_mode in ('spconv2_compat', 'paper')
+        self.discard_mode = discard_mode
+        norm_fn = partial(nn.BatchNorm1d, eps=1e-3, momentum=0.01)
+        gs = [int(g) for g in grid_size]
+        self.sparse_shape = [gs[2] + 1, gs[1], gs[0]]
+
+        self.conv_input = spconv.SparseSequential(
+            spconv.SubMConv3d(input_channels, f[0], 3, padding=1, bias=False, indice_key='subm1'), norm_fn(f[0]), nn.ReLU())
+        sub = lambda ci, co, key: sparse_block(ci, co, 3, norm_fn, 3, 'subm', padding=1, indice_key=key)
+        down = lambda ci, co, key, pad: sparse_block(ci, co, 3, norm_fn, 3, 'spconv', stride=2, padding=pad, indice_key=key)
+        self.conv1 = spconv.SparseSequential(sub(f[0], f[0], 'subm1'))
+        self.conv2 = spconv.SparseSequential(down(f[0], f[1], 'spconv2', 1), sub(f[1], f[1], 'subm2'), sub(f[1], f[1], 'subm2'))
+        self.conv3 = spconv.SparseSequential(down(f[1], f[2], 'spconv3', 1), sub(f[2], f[2], 'subm3'), sub(f[2], f[2], 'subm3'))
+        self.conv4 = spconv.SparseSequential(down(f[2], f[3], 'spconv4', (0, 1, 1)), sub(f[3], f[3], 'subm4'),
+                                             sub(f[3], f[3], 'subm4'))
+        last_pad = _cfg_get(model_cfg, 'last_pad', 0)
+        self.conv_out = spconv.SparseSequential(
+            spconv.SparseConv3d(f[3], self.out_features, (3, 1, 1), stride=(2, 1, 1), padding=last_pad, bias=False,
+                                indice_key='spconv_down2'), norm_fn(self.out_features), nn.ReLU())
+        if self.mm:
+            self.vir_conv1 = NRConvBlock(input_channels, f[0], stride=1, indice_key='vir1')
+            self.vir_conv2 = NRConvBlock(f[0], f[1], stride=2, indice_key='vir2')
+            self.vir_conv3 = NRConvBlock(f[1], f[2], stride=2, indice_key='vir3')
+            self.vir_conv4 = NRConvBlock(f[2], f[3], stride=2, padding=(0, 1, 1), indice_key='vir4')
+        spconv.set_precision(self, precision)
+        self.num_point_features = self.out_features
+        if self.return_num_features_as_dict:
+            self.num_point_features = {'x_conv%d' % (i + 1): f[i] for i in range(4)}
+
+    def _lidar_stream(self, feats, coords, shape, batch_size):
+        x = spconv.SparseConvTensor(feats, coords.int(), shape, batch_size)
+        x1 = self.conv1(self.conv_input(x))
+        x2 = self.conv2(x1)
+        x3 = self.conv3(x2)
+        x4 = self.conv4(x3)
+        return x1, x2, x3, x4, self.conv_out(x4)
+
+    def _maybe_discard(self, t, batch_dict, layer):
+        if not self.training or self.discard_mode != 'paper' or self.layer_discard_rate == 0:
+            return t
+        given = batch_dict.get('stvd_keep_rows')
+        keep = given[layer] if given is not None else stvd_keep_rows(t.features.shape[0], self.layer_discard_rate)
+        return discard_rows(t, keep)
+
+    def forward(self, batch_dict):
+        rot_num = batch_dict['transform_param'].shape[1] if 'transform_param' in batch_dict else 1
+        batch_size = batch_dict['batch_size']
+        sfx = [''] + [str(i) for i in range(1, rot_num)]
+        strides = {'x_conv1': 1, 'x_conv2': 2, 'x_conv3': 4, 'x_conv4': 8}
+        ops.stats_arena(batch_dict['voxel_features'].device).reset()
+        if self.training:
+            for s in sfx:
+                x1, x2, x3, x4, out = self._lidar_stream(batch_dict['voxel_features' + s], batch_dict['voxel_coords' + s],
+                                                         self.sparse_shape, batch_size)
+                batch_dict.update({
+                    'encoded_spconv_tensor' + s: out, 'encoded_spconv_tensor_stride' + s: 8,
+                    'multi_scale_3d_features' + s: {'x_conv1': x1, 'x_conv2': x2, 'x_conv3': x3, 'x_conv4': x4},
+                    'multi_scale_3d_strides' + s: dict(strides)})
+        else:
+            feats, coords = [], []
+            for i, s in enumerate(sfx):
+                feats.append(batch_dict['voxel_features' + s])
+                c = batch_dict['voxel_coords' + s].clone()
+                c[:, 3] += i * self.sparse_shape[2]
+                coords.append(c)
+            big = [self.sparse_shape[0], self.sparse_shape[1], self.sparse_shape[2] * 4]      # factor 4 is hard-coded (:360)
+            _, _, x3, x4, out = self._lidar_stream(torch.cat(feats, 0), torch.cat(coords), big, batch_size)
+            for i, s in enumerate(sfx):
+                batch_dict.update({
+                    'encoded_spconv_tensor' + s: decompose_tensor(out, i, batch_size),
+                    'encoded_spconv_tensor_stride' + s: 8,
+                    'multi_scale_3d_features' + s: {'x_conv1': None, 'x_conv2': None,
+                                                    'x_conv3': decompose_tensor(x3, i, batch_size),
+                                                    'x_conv4': decompose_tensor(x4, i, batch_size)},
+                    'multi_scale_3d_strides' + s: dict(strides)})
+        if self.mm:
+            calib = batch_dict['calib']
+            for i, s in enumerate(sfx):
+                feats, coords = batch_dict['voxel_features_mm' + s], batch_dict['voxel_coords_mm' + s]
+                trans = batch_dict['aug_param'] if 'aug_param' in batch_dict else None
+                if 'transform_param' in batch_dict:
+                    trans = batch_dict['transform_param'][:, i, :]
+                proj = ops.projection_params(calib, trans, batch_size, feats.device)
+                x = spconv.SparseConvTensor(feats, coords.int(), self.sparse_shape, batch_size)
+                x = self._maybe_discard(x, batch_dict, 0)              # VirConv8x also discards the input voxels (:489-490)
+                x1 = self._maybe_discard(self.vir_conv1(x, batch_size, proj, 1), batch_dict, 1)
+                x2 = self._maybe_discard(self.vir_conv2(x1, batch_size, proj, 2), batch_dict, 2)
+                x3 = self._maybe_discard(self.vir_conv3(x2, batch_size, proj, 4), batch_dict, 3)
+                x4 = self.vir_conv4(x3, batch_size, proj, 8)
+                batch_dict.update({
+                    'encoded_spconv_tensor_stride_mm' + s: 8,
+                    'multi_scale_3d_features_mm' + s: {'x_conv1': x1, 'x_conv2': x2, 'x_conv3': x3, 'x_conv4': x4},
+                    'multi_scale_3d_strides' + s: dict(strides)})
+        return batch_dict

@@ -239,3 +239,65 @@ def make_batch(scene_ids, n_lidar=16384, n_virtual=80000, max_voxels=40000, trai
                   / np.asarray(voxel_size, dtype=np.float64)).astype(np.int64)
     return SceneBatch(np.concatenate(feats), np.concatenate(coords), len(scene_ids), calibs,
                       np.stack(augs) if training else None, tuple(int(g) for g in gs))
+
+
+# ------------------------------------------------------------------------------------------------------
+# VirConv-T / -S: LiDAR stream + virtual ("MM") stream (LATER_FUSION, dataset.py:270-281), optional test-time
+# transformed copies (X_TRANS.input_transform, X_transform.py:156-193)
+# ------------------------------------------------------------------------------------------------------
+TEST_TRANSFORMS = np.array([[0.3, 0.0, 0.98], [0.3, 1.0, 1.02], [0.0, 1.0, 1.0]], dtype=np.float32)  # VirConv-T.yaml X_TRANS
+
+
+@dataclass
+class SceneBatchMM:
+    """batch_dict arrays for VirConv8x: keys carry the reference's suffixes ('', '1', '2') per transformed copy."""
+    arrays: dict                           # voxel_features{,i}, voxel_coords{,i}, voxel_features_mm{,i}, voxel_coords_mm{,i}
+    batch_size: int
+    calib: list
+    aug_param: np.ndarray | None = None          # [B,3] training
+    transform_param: np.ndarray | None = None    # [B,R,3] test
+    grid_size: tuple = (1408, 1600, 80)
+
+
+def _voxel_stream(pts, b, max_voxels, vfe_model, voxel_size, pc_range):
+    pts = mask_points_by_range(pts, pc_range)
+    vox, c, num = voxelize_first_come(pts, voxel_size, pc_range, 5, max_voxels)
+    f = mean_vfe(vox, num, vfe_model)
+    cb = np.concatenate([np.full((c.shape[0], 1), b, dtype=np.int32), c], axis=1).astype(np.float32)
+    return f, cb
+
+
+def make_batch_mm(scene_ids, n_lidar=16384, n_virtual=80000, max_voxels=16000, training=True, rot_num=1,
+                  voxel_size=VOXEL_SIZE, pc_range=POINT_CLOUD_RANGE) -> SceneBatchMM:
+    """training: one copy, random aug_param; test: `rot_num` copies transformed with TEST_TRANSFORMS[:rot_num]."""
+    n_copies = 1 if training else rot_num
+    parts = {(k, i): [] for k in ('voxel_features', 'voxel_coords', 'voxel_features_mm', 'voxel_coords_mm')
+             for i in range(n_copies)}
+    calibs, augs = [], []
+    for b, sid in enumerate(scene_ids):
+        calib = Calib()
+        calibs.append(calib)
+        pts = make_points(sid, n_lidar, n_virtual, calib)
+        if training:
+            rng = np.random.default_rng(10_000_019 * (sid + 1))
+            aug = np.array([rng.uniform(-0.78539816, 0.78539816), float(rng.integers(0, 2)), rng.uniform(0.95, 1.05)],
+                           dtype=np.float32)
+            augs.append(aug)
+            copies = [augment(pts, aug)]
+        else:
+            copies = [augment(pts, TEST_TRANSFORMS[i]) for i in range(n_copies)]
+        for i, p in enumerate(copies):
+            f, c = _voxel_stream(p[p[:, 7] == 2], b, max_voxels, 'max', voxel_size, pc_range)
+            fm, cm = _voxel_stream(p[p[:, 7] == 1], b, max_voxels, None, voxel_size, pc_range)   # mm stream: plain mean
+            parts[('voxel_features', i)].append(f)
+            parts[('voxel_coords', i)].append(c)
+            parts[('voxel_features_mm', i)].append(fm)
+            parts[('voxel_coords_mm', i)].append(cm)
+    arrays = {}
+    for (k, i), v in parts.items():
+        arrays[k + ('' if i == 0 else str(i))] = np.concatenate(v)
+    gs = np.round((np.asarray(pc_range[3:], dtype=np.float64) - np.asarray(pc_range[:3], dtype=np.float64))
+                  / np.asarray(voxel_size, dtype=np.float64)).astype(np.int64)
+    tp = None if training else np.tile(TEST_TRANSFORMS[None, :n_copies], (len(scene_ids), 1, 1)).astype(np.float32)
+    return SceneBatchMM(arrays, len(scene_ids), calibs, np.stack(augs) if training else None, tp,
+                        tuple(int(g) for g in gs))
