@@ -179,6 +179,28 @@ int vc_index2uv(const int32_t* indices /*[n,4] b,z,y,x*/, int n, int batch_size,
                 const float* grid /*host[6]*/, int stride, int u_max, int v_max, int32_t* uv_out,
                 vc_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Hash-grid voxelisation + MeanVFE.  Replaces `VoxelGeneratorWrapper.generate` -> spconv
+ * `Point2VoxelCPU3d.point_to_voxel` (pcdet/datasets/processor/data_processor.py:43-59, called :156,:173) and
+ * `MeanVFE.forward` (pcdet/models/backbones_3d/vfe/mean_vfe.py:39-58) with identical results.
+ * points [n, 1+c] float32 rows (batch, x, y, z, features...), samples contiguous in ascending batch order (what
+ * `collate_batch` produces, dataset.py:349-353).  Per sample: voxels in order of first appearance, at most max_voxels,
+ * at most max_points (<= 8) points per voxel in point order.  Outputs (capacity batch_size*max_voxels rows):
+ * out_features [*, c] = per-voxel mean (last channel = max over the zero-padded slots if vfe_max_last),
+ * out_coords [*, 4] = (b, z, y, x), out_num [*], optional out_voxels [*, max_points, c] (caller zeroes), *n_out_dev.
+ * pc_range host[6] = (x0,y0,z0,x1,y1,z1), voxel_size host[3].  ws >= vc_voxelize_ws_bytes(...).
+ * ---------------------------------------------------------------------------------------------- */
+size_t vc_voxelize_ws_bytes(int n_points, int batch_size, int max_points);
+int vc_voxelize_mean(const float* points, int n_points, int c, int batch_size, const float* pc_range,
+                     const float* voxel_size, int max_points, int max_voxels, int vfe_max_last, float* out_features,
+                     int32_t* out_coords, int32_t* out_num, float* out_voxels /*may be NULL*/, int32_t* n_out_dev,
+                     void* ws, size_t ws_bytes, vc_stream_t stream);
+
+/* `generate_voxel2pinds` (pcdet/utils/spconv_utils.py:13-21): dense [B, *spatial_shape] int32 map voxel -> row, -1 where
+ * empty (the RoI head's look-up table, ted_head.py:527,625). */
+int vc_voxel2pinds(const int32_t* indices, int n, int ndim, int batch_size, const int32_t* spatial_shape, int32_t* out,
+                   vc_stream_t stream);
+
 /* `SparseConvTensor.dense()` (height_compression.py:29): out [B, C, *shape] must be zeroed by the caller. */
 int vc_dense_f32(const float* features, const int32_t* indices, int n, int c, int ndim, int batch_size,
                  const int32_t* spatial_shape, float* out, vc_stream_t stream);

@@ -430,3 +430,52 @@ def test_tc_backbone_bf16_vs_fp32_oracle(lib_built):
     torch.cuda.synchronize()
     assert int(ops.tc_error_flag(_dev()).item()) == 0
     assert all(torch.isfinite(p.grad).all() for p in m.parameters())
+
+
+# ---------------------------------------------------------------------------------------------- voxelise + VFE
+@pytest.mark.parametrize('n_virtual,max_voxels,model', [(0, 40000, 'max'), (20000, 3000, 'max'), (20000, 40000, None)])
+def test_gpu_voxelize_mean_matches_first_come_reference(lib_built, n_virtual, max_voxels, model):
+    """bit-exact against the numpy restatement of Point2VoxelCPU3d + MeanVFE (itself pinned by tests/golden/mean_vfe.npz)"""
+    from virconv_b200 import ops, scenes
+    pts_all, want = [], []
+    for b, sid in enumerate([3, 4, 9]):
+        p = scenes.mask_points_by_range(scenes.make_points(sid, 4096, n_virtual))
+        if b == 1:
+            p = np.concatenate([p, p[:500], p[:500], p[:500], p[:500], p[:500], p[:500]])   # voxels with > 5 points
+            p[100:110, 2] = 5.0                                                             # z outside the range
+        vox, coords, num = scenes.voxelize_first_come(p, max_voxels=max_voxels)
+        want.append((scenes.mean_vfe(vox, num, model), np.concatenate([np.full((coords.shape[0], 1), b, np.int32), coords], 1),
+                     num, vox))
+        pts_all.append(np.concatenate([np.full((p.shape[0], 1), b, np.float32), p], 1))
+    pts = torch.from_numpy(np.concatenate(pts_all)).to(_dev())
+    f, c, nm, v = ops.voxelize_mean(pts, 3, max_voxels=max_voxels, vfe_model=model, want_voxels=True)
+    wf, wc, wn, wv = (np.concatenate([w[i] for w in want]) for i in range(4))
+    assert np.array_equal(c.cpu().numpy(), wc)
+    assert np.array_equal(nm.cpu().numpy(), wn)
+    assert np.array_equal(v.cpu().numpy(), wv)
+    assert np.array_equal(f.cpu().numpy(), wf)
+
+
+def test_gpu_voxelize_golden_and_empty_sample(lib_built):
+    import os
+    from virconv_b200 import ops
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'mean_vfe.npz'))
+    # rebuild a point list from the golden voxels (point order = voxel-major): voxelising it again must give the same voxels
+    vox, num = g['voxels'], g['num']
+    pts = np.concatenate([vox[i, :num[i]] for i in range(vox.shape[0])])
+    pts = np.concatenate([np.full((pts.shape[0], 1), 1, np.float32), pts], 1)          # only sample 1 has points
+    f, c, nm = ops.voxelize_mean(torch.from_numpy(pts).to(_dev()), 2, max_voxels=3000, vfe_model='max')
+    assert np.array_equal(f.cpu().numpy(), g['features'])                               # the reference MeanVFE's output
+    assert np.array_equal(c.cpu().numpy()[:, 1:], g['coords']) and np.all(c.cpu().numpy()[:, 0] == 1)
+    assert np.array_equal(nm.cpu().numpy(), num)
+
+
+def test_voxel2pinds(lib_built):
+    from virconv_b200 import ops
+    rng = np.random.default_rng(2)
+    shape = [10, 20, 18]
+    c = _coords(rng, 700, 2, shape)
+    got = ops.voxel2pinds(torch.from_numpy(c).to(_dev()), 2, shape).cpu().numpy()
+    want = -np.ones([2] + shape, np.int32)
+    want[c[:, 0], c[:, 1], c[:, 2], c[:, 3]] = np.arange(c.shape[0])
+    assert np.array_equal(got, want)

@@ -48,6 +48,9 @@ SIGNATURES = {
     'vc_index2uv': (_I, [_P, _I, _I, _P, _HOSTF, _I, _I, _I, _P, _P]),
     'vc_dense_f32': (_I, [_P, _P, _I, _I, _I, _I, _HOST, _P, _P]),
     'vc_dense_bwd_f32': (_I, [_P, _P, _I, _I, _I, _I, _HOST, _P, _P]),
+    'vc_voxelize_ws_bytes': (_Z, [_I, _I, _I]),
+    'vc_voxelize_mean': (_I, [_P, _I, _I, _I, _HOSTF, _HOSTF, _I, _I, _I, _P, _P, _P, _P, _P, _P, _Z, _P]),
+    'vc_voxel2pinds': (_I, [_P, _I, _I, _I, _HOST, _P, _P]),
     'vc_cat2_f32': (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     'vc_gather_rows': (_I, [_P, _P, _P, _I, _I, _P]),
 }

@@ -556,3 +556,42 @@ class GatherRowsFn(torch.autograd.Function):
         din = torch.zeros((ctx.n, dout.shape[1]), dtype=dout.dtype, device=dout.device)
         din.index_copy_(0, rows.long(), dout.contiguous())   # rows are unique (a subsample)
         return din, None
+
+
+# ------------------------------------------------------------------------------------------------
+# voxelisation + MeanVFE, voxel -> row map
+# ------------------------------------------------------------------------------------------------
+def voxelize_mean(points, batch_size, pc_range=(0, -40, -3, 70.4, 40, 1), voxel_size=(0.05, 0.05, 0.05), max_points=5,
+                  max_voxels=40000, vfe_model='max', want_voxels=False):
+    """points [N, 1+C] f32 (b, x, y, z, ...), batch-contiguous -> (voxel_features [M,C], voxel_coords [M,4] int32
+    (b,z,y,x), voxel_num_points [M] int32[, voxels [M,max_points,C]]): the dataloader's first-come voxeliser
+    (data_processor.py:43-59) fused with MeanVFE (mean_vfe.py:39-58), on the GPU."""
+    _require_cuda(points)
+    lib = _lib.load()
+    points = points.contiguous()
+    n, c = points.shape[0], points.shape[1] - 1
+    cap = int(batch_size) * int(max_voxels)
+    dev = points.device
+    feats = torch.empty((cap, c), dtype=torch.float32, device=dev)
+    coords = torch.empty((cap, 4), dtype=torch.int32, device=dev)
+    num = torch.empty((cap,), dtype=torch.int32, device=dev)
+    voxels = torch.zeros((cap, max_points, c), dtype=torch.float32, device=dev) if want_voxels else None
+    n_out = torch.empty((1,), dtype=torch.int32, device=dev)
+    ws = _ws(lib.vc_voxelize_ws_bytes(n, int(batch_size), int(max_points)), dev)
+    check(lib.vc_voxelize_mean(_p(points), n, c, int(batch_size), host_f32(pc_range), host_f32(voxel_size), int(max_points),
+                               int(max_voxels), int(vfe_model == 'max'), _p(feats), _p(coords), _p(num), _p(voxels),
+                               _p(n_out), _p(ws), ws.numel(), _stream()), 'vc_voxelize_mean')
+    m = int(n_out.item())
+    out = (feats[:m], coords[:m], num[:m])
+    return out + (voxels[:m],) if want_voxels else out
+
+
+def voxel2pinds(indices, batch_size, spatial_shape):
+    """Dense voxel -> row map (`generate_voxel2pinds`, pcdet/utils/spconv_utils.py:13-21)."""
+    _require_cuda(indices)
+    lib = _lib.load()
+    indices = indices.to(torch.int32).contiguous()
+    out = torch.empty((int(batch_size), *[int(s) for s in spatial_shape]), dtype=torch.int32, device=indices.device)
+    check(lib.vc_voxel2pinds(_p(indices), indices.shape[0], indices.shape[1] - 1, int(batch_size), host_i32(spatial_shape),
+                             _p(out), _stream()), 'vc_voxel2pinds')
+    return out
