@@ -22,8 +22,9 @@
 namespace vc {
 
 static constexpr int TCM = 128;        // rows per tile == UMMA M
-static constexpr int TC_THREADS = 128; // 4 warps: warp w owns TMEM lanes [32w, 32w+32)
-static constexpr int TC_STAGES = 3;
+static constexpr int TC_PRODUCERS = 128;  // warps 0-3: gather producers + epilogue (warp w owns TMEM lanes [32w, 32w+32))
+static constexpr int TC_THREADS = 160;    // + warp 4: MMA issuer
+static constexpr int TC_STAGES = 4;
 static constexpr int MAXK_TC = 32;
 static constexpr unsigned SPIN_LIMIT = 1u << 24;
 
@@ -135,6 +136,11 @@ __global__ void prep_weights_tc_kernel(const float* __restrict__ w, __nv_bfloat1
     img[off] = __float2bfloat16_rn(v);
 }
 
+// Warp-specialised: warps 0-3 are gather producers (each owns 32 rows of the tile and streams its 16-byte chunks of
+// every stage with cp.async; completion is signalled on the stage's `full` mbarrier with
+// cp.async.mbarrier.arrive.noinc, so no producer ever waits for another one), warp 4 issues the MMAs
+// (wait full -> fence.proxy.async -> C_in/16 tcgen05.mma -> tcgen05.commit onto the stage's `empty` mbarrier).
+// No block-wide barrier inside the main loop; the ring is TC_STAGES deep.
 template <int KC, int NR>
 __global__ void __launch_bounds__(TC_THREADS)
 tc_gather_gemm_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __restrict__ wimg,
@@ -144,7 +150,9 @@ tc_gather_gemm_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16*
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* ring = smem_raw;                                          // [stages][A | B]
     int* nbr_s = reinterpret_cast<int*>(smem_raw + C::RING_BYTES);           // [K][128]
-    __shared__ __align__(8) uint64_t mma_done[TC_STAGES];
+    __shared__ __align__(8) uint64_t full_bar[TC_STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[TC_STAGES];
+    __shared__ __align__(8) uint64_t accum_bar;
     __shared__ uint32_t tmem_base_s;
     __shared__ int klist[MAXK_TC];
     __shared__ unsigned kmask;
@@ -160,7 +168,11 @@ tc_gather_gemm_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16*
     }
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < TC_STAGES; ++s) mbar_init(&mma_done[s], 1);
+        for (int s = 0; s < TC_STAGES; ++s) {
+            mbar_init(&full_bar[s], TC_PRODUCERS);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(&accum_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         kmask = 0u;
     }
@@ -189,70 +201,68 @@ tc_gather_gemm_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16*
     }
     __syncthreads();
 
-    // gather mapping: per warp instruction 8 rows x (up to) 4 chunks -> conflict-free smem writes, full sectors
-    constexpr int CW = C::CPR < 4 ? C::CPR : 4;        // chunks of one row covered by one instruction
-    constexpr int RPI = 8 * (4 / CW);                  // rows per instruction
-    const int rl = lane & 7, xq = lane >> 3;
-    const int c_sub = xq % CW, r_sub = xq / CW;
-
-    auto issue_stage = [&](int t) {
-        const int k = klist[t];
-        unsigned char* A = ring + (t % TC_STAGES) * C::STAGE_BYTES;
-        unsigned char* B = A + C::A_BYTES;
-        const int* nk_ = nbr_s + k * TCM;
-#pragma unroll
-        for (int it = 0; it < 32 / RPI; ++it) {
-            const int r = warp * 32 + it * RPI + r_sub * 8 + rl;
-            const int src = nk_[r];
-            const __nv_bfloat16* srow = in + (size_t)(src < 0 ? 0 : src) * KC;
-#pragma unroll
-            for (int cg = 0; cg < C::CPR / CW; ++cg) {
-                const int c = cg * CW + c_sub;
-                cp_async16(A + ((r >> 3) * C::CPR + c) * 128 + (r & 7) * 16, srow + c * 8, src >= 0);
-            }
-        }
-        const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(wimg) + (size_t)k * C::B_BYTES;
-        for (int q = tid; q < C::B_BYTES / 16; q += TC_THREADS) cp_async16(B + q * 16, wsrc + q * 16, true);
-    };
-
     bool ok = true;
     if (nk > 0) {
+        if (warp < 4) {
+            // ---------------- gather producers ----------------
+            // per warp instruction 8 rows x (up to) 4 chunks: conflict-free smem writes, full 32-byte sectors
+            constexpr int CW = C::CPR < 4 ? C::CPR : 4;
+            constexpr int RPI = 8 * (4 / CW);
+            const int rl = lane & 7, xq = lane >> 3;
+            const int c_sub = xq % CW, r_sub = xq / CW;
+            for (int t = 0; t < nk; ++t) {
+                const int st = t % TC_STAGES;
+                if (t >= TC_STAGES) ok &= mbar_wait(&empty_bar[st], (uint32_t)((t / TC_STAGES - 1) & 1), err);
+                const int k = klist[t];
+                unsigned char* A = ring + st * C::STAGE_BYTES;
+                unsigned char* B = A + C::A_BYTES;
+                const int* nk_ = nbr_s + k * TCM;
 #pragma unroll
-        for (int t = 0; t < TC_STAGES - 1; ++t) {
-            if (t < nk) issue_stage(t);
-            cp_async_commit();
-        }
-        constexpr uint32_t IDESC = umma_idesc(TCM, NR);
-        for (int t = 0; t < nk; ++t) {
-            const int tn = t + TC_STAGES - 1;
-            if (tn < nk) {
-                if (tn >= TC_STAGES) ok &= mbar_wait(&mma_done[tn % TC_STAGES], (uint32_t)((tn / TC_STAGES - 1) & 1), err);
-                issue_stage(tn);
-            }
-            cp_async_commit();
-            cp_async_wait<TC_STAGES - 1>();     // this thread's chunks of stage t have landed
-            fence_async_smem();                 // generic-proxy writes -> visible to the tensor core (async proxy)
-            __syncthreads();
-            if (tid == 0) {
-                tc_fence_after();
-                const uint32_t a0 = smem_u32(ring + (t % TC_STAGES) * C::STAGE_BYTES);
-                const uint32_t b0 = a0 + C::A_BYTES;
+                for (int it = 0; it < 32 / RPI; ++it) {
+                    const int r = warp * 32 + it * RPI + r_sub * 8 + rl;
+                    const int src = nk_[r];
+                    const __nv_bfloat16* srow = in + (size_t)(src < 0 ? 0 : src) * KC;
 #pragma unroll
-                for (int m = 0; m < KC / 16; ++m) {
-                    const uint64_t ad = umma_desc(a0 + m * 256, 128, C::CPR * 128);
-                    const uint64_t bd = umma_desc(b0 + m * 256, 128, C::CPR * 128);
-                    umma_f16(tmem_base, ad, bd, IDESC, (t > 0 || m > 0) ? 1u : 0u);
+                    for (int cg = 0; cg < C::CPR / CW; ++cg) {
+                        const int c = cg * CW + c_sub;
+                        cp_async16(A + ((r >> 3) * C::CPR + c) * 128 + (r & 7) * 16, srow + c * 8, src >= 0);
+                    }
                 }
-                umma_commit(&mma_done[t % TC_STAGES]);
+                const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(wimg) + (size_t)k * C::B_BYTES;
+                for (int q = tid; q < C::B_BYTES / 16; q += TC_PRODUCERS) cp_async16(B + q * 16, wsrc + q * 16, true);
+                // arrive on full[st] once all of this thread's copies above have landed
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full_bar[st])) : "memory");
+            }
+        } else {
+            // ---------------- MMA issuer (one lane) ----------------
+            constexpr uint32_t IDESC = umma_idesc(TCM, NR);
+            for (int t = 0; t < nk; ++t) {
+                const int st = t % TC_STAGES;
+                ok &= mbar_wait(&full_bar[st], (uint32_t)((t / TC_STAGES) & 1), err);
+                fence_async_smem();     // generic-proxy (cp.async) writes -> visible to the tensor core's async proxy
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a0 = smem_u32(ring + st * C::STAGE_BYTES);
+                    const uint32_t b0 = a0 + C::A_BYTES;
+#pragma unroll
+                    for (int m = 0; m < KC / 16; ++m) {
+                        const uint64_t ad = umma_desc(a0 + m * 256, 128, C::CPR * 128);
+                        const uint64_t bd = umma_desc(b0 + m * 256, 128, C::CPR * 128);
+                        umma_f16(tmem_base, ad, bd, IDESC, (t > 0 || m > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[st]);
+                    if (t == nk - 1) umma_commit(&accum_bar);
+                }
+                __syncwarp();
             }
         }
-        ok &= mbar_wait(&mma_done[(nk - 1) % TC_STAGES], (uint32_t)(((nk - 1) / TC_STAGES) & 1), err);
+        ok &= mbar_wait(&accum_bar, 0u, err);
         tc_fence_after();
     }
-    __syncthreads();    // every thread is past the last operand use: the ring can be reused as epilogue staging
+    __syncthreads();    // every MMA has completed: the ring can be reused as epilogue staging
 
     float* stg = reinterpret_cast<float*>(ring);    // [128][NR+1]
-    {
+    if (warp < 4) {
         const int r = warp * 32 + lane;
 #pragma unroll
         for (int c0 = 0; c0 < NR; c0 += 16) {
@@ -396,6 +406,8 @@ extern "C" int vc_conv_dgrad_tc(const void* dout_bf16, const float* w, const int
 // ================================================================================================
 namespace vc {
 
+static constexpr int WG_THREADS = 128;   // 4 warps: gather + MMA issue (thread 0) + epilogue
+
 __host__ __device__ constexpr uint32_t umma_idesc_mn(int m, int n) {   // both operands MN-major (bits 15, 16)
     return umma_idesc(m, n) | (1u << 15) | (1u << 16);
 }
@@ -412,7 +424,7 @@ struct WgTc {
 };
 
 template <int CI, int CO>
-__global__ void __launch_bounds__(TC_THREADS)
+__global__ void __launch_bounds__(WG_THREADS)
 tc_wgrad_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __restrict__ dout,
                 const int32_t* __restrict__ nbr, float* __restrict__ partial, int n_out, int K, int groups_per_pass,
                 int tmem_cols, int* __restrict__ err) {
@@ -463,19 +475,19 @@ tc_wgrad_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __res
         // previous tile's MMAs still read Bt / were steered by nbr_s: wait for them before overwriting
         if (tiles_done > 0) ok &= mbar_wait(&tile_done, (tiles_done - 1) & 1u, err);
         if (tid == 0) gmask_s = 0u;
-        for (int i = tid; i < k_count * TCM; i += TC_THREADS) {
+        for (int i = tid; i < k_count * TCM; i += WG_THREADS) {
             int kk = i / TCM, r = i % TCM, row = base + r;
             nbr_s[i] = (row < n_out) ? __ldg(nbr + (size_t)(k_begin + kk) * n_out + row) : -1;
         }
         // dout tile, image [r/8][CPO][r%8][16 B]
-        for (int q = tid; q < TCM * C::CPO; q += TC_THREADS) {
+        for (int q = tid; q < TCM * C::CPO; q += WG_THREADS) {
             int r = (q / (8 * C::CPO)) * 8 + (q & 7), c = (q >> 3) % C::CPO;
             bool v = base + r < n_out;
             cp_async16(Bt + ((r >> 3) * C::CPO + c) * 128 + (r & 7) * 16, dout + (size_t)(v ? base + r : 0) * CO + c * 8, v);
         }
         cp_async_commit();
         __syncthreads();
-        for (int g = warp; g < g_count; g += TC_THREADS / 32) {
+        for (int g = warp; g < g_count; g += WG_THREADS / 32) {
             bool any = false;
             for (int j = 0; j < C::G; ++j) {
                 int kk = g * C::G + j;
@@ -637,7 +649,7 @@ static int launch_wgrad_tc(const __nv_bfloat16* in, const __nv_bfloat16* dout, c
     size_t smem = C::smem(kcount);
     auto kern = tc_wgrad_kernel<CI, CO>;
     VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<dim3(wgrad_tc_grid(n_out), passes), TC_THREADS, smem, stream>>>(in, dout, nbr, partial, n_out, K, gpp, cols, err);
+    kern<<<dim3(wgrad_tc_grid(n_out), passes), WG_THREADS, smem, stream>>>(in, dout, nbr, partial, n_out, K, gpp, cols, err);
     VC_LAUNCH_CHECK();
     return VC_OK;
 }
