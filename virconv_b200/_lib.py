@@ -10,7 +10,7 @@ import os
 from ctypes import c_char_p, c_float, c_int, c_int32, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libvirconv_sm100.so')
+LIB_PATH = os.environ.get('VIRCONV_LIB') or os.path.join(_HERE, 'lib', 'libvirconv_sm100.so')
 
 _P = c_void_p
 _I = c_int

@@ -35,8 +35,12 @@ def _digest(paths):
     return h.hexdigest()
 
 
-def build(verbose: bool = False, force: bool = False) -> str:
+def build(verbose: bool = False, force: bool = False, defines=(), suffix: str = '') -> str:
+    """`defines` / `suffix`: experiment variants (e.g. -DVC_TC_STAGES=6 -> libvirconv_sm100_s6.so, picked up through
+    the VIRCONV_LIB environment variable); the default build has neither."""
     os.makedirs(LIBDIR, exist_ok=True)
+    if suffix:
+        return _build_variant(list(defines), suffix, verbose)
     srcs = sources()
     deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cuh', '.h'))] + [
         os.path.join(os.path.dirname(HERE), 'include', 'virconv_b200.h')]
@@ -65,6 +69,22 @@ def build(verbose: bool = False, force: bool = False) -> str:
     with open(stamp, 'w') as f:
         f.write(dig)
     return LIB
+
+
+def _build_variant(defines, suffix, verbose):
+    lib = os.path.join(LIBDIR, f'libvirconv_sm100_{suffix}.so')
+    objs = []
+    for src in sources():
+        obj = os.path.join(LIBDIR, os.path.basename(src)[:-3] + f'_{suffix}.o')
+        r = subprocess.run([NVCC] + FLAGS + [f'-D{d}' for d in defines] + ['-c', src, '-o', obj], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError('nvcc failed for %s:\n%s' % (src, r.stderr))
+        objs.append(obj)
+    r = subprocess.run([NVCC, '-shared', '-o', lib] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a', '-lcudart'],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError('link failed:\n' + r.stderr)
+    return lib
 
 
 if __name__ == '__main__':

@@ -68,4 +68,27 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
 }
 
+// Stage the tile's slice nbr[k0 .. k0+kcount) x [base, base+128) of a neighbour table into shared memory.  Loads are
+// issued in batches of 8 independent LDGs per thread (a plain `nbr_s[i] = nbr[...]` loop serialises one global-memory
+// round trip per iteration: ~20 dependent round trips for K = 27, which was most of a conv CTA's prologue).
+template <int THREADS>
+__device__ __forceinline__ void stage_nbr_tile(const int32_t* __restrict__ nbr, int n_rows, int k0, int kcount, int base,
+                                               int* nbr_s) {
+    const int total = kcount * 128;
+    for (int i0 = threadIdx.x; i0 < total; i0 += THREADS * 8) {
+        int v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int i = i0 + j * THREADS;
+            const int k = i >> 7, row = base + (i & 127);
+            v[j] = (i < total && row < n_rows) ? __ldg(nbr + (size_t)(k0 + k) * n_rows + row) : -1;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int i = i0 + j * THREADS;
+            if (i < total) nbr_s[i] = v[j];
+        }
+    }
+}
+
 }  // namespace vc

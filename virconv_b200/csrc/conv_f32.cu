@@ -55,11 +55,8 @@ __global__ void prep_weights_kernel(const float* __restrict__ w, float* __restri
 __device__ __forceinline__ int stage_nbr(const int32_t* __restrict__ nbr, int n_rows, int K, int base, int* nbr_s,
                                          int* klist, unsigned* kmask) {
     if (threadIdx.x == 0) *kmask = 0u;
-    for (int i = threadIdx.x; i < K * TM; i += NTHREADS) {
-        int k = i / TM, r = i % TM;
-        int row = base + r;
-        nbr_s[i] = (row < n_rows) ? __ldg(nbr + (size_t)k * n_rows + row) : -1;
-    }
+    static_assert(TM == 128, "stage_nbr_tile assumes 128-row tiles");
+    stage_nbr_tile<NTHREADS>(nbr, n_rows, 0, K, base, nbr_s);
     __syncthreads();
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int k = warp; k < K; k += NTHREADS / 32) {

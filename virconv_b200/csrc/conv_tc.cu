@@ -24,7 +24,10 @@ namespace vc {
 static constexpr int TCM = 128;        // rows per tile == UMMA M
 static constexpr int TC_PRODUCERS = 128;  // warps 0-3: gather producers + epilogue (warp w owns TMEM lanes [32w, 32w+32))
 static constexpr int TC_THREADS = 160;    // + warp 4: MMA issuer
-static constexpr int TC_STAGES = 4;
+#ifndef VC_TC_STAGES
+#define VC_TC_STAGES 4
+#endif
+static constexpr int TC_STAGES = VC_TC_STAGES;
 static constexpr int MAXK_TC = 32;
 static constexpr unsigned SPIN_LIMIT = 1u << 24;
 
@@ -177,10 +180,7 @@ tc_gather_gemm_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16*
         kmask = 0u;
     }
     // stage the tile's slice of the neighbour table
-    for (int i = tid; i < K * TCM; i += TC_THREADS) {
-        int k = i / TCM, r = i % TCM, row = base + r;
-        nbr_s[i] = (row < n_out) ? __ldg(nbr + (size_t)k * n_out + row) : -1;
-    }
+    stage_nbr_tile<TC_THREADS>(nbr, n_out, 0, K, base, nbr_s);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -475,10 +475,7 @@ tc_wgrad_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __res
         // previous tile's MMAs still read Bt / were steered by nbr_s: wait for them before overwriting
         if (tiles_done > 0) ok &= mbar_wait(&tile_done, (tiles_done - 1) & 1u, err);
         if (tid == 0) gmask_s = 0u;
-        for (int i = tid; i < k_count * TCM; i += WG_THREADS) {
-            int kk = i / TCM, r = i % TCM, row = base + r;
-            nbr_s[i] = (row < n_out) ? __ldg(nbr + (size_t)(k_begin + kk) * n_out + row) : -1;
-        }
+        stage_nbr_tile<WG_THREADS>(nbr, n_out, k_begin, k_count, base, nbr_s);
         // dout tile, image [r/8][CPO][r%8][16 B]
         for (int q = tid; q < TCM * C::CPO; q += WG_THREADS) {
             int r = (q / (8 * C::CPO)) * 8 + (q & 7), c = (q >> 3) % C::CPO;
