@@ -313,7 +313,11 @@ def run_ours(args):
         g_flops = sum(kern[k][3] for k in dom if k in kern)
         all_ms = sum(v[1] for v in kern.values())
         ach = g_bytes / (g_ms * 1e-3) / 1e9 if g_ms > 0 else 0.0
-        roof = {'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'traffic': None,
+        traffic = None
+        tp = os.path.join(ROOT, 'profiles', 'traffic_tc_gather.json' if args.precision == 'bf16' else 'traffic_gather_f32.json')
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get('dram_bytes_per_launch')     # from the committed ncu --set full capture
+        roof = {'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'traffic': traffic,
                 'kernel': ('tc_gather_gemm_kernel<KC,NR> (tcgen05 conv forward + dgrad), weight-image prep included'
                            if args.precision == 'bf16' else
                            'gather_gemm_kernel<CI,CO> (fp32 conv forward + dgrad), prep_weights included'),

@@ -4,6 +4,7 @@
 """
 import collections
 import csv
+import os
 import re
 import subprocess
 import sys
@@ -56,5 +57,25 @@ def kernel(path):
                 print(f'  {k:75s} {r[i]:>18s} {units[i]}')
 
 
+def traffic(path, out_json):
+    """average DRAM bytes (read + write) per launch of the captured kernel -> small JSON bench.py reads"""
+    import json
+    out = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    ir, iw = hdr.index('dram__bytes_read.sum'), hdr.index('dram__bytes_write.sum')
+    scale = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    tot, n = 0.0, 0
+    for r in rows[2:]:
+        tot += float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]]
+        n += 1
+    json.dump({'kernel_capture': os.path.basename(path), 'launches': n, 'dram_bytes_per_launch': tot / max(n, 1)},
+              open(out_json, 'w'))
+    print(open(out_json).read())
+
+
 if __name__ == '__main__':
-    {'launches': launches, 'kernel': kernel}[sys.argv[1]](sys.argv[2])
+    if sys.argv[1] == 'traffic':
+        traffic(sys.argv[2], sys.argv[3])
+    else:
+        {'launches': launches, 'kernel': kernel}[sys.argv[1]](sys.argv[2])

@@ -172,7 +172,7 @@ tc_gather_gemm_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16*
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < TC_STAGES; ++s) {
-            mbar_init(&full_bar[s], TC_PRODUCERS);
+            mbar_init(&full_bar[s], TC_PRODUCERS + 1);   // 128 gather threads (cp.async arrive) + 1 expect_tx arrive (TMA)
             mbar_init(&empty_bar[s], 1);
         }
         mbar_init(&accum_bar, 1);
@@ -228,8 +228,18 @@ tc_gather_gemm_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16*
                         cp_async16(A + ((r >> 3) * C::CPR + c) * 128 + (r & 7) * 16, srow + c * 8, src >= 0);
                     }
                 }
-                const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(wimg) + (size_t)k * C::B_BYTES;
-                for (int q = tid; q < C::B_BYTES / 16; q += TC_PRODUCERS) cp_async16(B + q * 16, wsrc + q * 16, true);
+                if (tid == 0) {
+                    // the offset's weight image: ONE bulk (TMA-engine) copy, completion counted in bytes on full[st]
+                    const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(wimg) + (size_t)k * C::B_BYTES;
+                    const uint32_t bar = smem_u32(&full_bar[st]);
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)C::B_BYTES)
+                                 : "memory");
+                    asm volatile(
+                        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                            smem_u32(B)),
+                        "l"(wsrc), "r"((uint32_t)C::B_BYTES), "r"(bar)
+                        : "memory");
+                }
                 // arrive on full[st] once all of this thread's copies above have landed
                 asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full_bar[st])) : "memory");
             }
@@ -420,7 +430,7 @@ struct WgTc {
     static constexpr int B_BYTES = TCM * CO * 2;
     static constexpr int STAGES = 3;
     static constexpr int MAX_GROUPS = 512 / CO;        // TMEM budget per CTA
-    static constexpr size_t smem(int kcount) { return (size_t)STAGES * A_STAGE + B_BYTES + (size_t)kcount * TCM * 4; }
+    static constexpr size_t smem(int kcount) { return (size_t)STAGES * A_STAGE + B_BYTES + 2 * (size_t)kcount * TCM * 4; }
 };
 
 template <int CI, int CO>
@@ -432,7 +442,7 @@ tc_wgrad_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __res
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* ring = smem_raw;
     unsigned char* Bt = smem_raw + C::STAGES * C::A_STAGE;
-    int* nbr_s = reinterpret_cast<int*>(Bt + C::B_BYTES);
+    int* nbr_buf = reinterpret_cast<int*>(Bt + C::B_BYTES);   // [2][k_count][128]: current tile / prefetched next tile
     __shared__ __align__(8) uint64_t stage_done[C::STAGES];
     __shared__ __align__(8) uint64_t tile_done;
     __shared__ uint32_t tmem_base_s;
@@ -470,12 +480,34 @@ tc_wgrad_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __res
     bool ok = true;
     constexpr uint32_t IDESC = umma_idesc_mn(TCM, CO);
 
+    // neighbour-table slice of a tile: thread `tid` owns row base+tid for every offset of this pass (coalesced per
+    // offset).  The NEXT tile's slice is loaded into registers at the top of the current tile and parked in the
+    // other smem buffer at its end, so no tile ever waits for its table (it was 43 % of this kernel's stall samples).
+    int nv[MAXK_TC];
+    auto load_nbr_regs = [&](int tile_) {
+        const int row = tile_ * TCM + tid;
+#pragma unroll
+        for (int j = 0; j < MAXK_TC; ++j)
+            nv[j] = (j < k_count && tile_ < n_tiles && row < n_out) ? __ldg(nbr + (size_t)(k_begin + j) * n_out + row) : -1;
+    };
+    auto park_nbr_regs = [&](int* dst) {
+#pragma unroll
+        for (int j = 0; j < MAXK_TC; ++j)
+            if (j < k_count) dst[j * TCM + tid] = nv[j];
+    };
+    int cur = 0;
+    load_nbr_regs(blockIdx.x);
+    park_nbr_regs(nbr_buf);
+    __syncthreads();
+
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int base = tile * TCM;
-        // previous tile's MMAs still read Bt / were steered by nbr_s: wait for them before overwriting
+        int* nbr_s = nbr_buf + cur * k_count * TCM;
+        int* nbr_next = nbr_buf + (cur ^ 1) * k_count * TCM;
+        load_nbr_regs(tile + gridDim.x);             // in flight while this tile is processed
+        // previous tile's MMAs still read Bt: wait for them before overwriting it
         if (tiles_done > 0) ok &= mbar_wait(&tile_done, (tiles_done - 1) & 1u, err);
         if (tid == 0) gmask_s = 0u;
-        stage_nbr_tile<WG_THREADS>(nbr, n_out, k_begin, k_count, base, nbr_s);
         // dout tile, image [r/8][CPO][r%8][16 B]
         for (int q = tid; q < TCM * C::CPO; q += WG_THREADS) {
             int r = (q / (8 * C::CPO)) * 8 + (q & 7), c = (q >> 3) % C::CPO;
@@ -506,6 +538,8 @@ tc_wgrad_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __res
         __syncthreads();
         if (ng == 0) {
             cp_async_wait<0>();
+            park_nbr_regs(nbr_next);
+            cur ^= 1;
             __syncthreads();
             continue;
         }
@@ -569,6 +603,9 @@ tc_wgrad_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __res
         }
         it = it0 + ng;
         ++tiles_done;
+        park_nbr_regs(nbr_next);    // nbr_next was last read while tile-1's gathers were issued: free since then
+        cur ^= 1;
+        __syncthreads();
     }
     if (tiles_done > 0) ok &= mbar_wait(&tile_done, (tiles_done - 1) & 1u, err);
     cp_async_wait<0>();
