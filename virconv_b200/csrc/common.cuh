@@ -62,6 +62,11 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, boo
     int sz = valid ? 16 : 0;  // src-size 0 => 16 bytes of zeros
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz));
 }
+// same, destination given as a 32-bit shared-space address (saves the generic->shared conversion per copy)
+__device__ __forceinline__ void cp_async16_s(uint32_t smem_addr, const void* gsrc, bool valid) {
+    int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_addr), "l"(gsrc), "r"(sz));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
@@ -71,20 +76,20 @@ __device__ __forceinline__ void cp_async_wait() {
 // Stage the tile's slice nbr[k0 .. k0+kcount) x [base, base+128) of a neighbour table into shared memory.  Loads are
 // issued in batches of 8 independent LDGs per thread (a plain `nbr_s[i] = nbr[...]` loop serialises one global-memory
 // round trip per iteration: ~20 dependent round trips for K = 27, which was most of a conv CTA's prologue).
-template <int THREADS>
+template <int THREADS, int BATCH = 8>
 __device__ __forceinline__ void stage_nbr_tile(const int32_t* __restrict__ nbr, int n_rows, int k0, int kcount, int base,
                                                int* nbr_s) {
     const int total = kcount * 128;
-    for (int i0 = threadIdx.x; i0 < total; i0 += THREADS * 8) {
-        int v[8];
+    for (int i0 = threadIdx.x; i0 < total; i0 += THREADS * BATCH) {
+        int v[BATCH];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < BATCH; ++j) {
             const int i = i0 + j * THREADS;
             const int k = i >> 7, row = base + (i & 127);
             v[j] = (i < total && row < n_rows) ? __ldg(nbr + (size_t)(k0 + k) * n_rows + row) : -1;
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < BATCH; ++j) {
             const int i = i0 + j * THREADS;
             if (i < total) nbr_s[i] = v[j];
         }

@@ -21,6 +21,14 @@
 
 namespace vc {
 
+#ifdef VC_TC_TRACE
+// debug build only (profiles/trace_tc.py): per-CTA SM-clock timestamps of the pipeline events of the first CTAs
+__device__ long long* g_trace = nullptr;
+#define VC_TRACE(slot) do { if (g_trace && blockIdx.x < 64) g_trace[blockIdx.x * 64 + (slot)] = clock64(); } while (0)
+#else
+#define VC_TRACE(slot) do { } while (0)
+#endif
+
 static constexpr int TCM = 128;        // rows per tile == UMMA M
 static constexpr int TC_PRODUCERS = 128;  // warps 0-3: gather producers + epilogue (warp w owns TMEM lanes [32w, 32w+32))
 static constexpr int TC_THREADS = 160;    // + warp 4: MMA issuer
@@ -163,6 +171,7 @@ tc_gather_gemm_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16*
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int base = blockIdx.x * TCM;
+    if (tid == 0) VC_TRACE(0);
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
@@ -170,6 +179,7 @@ tc_gather_gemm_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16*
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     if (tid == 0) {
+        VC_TRACE(1);
 #pragma unroll
         for (int s = 0; s < TC_STAGES; ++s) {
             mbar_init(&full_bar[s], TC_PRODUCERS + 1);   // 128 gather threads (cp.async arrive) + 1 expect_tx arrive (TMA)
@@ -180,7 +190,7 @@ tc_gather_gemm_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16*
         kmask = 0u;
     }
     // stage the tile's slice of the neighbour table
-    stage_nbr_tile<TC_THREADS>(nbr, n_out, 0, K, base, nbr_s);
+    stage_nbr_tile<TC_THREADS, 24>(nbr, n_out, 0, K, base, nbr_s);   // all of a thread's loads in one round trip
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -202,31 +212,45 @@ tc_gather_gemm_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16*
     __syncthreads();
 
     bool ok = true;
+    if (tid == 0) { VC_TRACE(2); VC_TRACE(63); }
+#ifdef VC_TC_TRACE
+    if (tid == 0 && g_trace && blockIdx.x < 64) g_trace[blockIdx.x * 64 + 62] = nk;
+#endif
     if (nk > 0) {
         if (warp < 4) {
             // ---------------- gather producers ----------------
             // per warp instruction 8 rows x (up to) 4 chunks: conflict-free smem writes, full 32-byte sectors
             constexpr int CW = C::CPR < 4 ? C::CPR : 4;
             constexpr int RPI = 8 * (4 / CW);
+            constexpr int NIT = 32 / RPI, NCG = C::CPR / CW;
             const int rl = lane & 7, xq = lane >> 3;
             const int c_sub = xq % CW, r_sub = xq / CW;
+            // everything that does not depend on the stage is computed once: the rows this thread gathers, their chunk
+            // offsets inside a stage image, the shared-space base address
+            int rows[NIT];
+            uint32_t dst_off[NIT][NCG];
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) {
+                const int r = warp * 32 + it * RPI + r_sub * 8 + rl;
+                rows[it] = r;
+#pragma unroll
+                for (int cg = 0; cg < NCG; ++cg) dst_off[it][cg] = (uint32_t)(((r >> 3) * C::CPR + cg * CW + c_sub) * 128 + (r & 7) * 16);
+            }
+            const uint32_t ring_s = smem_u32(ring);
             for (int t = 0; t < nk; ++t) {
                 const int st = t % TC_STAGES;
-                if (t >= TC_STAGES) ok &= mbar_wait(&empty_bar[st], (uint32_t)((t / TC_STAGES - 1) & 1), err);
                 const int k = klist[t];
-                unsigned char* A = ring + st * C::STAGE_BYTES;
-                unsigned char* B = A + C::A_BYTES;
-                const int* nk_ = nbr_s + k * TCM;
+                int src[NIT];
 #pragma unroll
-                for (int it = 0; it < 32 / RPI; ++it) {
-                    const int r = warp * 32 + it * RPI + r_sub * 8 + rl;
-                    const int src = nk_[r];
-                    const __nv_bfloat16* srow = in + (size_t)(src < 0 ? 0 : src) * KC;
+                for (int it = 0; it < NIT; ++it) src[it] = nbr_s[k * TCM + rows[it]];     // independent loads first
+                if (t >= TC_STAGES) ok &= mbar_wait(&empty_bar[st], (uint32_t)((t / TC_STAGES - 1) & 1), err);
+                const uint32_t a_s = ring_s + st * C::STAGE_BYTES;
+                unsigned char* B = ring + st * C::STAGE_BYTES + C::A_BYTES;
 #pragma unroll
-                    for (int cg = 0; cg < C::CPR / CW; ++cg) {
-                        const int c = cg * CW + c_sub;
-                        cp_async16(A + ((r >> 3) * C::CPR + c) * 128 + (r & 7) * 16, srow + c * 8, src >= 0);
-                    }
+                for (int it = 0; it < NIT; ++it) {
+                    const __nv_bfloat16* srow = in + (size_t)(src[it] < 0 ? 0 : src[it]) * KC + c_sub * 8;
+#pragma unroll
+                    for (int cg = 0; cg < NCG; ++cg) cp_async16_s(a_s + dst_off[it][cg], srow + cg * CW * 8, src[it] >= 0);
                 }
                 if (tid == 0) {
                     // the offset's weight image: ONE bulk (TMA-engine) copy, completion counted in bytes on full[st]
@@ -249,6 +273,7 @@ tc_gather_gemm_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16*
             for (int t = 0; t < nk; ++t) {
                 const int st = t % TC_STAGES;
                 ok &= mbar_wait(&full_bar[st], (uint32_t)((t / TC_STAGES) & 1), err);
+                if (lane == 0 && t < 27) VC_TRACE(4 + t);
                 fence_async_smem();     // generic-proxy (cp.async) writes -> visible to the tensor core's async proxy
                 tc_fence_after();
                 if (lane == 0) {
@@ -268,6 +293,7 @@ tc_gather_gemm_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16*
         }
         ok &= mbar_wait(&accum_bar, 0u, err);
         tc_fence_after();
+        if (tid == 0) VC_TRACE(40);
     }
     __syncthreads();    // every MMA has completed: the ring can be reused as epilogue staging
 
@@ -319,6 +345,7 @@ tc_gather_gemm_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16*
         }
     }
     __syncthreads();
+    if (tid == 0) VC_TRACE(41);
     if (warp == 0) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS));
     }
@@ -546,18 +573,24 @@ tc_wgrad_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __res
 
         auto issue_group = [&](int t, unsigned use) {
             const int g = glist[t];
-            unsigned char* A = ring + (use % C::STAGES) * C::A_STAGE;
+            const uint32_t a_s = smem_u32(ring + (use % C::STAGES) * C::A_STAGE);
+            int src[4][4];
+#pragma unroll
+            for (int sg = 0; sg < 4; ++sg) {                    // 16 slots = 4 x 4; independent table reads first
+                const int kk = g * C::G + (sg * 4 + xq) / C::CPR;
+#pragma unroll
+                for (int itr = 0; itr < 4; ++itr)
+                    src[itr][sg] = (kk < k_count) ? nbr_s[kk * TCM + warp * 32 + itr * 8 + rl] : -1;
+            }
 #pragma unroll
             for (int itr = 0; itr < 4; ++itr) {                 // 4 x 8 rows per warp
                 const int r = warp * 32 + itr * 8 + rl;
 #pragma unroll
-                for (int sg = 0; sg < 4; ++sg) {                // 16 slots = 4 x 4
+                for (int sg = 0; sg < 4; ++sg) {
                     const int slot = sg * 4 + xq;
-                    const int j = slot / C::CPR, c = slot % C::CPR;
-                    const int kk = g * C::G + j;
-                    const int src = (kk < k_count) ? nbr_s[kk * TCM + r] : -1;
-                    cp_async16(A + ((r >> 3) * 16 + slot) * 128 + (r & 7) * 16,
-                               in + (size_t)(src < 0 ? 0 : src) * CI + c * 8, src >= 0);
+                    const int sv = src[itr][sg];
+                    cp_async16_s(a_s + (uint32_t)(((r >> 3) * 16 + slot) * 128 + (r & 7) * 16),
+                                 in + (size_t)(sv < 0 ? 0 : sv) * CI + (slot % C::CPR) * 8, sv >= 0);
                 }
             }
         };
@@ -728,3 +761,9 @@ extern "C" int vc_conv_wgrad_tc(const void* in_bf16, const void* dout_bf16, cons
     VC_LAUNCH_CHECK();
     return VC_OK;
 }
+
+#ifdef VC_TC_TRACE
+extern "C" int vc_debug_set_trace(long long* buf) {
+    return cudaMemcpyToSymbol(vc::g_trace, &buf, sizeof(buf)) == cudaSuccess ? 0 : -2;
+}
+#endif
