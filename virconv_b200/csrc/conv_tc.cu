@@ -36,6 +36,7 @@ static constexpr int TC_THREADS = 160;    // + warp 4: MMA issuer
 #define VC_TC_STAGES 4
 #endif
 static constexpr int TC_STAGES = VC_TC_STAGES;
+static constexpr int TC_LAG = TC_STAGES - 1;   // stages a producer thread keeps in flight before it signals `full`
 static constexpr int MAXK_TC = 32;
 static constexpr unsigned SPIN_LIMIT = 1u << 24;
 
@@ -264,9 +265,20 @@ tc_gather_gemm_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16*
                         "l"(wsrc), "r"((uint32_t)C::B_BYTES), "r"(bar)
                         : "memory");
                 }
-                // arrive on full[st] once all of this thread's copies above have landed
-                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full_bar[st])) : "memory");
+                // Signal `full` with a LAG of TC_LAG stages: commit this stage's copies as one cp.async group, then wait only
+                // until the group issued TC_LAG stages ago has landed and arrive for THAT stage.  (Arriving for the
+                // current stage with cp.async.mbarrier.arrive.noinc measured as one memory round trip per stage: the
+                // producer did not run ahead.  This keeps TC_LAG+1 stages of gathers in flight per thread.)
+                cp_async_commit();
+                if (t >= TC_LAG) {
+                    cp_async_wait<TC_LAG>();
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full_bar[(t - TC_LAG) % TC_STAGES]))
+                                 : "memory");
+                }
             }
+            cp_async_wait<0>();
+            for (int t = (nk > TC_LAG ? nk - TC_LAG : 0); t < nk; ++t)
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full_bar[t % TC_STAGES])) : "memory");
         } else {
             // ---------------- MMA issuer (one lane) ----------------
             constexpr uint32_t IDESC = umma_idesc(TCM, NR);
