@@ -68,9 +68,30 @@ class NRConvBlock(nn.Module):
     def forward(self, sp_tensor, batch_size, proj_params, stride):
         if self.stride > 1:
             sp_tensor = self.down_layer(sp_tensor)
+        idx = spconv._as_i32(sp_tensor.indices)
+        rb2d = None
+        if ops.OVERLAP and idx.shape[0] > 0:
+            # projection + the image-space rulebook only need the indices: build them on the side stream while the two
+            # 3-D convs run on the main one
+            sd = ops.side(idx.device)
+            main = torch.cuda.current_stream()
+            sd.stream.wait_stream(main)
+            with torch.cuda.stream(sd.stream):
+                uv = ops.index2uv(idx, batch_size, proj_params, stride)
+                conv2d = self.d2_conv1[0]
+                rb2d = ops.build_subm_rulebook(uv, batch_size, [1600, 600], conv2d.kernel_size, conv2d.dilation)
+            ops._keep_alive_on(sd.stream, idx, proj_params)
+            ops._keep_alive_on(main, uv, rb2d.nbr, rb2d.pair_num)
         d3 = self.d3_conv2(self.d3_conv1(sp_tensor))
-        uv = ops.index2uv(spconv._as_i32(d3.indices), batch_size, proj_params, stride)
+        if rb2d is None:
+            uv = ops.index2uv(spconv._as_i32(d3.indices), batch_size, proj_params, stride)
+        else:
+            torch.cuda.current_stream().wait_stream(sd.stream)
         img = spconv.SparseConvTensor(d3.features, uv, [1600, 600], batch_size)
+        if rb2d is not None:
+            rb2d._keepalive = uv
+            img.indice_dict[self.d2_conv1[0].indice_key] = rb2d       # both image convs see identical indices
+            img.indice_dict[self.d2_conv2[0].indice_key] = rb2d
         img.features_bf16 = d3.features_bf16
         d2 = self.d2_conv2(self.d2_conv1(img))
         cat = ops.Cat2Fn.apply(d3.features, d2.features, d3.features_bf16 is not None)

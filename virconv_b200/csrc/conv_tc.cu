@@ -30,8 +30,12 @@ __device__ long long* g_trace = nullptr;
 #endif
 
 static constexpr int TCM = 128;        // rows per tile == UMMA M
-static constexpr int TC_PRODUCERS = 128;  // warps 0-3: gather producers + epilogue (warp w owns TMEM lanes [32w, 32w+32))
-static constexpr int TC_THREADS = 160;    // + warp 4: MMA issuer
+#ifndef VC_TC_NPW
+#define VC_TC_NPW 4
+#endif
+static constexpr int TC_NPW = VC_TC_NPW;               // gather-producer warps (4 or 8); warps 0-3 also run the epilogue
+static constexpr int TC_PRODUCERS = 32 * TC_NPW;       // (warp w < 4 owns TMEM lanes [32w, 32w+32))
+static constexpr int TC_THREADS = TC_PRODUCERS + 32;   // + the last warp: MMA issuer
 #ifndef VC_TC_STAGES
 #define VC_TC_STAGES 4
 #endif
@@ -218,12 +222,14 @@ tc_gather_gemm_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16*
     if (tid == 0 && g_trace && blockIdx.x < 64) g_trace[blockIdx.x * 64 + 62] = nk;
 #endif
     if (nk > 0) {
-        if (warp < 4) {
+        if (warp < TC_NPW) {
             // ---------------- gather producers ----------------
             // per warp instruction 8 rows x (up to) 4 chunks: conflict-free smem writes, full 32-byte sectors
             constexpr int CW = C::CPR < 4 ? C::CPR : 4;
             constexpr int RPI = 8 * (4 / CW);
-            constexpr int NIT = 32 / RPI, NCG = C::CPR / CW;
+            constexpr int RPW = TCM / TC_NPW;             // rows per producer warp
+            constexpr int NIT = RPW / RPI, NCG = C::CPR / CW;
+            static_assert(RPW % RPI == 0, "producer warp rows must be a multiple of the rows per instruction");
             const int rl = lane & 7, xq = lane >> 3;
             const int c_sub = xq % CW, r_sub = xq / CW;
             // everything that does not depend on the stage is computed once: the rows this thread gathers, their chunk
@@ -232,7 +238,7 @@ tc_gather_gemm_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16*
             uint32_t dst_off[NIT][NCG];
 #pragma unroll
             for (int it = 0; it < NIT; ++it) {
-                const int r = warp * 32 + it * RPI + r_sub * 8 + rl;
+                const int r = warp * RPW + it * RPI + r_sub * 8 + rl;
                 rows[it] = r;
 #pragma unroll
                 for (int cg = 0; cg < NCG; ++cg) dst_off[it][cg] = (uint32_t)(((r >> 3) * C::CPR + cg * CW + c_sub) * 128 + (r & 7) * 16);

@@ -49,13 +49,44 @@ def _ws(nbytes, device):
     sequence enqueued on the current stream by a single call (or the count/fill pair of the strided rulebook, which
     has no other call in between), so stream order makes reuse safe."""
     nbytes = max(int(nbytes), 256)
-    key = (device.type, device.index)
+    key = (device.type, device.index, _stream())      # one scratch buffer per stream (side-stream work has its own)
     buf = _WS.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(nbytes, 2 * (buf.numel() if buf is not None else 0), 1 << 24), dtype=torch.uint8,
                           device=device)
         _WS[key] = buf
     return buf
+
+
+# ------------------------------------------------------------------------------------------------
+# side stream: independent work that would otherwise serialise behind latency-bound kernels runs concurrently —
+#   * backward: wgrad of layer i next to BN-backward + dgrad of layer i-1 (they only share read-only inputs);
+#   * forward : voxel->pixel projection + the 2-D rulebook of an NRConv block next to its two 3-D convs.
+# Joined back into the main stream before anything consumes the results; disable with VIRCONV_OVERLAP=0.
+# ------------------------------------------------------------------------------------------------
+import os as _os
+
+OVERLAP = _os.environ.get('VIRCONV_OVERLAP', '1') != '0'
+_SIDE = {}
+
+
+class _Side:
+    def __init__(self, device):
+        self.stream = torch.cuda.Stream(device=device)
+        self.join_queued = False
+
+
+def side(device) -> _Side:
+    key = (device.type, device.index)
+    if key not in _SIDE:
+        _SIDE[key] = _Side(device)
+    return _SIDE[key]
+
+
+def _keep_alive_on(stream, *tensors):
+    for t in tensors:
+        if t is not None:
+            t.record_stream(stream)
 
 
 class StatsArena:
@@ -420,8 +451,26 @@ class ConvBNReLUFn(torch.autograd.Function):
             bsums = torch.zeros(2 * cout, dtype=torch.float64, device=dy.device)
         check(lib.vc_bn_relu_bwd_f32(_p(dy), _p(x), _p(y), _p(gamma), _p(stats), _p(dx), _p(db), _p(dgamma), _p(dbeta),
                                      rb.n_out, cout, int(ctx.training), _p(bsums), _stream()), 'vc_bn_relu_bwd_f32')
+        dw = None
+        if ctx.needs_input_grad[1] and OVERLAP:
+            # wgrad on the side stream, concurrent with this layer's dgrad and the next layer's BN backward
+            sd = side(dy.device)
+            main = torch.cuda.current_stream()
+            sd.stream.wait_stream(main)                     # dx / db are ready
+            with torch.cuda.stream(sd.stream):
+                dw = conv_wgrad(feats, dx, weight.shape, rb, ctx.precision, ctx.fb, db)
+            _keep_alive_on(sd.stream, feats, dx, ctx.fb, db, rb.nbr)
+            dw.record_stream(main)
+            if not sd.join_queued:                          # join once, when this backward pass ends
+                sd.join_queued = True
+
+                def _join(sd=sd, main=main):
+                    main.wait_stream(sd.stream)
+                    sd.join_queued = False
+                torch.autograd.Variable._execution_engine.queue_callback(_join)
+        elif ctx.needs_input_grad[1]:
+            dw = conv_wgrad(feats, dx, weight.shape, rb, ctx.precision, ctx.fb, db)
         din = conv_dgrad(dx, weight, rb, ctx.precision, db) if ctx.needs_input_grad[0] else None
-        dw = conv_wgrad(feats, dx, weight.shape, rb, ctx.precision, ctx.fb, db) if ctx.needs_input_grad[1] else None
         return din, dw, dgamma, dbeta, None, None, None, None, None, None, None, None, None
 
 
