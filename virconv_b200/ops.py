@@ -60,13 +60,16 @@ def _ws(nbytes, device):
 
 # ------------------------------------------------------------------------------------------------
 # side stream: independent work that would otherwise serialise behind latency-bound kernels runs concurrently —
-#   * backward: wgrad of layer i next to BN-backward + dgrad of layer i-1 (they only share read-only inputs);
-#   * forward : voxel->pixel projection + the 2-D rulebook of an NRConv block next to its two 3-D convs.
+#   * forward : voxel->pixel projection + the 2-D rulebook of an NRConv block next to its two 3-D convs (on);
+#   * backward: wgrad of layer i next to BN-backward + dgrad of layer i-1 (implemented, off by default, see below).
 # Joined back into the main stream before anything consumes the results; disable with VIRCONV_OVERLAP=0.
 # ------------------------------------------------------------------------------------------------
 import os as _os
 
-OVERLAP = _os.environ.get('VIRCONV_OVERLAP', '1') != '0'
+OVERLAP = _os.environ.get('VIRCONV_OVERLAP', '1') != '0'                      # forward: projection + 2-D rulebook
+# backward wgrad overlap measured SLOWER on B200 (5.85 vs 5.21 ms/step: the persistent wgrad CTAs hold up to 126 KB of
+# shared memory and 512 TMEM columns per SM, so the dgrad CTAs behind them cannot co-reside) -> off unless asked for
+OVERLAP_WGRAD = _os.environ.get('VIRCONV_OVERLAP_WGRAD', '0') != '0' and OVERLAP
 _SIDE = {}
 
 
@@ -452,7 +455,7 @@ class ConvBNReLUFn(torch.autograd.Function):
         check(lib.vc_bn_relu_bwd_f32(_p(dy), _p(x), _p(y), _p(gamma), _p(stats), _p(dx), _p(db), _p(dgamma), _p(dbeta),
                                      rb.n_out, cout, int(ctx.training), _p(bsums), _stream()), 'vc_bn_relu_bwd_f32')
         dw = None
-        if ctx.needs_input_grad[1] and OVERLAP:
+        if ctx.needs_input_grad[1] and OVERLAP_WGRAD:
             # wgrad on the side stream, concurrent with this layer's dgrad and the next layer's BN backward
             sd = side(dy.device)
             main = torch.cuda.current_stream()
