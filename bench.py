@@ -229,11 +229,14 @@ def run_ours(args):
         h2d = hv.numel() * 4 + hc.numel() * 4 + b.batch_size * 28 * 4
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
-    def step(vf, vc, b, sync_loss):
+    def step(vf, vc, b, sync_loss, resident=False):
         for p in params:
             p.grad = None
         bd = {'voxel_features': vf, 'voxel_coords': vc, 'batch_size': b.batch_size, 'calib': b.calib,
-              'aug_param': b.aug_param}
+              'aug_param': b.aug_param,
+              # resident int32 coordinates (the `value` loop): this step's rulebook pipeline may overlap the previous
+              # step's backward; the e2e loop uploads on the main stream every step and makes no such promise
+              'virconv_inputs_ready': resident}
         out = model(bd)
         loss = out['encoded_spconv_tensor'].features.mean()
         for t in out['multi_scale_3d_features'].values():
@@ -253,7 +256,7 @@ def run_ours(args):
                 step(hv.to(dev, non_blocking=True), hc.to(dev, non_blocking=True), b, True)
             else:
                 vf, vc, b = devb[s % POOL]
-                step(vf, vc, b, False)
+                step(vf, vc, b, False, resident=True)
             e.record()
             evs.append((a, e))
         torch.cuda.synchronize()
@@ -292,19 +295,36 @@ def run_ours(args):
     ms_e2e = float(tot[1]) / args.steps
     scenes_per_step = SCENES_PER_GPU * world
 
-    # roofline pass: the same step with CUDA events around every conv C-ABI call (not part of the timed loops)
+    # roofline pass: the same step with CUDA events around every conv kernel launch (not part of the timed loops).
+    # Plan-executor path: the events are recorded inside vc_exec_forward / vc_exec_backward (executor.timing_*);
+    # module path (VIRCONV_EXECUTOR=0): around every conv C-ABI call (ops.KernelTimer).
+    from virconv_b200 import executor
     roof, kern = None, {}
     nprof = 3
-    if rank == 0:
+    use_exec = executor.ENABLED
+    if rank == 0 and not use_exec:
         ops.TIMER = ops.KernelTimer()
     for s in range(nprof):               # every rank runs the steps (they contain the gradient all-reduce)
         flush_buf.zero_()
         vf, vc, b = devb[s % POOL]
+        if rank == 0 and use_exec:
+            executor.timing_start()
         step(vf, vc, b, False)
+        if rank == 0 and use_exec:
+            run = executor.LAST_RUN
+            for kind, layer, ms in executor.timing_stop():
+                by, fl = executor.alg_bytes_flops(run, kind, layer)
+                c = kern.setdefault(kind, [0, 0.0, 0, 0])
+                c[0] += 1
+                c[1] += ms
+                c[2] += by
+                c[3] += fl
+            executor.LAST_RUN = None
     barrier()
     if rank == 0:
-        kern = ops.TIMER.summary()
-        ops.TIMER = None
+        if not use_exec:
+            kern = ops.TIMER.summary()
+            ops.TIMER = None
         peak, how = peaks()
         dom = ('conv_fwd_tc', 'conv_dgrad_tc') if args.precision == 'bf16' else ('conv_fwd', 'conv_dgrad')
         g_calls = sum(kern[k][0] for k in dom if k in kern)
@@ -318,7 +338,7 @@ def run_ours(args):
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get('dram_bytes_per_launch')     # from the committed ncu --set full capture
         roof = {'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'traffic': traffic,
-                'kernel': ('tc_gather_gemm_kernel<KC,NR> (tcgen05 conv forward + dgrad), weight-image prep included'
+                'kernel': ('tc_gather_gemm_kernel<KC,NR> (tcgen05 conv forward + dgrad)'
                            if args.precision == 'bf16' else
                            'gather_gemm_kernel<CI,CO> (fp32 conv forward + dgrad), prep_weights included'),
                 'peak_source': how, 'launches_per_step': g_calls / nprof,
@@ -327,7 +347,8 @@ def run_ours(args):
                 'share_of_conv_kernel_time': g_ms / all_ms if all_ms > 0 else None,
                 'per_step_ms': {k: v[1] / nprof for k, v in kern.items()},
                 'note': ('tcgen05 bf16 operands / fp32 TMEM accumulators; bytes = bf16 gathered operand + fp32 output + P*8 '
-                         '+ bf16 weights' if args.precision == 'bf16' else
+                         '+ bf16 weights; CUDA events around each launch inside the plan executor'
+                         if args.precision == 'bf16' else
                          'fp32 CUDA-core parity path: FP32-FMA bound, HBM is the bound it is designed toward')}
 
     if rank != 0:
@@ -350,6 +371,8 @@ def run_ours(args):
             'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_step,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'scenes_per_step': scenes_per_step, 'parallelism': f'dp{world}',
+                       'host_path': ('native plan executor: one C-ABI call per forward / backward, index ops on a side stream'
+                                     if executor.ENABLED else 'per-operator C-ABI calls from Python autograd'),
                        'l2': 'flushed between timed steps (256 MiB write)', 'timing': 'per-step CUDA events, max over ranks',
                        'precision': ('bf16 operands on tcgen05 for conv forward/dgrad (C>=16), fp32 accumulate, fp32 features, '
                                      'fp32 wgrad/BN' if args.precision == 'bf16' else 'fp32 storage, fp32 accumulate (parity path)')},

@@ -215,6 +215,58 @@ int vc_cat2_f32(const float* a, const float* b, float* out, void* out_bf16 /*may
 /* Row gather for StVD layer discard (spconv_backbone.py:134-147): out[r] = in[rows[r]]. */
 int vc_gather_rows(const void* in, const int32_t* rows, void* out, int n_rows, int row_bytes, vc_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Plan executor: a whole backbone forward / backward in ONE call.  Replaces the Python layer loop of
+ * `VirConvL8x.forward` (spconv_backbone.py:609-699), `NRConvBlock.forward` (:207-229) and the two streams of
+ * `VirConv8x.forward` (:339-535) together with autograd's reverse walk over them: the host side of ~100 operator
+ * calls per step becomes native.  The caller describes the layer graph once as a PLAN:
+ *   ops_i [n_ops, 24] int32, ops_f [n_ops, 8] float32, one row per op, executed in order:
+ *     [0] kind  1 SUBM_RB   index set a            -> rulebook c            ([21] = 1 if coordinates are unique)
+ *               2 CONV_RB   index set a            -> index set b, rulebook c   (host reads the row count once)
+ *               3 INDEX2UV  3-D index set a        -> 2-D index set b       ([6],[7] = image shape, [21] stride,
+ *                                                                            [22] u_max, [23] v_max, ops_f[0..5] = grid)
+ *               4 CBR       features a, rulebook c -> features b            conv + BatchNorm1d + ReLU of layer [20]
+ *                                                                            ([18] cin, [19] cout, [21] = input needs grad)
+ *               5 CAT       features a, features b -> features c            channel concat
+ *     [1] stream (0 main: feature ops, 1 side: index ops)   [2..4] a, b, c   [5] ndim   [6..8] kernel size
+ *     [9..11] stride   [12..14] padding   [15..17] dilation
+ *   layer_ptrs [n_layers, 9] uint64: weight, gamma, beta, running_mean, running_var, num_batches_tracked, then the
+ *   caller's gradient buffers d_weight, d_gamma, d_beta (written by vc_exec_backward); layer_f [n_layers, 2] = eps, momentum.
+ *   Feature slot 0 / index set 0 are the network input (feats0 [n0, c0] fp32, idx0 [n0, 4] int32, shape0 host[3]).
+ * Memory: every activation, rulebook and scratch buffer is carved out of `arena` (bump allocation, nothing reused
+ * inside a step; VC_ERR_WORKSPACE if it is too small).  `state` (>= vc_exec_state_bytes(), host) receives the buffer
+ * addresses and row counts that vc_exec_backward and vc_exec_query read; the library keeps nothing else between calls
+ * (apart from a pool of CUDA events for cross-stream ordering).  `pinned_host`: >= 16 int32 of page-locked host memory
+ * for the row-count read-backs.  precision 0 = fp32 kernels, 1 = bf16 tensor-core kernels where channels allow.
+ * Index ops run on side_stream (may be NULL = single stream); on return every later use of main_stream is ordered
+ * after all of the step's work.  side_waits_main != 0: the side stream first waits for everything already queued on
+ * main_stream (always safe).  0: the caller guarantees idx0 / proj_params are valid in side_stream order and that the
+ * arena may be written from side_stream right away (e.g. it was allocated there) — the index ops of this step then
+ * overlap the previous step's backward.
+ * ---------------------------------------------------------------------------------------------- */
+size_t vc_exec_state_bytes(void);
+int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_ops, const uint64_t* layer_ptrs, const float* layer_f,
+                    int n_layers, const float* feats0, int c0, const int32_t* idx0, int n0, const int32_t* shape0 /*host[3]*/,
+                    int batch_size, const float* proj_params /*device [B,28], may be NULL without INDEX2UV ops*/,
+                    int training, int precision, int want_pair_num, void* arena, size_t arena_bytes,
+                    int32_t* pinned_host, int32_t* err_flag, void* state, size_t state_bytes, vc_stream_t main_stream,
+                    vc_stream_t side_stream, int side_waits_main);
+/* Reverse walk.  pub_slots [n_pub]: feature slots whose gradients come from outside (the published tensors), ext_grads
+ * [n_pub]: device pointers to those gradients ([rows, c] fp32 contiguous, read only) or 0.  Writes d_weight / d_gamma /
+ * d_beta of every layer (zeros where nothing flowed back).  Same arena as the forward (it continues allocating). */
+int vc_exec_backward(const int32_t* ops_i, const float* ops_f, int n_ops, const uint64_t* layer_ptrs, const float* layer_f,
+                     int n_layers, const int32_t* pub_slots, const uint64_t* ext_grads, int n_pub, void* arena,
+                     size_t arena_bytes, int32_t* err_flag, void* state, vc_stream_t stream);
+/* Read a state blob.  what 0: out[0] = arena bytes in use;  1 (feature slot id): f32 ptr, bf16 ptr, rows, c;
+ * 2 (index set): idx ptr, n, ndim, shape[3];  3 (rulebook): nbr, nbr_bwd, pair_num ptrs, K, n_in, n_out, subm, unique;
+ * 4 (layer): x ptr, y ptr, stats ptr, use_tc, rulebook id, in slot, out slot.  out: >= 8 int64 (host). */
+int vc_exec_query(const void* state, int what, int id, long long* out);
+/* Optional per-launch timing of the conv kernels (bench.py's roofline pass): vc_exec_timing(1) clears and arms it,
+ * vc_exec_timing_read synchronises and returns up to max_records (ms, [kind, layer]) records; kind 0 fwd f32, 1 fwd tc,
+ * 2 dgrad f32, 3 dgrad tc, 4 dgrad scatter, 5 wgrad f32, 6 wgrad tc. */
+int vc_exec_timing(int enable);
+int vc_exec_timing_read(float* ms_out, int32_t* kind_layer_out, int max_records);
+
 #ifdef __cplusplus
 }
 #endif

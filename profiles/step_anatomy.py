@@ -23,7 +23,8 @@ vf, vc = torch.from_numpy(b.voxel_features).to(dev), torch.from_numpy(b.voxel_co
 def step():
     for p in params:
         p.grad = None
-    out = model({'voxel_features': vf, 'voxel_coords': vc, 'batch_size': 2, 'calib': b.calib, 'aug_param': b.aug_param})
+    out = model({'voxel_features': vf, 'voxel_coords': vc, 'batch_size': 2, 'calib': b.calib, 'aug_param': b.aug_param,
+                 'virconv_inputs_ready': True})
     loss = out['encoded_spconv_tensor'].features.mean()
     for t in out['multi_scale_3d_features'].values():
         loss = loss + t.features.mean()

@@ -135,3 +135,45 @@ def test_stvd_keep_rows_follow_reference_rng():
     np.random.seed(5)
     got = stvd_keep_rows(1000, 0.1)
     assert np.array_equal(got, np.sort(want)) and got.shape[0] == 900
+
+
+def test_executor_plan_layout_and_host_side_validation(lib_built):
+    """The plan a VirConvL8x hands to the native executor: 40 ops (12 rulebook builds, 4 projections, 20 conv+BN+ReLU,
+    4 concats), index ops on the side stream, reference indice_keys attached to the rulebooks; a malformed plan is
+    rejected on the host before any CUDA call."""
+    import ctypes
+    import numpy as np
+    from virconv_b200 import _lib, executor
+    from virconv_b200.backbone import VirConvL8x
+    cfg = dict(RETURN_NUM_FEATURES_AS_DICT=True, OUT_FEATURES=64, LAYER_DISCARD_RATE=0.1, NUM_FILTERS=[16, 32, 64, 64])
+    m = VirConvL8x(cfg, 8, [1408, 1600, 80])
+    plan = m._plan()
+    oi, of, lf, sizes, offs = plan.finalize()
+    assert oi.shape == (40, executor.OPI) and of.shape == (40, executor.OPF) and lf.shape == (20, 2)
+    kinds = oi[:, 0].tolist()
+    assert (kinds.count(executor.OP_SUBM_RB), kinds.count(executor.OP_CONV_RB), kinds.count(executor.OP_INDEX2UV),
+            kinds.count(executor.OP_CBR), kinds.count(executor.OP_CAT)) == (8, 4, 4, 20, 4)
+    assert all(oi[i, 1] == (0 if oi[i, 0] in (executor.OP_CBR, executor.OP_CAT) else 1) for i in range(40))
+    assert int(offs[-1]) == sum(p.numel() for p in m.parameters())
+    assert [n for n, _, _ in plan.published] == ['x_conv1', 'x_conv2', 'x_conv3', 'x_conv4', 'out']
+    keys = sorted(k for ks, *_ in plan.rb_keys.values() for k in ks)
+    assert keys == sorted(mod.indice_key for mod in m.modules() if hasattr(mod, 'indice_key'))
+    assert plan.eligible()
+    # every conv's input slot was produced before it is consumed; slot 0 needs no input gradient
+    made = {0}
+    for r in oi:
+        if r[0] == executor.OP_CBR:
+            assert r[2] in made and (r[21] == 0) == (r[2] == 0)
+            made.add(r[3])
+        elif r[0] == executor.OP_CAT:
+            assert r[2] in made and r[3] in made
+            made.add(r[4])
+    lib = _lib.load()
+    bad = oi.copy()
+    bad[3, 0] = 99
+    state = np.zeros(lib.vc_exec_state_bytes(), dtype=np.uint8)
+    rc = lib.vc_exec_forward(bad.ctypes.data, of.ctypes.data, 40, None, None, 20, None, 8, None, 1, _lib.host_i32([41, 1600, 1408]),
+                             2, None, 1, 0, 1, None, 0, None, None, state.ctypes.data, state.size, None, None, 1)
+    assert rc == -1 and b'unknown kind' in lib.vc_last_error()
+    out = (ctypes.c_longlong * 8)()
+    assert lib.vc_exec_query(state.ctypes.data, 0, 0, out) == -1        # not a valid state blob

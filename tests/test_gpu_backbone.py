@@ -91,6 +91,87 @@ def test_virconv_l_forward_backward_vs_oracle(lib_built, training):
     print('worst parameter-grad rel err', worst)
 
 
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+@pytest.mark.parametrize('training', [True, False])
+def test_plan_executor_matches_module_path(lib_built, precision, training):
+    """The native plan executor (csrc/executor.cu: one C-ABI call per forward / backward, index ops on a side stream)
+    launches the same kernels as the per-operator module path: published tensors, rulebooks, parameter gradients and
+    BatchNorm running statistics must agree (up to the order of the float64 / scatter atomics)."""
+    import copy
+    from virconv_b200 import scenes, executor
+    from virconv_b200 import spconv_compat as spc
+    batch = scenes.make_batch([11, 12], n_lidar=4096, n_virtual=9000, max_voxels=7000, training=training)
+    model, _ = _models()
+    spc.set_precision(model, precision)
+    model.train(training)
+    twin = copy.deepcopy(model)
+    res = {}
+    for name, m, flag in (('plan', model, True), ('module', twin, False)):
+        executor.ENABLED = flag
+        try:
+            named, out = _run_gpu(m, batch.voxel_features, batch.voxel_coords, 2, batch.calib, batch.aug_param)
+            loss = sum(t.features.mean() for t in named.values())
+            loss.backward()
+            torch.cuda.synchronize()
+        finally:
+            executor.ENABLED = True
+        res[name] = (named, float(loss), m)
+    assert int(ops_err_flag()) == 0
+    (pn, pl, pm), (mn, ml, mm) = res['plan'], res['module']
+    assert isinstance(pn['x_conv1'].indice_dict, executor.LazyIndiceDict)
+    for k in pn:
+        assert torch.equal(pn[k].indices, mn[k].indices), k
+        assert pn[k].spatial_shape == mn[k].spatial_shape
+        assert rel_err(pn[k].features.detach().cpu(), mn[k].features.detach().cpu()) < 1e-5, k
+    for key, rb in mn['x_conv1'].indice_dict.items():
+        if isinstance(key, str):
+            prb = pn['x_conv1'].indice_dict[key]
+            assert torch.equal(prb.nbr, rb.nbr), key
+            assert torch.equal(prb.pair_num, rb.pair_num), key
+            if rb.nbr_bwd is not None:
+                assert torch.equal(prb.nbr_bwd, rb.nbr_bwd), key
+    assert abs(pl - ml) < 1e-5 * max(1.0, abs(ml))
+    gm = dict(mm.named_parameters())
+    for name, p in pm.named_parameters():
+        assert p.grad is not None, name
+        # bf16: the scatter-dgrad atomics' order differs run to run and a 1-ulp change can flip a bf16 rounding downstream
+        assert rel_err(p.grad.cpu(), gm[name].grad.cpu()) < (2e-3 if precision == 'bf16' else 2e-4), name
+    bm = dict(mm.named_buffers())
+    for name, b in pm.named_buffers():
+        assert torch.allclose(b.float().cpu(), bm[name].float().cpu(), rtol=1e-5, atol=1e-7), name
+
+
+def ops_err_flag():
+    from virconv_b200 import ops
+    return ops.tc_error_flag(torch.device('cuda:0')).item()
+
+
+def test_plan_executor_partial_loss_and_single_stream(lib_built):
+    """Loss on ONE published tensor only (the others get no gradient: conv_out's parameters must come back as zeros),
+    and the single-stream mode of the executor."""
+    from virconv_b200 import scenes, executor
+    batch = scenes.make_batch([21, 22], n_lidar=2048, n_virtual=4000, max_voxels=3000, training=True)
+    model, ref = _models()
+    model.train()
+    ref.train()
+    executor.TWO_STREAMS = False
+    try:
+        named, _ = _run_gpu(model, batch.voxel_features, batch.voxel_coords, 2, batch.calib, batch.aug_param)
+        named['x_conv4'].features.square().mean().backward()
+    finally:
+        executor.TWO_STREAMS = True
+    o = ref(torch.from_numpy(batch.voxel_features.copy()), torch.from_numpy(batch.voxel_coords.copy()), 2, batch.calib,
+            batch.aug_param)
+    o['x_conv4'].features.square().mean().backward()
+    gp = dict(model.named_parameters())
+    for name, p in ref.named_parameters():
+        g = gp[name].grad
+        if name.startswith('conv_out'):
+            assert g is not None and float(g.abs().max()) == 0.0, name
+        else:
+            assert rel_err(g.cpu(), p.grad) < 2e-3, name
+
+
 def test_virconv_l_paper_discard(lib_built):
     """StVD layer discard really applied (paper mode), kept rows supplied by the host RNG like the reference."""
     from virconv_b200 import scenes

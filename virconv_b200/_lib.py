@@ -53,6 +53,12 @@ SIGNATURES = {
     'vc_voxel2pinds': (_I, [_P, _I, _I, _I, _HOST, _P, _P]),
     'vc_cat2_f32': (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     'vc_gather_rows': (_I, [_P, _P, _P, _I, _I, _P]),
+    'vc_exec_state_bytes': (_Z, []),
+    'vc_exec_forward': (_I, [_P, _P, _I, _P, _P, _I, _P, _I, _P, _I, _HOST, _I, _P, _I, _I, _I, _P, _Z, _P, _P, _P, _Z, _P, _P, _I]),
+    'vc_exec_backward': (_I, [_P, _P, _I, _P, _P, _I, _P, _P, _I, _P, _Z, _P, _P, _P]),
+    'vc_exec_query': (_I, [_P, _I, _I, _P]),
+    'vc_exec_timing': (_I, [_I]),
+    'vc_exec_timing_read': (_I, [_P, _P, _I]),
 }
 
 _lib = None

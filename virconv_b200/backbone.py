@@ -21,7 +21,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import executor, ops
 from . import spconv_compat as spconv
 
 
@@ -102,6 +102,32 @@ class NRConvBlock(nn.Module):
         return d3.replace_feature(cat)
 
 
+def plan_nrconv(plan, block, f, iset, proj_stride):
+    """Record one NRConvBlock (NRConvBlock.forward above; spconv_backbone.py:207-229) into an executor plan.  Index ops
+    first (they go to the side stream), then the feature ops.  -> (feature slot of the concat, index set of the block)."""
+    if block.stride > 1:
+        conv = block.down_layer[0]
+        iset, rb = plan.conv_rb(iset, 3, conv.kernel_size, conv.stride, conv.padding, conv.dilation, keys=[conv.indice_key])
+        f = plan.cbr(f, rb, conv, block.down_layer[1])
+    c3, c2 = block.d3_conv1[0], block.d2_conv1[0]
+    assert (block.d3_conv2[0].kernel_size, block.d3_conv2[0].dilation) == (c3.kernel_size, c3.dilation)
+    assert (block.d2_conv2[0].kernel_size, block.d2_conv2[0].dilation) == (c2.kernel_size, c2.dilation)
+    rb3 = plan.subm_rb(iset, 3, c3.kernel_size, c3.dilation, unique=True, keys=[c3.indice_key, block.d3_conv2[0].indice_key])
+    uv = plan.index2uv(iset, proj_stride)
+    rb2 = plan.subm_rb(uv, 2, c2.kernel_size, c2.dilation, unique=False,      # projected pixels collide
+                       keys=[c2.indice_key, block.d2_conv2[0].indice_key])
+    d3 = plan.cbr(plan.cbr(f, rb3, c3, block.d3_conv1[1]), rb3, block.d3_conv2[0], block.d3_conv2[1])
+    d2 = plan.cbr(plan.cbr(d3, rb2, c2, block.d2_conv1[1]), rb2, block.d2_conv2[0], block.d2_conv2[1])
+    return plan.cat(d3, d2), iset
+
+
+def _published_tensor(res, name, batch_size, indice_dict):
+    f, idx, shape, fb = res[name]
+    t = spconv.SparseConvTensor(f, idx, shape, batch_size, indice_dict=indice_dict)
+    t.features_bf16 = fb
+    return t
+
+
 def stvd_keep_rows(n, rate, rng=np.random):
     """Rows kept by StVD layer discard: the reference draws `np.random.permutation(n)[:int(n*(1-rate))]`
     (:143-144); kept order-preserving (sorted) so published tensors stay batch-contiguous."""
@@ -154,6 +180,28 @@ class VirConvL8x(nn.Module):
         keep = given[layer] if given is not None else stvd_keep_rows(t.features.shape[0], self.layer_discard_rate)
         return discard_rows(t, keep)
 
+    # -- native plan (csrc/executor.cu): the whole forward / backward in one C-ABI call each -------------------
+    def _plan(self):
+        if getattr(self, '_plan_cache', None) is None:
+            plan = executor.Plan(self.vir_conv1.d3_conv1[0].in_channels)
+            f, iset = 0, 0
+            for i, (blk, s) in enumerate(zip((self.vir_conv1, self.vir_conv2, self.vir_conv3, self.vir_conv4), (1, 2, 4, 8))):
+                f, iset = plan_nrconv(plan, blk, f, iset, s)
+                plan.publish('x_conv%d' % (i + 1), f, iset)
+            conv = self.conv_out[0]
+            iset, rb = plan.conv_rb(iset, 3, conv.kernel_size, conv.stride, conv.padding, conv.dilation, keys=[conv.indice_key])
+            plan.publish('out', plan.cbr(f, rb, conv, self.conv_out[1]), iset)
+            self._plan_cache = plan
+        return self._plan_cache
+
+    def _use_plan(self, feats):
+        if not executor.ENABLED or not feats.is_cuda or feats.shape[0] == 0:
+            return False
+        if self.training and self.discard_mode == 'paper' and self.layer_discard_rate != 0:
+            return False             # row-dropping StVD between the blocks is only on the module path
+        bns = [m for m in self.modules() if isinstance(m, nn.BatchNorm1d)]
+        return self._plan().eligible() and len({m.training for m in bns}) == 1
+
     def forward(self, batch_dict):
         rot_num = batch_dict['transform_param'].shape[1] if 'transform_param' in batch_dict else 1
         batch_size = batch_dict['batch_size']
@@ -163,11 +211,31 @@ class VirConvL8x(nn.Module):
             rid = '' if i == 0 else str(i)
             feats, coords = batch_dict['voxel_features' + rid], batch_dict['voxel_coords' + rid]
             feats[:, 4:7] = 0                                    # RGB channels unused (:636), in place like the reference
-            x = spconv.SparseConvTensor(feats, coords.int(), self.sparse_shape, batch_size)
             trans = batch_dict['aug_param'] if 'aug_param' in batch_dict else None
             if 'transform_param' in batch_dict:
                 trans = batch_dict['transform_param'][:, i, :]
+            if self._use_plan(feats):
+                bn_training = self.conv_out[1].training
+                ci = spconv._as_i32(coords)
+                # 'virconv_inputs_ready': the caller's promise that voxel_coords is int32, resident and complete (e.g. a
+                # prefetched batch) -> the index pipeline of this step may overlap the previous step's backward
+                ready = bool(batch_dict.get('virconv_inputs_ready', False)) and ci is coords and executor.TWO_STREAMS
+                proj = ops.projection_params(calib, trans, batch_size, feats.device,
+                                             ops.side(feats.device).stream if executor.TWO_STREAMS else None)
+                run, res = executor.run_plan(self._plan(), feats, ci, self.sparse_shape, batch_size, proj, bn_training,
+                                             self.conv_out[0].precision, inputs_ready=ready)
+                idict = executor.LazyIndiceDict(run, ci, self.sparse_shape)
+                x1, x2, x3, x4, out = (_published_tensor(res, k, batch_size, idict)
+                                       for k in ('x_conv1', 'x_conv2', 'x_conv3', 'x_conv4', 'out'))
+                batch_dict.update({
+                    'encoded_spconv_tensor' + rid: out,
+                    'encoded_spconv_tensor_stride' + rid: 8,
+                    'multi_scale_3d_features' + rid: {'x_conv1': x1, 'x_conv2': x2, 'x_conv3': x3, 'x_conv4': x4},
+                    'multi_scale_3d_strides' + rid: {'x_conv1': 1, 'x_conv2': 2, 'x_conv3': 4, 'x_conv4': 8},
+                })
+                continue
             proj = ops.projection_params(calib, trans, batch_size, feats.device)
+            x = spconv.SparseConvTensor(feats, coords.int(), self.sparse_shape, batch_size)
 
             x1 = self.vir_conv1(x, batch_size, proj, 1)
             x1 = self._maybe_discard(x1, batch_dict, 0)

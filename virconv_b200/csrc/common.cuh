@@ -96,4 +96,22 @@ __device__ __forceinline__ void stage_nbr_tile(const int32_t* __restrict__ nbr, 
     }
 }
 
+// ---- shared between conv_tc.cu and executor.cu ----
+struct TcPrepEntry {
+    const float* w;   // parameter, spconv layout [C_out, K, C_in]
+    void* img;        // bf16 UMMA image, K * cin * cout elements
+    int cin, cout, K;
+    int mode;         // 0 forward image, 1 dgrad image
+    int mirror;       // dgrad: kernel offsets mirrored (submanifold table re-used as its own transpose)
+    int first;        // element prefix (filled by tc_prep_images)
+};
+static constexpr int TC_PREP_MAX = 64;
+struct TcPrepTable {
+    TcPrepEntry e[TC_PREP_MAX];
+    int n, total;
+};
+int tc_prep_images(TcPrepTable& t, cudaStream_t stream);
+int tc_conv_with_image(int kc, int nr, const void* in_bf16, const void* wimg, const int32_t* nbr, float* out, int n_rows,
+                       int K, double* bn_sums, int* err, cudaStream_t stream);
+
 }  // namespace vc

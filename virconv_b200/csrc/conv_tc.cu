@@ -395,6 +395,53 @@ static int dispatch_tc(int kc, int nr, const __nv_bfloat16* in, const __nv_bfloa
     return VC_ERR_UNSUPPORTED;
 }
 
+// ---- entry points for the plan executor (executor.cu): pre-built weight images, one batched prep launch ----
+int tc_conv_with_image(int kc, int nr, const void* in_bf16, const void* wimg, const int32_t* nbr, float* out, int n_rows,
+                       int K, double* bn_sums, int* err, cudaStream_t stream) {
+    if (n_rows == 0) return VC_OK;
+    return dispatch_tc(kc, nr, (const __nv_bfloat16*)in_bf16, (const __nv_bfloat16*)wimg, nbr, out, n_rows, K, bn_sums, err,
+                       stream);
+}
+
+// every layer's forward / dgrad weight image in ONE launch: thread i -> (entry, element) by binary search over the
+// entries' element prefix
+__global__ void __launch_bounds__(256) prep_weights_tc_batch_kernel(TcPrepTable t) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= t.total) return;
+    int lo = 0, hi = t.n - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (t.e[mid].first <= i) lo = mid; else hi = mid - 1;
+    }
+    const TcPrepEntry& e = t.e[lo];
+    const int j = i - e.first;
+    const int cin = e.cin, cout = e.cout, K = e.K;
+    const int NRr = e.mode == 0 ? cout : cin, KCc = e.mode == 0 ? cin : cout;
+    const int kk = j % KCc, n = (j / KCc) % NRr, k = j / (KCc * NRr);
+    float v;
+    if (e.mode == 0) {
+        v = e.w[((size_t)n * K + k) * cin + kk];
+    } else {
+        const int ks = e.mirror ? (K - 1 - k) : k;
+        v = e.w[((size_t)kk * K + ks) * cin + n];
+    }
+    const size_t off = (size_t)k * NRr * KCc + ((size_t)((n >> 3) * (KCc >> 3) + (kk >> 3)) * 64) + (n & 7) * 8 + (kk & 7);
+    reinterpret_cast<__nv_bfloat16*>(e.img)[off] = __float2bfloat16_rn(v);
+}
+
+int tc_prep_images(TcPrepTable& t, cudaStream_t stream) {
+    if (t.n == 0) return VC_OK;
+    int total = 0;
+    for (int i = 0; i < t.n; ++i) {
+        t.e[i].first = total;
+        total += t.e[i].K * t.e[i].cin * t.e[i].cout;
+    }
+    t.total = total;
+    prep_weights_tc_batch_kernel<<<cdiv(total, 256), 256, 0, stream>>>(t);
+    VC_LAUNCH_CHECK();
+    return VC_OK;
+}
+
 }  // namespace vc
 
 using namespace vc;

@@ -1,0 +1,701 @@
+// Plan executor: one C-ABI call runs a whole backbone forward (or backward) — sm_100a.
+//
+// The reference drives its backbone layer by layer from Python (spconv_backbone.py:609-699 VirConvL8x.forward, :207-229
+// NRConvBlock.forward, :339-535 VirConv8x.forward): ~100 operator calls and ~220 kernel launches per training step,
+// which on a B200 costs more host time (5.0 ms) than the kernels take to run (3.9 ms; profiles/step_anatomy_r1.txt).
+// Here the host side of that loop is native: Python describes the layer graph ONCE as a small op list (the "plan"),
+// and vc_exec_forward / vc_exec_backward walk it, carving every activation, rulebook and scratch buffer out of one
+// caller-owned arena and enqueueing the same kernels the per-operator entry points launch.
+//
+//   * two streams: index ops (rulebooks, voxel->pixel projection; they depend on coordinates only) run on the SIDE
+//     stream and run ahead of the feature ops (conv+BN+ReLU, concat) on the MAIN stream; the four data-dependent row
+//     counts of the strided convs are read back on the side stream, so the host never waits for feature kernels;
+//   * cross-stream dependencies are CUDA events from a small library-owned pool; the arena is bump-allocated and never
+//     reused inside a step, so there are no memory hazards between the streams;
+//   * all tensor-core weight images of the step are produced by one launch (tc_prep_images);
+//   * backward walks the list in reverse with gradient accumulation rules (first contribution writes, later ones add).
+// The state a forward leaves behind for its backward (buffer addresses, row counts) is a plain host struct in a
+// caller-owned blob; the library keeps nothing between calls except the event pool.
+#include <cuda_bf16.h>
+
+#include <new>
+
+#include "common.cuh"
+
+namespace vc {
+namespace {
+
+constexpr int MAX_OPS = 256, MAX_F = 160, MAX_I = 64, MAX_RB = 64, MAX_L = 96, OPI = 24, OPF = 8;
+constexpr uint64_t STATE_MAGIC = 0x5643455845433031ULL;  // "VCEXEC01"
+enum { OP_SUBM_RB = 1, OP_CONV_RB = 2, OP_INDEX2UV = 3, OP_CBR = 4, OP_CAT = 5 };
+enum { G_EMPTY = 0, G_EXT = 1, G_OWN = 2 };
+// op int fields
+enum { F_KIND = 0, F_STREAM = 1, F_A = 2, F_B = 3, F_C = 4, F_NDIM = 5, F_KS = 6, F_ST = 9, F_PD = 12, F_DL = 15, F_CIN = 18,
+       F_COUT = 19, F_LAYER = 20, F_X0 = 21, F_X1 = 22, F_X2 = 23 };
+// layer pointer table columns
+enum { P_W = 0, P_GAMMA, P_BETA, P_RM, P_RV, P_NBT, P_DW, P_DGAMMA, P_DBETA, P_COLS };
+
+struct ISet {
+    int32_t* idx;
+    int n, ndim, shape[3];
+    int ev;  // event to wait on when consumed from the other stream (-1: none), stream that produced it
+    int prod;
+};
+struct FSlot {
+    float* f32;
+    void* bf16;
+    float* grad;
+    int rows, c, grad_state, ev, prod;
+};
+struct RBk {
+    int32_t *nbr, *nbr_bwd, *pair_num;
+    int K, n_in, n_out, subm, unique, ev, prod;
+};
+struct Layer {
+    float *x, *y, *stats;
+    double* sums;          // [4*cout]: forward sums, backward sums
+    void *wimg_fwd, *wimg_dgrad;
+    int in_slot, out_slot, rb, use_tc, cin, cout, need_dgrad;
+};
+struct State {
+    uint64_t magic;
+    size_t used;           // arena bytes in use after the last call
+    int n_ops, n_layers, training, precision, batch_size;
+    ISet iset[MAX_I];
+    FSlot f[MAX_F];
+    RBk rb[MAX_RB];
+    Layer layer[MAX_L];
+};
+
+struct Arena {
+    char* base;
+    size_t cap, used;
+    bool failed;
+    void* alloc(size_t bytes) {
+        size_t a = (used + 255) & ~(size_t)255;
+        if (a + bytes > cap) {
+            failed = true;
+            used = a + bytes;   // keep counting: the error message reports what would have been needed so far
+            return nullptr;
+        }
+        used = a + bytes;
+        return base + a;
+    }
+};
+
+// library-owned event pool (cross-stream ordering only; timing disabled).  An event may be re-recorded as soon as the
+// wait on its previous recording has been ENQUEUED, so a small round-robin pool is enough.
+constexpr int EV_POOL = 64;
+// (process-wide, not thread_local: autograd runs backward on its own thread; one process drives one device)
+cudaEvent_t g_ev[EV_POOL];
+int g_ev_dev = -1, g_ev_next = 0;
+
+int ev_init() {
+    int dev = 0;
+    VC_CUDA(cudaGetDevice(&dev));
+    if (g_ev_dev == dev) return VC_OK;
+    if (g_ev_dev >= 0)
+        for (int i = 0; i < EV_POOL; ++i) cudaEventDestroy(g_ev[i]);
+    for (int i = 0; i < EV_POOL; ++i) VC_CUDA(cudaEventCreateWithFlags(&g_ev[i], cudaEventDisableTiming));
+    g_ev_dev = dev;
+    g_ev_next = 0;
+    return VC_OK;
+}
+
+// optional per-kernel timing (bench.py's roofline pass): event pairs around the conv launches
+struct TimeRec {
+    cudaEvent_t a, b;
+    int kind, layer;   // kind: 0 conv fwd f32, 1 conv fwd tc, 2 dgrad f32, 3 dgrad tc, 4 dgrad scatter, 5 wgrad f32, 6 wgrad tc
+};
+constexpr int T_MAX = 4096;
+TimeRec g_t[T_MAX];
+int g_t_n = 0, g_t_created = 0;
+bool g_timing = false;
+
+struct Timed {
+    int idx;
+    cudaStream_t st;
+    Timed(int kind, int layer, cudaStream_t s) : idx(-1), st(s) {
+        if (!g_timing || g_t_n >= T_MAX) return;
+        if (g_t_n >= g_t_created) {
+            if (cudaEventCreate(&g_t[g_t_n].a) != cudaSuccess || cudaEventCreate(&g_t[g_t_n].b) != cudaSuccess) return;
+            g_t_created = g_t_n + 1;
+        }
+        idx = g_t_n++;
+        g_t[idx].kind = kind;
+        g_t[idx].layer = layer;
+        cudaEventRecord(g_t[idx].a, st);
+    }
+    ~Timed() {
+        if (idx >= 0) cudaEventRecord(g_t[idx].b, st);
+    }
+};
+
+__global__ void __launch_bounds__(256) add_kernel(const float4* a, const float4* b, float4* c, size_t n4) {   // c may alias a or b
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n4; i += stride) {
+        float4 x = a[i], y = b[i];
+        c[i] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+    }
+}
+
+// backward of the channel concat: da = dcat[:, :ca] (+ a_add), db = dcat[:, ca:] (+ b_add); add pointers may alias
+// the outputs (in-place accumulation) or be NULL
+__global__ void __launch_bounds__(256) cat2_bwd_kernel(const float4* __restrict__ dcat, int n, int ca4, int cb4,
+                                                       float4* da, const float4* a_add, float4* db, const float4* b_add) {
+    const int c4 = ca4 + cb4;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)n * c4, stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        const size_t r = i / c4;
+        const int c = (int)(i % c4);
+        float4 v = dcat[i];
+        if (c < ca4) {
+            const size_t o = r * ca4 + c;
+            if (a_add) { float4 w = a_add[o]; v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w; }
+            da[o] = v;
+        } else {
+            const size_t o = r * cb4 + (c - ca4);
+            if (b_add) { float4 w = b_add[o]; v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w; }
+            db[o] = v;
+        }
+    }
+}
+
+int ew_grid(size_t n4) {
+    size_t b = (n4 + 255) / 256;
+    if (b > 148 * 8) b = 148 * 8;
+    return (int)(b < 1 ? 1 : b);
+}
+
+int launch_add(const float* a, const float* b, float* c, size_t n, cudaStream_t st) {
+    if (n == 0) return VC_OK;
+    add_kernel<<<ew_grid(n / 4), 256, 0, st>>>((const float4*)a, (const float4*)b, (float4*)c, n / 4);
+    VC_LAUNCH_CHECK();
+    return VC_OK;
+}
+
+bool tc_ok(int c) { return c == 16 || c == 32 || c == 64; }
+
+struct Ctx {
+    const int32_t* oi;
+    const float* of;
+    int n_ops;
+    const uint64_t* lp;
+    const float* lf;
+    int n_layers;
+    State* S;
+    Arena A;
+    cudaStream_t st[2];
+    int32_t* err;
+    const int* op(int i) const { return oi + (size_t)i * OPI; }
+    template <class T>
+    T* P(int layer, int col) const { return reinterpret_cast<T*>(lp[(size_t)layer * P_COLS + col]); }
+};
+
+#define VC_TRY(expr)              \
+    do {                          \
+        int rc__ = (expr);        \
+        if (rc__) return rc__;    \
+    } while (0)
+
+#define VC_ALLOC(var, type, bytes)                                                                     \
+    type var = (type)C.A.alloc(bytes);                                                                 \
+    if (!var && (bytes) > 0) {                                                                         \
+        set_error("plan executor: arena too small (%zu bytes given, > %zu needed)", C.A.cap, C.A.used); \
+        return VC_ERR_WORKSPACE;                                                                       \
+    }
+
+// make `consumer` stream wait for a resource produced on the other stream
+int wait_for(Ctx& C, int& ev, int prod, int consumer) {
+    if (ev >= 0 && prod != consumer && C.st[0] != C.st[1]) {
+        VC_CUDA(cudaStreamWaitEvent(C.st[consumer], g_ev[ev], 0));
+        ev = -1;   // two streams only: the consumer stream is now ordered after the producer for good
+    }
+    return VC_OK;
+}
+int record_on(Ctx& C, int s) {   // -> event id recorded at the current tail of stream s
+    if (C.st[0] == C.st[1]) return -1;
+    int e = g_ev_next;
+    g_ev_next = (g_ev_next + 1) % EV_POOL;
+    if (cudaEventRecord(g_ev[e], C.st[s]) != cudaSuccess) return -1;
+    return e;
+}
+
+int check_plan(const int32_t* oi, int n_ops, int n_layers) {
+    VC_CHECK_ARG(oi && n_ops > 0 && n_ops <= MAX_OPS && n_layers >= 0 && n_layers <= MAX_L, "bad plan size");
+    for (int i = 0; i < n_ops; ++i) {
+        const int* o = oi + (size_t)i * OPI;
+        VC_CHECK_ARG(o[F_KIND] >= OP_SUBM_RB && o[F_KIND] <= OP_CAT, "op %d: unknown kind %d", i, o[F_KIND]);
+        VC_CHECK_ARG(o[F_STREAM] == 0 || o[F_STREAM] == 1, "op %d: bad stream", i);
+        const int lim_a = (o[F_KIND] == OP_CBR || o[F_KIND] == OP_CAT) ? MAX_F : MAX_I;
+        VC_CHECK_ARG(o[F_A] >= 0 && o[F_A] < lim_a, "op %d: slot a out of range", i);
+        if (o[F_KIND] == OP_CBR) {
+            VC_CHECK_ARG(o[F_B] >= 0 && o[F_B] < MAX_F && o[F_C] >= 0 && o[F_C] < MAX_RB, "op %d: bad slots", i);
+            VC_CHECK_ARG(o[F_LAYER] >= 0 && o[F_LAYER] < n_layers, "op %d: bad layer", i);
+        } else if (o[F_KIND] == OP_CAT) {
+            VC_CHECK_ARG(o[F_B] >= 0 && o[F_B] < MAX_F && o[F_C] >= 0 && o[F_C] < MAX_F, "op %d: bad slots", i);
+        } else if (o[F_KIND] == OP_SUBM_RB) {
+            VC_CHECK_ARG(o[F_C] >= 0 && o[F_C] < MAX_RB, "op %d: bad rulebook id", i);
+        } else if (o[F_KIND] == OP_CONV_RB) {
+            VC_CHECK_ARG(o[F_B] >= 0 && o[F_B] < MAX_I && o[F_C] >= 0 && o[F_C] < MAX_RB, "op %d: bad ids", i);
+        } else {
+            VC_CHECK_ARG(o[F_B] >= 0 && o[F_B] < MAX_I, "op %d: bad index-set id", i);
+        }
+    }
+    return VC_OK;
+}
+
+}  // namespace
+}  // namespace vc
+
+using namespace vc;
+
+extern "C" size_t vc_exec_state_bytes(void) { return sizeof(State); }
+
+extern "C" int vc_exec_timing(int enable) {
+    g_timing = enable != 0;
+    g_t_n = 0;
+    return VC_OK;
+}
+
+// ms_out[i], kind_layer_out[2*i..] for the records since vc_exec_timing(1); synchronises the device.  Returns the count.
+extern "C" int vc_exec_timing_read(float* ms_out, int32_t* kind_layer_out, int max_records) {
+    if (cudaDeviceSynchronize() != cudaSuccess) return VC_ERR_CUDA;
+    int n = g_t_n < max_records ? g_t_n : max_records;
+    for (int i = 0; i < n; ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, g_t[i].a, g_t[i].b);
+        ms_out[i] = ms;
+        kind_layer_out[2 * i] = g_t[i].kind;
+        kind_layer_out[2 * i + 1] = g_t[i].layer;
+    }
+    return n;
+}
+
+extern "C" int vc_exec_query(const void* state, int what, int id, long long* out) {
+    const State* S = (const State*)state;
+    VC_CHECK_ARG(S && S->magic == STATE_MAGIC && out, "not an executor state");
+    switch (what) {
+        case 0:
+            out[0] = (long long)S->used;
+            return VC_OK;
+        case 1: {
+            VC_CHECK_ARG(id >= 0 && id < MAX_F, "slot id");
+            const FSlot& f = S->f[id];
+            out[0] = (long long)(uintptr_t)f.f32; out[1] = (long long)(uintptr_t)f.bf16; out[2] = f.rows; out[3] = f.c;
+            return VC_OK;
+        }
+        case 2: {
+            VC_CHECK_ARG(id >= 0 && id < MAX_I, "index-set id");
+            const ISet& s = S->iset[id];
+            out[0] = (long long)(uintptr_t)s.idx; out[1] = s.n; out[2] = s.ndim; out[3] = s.shape[0]; out[4] = s.shape[1];
+            out[5] = s.shape[2];
+            return VC_OK;
+        }
+        case 3: {
+            VC_CHECK_ARG(id >= 0 && id < MAX_RB, "rulebook id");
+            const RBk& r = S->rb[id];
+            out[0] = (long long)(uintptr_t)r.nbr; out[1] = (long long)(uintptr_t)r.nbr_bwd;
+            out[2] = (long long)(uintptr_t)r.pair_num; out[3] = r.K; out[4] = r.n_in; out[5] = r.n_out; out[6] = r.subm;
+            out[7] = r.unique;
+            return VC_OK;
+        }
+        case 4: {
+            VC_CHECK_ARG(id >= 0 && id < MAX_L, "layer id");
+            const Layer& l = S->layer[id];
+            out[0] = (long long)(uintptr_t)l.x; out[1] = (long long)(uintptr_t)l.y; out[2] = (long long)(uintptr_t)l.stats;
+            out[3] = l.use_tc; out[4] = l.rb; out[5] = l.in_slot; out[6] = l.out_slot;
+            return VC_OK;
+        }
+    }
+    set_error("vc_exec_query: unknown selector %d", what);
+    return VC_ERR_INVALID;
+}
+
+extern "C" int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_ops, const uint64_t* layer_ptrs,
+                               const float* layer_f, int n_layers, const float* feats0, int c0, const int32_t* idx0, int n0,
+                               const int32_t* shape0, int batch_size, const float* proj_params, int training, int precision,
+                               int want_pair_num, void* arena, size_t arena_bytes, int32_t* pinned_host, int32_t* err_flag,
+                               void* state, size_t state_bytes, vc_stream_t main_stream, vc_stream_t side_stream,
+                               int side_waits_main) {
+    VC_TRY(check_plan(ops_i, n_ops, n_layers));
+    VC_CHECK_ARG(state && state_bytes >= sizeof(State), "state blob too small (%zu < %zu)", state_bytes, sizeof(State));
+    VC_CHECK_ARG(feats0 && idx0 && n0 > 0 && shape0 && batch_size > 0 && arena && pinned_host && ops_f && layer_ptrs && layer_f,
+                 "null / empty argument");
+    VC_CHECK_ARG(precision == 0 || precision == 1, "precision must be 0 (fp32) or 1 (bf16)");
+    VC_TRY(ev_init());
+    State* S = new (state) State();
+    memset(S, 0, sizeof(State));
+    S->n_ops = n_ops; S->n_layers = n_layers; S->training = training; S->precision = precision; S->batch_size = batch_size;
+    for (int i = 0; i < MAX_I; ++i) S->iset[i].ev = -1;
+    for (int i = 0; i < MAX_F; ++i) S->f[i].ev = -1;
+    for (int i = 0; i < MAX_RB; ++i) S->rb[i].ev = -1;
+
+    Ctx C;
+    C.oi = ops_i; C.of = ops_f; C.n_ops = n_ops; C.lp = layer_ptrs; C.lf = layer_f; C.n_layers = n_layers; C.S = S;
+    C.A = Arena{(char*)arena, arena_bytes, 0, false};
+    C.st[0] = (cudaStream_t)main_stream;
+    C.st[1] = side_stream ? (cudaStream_t)side_stream : (cudaStream_t)main_stream;
+    C.err = err_flag;
+    const bool two = C.st[0] != C.st[1];
+
+    S->iset[0].idx = const_cast<int32_t*>(idx0); S->iset[0].n = n0; S->iset[0].ndim = 3;
+    for (int d = 0; d < 3; ++d) S->iset[0].shape[d] = shape0[d];
+    S->f[0].f32 = const_cast<float*>(feats0); S->f[0].rows = n0; S->f[0].c = c0;
+
+    // rulebook meta known from the plan alone (needed to choose the dgrad weight images)
+    int rb_subm[MAX_RB] = {0}, rb_unique[MAX_RB] = {0}, rb_K[MAX_RB] = {0};
+    for (int i = 0; i < n_ops; ++i) {
+        const int* o = C.op(i);
+        if (o[F_KIND] == OP_SUBM_RB || o[F_KIND] == OP_CONV_RB) {
+            int K = 1;
+            for (int d = 0; d < o[F_NDIM]; ++d) K *= o[F_KS + d];
+            rb_K[o[F_C]] = K;
+            rb_subm[o[F_C]] = o[F_KIND] == OP_SUBM_RB;
+            rb_unique[o[F_C]] = o[F_KIND] == OP_CONV_RB ? 1 : o[F_X0];
+        }
+    }
+
+    // BatchNorm accumulators of every layer: one region, one memset
+    size_t sums_doubles = 0;
+    for (int i = 0; i < n_ops; ++i)
+        if (C.op(i)[F_KIND] == OP_CBR) sums_doubles += 4 * (size_t)C.op(i)[F_COUT];
+    VC_ALLOC(sums_all, double*, sums_doubles * 8);
+    if (sums_doubles) VC_CUDA(cudaMemsetAsync(sums_all, 0, sums_doubles * 8, C.st[0]));
+    size_t sums_cur = 0;
+
+    // tensor-core weight images of every layer, one launch
+    for (int i = 0; i < n_ops; ++i) {
+        const int* o = C.op(i);
+        if (o[F_KIND] != OP_CBR) continue;
+        Layer& L = S->layer[o[F_LAYER]];
+        L.cin = o[F_CIN]; L.cout = o[F_COUT]; L.in_slot = o[F_A]; L.out_slot = o[F_B]; L.rb = o[F_C];
+        L.need_dgrad = o[F_X0];
+        L.use_tc = precision == 1 && tc_ok(L.cin) && tc_ok(L.cout);
+        L.sums = sums_all + sums_cur;
+        sums_cur += 4 * (size_t)L.cout;
+    }
+    if (precision == 1) {
+        TcPrepTable T;
+        T.n = 0;
+        for (int i = 0; i < n_ops; ++i) {
+            const int* o = C.op(i);
+            if (o[F_KIND] != OP_CBR) continue;
+            Layer& L = S->layer[o[F_LAYER]];
+            if (!L.use_tc) continue;
+            const int K = rb_K[L.rb];
+            const size_t bytes = (size_t)K * L.cin * L.cout * 2;
+            const bool dgrad_tc = training && L.need_dgrad && !(rb_subm[L.rb] && !rb_unique[L.rb]);
+            for (int mode = 0; mode < (dgrad_tc ? 2 : 1); ++mode) {
+                VC_ALLOC(img, void*, bytes);
+                (mode == 0 ? L.wimg_fwd : L.wimg_dgrad) = img;
+                if (T.n == TC_PREP_MAX) {
+                    VC_TRY(tc_prep_images(T, C.st[0]));
+                    T.n = 0;
+                }
+                TcPrepEntry& e = T.e[T.n++];
+                e.w = C.P<const float>(o[F_LAYER], P_W); e.img = img; e.cin = L.cin; e.cout = L.cout; e.K = K; e.mode = mode;
+                e.mirror = mode == 1 && rb_subm[L.rb];
+            }
+        }
+        VC_TRY(tc_prep_images(T, C.st[0]));
+    }
+
+    // the side stream starts after everything already queued on main (the caller's inputs) — unless the caller vouches
+    // that idx0 / proj_params are already valid for the side stream and the arena is safe to write from it
+    // (side_waits_main = 0): the index pipeline of this step then overlaps whatever main is still running (the
+    // previous step's backward)
+    if (two && side_waits_main) {
+        int e = record_on(C, 0);
+        if (e >= 0) VC_CUDA(cudaStreamWaitEvent(C.st[1], g_ev[e], 0));
+    }
+    int last_side_ev = -1;
+    int n_syncs = 0;
+
+    for (int i = 0; i < n_ops; ++i) {
+        const int* o = C.op(i);
+        const float* fo = C.of + (size_t)i * OPF;
+        const int s = two ? o[F_STREAM] : 0;
+        cudaStream_t st = C.st[s];
+        switch (o[F_KIND]) {
+            case OP_SUBM_RB: {
+                ISet& I = S->iset[o[F_A]];
+                RBk& R = S->rb[o[F_C]];
+                VC_CHECK_ARG(I.idx && I.ndim == o[F_NDIM], "op %d: index set %d not built / wrong ndim", i, o[F_A]);
+                VC_TRY(wait_for(C, I.ev, I.prod, s));
+                R.K = rb_K[o[F_C]]; R.n_in = R.n_out = I.n; R.subm = 1; R.unique = o[F_X0];
+                VC_ALLOC(nbr, int32_t*, (size_t)R.K * I.n * 4);
+                R.nbr = nbr;
+                if (want_pair_num) {
+                    VC_ALLOC(pn, int32_t*, (size_t)R.K * 4);
+                    R.pair_num = pn;
+                }
+                const size_t wsb = vc_subm_rulebook_ws_bytes(I.n);
+                VC_ALLOC(ws, void*, wsb);
+                VC_TRY(vc_subm_rulebook(I.idx, I.n, I.ndim, batch_size, I.shape, o + F_KS, o + F_DL, R.nbr, R.pair_num, ws, wsb, st));
+                R.prod = s;
+                R.ev = s == 1 ? (last_side_ev = record_on(C, 1)) : -1;
+                break;
+            }
+            case OP_CONV_RB: {
+                ISet& I = S->iset[o[F_A]];
+                ISet& O = S->iset[o[F_B]];
+                RBk& R = S->rb[o[F_C]];
+                VC_CHECK_ARG(I.idx && I.ndim == o[F_NDIM], "op %d: index set %d not built / wrong ndim", i, o[F_A]);
+                VC_TRY(wait_for(C, I.ev, I.prod, s));
+                int32_t oshape[3] = {0, 0, 0};
+                VC_TRY(vc_conv_out_shape(I.ndim, I.shape, o + F_KS, o + F_ST, o + F_PD, o + F_DL, oshape));
+                const size_t wsb = vc_conv_rulebook_ws_bytes(I.ndim, batch_size, oshape);
+                VC_ALLOC(ws, void*, wsb);
+                VC_ALLOC(n_dev, int32_t*, 4);
+                VC_TRY(vc_conv_rulebook_count(I.idx, I.n, I.ndim, batch_size, I.shape, o + F_KS, o + F_ST, o + F_PD, o + F_DL, n_dev,
+                                              ws, wsb, st));
+                VC_CUDA(cudaMemcpyAsync(pinned_host + (n_syncs & 15), n_dev, 4, cudaMemcpyDeviceToHost, st));
+                VC_CUDA(cudaStreamSynchronize(st));        // the one data-dependent size per strided conv
+                const int n_out = pinned_host[n_syncs & 15];
+                ++n_syncs;
+                R.K = rb_K[o[F_C]]; R.n_in = I.n; R.n_out = n_out; R.subm = 0; R.unique = 1;
+                O.n = n_out; O.ndim = I.ndim;
+                for (int d = 0; d < 3; ++d) O.shape[d] = oshape[d];
+                VC_ALLOC(oidx, int32_t*, (size_t)(n_out > 0 ? n_out : 1) * (1 + I.ndim) * 4);
+                VC_ALLOC(nbr, int32_t*, (size_t)R.K * (n_out > 0 ? n_out : 1) * 4);
+                VC_ALLOC(nbr_bwd, int32_t*, (size_t)R.K * I.n * 4);
+                O.idx = oidx; R.nbr = nbr; R.nbr_bwd = nbr_bwd;
+                if (want_pair_num) {
+                    VC_ALLOC(pn, int32_t*, (size_t)R.K * 4);
+                    R.pair_num = pn;
+                }
+                VC_TRY(vc_conv_rulebook_fill(I.idx, I.n, I.ndim, batch_size, I.shape, o + F_KS, o + F_ST, o + F_PD, o + F_DL, n_out,
+                                             O.idx, R.nbr, R.nbr_bwd, R.pair_num, ws, wsb, st));
+                R.prod = O.prod = s;
+                R.ev = O.ev = s == 1 ? (last_side_ev = record_on(C, 1)) : -1;
+                break;
+            }
+            case OP_INDEX2UV: {
+                ISet& I = S->iset[o[F_A]];
+                ISet& O = S->iset[o[F_B]];
+                VC_CHECK_ARG(I.idx && I.ndim == 3 && proj_params, "op %d: index2uv needs a built 3-D index set and projection params", i);
+                VC_TRY(wait_for(C, I.ev, I.prod, s));
+                VC_ALLOC(uv, int32_t*, (size_t)I.n * 3 * 4);
+                O.idx = uv; O.n = I.n; O.ndim = 2; O.shape[0] = o[F_KS]; O.shape[1] = o[F_KS + 1]; O.shape[2] = 0;
+                VC_TRY(vc_index2uv(I.idx, I.n, batch_size, proj_params, fo, o[F_X0], o[F_X1], o[F_X2], uv, st));
+                O.prod = s;
+                O.ev = s == 1 ? (last_side_ev = record_on(C, 1)) : -1;
+                break;
+            }
+            case OP_CBR: {
+                const int li = o[F_LAYER];
+                Layer& L = S->layer[li];
+                FSlot& X = S->f[L.in_slot];
+                FSlot& Y = S->f[L.out_slot];
+                RBk& R = S->rb[L.rb];
+                VC_CHECK_ARG(X.f32 && R.nbr && X.c == L.cin && X.rows == R.n_in, "op %d: input slot / rulebook mismatch (rows %d vs %d, c %d vs %d)",
+                             i, X.rows, R.n_in, X.c, L.cin);
+                VC_TRY(wait_for(C, R.ev, R.prod, s));
+                VC_TRY(wait_for(C, X.ev, X.prod, s));
+                const size_t elems = (size_t)R.n_out * L.cout;
+                VC_ALLOC(x, float*, elems * 4);
+                VC_ALLOC(y, float*, elems * 4);
+                VC_ALLOC(stats, float*, (size_t)4 * L.cout * 4);
+                void* yb = nullptr;
+                if (precision == 1) {
+                    VC_ALLOC(yb_, void*, elems * 2);
+                    yb = yb_;
+                }
+                L.x = x; L.y = y; L.stats = stats;
+                double* sums = training ? L.sums : nullptr;
+                if (L.use_tc && R.n_out > 0) {
+                    if (!X.bf16) {   // no producer wrote a shadow (network input): cast once
+                        VC_ALLOC(xb, void*, (size_t)X.rows * X.c * 2);
+                        VC_TRY(vc_cast_f32_bf16(X.f32, xb, (long long)X.rows * X.c, st));
+                        X.bf16 = xb;
+                    }
+                    Timed t(1, li, st);
+                    VC_TRY(tc_conv_with_image(L.cin, L.cout, X.bf16, L.wimg_fwd, R.nbr, x, R.n_out, R.K, sums, C.err, st));
+                } else {
+                    const size_t wsb = vc_conv_ws_bytes(L.cin, L.cout, R.K);
+                    VC_ALLOC(ws, void*, wsb);
+                    Timed t(0, li, st);
+                    VC_TRY(vc_conv_fwd_f32(X.f32, C.P<const float>(li, P_W), R.nbr, x, R.n_out, L.cin, L.cout, R.K, sums, ws, wsb, st));
+                }
+                VC_TRY(vc_bn_apply_relu_f32(x, L.sums, R.n_out, L.cout, C.P<const float>(li, P_GAMMA), C.P<const float>(li, P_BETA),
+                                            C.P<float>(li, P_RM), C.P<float>(li, P_RV), C.P<long long>(li, P_NBT),
+                                            C.lf[2 * li + 1], C.lf[2 * li], training, y, yb, stats, 1, st));
+                Y.f32 = y; Y.bf16 = yb; Y.rows = R.n_out; Y.c = L.cout; Y.prod = s;
+                Y.ev = s == 1 ? (last_side_ev = record_on(C, 1)) : -1;
+                break;
+            }
+            case OP_CAT: {
+                FSlot& Aa = S->f[o[F_A]];
+                FSlot& Bb = S->f[o[F_B]];
+                FSlot& O = S->f[o[F_C]];
+                VC_CHECK_ARG(Aa.f32 && Bb.f32 && Aa.rows == Bb.rows, "op %d: concat inputs not built / row mismatch", i);
+                VC_TRY(wait_for(C, Aa.ev, Aa.prod, s));
+                VC_TRY(wait_for(C, Bb.ev, Bb.prod, s));
+                const size_t elems = (size_t)Aa.rows * (Aa.c + Bb.c);
+                VC_ALLOC(out, float*, elems * 4);
+                void* ob = nullptr;
+                if (precision == 1) {
+                    VC_ALLOC(ob_, void*, elems * 2);
+                    ob = ob_;
+                }
+                VC_TRY(vc_cat2_f32(Aa.f32, Bb.f32, out, ob, Aa.rows, Aa.c, Bb.c, st));
+                O.f32 = out; O.bf16 = ob; O.rows = Aa.rows; O.c = Aa.c + Bb.c; O.prod = s;
+                O.ev = s == 1 ? (last_side_ev = record_on(C, 1)) : -1;
+                break;
+            }
+        }
+    }
+    if (two && last_side_ev >= 0) VC_CUDA(cudaStreamWaitEvent(C.st[0], g_ev[last_side_ev], 0));   // join
+    S->used = C.A.used;
+    S->magic = STATE_MAGIC;
+    return VC_OK;
+}
+
+namespace vc {
+namespace {
+
+// hand a gradient contribution of shape [rows, c] to slot F: `write(dst)` must enqueue kernels that OVERWRITE dst
+template <class W>
+int contribute(Ctx& C, FSlot& F, cudaStream_t st, W&& write) {
+    const size_t n = (size_t)F.rows * F.c;
+    if (F.grad_state == G_EMPTY) {
+        VC_ALLOC(buf, float*, n * 4);
+        VC_TRY(write(buf));
+        F.grad = buf;
+    } else if (F.grad_state == G_EXT) {
+        VC_ALLOC(buf, float*, n * 4);
+        VC_TRY(write(buf));
+        VC_TRY(launch_add(buf, F.grad, buf, n, st));
+        F.grad = buf;
+    } else {
+        VC_ALLOC(tmp, float*, n * 4);
+        VC_TRY(write(tmp));
+        VC_TRY(launch_add(F.grad, tmp, F.grad, n, st));
+    }
+    F.grad_state = G_OWN;
+    return VC_OK;
+}
+
+}  // namespace
+}  // namespace vc
+
+extern "C" int vc_exec_backward(const int32_t* ops_i, const float* ops_f, int n_ops, const uint64_t* layer_ptrs,
+                                const float* layer_f, int n_layers, const int32_t* pub_slots, const uint64_t* ext_grads,
+                                int n_pub, void* arena, size_t arena_bytes, int32_t* err_flag, void* state,
+                                vc_stream_t stream_) {
+    VC_TRY(check_plan(ops_i, n_ops, n_layers));
+    State* S = (State*)state;
+    VC_CHECK_ARG(S && S->magic == STATE_MAGIC && S->n_ops == n_ops && S->n_layers == n_layers, "state does not belong to this plan");
+    VC_CHECK_ARG(arena && layer_ptrs && (n_pub == 0 || (pub_slots && ext_grads)), "null argument");
+    Ctx C;
+    C.oi = ops_i; C.of = ops_f; C.n_ops = n_ops; C.lp = layer_ptrs; C.lf = layer_f; C.n_layers = n_layers; C.S = S;
+    C.A = Arena{(char*)arena, arena_bytes, S->used, false};
+    C.st[0] = C.st[1] = (cudaStream_t)stream_;
+    C.err = err_flag;
+    cudaStream_t st = C.st[0];
+    const int training = S->training;
+
+    for (int i = 0; i < MAX_F; ++i) { S->f[i].grad = nullptr; S->f[i].grad_state = G_EMPTY; }
+    for (int i = 0; i < n_pub; ++i) {
+        VC_CHECK_ARG(pub_slots[i] > 0 && pub_slots[i] < MAX_F, "published slot id");
+        if (ext_grads[i]) {
+            FSlot& F = S->f[pub_slots[i]];
+            VC_CHECK_ARG(F.grad_state == G_EMPTY, "slot %d published twice", pub_slots[i]);
+            F.grad = reinterpret_cast<float*>(ext_grads[i]);
+            F.grad_state = G_EXT;
+        }
+    }
+
+    for (int i = n_ops - 1; i >= 0; --i) {
+        const int* o = C.op(i);
+        if (o[F_KIND] == OP_CAT) {
+            FSlot& Aa = S->f[o[F_A]];
+            FSlot& Bb = S->f[o[F_B]];
+            FSlot& O = S->f[o[F_C]];
+            if (O.grad_state == G_EMPTY) continue;
+            float *da, *db;
+            const float *a_add = nullptr, *b_add = nullptr;
+            if (Aa.grad_state == G_OWN) { da = Aa.grad; a_add = Aa.grad; }
+            else { VC_ALLOC(t, float*, (size_t)Aa.rows * Aa.c * 4); da = t; a_add = Aa.grad_state == G_EXT ? Aa.grad : nullptr; }
+            if (Bb.grad_state == G_OWN) { db = Bb.grad; b_add = Bb.grad; }
+            else { VC_ALLOC(t, float*, (size_t)Bb.rows * Bb.c * 4); db = t; b_add = Bb.grad_state == G_EXT ? Bb.grad : nullptr; }
+            if (O.rows > 0) {
+                cat2_bwd_kernel<<<ew_grid((size_t)O.rows * O.c / 4), 256, 0, st>>>((const float4*)O.grad, O.rows, Aa.c / 4, Bb.c / 4,
+                                                                                   (float4*)da, (const float4*)a_add, (float4*)db,
+                                                                                   (const float4*)b_add);
+                VC_LAUNCH_CHECK();
+            }
+            Aa.grad = da; Aa.grad_state = G_OWN;
+            Bb.grad = db; Bb.grad_state = G_OWN;
+            continue;
+        }
+        if (o[F_KIND] != OP_CBR) continue;
+        const int li = o[F_LAYER];
+        Layer& L = S->layer[li];
+        FSlot& X = S->f[L.in_slot];
+        FSlot& Y = S->f[L.out_slot];
+        RBk& R = S->rb[L.rb];
+        float* dw = C.P<float>(li, P_DW);
+        float* dgamma = C.P<float>(li, P_DGAMMA);
+        float* dbeta = C.P<float>(li, P_DBETA);
+        const size_t wn = (size_t)R.K * L.cin * L.cout;
+        if (Y.grad_state == G_EMPTY || R.n_out == 0) {   // nothing flowed back into this layer
+            VC_CUDA(cudaMemsetAsync(dw, 0, wn * 4, st));
+            VC_CUDA(cudaMemsetAsync(dgamma, 0, (size_t)L.cout * 4, st));
+            VC_CUDA(cudaMemsetAsync(dbeta, 0, (size_t)L.cout * 4, st));
+            continue;
+        }
+        const size_t elems = (size_t)R.n_out * L.cout;
+        VC_ALLOC(dx, float*, elems * 4);
+        void* dxb = nullptr;
+        if (L.use_tc) {
+            VC_ALLOC(t, void*, elems * 2);
+            dxb = t;
+        }
+        VC_TRY(vc_bn_relu_bwd_f32(Y.grad, L.x, L.y, C.P<const float>(li, P_GAMMA), L.stats, dx, dxb, dgamma, dbeta, R.n_out, L.cout,
+                                  training, L.sums + 2 * L.cout, st));
+        // wgrad
+        if (L.use_tc) {
+            const size_t wsb = vc_conv_wgrad_tc_ws_bytes(R.n_out, L.cin, L.cout, R.K);
+            VC_ALLOC(ws, void*, wsb);
+            Timed t(6, li, st);
+            VC_TRY(vc_conv_wgrad_tc(X.bf16, dxb, R.nbr, dw, R.n_out, L.cin, L.cout, R.K, ws, wsb, C.err, st));
+        } else {
+            const size_t wsb = vc_conv_wgrad_ws_bytes(R.n_out, L.cin, L.cout, R.K);
+            VC_ALLOC(ws, void*, wsb);
+            Timed t(5, li, st);
+            VC_TRY(vc_conv_wgrad_f32(X.f32, dx, R.nbr, dw, R.n_out, L.cin, L.cout, R.K, ws, wsb, st));
+        }
+        // dgrad
+        if (!L.need_dgrad || L.in_slot == 0) continue;
+        if (R.subm && !R.unique) {
+            const size_t wsb = vc_conv_ws_bytes(L.cin, L.cout, R.K);
+            VC_ALLOC(ws, void*, wsb);
+            VC_TRY(contribute(C, X, st, [&](float* dst) -> int {
+                VC_CUDA(cudaMemsetAsync(dst, 0, (size_t)X.rows * X.c * 4, st));
+                Timed t(4, li, st);
+                return vc_conv_dgrad_scatter_f32(dx, C.P<const float>(li, P_W), R.nbr, dst, R.n_out, L.cin, L.cout, R.K, ws, wsb, st);
+            }));
+        } else if (L.use_tc && L.wimg_dgrad) {
+            const int32_t* table = R.subm ? R.nbr : R.nbr_bwd;
+            VC_TRY(contribute(C, X, st, [&](float* dst) -> int {
+                Timed t(3, li, st);
+                return tc_conv_with_image(L.cout, L.cin, dxb, L.wimg_dgrad, table, dst, R.n_in, R.K, nullptr, C.err, st);
+            }));
+        } else {
+            const size_t wsb = vc_conv_ws_bytes(L.cin, L.cout, R.K);
+            VC_ALLOC(ws, void*, wsb);
+            const int32_t* table = R.subm ? R.nbr : R.nbr_bwd;
+            VC_TRY(contribute(C, X, st, [&](float* dst) -> int {
+                Timed t(2, li, st);
+                return vc_conv_dgrad_f32(dx, C.P<const float>(li, P_W), table, dst, R.n_in, L.cin, L.cout, R.K, R.subm ? 1 : 0, ws, wsb,
+                                         st);
+            }));
+        }
+    }
+    S->used = C.A.used;
+    return VC_OK;
+}

@@ -1,0 +1,401 @@
+"""Plan executor front end: describe a backbone's layer graph once, run its whole forward / backward through ONE
+C-ABI call each (`vc_exec_forward` / `vc_exec_backward`, include/virconv_b200.h; host loop in csrc/executor.cu).
+
+The reference walks the backbone layer by layer in Python (`VirConvL8x.forward` spconv_backbone.py:609-699,
+`NRConvBlock.forward` :207-229, `VirConv8x.forward` :339-535) and autograd walks it back; on a B200 that host work is
+longer than the kernels it launches.  `Plan` records the same graph as a flat op list; `run_plan` executes it natively
+and returns ordinary tensors (features with autograd history, indices) that live in one arena allocated per step.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from ._lib import check
+
+ENABLED = os.environ.get('VIRCONV_EXECUTOR', '1') != '0'
+TWO_STREAMS = os.environ.get('VIRCONV_EXEC_STREAMS', '2') != '1'
+TIMING = False                     # bench.py's roofline pass: per-launch events around the conv kernels
+LAST_RUN = None                    # the most recent forward's record while TIMING is on (bench.py reads its row counts)
+
+OP_SUBM_RB, OP_CONV_RB, OP_INDEX2UV, OP_CBR, OP_CAT = 1, 2, 3, 4, 5
+VC_ERR_WORKSPACE = -3
+OPI, OPF, PCOLS = 24, 8, 9
+KIND_NAMES = {0: 'conv_fwd', 1: 'conv_fwd_tc', 2: 'conv_dgrad', 3: 'conv_dgrad_tc', 4: 'conv_dgrad_scatter',
+              5: 'conv_wgrad', 6: 'conv_wgrad_tc'}
+
+
+def _t3(v, nd, fill):
+    v = list(v) if isinstance(v, (list, tuple)) else [v] * nd
+    assert len(v) == nd
+    return [int(x) for x in v] + [fill] * (3 - nd)
+
+
+class Plan:
+    """Flat op list over numbered feature slots / index sets / rulebooks (slot 0 / set 0 = the network input)."""
+
+    def __init__(self, in_channels):
+        self.rows_i, self.rows_f = [], []
+        self.layers = []              # (conv module, bn module)
+        self.n_f, self.n_i, self.n_rb = 1, 1, 0
+        self.f_channels = {0: in_channels}
+        self.published = []           # (name, feature slot, index set)
+        self.rb_keys = {}             # rulebook id -> (indice_keys, ndim, in index set, out index set)
+        self._final = None
+
+    def _row(self, kind, stream, a=0, b=0, c=0, ndim=0, ks=(0, 0, 0), st=(1, 1, 1), pd=(0, 0, 0), dl=(1, 1, 1), cin=0,
+             cout=0, layer=0, x0=0, x1=0, x2=0, f=()):
+        self.rows_i.append([kind, stream, a, b, c, ndim, *ks, *st, *pd, *dl, cin, cout, layer, x0, x1, x2])
+        self.rows_f.append(list(f) + [0.0] * (OPF - len(f)))
+        self._final = None
+
+    def subm_rb(self, iset, ndim, ksize, dilation=1, unique=True, keys=()):
+        rb = self.n_rb
+        self.n_rb += 1
+        self.rb_keys[rb] = (tuple(keys), ndim, iset, iset)
+        self._row(OP_SUBM_RB, 1, a=iset, c=rb, ndim=ndim, ks=_t3(ksize, ndim, 1), dl=_t3(dilation, ndim, 1), x0=int(unique))
+        return rb
+
+    def conv_rb(self, iset, ndim, ksize, stride, padding, dilation=1, keys=()):
+        rb, out = self.n_rb, self.n_i
+        self.n_rb += 1
+        self.n_i += 1
+        self.rb_keys[rb] = (tuple(keys), ndim, iset, out)
+        self._row(OP_CONV_RB, 1, a=iset, b=out, c=rb, ndim=ndim, ks=_t3(ksize, ndim, 1), st=_t3(stride, ndim, 1),
+                  pd=_t3(padding, ndim, 0), dl=_t3(dilation, ndim, 1))
+        return out, rb
+
+    def index2uv(self, iset, stride, pts_range=(0, -40, -3, 70.4, 40, 1), voxel_size=(0.05, 0.05, 0.05), u_max=1400,
+                 v_max=600, image_shape=(1600, 600)):
+        out = self.n_i
+        self.n_i += 1
+        vs = np.array(voxel_size, dtype=np.float64) * stride      # same host arithmetic as ops.index2uv
+        grid = [vs[0], vs[1], vs[2], pts_range[0] + vs[0] / 2, pts_range[1] + vs[1] / 2, pts_range[2] + vs[2] / 2]
+        self._row(OP_INDEX2UV, 1, a=iset, b=out, ndim=3, ks=(int(image_shape[0]), int(image_shape[1]), 0), x0=int(stride),
+                  x1=int(u_max), x2=int(v_max), f=[float(np.float32(g)) for g in grid])
+        return out
+
+    def cbr(self, f_in, rb, conv, bn):
+        out = self.n_f
+        self.n_f += 1
+        layer = len(self.layers)
+        self.layers.append((conv, bn))
+        assert self.f_channels[f_in] == conv.in_channels, (self.f_channels[f_in], conv.in_channels)
+        self.f_channels[out] = conv.out_channels
+        self._row(OP_CBR, 0, a=f_in, b=out, c=rb, cin=conv.in_channels, cout=conv.out_channels, layer=layer,
+                  x0=int(f_in != 0))
+        return out
+
+    def cat(self, fa, fb):
+        out = self.n_f
+        self.n_f += 1
+        self.f_channels[out] = self.f_channels[fa] + self.f_channels[fb]
+        self._row(OP_CAT, 0, a=fa, b=fb, c=out)
+        return out
+
+    def publish(self, name, f_slot, iset):
+        self.published.append((name, f_slot, iset))
+
+    def finalize(self):
+        if self._final is None:
+            oi = np.ascontiguousarray(np.array(self.rows_i, dtype=np.int32).reshape(-1, OPI))
+            of = np.ascontiguousarray(np.array(self.rows_f, dtype=np.float32).reshape(-1, OPF))
+            lf = np.ascontiguousarray(np.array([[bn.eps, 0.0 if bn.momentum is None else bn.momentum] for _, bn in self.layers],
+                                               dtype=np.float32).reshape(-1, 2))
+            sizes = []
+            for conv, bn in self.layers:
+                sizes += [conv.weight.numel(), bn.weight.numel(), bn.bias.numel()]
+            offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+            self._final = (oi, of, lf, sizes, offs)
+        return self._final
+
+    def params(self):
+        out = []
+        for conv, bn in self.layers:
+            out += [conv.weight, bn.weight, bn.bias]
+        return out
+
+    def eligible(self):
+        """Every layer is conv(bias=False) + affine BatchNorm1d with running statistics (what the VirConv blocks build)."""
+        return all(conv.bias is None and bn.affine and bn.track_running_stats for conv, bn in self.layers)
+
+
+_PINNED = {}
+_ARENA_BYTES = {}
+
+
+def _pinned(device):
+    key = (device.type, device.index)
+    if key not in _PINNED:
+        _PINNED[key] = torch.empty(16, dtype=torch.int32).pin_memory()
+    return _PINNED[key]
+
+
+def _arena_bytes(plan, n0, device):
+    """Arena size for a step: generous (rows * 48 KB + 256 MB, rounded up to 256 MB), grown from what earlier steps of
+    the same plan actually used, never shrunk — so the caching allocator hands back the same block every step."""
+    key = (id(plan), device.index)
+    want = int(n0) * 49152 + (256 << 20)
+    want = max(want, _ARENA_BYTES.get(key, 0))
+    want = (want + (256 << 20) - 1) // (256 << 20) * (256 << 20)
+    _ARENA_BYTES[key] = want
+    return want
+
+
+def _view(arena, ptr, shape, dtype):
+    """A tensor over arena memory at device address `ptr` that is NOT an autograd view of the arena (Tensor.set_ on the
+    shared storage), so it can be returned from an autograd Function and outlive the arena tensor object."""
+    esz = torch.empty(0, dtype=dtype).element_size()
+    off = ptr - arena.data_ptr()
+    assert off >= 0 and off % esz == 0
+    n = 1
+    for s in shape:
+        n *= int(s)
+    assert off + n * esz <= arena.numel()
+    t = torch.empty(0, dtype=dtype, device=arena.device)
+    strides, acc = [], 1
+    for s in reversed(shape):
+        strides.append(acc)
+        acc *= int(s)
+    t.set_(arena.untyped_storage(), off // esz + arena.storage_offset() // esz, tuple(int(s) for s in shape),
+           tuple(reversed(strides)))
+    return t
+
+
+class _Run:
+    """One forward's record: arena + state blob, enough for the backward call and for queries."""
+
+    def __init__(self, plan, arena, state, precision):
+        self.plan, self.arena, self.state, self.precision = plan, arena, state, precision
+
+    def query(self, what, idx):
+        out = (ctypes.c_longlong * 8)()
+        check(_lib.load().vc_exec_query(self.state.ctypes.data, what, idx, out), 'vc_exec_query')
+        return [int(v) for v in out]
+
+    def feature(self, slot):
+        p, _, rows, c = self.query(1, slot)[:4]
+        return _view(self.arena, p, (rows, c), torch.float32)
+
+    def feature_bf16(self, slot):
+        _, pb, rows, c = self.query(1, slot)[:4]
+        return _view(self.arena, pb, (rows, c), torch.bfloat16) if pb else None
+
+    def indices(self, iset):
+        p, n, ndim, s0, s1, s2 = self.query(2, iset)[:6]
+        return _view(self.arena, p, (n, 1 + ndim), torch.int32), [s0, s1, s2][:ndim]
+
+    def rulebook(self, rb):
+        """(nbr [K, n_out] int32, nbr_bwd or None, pair_num or None, meta dict) — tests compare these with the oracle."""
+        p, pbw, ppn, K, n_in, n_out, subm, unique = self.query(3, rb)
+        nbr = _view(self.arena, p, (K, n_out), torch.int32)
+        nbw = _view(self.arena, pbw, (K, n_in), torch.int32) if pbw else None
+        pn = _view(self.arena, ppn, (K,), torch.int32) if ppn else None
+        return nbr, nbw, pn, dict(K=K, n_in=n_in, n_out=n_out, subm=bool(subm), unique=bool(unique))
+
+
+class LazyIndiceDict(dict):
+    """`SparseConvTensor.indice_dict` of the tensors a plan publishes: {indice_key: ops.Rulebook} like the module path
+    leaves behind (spconv caches its indice pairs there), but materialised on first access — building a dozen tensor
+    views per step for a dictionary nobody reads would be pure host overhead."""
+
+    def __init__(self, run, coords0, shape0):
+        super().__init__()
+        self._src = (run, coords0, shape0)
+
+    def _fill(self):
+        if self._src is None:
+            return
+        run, coords0, shape0 = self._src
+        self._src = None
+        for rb, (keys, ndim, i_in, i_out) in run.plan.rb_keys.items():
+            if not keys:
+                continue
+            nbr, nbw, pn, meta = run.rulebook(rb)
+            oidx, oshape = (coords0, list(shape0)) if i_out == 0 else run.indices(i_out)
+            book = ops.Rulebook(meta['subm'], ndim, meta['K'], meta['n_in'], meta['n_out'], nbr, nbw, pn, oidx, oshape,
+                                meta['unique'])
+            book._keepalive = run
+            for k in keys:
+                dict.__setitem__(self, k, book)
+
+    def __getitem__(self, k):
+        self._fill()
+        return dict.__getitem__(self, k)
+
+    def __contains__(self, k):
+        self._fill()
+        return dict.__contains__(self, k)
+
+    def __iter__(self):
+        self._fill()
+        return dict.__iter__(self)
+
+    def __len__(self):
+        self._fill()
+        return dict.__len__(self)
+
+    def get(self, k, default=None):
+        self._fill()
+        return dict.get(self, k, default)
+
+    def items(self):
+        self._fill()
+        return dict.items(self)
+
+    def keys(self):
+        self._fill()
+        return dict.keys(self)
+
+    def values(self):
+        self._fill()
+        return dict.values(self)
+
+
+def _layer_ptrs(plan, grad_base=0):
+    oi, of, lf, sizes, offs = plan.finalize()
+    tab = np.zeros((len(plan.layers), PCOLS), dtype=np.uint64)
+    for i, (conv, bn) in enumerate(plan.layers):
+        nbt = bn.num_batches_tracked
+        tab[i, 0] = conv.weight.data_ptr()
+        tab[i, 1] = bn.weight.data_ptr()
+        tab[i, 2] = bn.bias.data_ptr()
+        tab[i, 3] = bn.running_mean.data_ptr()
+        tab[i, 4] = bn.running_var.data_ptr()
+        tab[i, 5] = nbt.data_ptr() if nbt is not None else 0
+        if grad_base:
+            tab[i, 6] = grad_base + 4 * int(offs[3 * i])
+            tab[i, 7] = grad_base + 4 * int(offs[3 * i + 1])
+            tab[i, 8] = grad_base + 4 * int(offs[3 * i + 2])
+    return tab
+
+
+class PlanFn(torch.autograd.Function):
+    """forward: (features of the published slots..., ) ; backward: gradients of every layer's weight / gamma / beta."""
+
+    @staticmethod
+    def forward(ctx, plan, holder, feats, coords, spatial_shape, batch_size, proj, training, precision, inputs_ready, *params):
+        lib = _lib.load()
+        dev = feats.device
+        oi, of, lf, sizes, offs = plan.finalize()
+        feats = feats.contiguous()
+        n0 = feats.shape[0]
+        nbytes = _arena_bytes(plan, n0, dev)
+        main = ops._stream()
+        side_obj = ops.side(dev).stream if TWO_STREAMS else None
+        side = side_obj.cuda_stream if side_obj is not None else None
+        if side_obj is not None:
+            # The arena belongs to the SIDE stream (its index kernels are the first writers, possibly while main still
+            # runs the previous step); main's uses are registered with record_stream, so the caching allocator recycles
+            # the block only after both streams are done with it.
+            with torch.cuda.stream(side_obj):
+                arena = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            arena.record_stream(torch.cuda.current_stream(dev))
+        else:
+            arena = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        state = np.zeros(lib.vc_exec_state_bytes(), dtype=np.uint8)
+        tab = _layer_ptrs(plan)
+        rc = lib.vc_exec_forward(oi.ctypes.data, of.ctypes.data, oi.shape[0], tab.ctypes.data, lf.ctypes.data, len(plan.layers),
+                                 feats.data_ptr(), feats.shape[1], coords.data_ptr(), n0, _lib.host_i32(spatial_shape),
+                                 int(batch_size), proj.data_ptr() if proj is not None else None, int(training),
+                                 int(precision == 'bf16'), 1, arena.data_ptr(), arena.numel(),
+                                 _pinned(dev).data_ptr(), ops.tc_error_flag(dev).data_ptr(), state.ctypes.data, state.size,
+                                 main, side, 0 if (inputs_ready and side is not None) else 1)
+        if rc == VC_ERR_WORKSPACE:
+            _ARENA_BYTES[(id(plan), dev.index)] = 2 * arena.numel()     # the next call gets twice as much
+        check(rc, 'vc_exec_forward')
+        run = _Run(plan, arena, state, precision)
+        holder.append(run)
+        if TIMING:
+            global LAST_RUN
+            LAST_RUN = run
+        ctx.run, ctx.feats, ctx.coords, ctx.proj = run, feats, coords, proj
+        return tuple(run.feature(slot) for _, slot, _ in plan.published)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        lib = _lib.load()
+        run = ctx.run
+        plan = run.plan
+        oi, of, lf, sizes, offs = plan.finalize()
+        dev = run.arena.device
+        flat = torch.empty(int(offs[-1]), dtype=torch.float32, device=dev)
+        tab = _layer_ptrs(plan, flat.data_ptr())
+        gs = [None if g is None else g.contiguous() for g in grads]
+        slots = np.array([slot for _, slot, _ in plan.published], dtype=np.int32)
+        ext = np.array([0 if g is None else g.data_ptr() for g in gs], dtype=np.uint64)
+        rc = lib.vc_exec_backward(oi.ctypes.data, of.ctypes.data, oi.shape[0], tab.ctypes.data, lf.ctypes.data, len(plan.layers),
+                                  slots.ctypes.data, ext.ctypes.data, len(gs), run.arena.data_ptr(), run.arena.numel(),
+                                  ops.tc_error_flag(dev).data_ptr(), run.state.ctypes.data, ops._stream())
+        key = (id(plan), dev.index)
+        if rc == VC_ERR_WORKSPACE:
+            _ARENA_BYTES[key] = 2 * run.arena.numel()
+        check(rc, 'vc_exec_backward')
+        _ARENA_BYTES[key] = max(_ARENA_BYTES.get(key, 0), int(1.5 * run.query(0, 0)[0]))   # keep ahead of what steps really use
+        run.flat_grad = flat
+        views = flat.split(sizes)
+        out = [v.view_as(p) for v, p in zip(views, plan.params())]
+        return (None,) * 10 + tuple(out)
+
+
+def run_plan(plan, feats, coords_i32, spatial_shape, batch_size, proj, training, precision, inputs_ready=False):
+    """-> (run record, {name: (features, indices, spatial_shape, bf16 shadow)}).  `coords_i32` [N,4] int32 contiguous
+    (b,z,y,x).  inputs_ready: the caller vouches that `coords_i32` and `proj` are complete in the SIDE stream's order
+    (resident from an earlier step, or produced on / synchronised with ops.side(device).stream): the index pipeline then
+    does not wait for the main stream and overlaps the previous step's backward."""
+    ops._require_cuda(feats, coords_i32)
+    assert coords_i32.dtype == torch.int32 and coords_i32.is_contiguous()
+    holder = []
+    outs = PlanFn.apply(plan, holder, feats, coords_i32, list(spatial_shape), batch_size, proj, training, precision,
+                        bool(inputs_ready), *plan.params())
+    run = holder[0]
+    res = {}
+    for (name, slot, iset), f in zip(plan.published, outs):
+        idx, shape = (coords_i32, list(spatial_shape)) if iset == 0 else run.indices(iset)
+        res[name] = (f, idx, shape, run.feature_bf16(slot))
+    return run, res
+
+
+def timing_start():
+    global TIMING
+    TIMING = True
+    check(_lib.load().vc_exec_timing(1), 'vc_exec_timing')
+
+
+def timing_stop():
+    """-> list of (kind name, layer, ms)."""
+    global TIMING
+    lib = _lib.load()
+    n_max = 4096
+    ms = (ctypes.c_float * n_max)()
+    kl = (ctypes.c_int32 * (2 * n_max))()
+    n = lib.vc_exec_timing_read(ms, kl, n_max)
+    if n < 0:
+        check(n, 'vc_exec_timing_read')
+    TIMING = False
+    check(lib.vc_exec_timing(0), 'vc_exec_timing')
+    return [(KIND_NAMES[kl[2 * i]], int(kl[2 * i + 1]), float(ms[i])) for i in range(n)]
+
+
+def alg_bytes_flops(run, kind, layer):
+    """Algorithmic bytes / FLOPs of one timed conv launch (same formulas as ops.py's per-call accounting):
+    every input row read once, every output row written once, one (in, out) pair per rulebook entry, the weights."""
+    rb_id, in_slot, out_slot = run.query(4, layer)[4:7]
+    _, _, pn, meta = run.rulebook(rb_id)
+    conv = run.plan.layers[layer][0]
+    cin, cout, K = conv.in_channels, conv.out_channels, meta['K']
+    n_in, n_out, P = meta['n_in'], meta['n_out'], int(pn.sum().item())
+    w = K * cin * cout
+    if kind == 'conv_fwd_tc':
+        b = n_in * cin * 2 + n_out * cout * 4 + w * 2
+    elif kind == 'conv_dgrad_tc':
+        b = n_out * cout * 2 + n_in * cin * 4 + w * 2
+    elif kind == 'conv_wgrad_tc':
+        b = (n_in * cin + n_out * cout) * 2 + w * 4
+    else:
+        b = (n_in * cin + n_out * cout + w) * 4
+    return b + P * 8, 2 * P * cin * cout

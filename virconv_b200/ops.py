@@ -521,8 +521,9 @@ def compose_lidar_to_rect(V2C, R0):
     return m
 
 
-def projection_params(calib, trans_param, batch_size, device):
-    """[B, 28] float32 parameter block of vc_index2uv (layout: include/virconv_b200.h)."""
+def projection_params(calib, trans_param, batch_size, device, stream=None):
+    """[B, 28] float32 parameter block of vc_index2uv (layout: include/virconv_b200.h).  `stream`: upload on that
+    torch stream (the plan executor consumes the block on its side stream only)."""
     tp = None
     if trans_param is not None:
         tp = trans_param.detach().cpu().numpy() if torch.is_tensor(trans_param) else np.asarray(trans_param)
@@ -538,6 +539,9 @@ def projection_params(calib, trans_param, batch_size, device):
             out[b, 22] = flip
             out[b, 23] = np.cos(_f32(-rot))
             out[b, 24] = np.sin(_f32(-rot))
+    if stream is not None:
+        with torch.cuda.stream(stream):
+            return torch.from_numpy(out).to(device, non_blocking=True)
     return torch.from_numpy(out).to(device, non_blocking=True)
 
 

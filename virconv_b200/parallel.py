@@ -15,6 +15,22 @@ def shard_scene_ids(step: int, rank: int, world_size: int, scenes_per_gpu: int, 
     return list(range(start, start + scenes_per_gpu))
 
 
+def _as_one_buffer(grads):
+    """If the gradient tensors are back-to-back fp32 slices of one storage, return that span as a 1-D tensor, else None."""
+    g0 = grads[0]
+    if any(g.dtype != torch.float32 or not g.is_contiguous() for g in grads):
+        return None
+    st = g0.untyped_storage()
+    ptr = g0.data_ptr()
+    for g in grads:
+        if g.untyped_storage().data_ptr() != st.data_ptr() or g.data_ptr() != ptr:
+            return None
+        ptr += g.numel() * 4
+    flat = torch.empty(0, dtype=torch.float32, device=g0.device)
+    flat.set_(st, g0.storage_offset(), ((ptr - g0.data_ptr()) // 4,), (1,))
+    return flat
+
+
 def allreduce_gradients(params, average: bool = True, group=None) -> int:
     """ONE all-reduce for all gradients: flatten (one kernel), reduce, scatter back into the existing .grad tensors.
     The whole VirConv-L backbone is 1.7 MB of fp32 gradients: a latency-bound message, so a single bucket is optimal
@@ -25,6 +41,14 @@ def allreduce_gradients(params, average: bool = True, group=None) -> int:
     grads = [p.grad for p in params if p.grad is not None]
     if world == 1 or not grads:
         return 0
+    flat = _as_one_buffer(grads)
+    if flat is not None:
+        # the plan executor writes every gradient into ONE flat buffer (executor.PlanFn.backward): reduce it in place,
+        # no flatten / scatter-back kernels
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        if average:
+            flat.div_(world)
+        return flat.numel() * flat.element_size()
     flat = torch.cat([g.reshape(-1) for g in grads])
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     if average:
