@@ -299,11 +299,15 @@ def run_ours(args):
     # Plan-executor path: the events are recorded inside vc_exec_forward / vc_exec_backward (executor.timing_*);
     # module path (VIRCONV_EXECUTOR=0): around every conv C-ABI call (ops.KernelTimer).
     from virconv_b200 import executor
-    roof, kern = None, {}
+    roof, kern, run = None, {}, None
     nprof = 3
     use_exec = executor.ENABLED
     if rank == 0 and not use_exec:
         ops.TIMER = ops.KernelTimer()
+    # kernels are timed ALONE here: one stream, no concurrent wgrad (in the timed loops above the executor overlaps the
+    # index / feature / wgrad streams, which stretches every individual kernel and is not what a roofline describes)
+    saved = (executor.TWO_STREAMS, executor.WGRAD_STREAM)
+    executor.TWO_STREAMS, executor.WGRAD_STREAM = False, False
     for s in range(nprof):               # every rank runs the steps (they contain the gradient all-reduce)
         flush_buf.zero_()
         vf, vc, b = devb[s % POOL]
@@ -320,7 +324,10 @@ def run_ours(args):
                 c[2] += by
                 c[3] += fl
             executor.LAST_RUN = None
+    executor.TWO_STREAMS, executor.WGRAD_STREAM = saved
     barrier()
+    if rank == 0 and use_exec and run is not None:
+        sys.stderr.write('plan executor arena: %.0f MB used of %.0f MB per step\n' % (run.query(0, 0)[0] / 2**20, run.arena.numel() / 2**20))
     if rank == 0:
         if not use_exec:
             kern = ops.TIMER.summary()
@@ -347,7 +354,7 @@ def run_ours(args):
                 'share_of_conv_kernel_time': g_ms / all_ms if all_ms > 0 else None,
                 'per_step_ms': {k: v[1] / nprof for k, v in kern.items()},
                 'note': ('tcgen05 bf16 operands / fp32 TMEM accumulators; bytes = bf16 gathered operand + fp32 output + P*8 '
-                         '+ bf16 weights; CUDA events around each launch inside the plan executor'
+                         '+ bf16 weights; CUDA events around each launch inside the plan executor, kernels timed alone (single stream)'
                          if args.precision == 'bf16' else
                          'fp32 CUDA-core parity path: FP32-FMA bound, HBM is the bound it is designed toward')}
 

@@ -140,6 +140,11 @@ int vc_conv_dgrad_tc(const void* dout_bf16, const float* w, const int32_t* nbr_t
  * kernel offsets stacked along the MMA M dimension, accumulators resident in TMEM across all tiles of a
  * persistent CTA, fixed-order reduction of the per-CTA partials.  ws >= vc_conv_wgrad_tc_ws_bytes(...). */
 size_t vc_conv_wgrad_tc_ws_bytes(int n_out, int cin, int cout, int K);
+/* Process-wide launch shape of vc_conv_wgrad_tc: at most max_ctas persistent CTAs (default 148 = one per SM), each asking
+ * for at least smem_floor_bytes of dynamic shared memory (default 0).  The plan executor's backward uses (fewer CTAs,
+ * a floor no gather-GEMM CTA fits beside) to run wgrad on its own stream next to the dgrad chain.  Affects
+ * vc_conv_wgrad_tc_ws_bytes. */
+int vc_conv_wgrad_tc_config(int max_ctas, int smem_floor_bytes);
 int vc_conv_wgrad_tc(const void* in_bf16, const void* dout_bf16, const int32_t* nbr, float* dw, int n_out, int cin,
                      int cout, int K, void* ws, size_t ws_bytes, int32_t* err_flag, vc_stream_t stream);
 
@@ -253,10 +258,12 @@ int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_ops, const u
                     vc_stream_t side_stream, int side_waits_main);
 /* Reverse walk.  pub_slots [n_pub]: feature slots whose gradients come from outside (the published tensors), ext_grads
  * [n_pub]: device pointers to those gradients ([rows, c] fp32 contiguous, read only) or 0.  Writes d_weight / d_gamma /
- * d_beta of every layer (zeros where nothing flowed back).  Same arena as the forward (it continues allocating). */
+ * d_beta of every layer (zeros where nothing flowed back).  Same arena as the forward (it continues allocating).
+ * wgrad_stream (may be NULL): the weight-gradient kernels go there, concurrent with the BN-backward / dgrad chain on
+ * `stream`; `stream` is joined with it before the call returns. */
 int vc_exec_backward(const int32_t* ops_i, const float* ops_f, int n_ops, const uint64_t* layer_ptrs, const float* layer_f,
                      int n_layers, const int32_t* pub_slots, const uint64_t* ext_grads, int n_pub, void* arena,
-                     size_t arena_bytes, int32_t* err_flag, void* state, vc_stream_t stream);
+                     size_t arena_bytes, int32_t* err_flag, void* state, vc_stream_t stream, vc_stream_t wgrad_stream);
 /* Read a state blob.  what 0: out[0] = arena bytes in use;  1 (feature slot id): f32 ptr, bf16 ptr, rows, c;
  * 2 (index set): idx ptr, n, ndim, shape[3];  3 (rulebook): nbr, nbr_bwd, pair_num ptrs, K, n_in, n_out, subm, unique;
  * 4 (layer): x ptr, y ptr, stats ptr, use_tc, rulebook id, in slot, out slot.  out: >= 8 int64 (host). */

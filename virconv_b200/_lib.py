@@ -55,7 +55,8 @@ SIGNATURES = {
     'vc_gather_rows': (_I, [_P, _P, _P, _I, _I, _P]),
     'vc_exec_state_bytes': (_Z, []),
     'vc_exec_forward': (_I, [_P, _P, _I, _P, _P, _I, _P, _I, _P, _I, _HOST, _I, _P, _I, _I, _I, _P, _Z, _P, _P, _P, _Z, _P, _P, _I]),
-    'vc_exec_backward': (_I, [_P, _P, _I, _P, _P, _I, _P, _P, _I, _P, _Z, _P, _P, _P]),
+    'vc_exec_backward': (_I, [_P, _P, _I, _P, _P, _I, _P, _P, _I, _P, _Z, _P, _P, _P, _P]),
+    'vc_conv_wgrad_tc_config': (_I, [_I, _I]),
     'vc_exec_query': (_I, [_P, _I, _I, _P]),
     'vc_exec_timing': (_I, [_I]),
     'vc_exec_timing_read': (_I, [_P, _P, _I]),

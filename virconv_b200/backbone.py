@@ -199,8 +199,11 @@ class VirConvL8x(nn.Module):
             return False
         if self.training and self.discard_mode == 'paper' and self.layer_discard_rate != 0:
             return False             # row-dropping StVD between the blocks is only on the module path
-        bns = [m for m in self.modules() if isinstance(m, nn.BatchNorm1d)]
-        return self._plan().eligible() and len({m.training for m in bns}) == 1
+        plan = self._plan()
+        if getattr(self, '_plan_ok', None) is None:
+            self._plan_ok = plan.eligible()
+        mode = plan.layers[0][1].training
+        return self._plan_ok and all(bn.training == mode for _, bn in plan.layers)
 
     def forward(self, batch_dict):
         rot_num = batch_dict['transform_param'].shape[1] if 'transform_param' in batch_dict else 1
@@ -216,12 +219,18 @@ class VirConvL8x(nn.Module):
                 trans = batch_dict['transform_param'][:, i, :]
             if self._use_plan(feats):
                 bn_training = self.conv_out[1].training
-                ci = spconv._as_i32(coords)
-                # 'virconv_inputs_ready': the caller's promise that voxel_coords is int32, resident and complete (e.g. a
-                # prefetched batch) -> the index pipeline of this step may overlap the previous step's backward
-                ready = bool(batch_dict.get('virconv_inputs_ready', False)) and ci is coords and executor.TWO_STREAMS
-                proj = ops.projection_params(calib, trans, batch_size, feats.device,
-                                             ops.side(feats.device).stream if executor.TWO_STREAMS else None)
+                # 'virconv_inputs_ready': the caller's promise that voxel_coords is resident and complete (a prefetched
+                # batch) -> the index pipeline of this step (starting with the .int() of the coordinates, :641) runs on
+                # the side stream without waiting for main, i.e. it may overlap the previous step's backward
+                side = ops.side(feats.device).stream if executor.TWO_STREAMS else None
+                ready = side is not None and bool(batch_dict.get('virconv_inputs_ready', False))
+                if ready and (coords.dtype != torch.int32 or not coords.is_contiguous()):
+                    with torch.cuda.stream(side):
+                        ci = spconv._as_i32(coords)
+                    ci.record_stream(torch.cuda.current_stream(feats.device))   # published as x_conv1's indices
+                else:
+                    ci = spconv._as_i32(coords)
+                proj = ops.projection_params(calib, trans, batch_size, feats.device, side)
                 run, res = executor.run_plan(self._plan(), feats, ci, self.sparse_shape, batch_size, proj, bn_training,
                                              self.conv_out[0].precision, inputs_ready=ready)
                 idict = executor.LazyIndiceDict(run, ci, self.sparse_shape)

@@ -762,9 +762,16 @@ __global__ void __launch_bounds__(256) wgrad_tc_reduce_kernel(const float* __res
     dw[((size_t)co * K + k) * cin + ci] = (v0 + v1) + (v2 + v3);
 }
 
+// Background mode (vc_conv_wgrad_tc_config): wgrad runs on its own stream next to the BN-backward / dgrad chain.  Its
+// persistent CTAs then (a) number fewer than the SMs and (b) pad their dynamic shared memory so that no gather-GEMM CTA
+// fits beside them: a co-resident gather CTA would block in tcgen05.alloc behind the wgrad CTA's TMEM columns for the
+// whole lifetime of the persistent CTA.  The chain keeps the remaining SMs to itself.
+static int g_wgrad_ctas = 148;
+static int g_wgrad_smem_floor = 0;
+
 static int wgrad_tc_grid(int n_out) {
     int tiles = (n_out + TCM - 1) / TCM;
-    return tiles < 148 ? (tiles < 1 ? 1 : tiles) : 148;
+    return tiles < g_wgrad_ctas ? (tiles < 1 ? 1 : tiles) : g_wgrad_ctas;
 }
 
 template <int CI, int CO>
@@ -779,6 +786,7 @@ static int launch_wgrad_tc(const __nv_bfloat16* in, const __nv_bfloat16* dout, c
     while (cols < gpp * CO) cols <<= 1;
     int kcount = gpp * C::G < K ? gpp * C::G : K;
     size_t smem = C::smem(kcount);
+    if (smem < (size_t)g_wgrad_smem_floor) smem = (size_t)g_wgrad_smem_floor;
     auto kern = tc_wgrad_kernel<CI, CO>;
     VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<dim3(wgrad_tc_grid(n_out), passes), WG_THREADS, smem, stream>>>(in, dout, nbr, partial, n_out, K, gpp, cols, err);
@@ -787,6 +795,14 @@ static int launch_wgrad_tc(const __nv_bfloat16* in, const __nv_bfloat16* dout, c
 }
 
 }  // namespace vc
+
+extern "C" int vc_conv_wgrad_tc_config(int max_ctas, int smem_floor_bytes) {
+    VC_CHECK_ARG(max_ctas >= 1 && max_ctas <= 148 && smem_floor_bytes >= 0 && smem_floor_bytes <= 227 * 1024,
+                 "wgrad config out of range (ctas %d, smem floor %d)", max_ctas, smem_floor_bytes);
+    vc::g_wgrad_ctas = max_ctas;
+    vc::g_wgrad_smem_floor = smem_floor_bytes;
+    return VC_OK;
+}
 
 extern "C" size_t vc_conv_wgrad_tc_ws_bytes(int n_out, int cin, int cout, int K) {
     return (size_t)vc::wgrad_tc_grid(n_out) * K * cin * cout * sizeof(float);

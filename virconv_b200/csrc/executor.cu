@@ -585,7 +585,7 @@ int contribute(Ctx& C, FSlot& F, cudaStream_t st, W&& write) {
 extern "C" int vc_exec_backward(const int32_t* ops_i, const float* ops_f, int n_ops, const uint64_t* layer_ptrs,
                                 const float* layer_f, int n_layers, const int32_t* pub_slots, const uint64_t* ext_grads,
                                 int n_pub, void* arena, size_t arena_bytes, int32_t* err_flag, void* state,
-                                vc_stream_t stream_) {
+                                vc_stream_t stream_, vc_stream_t wgrad_stream_) {
     VC_TRY(check_plan(ops_i, n_ops, n_layers));
     State* S = (State*)state;
     VC_CHECK_ARG(S && S->magic == STATE_MAGIC && S->n_ops == n_ops && S->n_layers == n_layers, "state does not belong to this plan");
@@ -593,9 +593,14 @@ extern "C" int vc_exec_backward(const int32_t* ops_i, const float* ops_f, int n_
     Ctx C;
     C.oi = ops_i; C.of = ops_f; C.n_ops = n_ops; C.lp = layer_ptrs; C.lf = layer_f; C.n_layers = n_layers; C.S = S;
     C.A = Arena{(char*)arena, arena_bytes, S->used, false};
-    C.st[0] = C.st[1] = (cudaStream_t)stream_;
+    C.st[0] = (cudaStream_t)stream_;
+    C.st[1] = wgrad_stream_ ? (cudaStream_t)wgrad_stream_ : (cudaStream_t)stream_;
     C.err = err_flag;
     cudaStream_t st = C.st[0];
+    cudaStream_t wst = C.st[1];      // weight gradients: off the dgrad chain's critical path
+    const bool two = st != wst;
+    if (two) VC_TRY(ev_init());
+    int last_w_ev = -1;
     const int training = S->training;
 
     for (int i = 0; i < MAX_F; ++i) { S->f[i].grad = nullptr; S->f[i].grad_state = G_EMPTY; }
@@ -657,18 +662,23 @@ extern "C" int vc_exec_backward(const int32_t* ops_i, const float* ops_f, int n_
         }
         VC_TRY(vc_bn_relu_bwd_f32(Y.grad, L.x, L.y, C.P<const float>(li, P_GAMMA), L.stats, dx, dxb, dgamma, dbeta, R.n_out, L.cout,
                                   training, L.sums + 2 * L.cout, st));
-        // wgrad
+        // wgrad (needs dx / its bf16 shadow: ordered after the BN backward through an event when on its own stream)
+        if (two) {
+            int e = record_on(C, 0);
+            if (e >= 0) VC_CUDA(cudaStreamWaitEvent(wst, g_ev[e], 0));
+        }
         if (L.use_tc) {
             const size_t wsb = vc_conv_wgrad_tc_ws_bytes(R.n_out, L.cin, L.cout, R.K);
             VC_ALLOC(ws, void*, wsb);
-            Timed t(6, li, st);
-            VC_TRY(vc_conv_wgrad_tc(X.bf16, dxb, R.nbr, dw, R.n_out, L.cin, L.cout, R.K, ws, wsb, C.err, st));
+            Timed t(6, li, wst);
+            VC_TRY(vc_conv_wgrad_tc(X.bf16, dxb, R.nbr, dw, R.n_out, L.cin, L.cout, R.K, ws, wsb, C.err, wst));
         } else {
             const size_t wsb = vc_conv_wgrad_ws_bytes(R.n_out, L.cin, L.cout, R.K);
             VC_ALLOC(ws, void*, wsb);
-            Timed t(5, li, st);
-            VC_TRY(vc_conv_wgrad_f32(X.f32, dx, R.nbr, dw, R.n_out, L.cin, L.cout, R.K, ws, wsb, st));
+            Timed t(5, li, wst);
+            VC_TRY(vc_conv_wgrad_f32(X.f32, dx, R.nbr, dw, R.n_out, L.cin, L.cout, R.K, ws, wsb, wst));
         }
+        if (two) last_w_ev = record_on(C, 1);
         // dgrad
         if (!L.need_dgrad || L.in_slot == 0) continue;
         if (R.subm && !R.unique) {
@@ -696,6 +706,7 @@ extern "C" int vc_exec_backward(const int32_t* ops_i, const float* ops_f, int n_
             }));
         }
     }
+    if (two && last_w_ev >= 0) VC_CUDA(cudaStreamWaitEvent(st, g_ev[last_w_ev], 0));   // join: gradients complete on `stream`
     S->used = C.A.used;
     return VC_OK;
 }

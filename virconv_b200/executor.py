@@ -19,6 +19,28 @@ from ._lib import check
 
 ENABLED = os.environ.get('VIRCONV_EXECUTOR', '1') != '0'
 TWO_STREAMS = os.environ.get('VIRCONV_EXEC_STREAMS', '2') != '1'
+# weight gradients on their own stream next to the BN-backward / dgrad chain (vc_exec_backward's wgrad_stream), with the
+# wgrad CTAs limited to WGRAD_CTAS SMs they keep to themselves (vc_conv_wgrad_tc_config)
+# (measured, profiles/sweep_wgrad_r1.txt: 3.91 ms/step without, 3.29-3.31 with 96-112 CTAs; the shared-memory floor that
+# keeps gather CTAs off the wgrad SMs made no difference at 96 CTAs, so it is off)
+WGRAD_STREAM = os.environ.get('VIRCONV_WGRAD_STREAM', '1') != '0'
+WGRAD_CTAS = int(os.environ.get('VIRCONV_WGRAD_CTAS', '96'))
+WGRAD_SMEM_KB = int(os.environ.get('VIRCONV_WGRAD_SMEM_KB', '0'))
+_WSTREAM = {}
+_WCFG = [None]
+
+
+def _wgrad_stream(device):
+    key = (device.type, device.index)
+    if key not in _WSTREAM:
+        _WSTREAM[key] = torch.cuda.Stream(device=device)
+    cfg = (WGRAD_CTAS, WGRAD_SMEM_KB * 1024) if WGRAD_STREAM else (148, 0)
+    if _WCFG[0] != cfg:
+        check(_lib.load().vc_conv_wgrad_tc_config(*cfg), 'vc_conv_wgrad_tc_config')
+        _WCFG[0] = cfg
+    return _WSTREAM[key] if WGRAD_STREAM else None
+
+
 TIMING = False                     # bench.py's roofline pass: per-launch events around the conv kernels
 LAST_RUN = None                    # the most recent forward's record while TIMING is on (bench.py reads its row counts)
 
@@ -136,10 +158,11 @@ def _pinned(device):
 
 
 def _arena_bytes(plan, n0, device):
-    """Arena size for a step: generous (rows * 48 KB + 256 MB, rounded up to 256 MB), grown from what earlier steps of
-    the same plan actually used, never shrunk — so the caching allocator hands back the same block every step."""
+    """Arena size for a step: generous (rows * 24 KB + 256 MB, rounded up to 256 MB; VirConv-L uses ~16 KB per input
+    voxel, forward + backward), grown from what earlier steps of the same plan actually used, never shrunk — so the
+    caching allocator hands back the same block every step."""
     key = (id(plan), device.index)
-    want = int(n0) * 49152 + (256 << 20)
+    want = int(n0) * 24576 + (256 << 20)
     want = max(want, _ARENA_BYTES.get(key, 0))
     want = (want + (256 << 20) - 1) // (256 << 20) * (256 << 20)
     _ARENA_BYTES[key] = want
@@ -257,20 +280,27 @@ class LazyIndiceDict(dict):
 
 
 def _layer_ptrs(plan, grad_base=0):
+    """[n_layers, 9] uint64 pointer table of vc_exec_*.  The parameter / buffer columns are cached per plan and re-read
+    only when a weight's address changes (module.to(), load of a new tensor object); the gradient columns are
+    `grad_base` + fixed offsets into the step's flat gradient buffer."""
     oi, of, lf, sizes, offs = plan.finalize()
-    tab = np.zeros((len(plan.layers), PCOLS), dtype=np.uint64)
-    for i, (conv, bn) in enumerate(plan.layers):
-        nbt = bn.num_batches_tracked
-        tab[i, 0] = conv.weight.data_ptr()
-        tab[i, 1] = bn.weight.data_ptr()
-        tab[i, 2] = bn.bias.data_ptr()
-        tab[i, 3] = bn.running_mean.data_ptr()
-        tab[i, 4] = bn.running_var.data_ptr()
-        tab[i, 5] = nbt.data_ptr() if nbt is not None else 0
-        if grad_base:
-            tab[i, 6] = grad_base + 4 * int(offs[3 * i])
-            tab[i, 7] = grad_base + 4 * int(offs[3 * i + 1])
-            tab[i, 8] = grad_base + 4 * int(offs[3 * i + 2])
+    key = tuple(conv.weight.data_ptr() for conv, _ in plan.layers)
+    cached = getattr(plan, '_ptr_cache', None)
+    if cached is None or cached[0] != key:
+        tab = np.zeros((len(plan.layers), PCOLS), dtype=np.uint64)
+        for i, (conv, bn) in enumerate(plan.layers):
+            nbt = bn.num_batches_tracked
+            tab[i, 0] = conv.weight.data_ptr()
+            tab[i, 1] = bn.weight.data_ptr()
+            tab[i, 2] = bn.bias.data_ptr()
+            tab[i, 3] = bn.running_mean.data_ptr()
+            tab[i, 4] = bn.running_var.data_ptr()
+            tab[i, 5] = nbt.data_ptr() if nbt is not None else 0
+        goff = (4 * offs[:-1].reshape(-1, 3)).astype(np.uint64)
+        plan._ptr_cache = cached = (key, tab, goff)
+    tab = cached[1].copy()
+    if grad_base:
+        tab[:, 6:9] = cached[2] + np.uint64(grad_base)
     return tab
 
 
@@ -280,6 +310,7 @@ class PlanFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, plan, holder, feats, coords, spatial_shape, batch_size, proj, training, precision, inputs_ready, *params):
         lib = _lib.load()
+        ctx.set_materialize_grads(False)     # published tensors the loss does not touch arrive as None, not as zeros
         dev = feats.device
         oi, of, lf, sizes, offs = plan.finalize()
         feats = feats.contiguous()
@@ -328,9 +359,14 @@ class PlanFn(torch.autograd.Function):
         gs = [None if g is None else g.contiguous() for g in grads]
         slots = np.array([slot for _, slot, _ in plan.published], dtype=np.int32)
         ext = np.array([0 if g is None else g.data_ptr() for g in gs], dtype=np.uint64)
+        ws = _wgrad_stream(dev)
+        if ws is not None:
+            flat.record_stream(ws)
+            run.arena.record_stream(ws)
         rc = lib.vc_exec_backward(oi.ctypes.data, of.ctypes.data, oi.shape[0], tab.ctypes.data, lf.ctypes.data, len(plan.layers),
                                   slots.ctypes.data, ext.ctypes.data, len(gs), run.arena.data_ptr(), run.arena.numel(),
-                                  ops.tc_error_flag(dev).data_ptr(), run.state.ctypes.data, ops._stream())
+                                  ops.tc_error_flag(dev).data_ptr(), run.state.ctypes.data, ops._stream(),
+                                  ws.cuda_stream if ws is not None else None)
         key = (id(plan), dev.index)
         if rc == VC_ERR_WORKSPACE:
             _ARENA_BYTES[key] = 2 * run.arena.numel()

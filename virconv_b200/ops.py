@@ -75,7 +75,9 @@ _SIDE = {}
 
 class _Side:
     def __init__(self, device):
-        self.stream = torch.cuda.Stream(device=device)
+        # high priority: the side stream carries the small index kernels the HOST waits on (row counts of the strided
+        # convs); they must not queue behind the wide feature kernels of the main stream
+        self.stream = torch.cuda.Stream(device=device, priority=-1)
         self.join_queued = False
 
 
