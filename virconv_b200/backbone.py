@@ -320,7 +320,60 @@ class VirConv8x(nn.Module):
         if self.return_num_features_as_dict:
             self.num_point_features = {'x_conv%d' % (i + 1): f[i] for i in range(4)}
 
+    # -- native plans (csrc/executor.cu) -----------------------------------------------------------------------
+    def _plan_lidar(self):
+        """LiDAR stream (:248-291): the submanifold convs of a stage share one rulebook ('subm1'..'subm4')."""
+        if getattr(self, '_plan_lidar_cache', None) is None:
+            plan = executor.Plan(self.conv_input[0].in_channels)
+            c0 = self.conv_input[0]
+            rb = plan.subm_rb(0, 3, c0.kernel_size, c0.dilation, unique=True, keys=[c0.indice_key])
+            f = plan.cbr(0, rb, c0, self.conv_input[1])
+            f = plan.cbr(f, rb, self.conv1[0][0], self.conv1[0][1])
+            iset = 0
+            plan.publish('x_conv1', f, iset)
+            for name, stage in (('x_conv2', self.conv2), ('x_conv3', self.conv3), ('x_conv4', self.conv4)):
+                down = stage[0][0]
+                iset, rbd = plan.conv_rb(iset, 3, down.kernel_size, down.stride, down.padding, down.dilation, keys=[down.indice_key])
+                c1 = stage[1][0]
+                rb = plan.subm_rb(iset, 3, c1.kernel_size, c1.dilation, unique=True, keys=[c1.indice_key])
+                f = plan.cbr(f, rbd, down, stage[0][1])
+                f = plan.cbr(f, rb, c1, stage[1][1])
+                f = plan.cbr(f, rb, stage[2][0], stage[2][1])
+                plan.publish(name, f, iset)
+            co = self.conv_out[0]
+            iset, rbo = plan.conv_rb(iset, 3, co.kernel_size, co.stride, co.padding, co.dilation, keys=[co.indice_key])
+            plan.publish('out', plan.cbr(f, rbo, co, self.conv_out[1]), iset)
+            self._plan_lidar_cache = plan
+        return self._plan_lidar_cache
+
+    def _plan_mm(self):
+        if getattr(self, '_plan_mm_cache', None) is None:
+            plan = executor.Plan(self.vir_conv1.d3_conv1[0].in_channels)
+            f, iset = 0, 0
+            for i, (blk, s) in enumerate(zip((self.vir_conv1, self.vir_conv2, self.vir_conv3, self.vir_conv4), (1, 2, 4, 8))):
+                f, iset = plan_nrconv(plan, blk, f, iset, s)
+                plan.publish('x_conv%d' % (i + 1), f, iset)
+            self._plan_mm_cache = plan
+        return self._plan_mm_cache
+
+    @staticmethod
+    def _plan_usable(plan, feats):
+        if not executor.ENABLED or not feats.is_cuda or feats.shape[0] == 0 or not plan.eligible():
+            return False
+        mode = plan.layers[0][1].training
+        return all(bn.training == mode for _, bn in plan.layers)
+
+    def _run(self, plan, feats, coords, shape, batch_size, proj, names):
+        ci = spconv._as_i32(coords)
+        run, res = executor.run_plan(plan, feats, ci, shape, batch_size, proj, plan.layers[0][1].training,
+                                     plan.layers[0][0].precision)
+        idict = executor.LazyIndiceDict(run, ci, shape)
+        return tuple(_published_tensor(res, k, batch_size, idict) for k in names)
+
     def _lidar_stream(self, feats, coords, shape, batch_size):
+        plan = self._plan_lidar()
+        if self._plan_usable(plan, feats):
+            return self._run(plan, feats, coords, shape, batch_size, None, ('x_conv1', 'x_conv2', 'x_conv3', 'x_conv4', 'out'))
         x = spconv.SparseConvTensor(feats, coords.int(), shape, batch_size)
         x1 = self.conv1(self.conv_input(x))
         x2 = self.conv2(x1)
@@ -373,6 +426,17 @@ class VirConv8x(nn.Module):
                 trans = batch_dict['aug_param'] if 'aug_param' in batch_dict else None
                 if 'transform_param' in batch_dict:
                     trans = batch_dict['transform_param'][:, i, :]
+                discarding = self.training and self.discard_mode == 'paper' and self.layer_discard_rate != 0
+                if not discarding and self._plan_usable(self._plan_mm(), feats):
+                    side = ops.side(feats.device).stream if executor.TWO_STREAMS else None
+                    proj = ops.projection_params(calib, trans, batch_size, feats.device, side)
+                    x1, x2, x3, x4 = self._run(self._plan_mm(), feats, coords, self.sparse_shape, batch_size, proj,
+                                               ('x_conv1', 'x_conv2', 'x_conv3', 'x_conv4'))
+                    batch_dict.update({
+                        'encoded_spconv_tensor_stride_mm' + s: 8,
+                        'multi_scale_3d_features_mm' + s: {'x_conv1': x1, 'x_conv2': x2, 'x_conv3': x3, 'x_conv4': x4},
+                        'multi_scale_3d_strides' + s: dict(strides)})
+                    continue
                 proj = ops.projection_params(calib, trans, batch_size, feats.device)
                 x = spconv.SparseConvTensor(feats, coords.int(), self.sparse_shape, batch_size)
                 x = self._maybe_discard(x, batch_dict, 0)              # VirConv8x also discards the input voxels (:489-490)

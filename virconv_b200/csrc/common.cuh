@@ -96,6 +96,12 @@ __device__ __forceinline__ void stage_nbr_tile(const int32_t* __restrict__ nbr, 
     }
 }
 
+// ---- shared between rulebook.cu and executor.cu ----
+int conv_rulebook_fill_phases(const int32_t* indices, int n, int ndim, int batch_size, const int32_t* spatial_shape,
+                              const int32_t* ksize, const int32_t* stride, const int32_t* padding, const int32_t* dilation,
+                              int n_out, int32_t* out_indices, int32_t* nbr_fwd, int32_t* nbr_bwd, int32_t* pair_num,
+                              void* ws, size_t ws_bytes, cudaStream_t stream, int phases);
+
 // ---- shared between conv_tc.cu and executor.cu ----
 struct TcPrepEntry {
     const float* w;   // parameter, spconv layout [C_out, K, C_in]

@@ -413,6 +413,43 @@ extern "C" int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_o
     }
     int last_side_ev = -1;
     int n_syncs = 0;
+    static thread_local void* chain_ws[MAX_OPS];
+    static thread_local size_t chain_wsb[MAX_OPS];
+    static thread_local bool chain_done[MAX_OPS];
+    for (int i = 0; i < n_ops; ++i) chain_done[i] = false;
+    // count + row-count read-back + output indices of strided conv op j (its input index set must exist)
+    auto count_emit = [&](int j) -> int {
+        const int* o = C.op(j);
+        const int s = two ? o[F_STREAM] : 0;
+        cudaStream_t st = C.st[s];
+        ISet& I = S->iset[o[F_A]];
+        ISet& O = S->iset[o[F_B]];
+        RBk& R = S->rb[o[F_C]];
+        VC_CHECK_ARG(I.ndim == o[F_NDIM], "op %d: index set %d has the wrong ndim", j, o[F_A]);
+        VC_TRY(wait_for(C, I.ev, I.prod, s));
+        int32_t oshape[3] = {0, 0, 0};
+        VC_TRY(vc_conv_out_shape(I.ndim, I.shape, o + F_KS, o + F_ST, o + F_PD, o + F_DL, oshape));
+        const size_t wsb = vc_conv_rulebook_ws_bytes(I.ndim, batch_size, oshape);
+        VC_ALLOC(ws, void*, wsb);
+        VC_ALLOC(n_dev, int32_t*, 4);
+        VC_TRY(vc_conv_rulebook_count(I.idx, I.n, I.ndim, batch_size, I.shape, o + F_KS, o + F_ST, o + F_PD, o + F_DL, n_dev, ws, wsb,
+                                      st));
+        VC_CUDA(cudaMemcpyAsync(pinned_host + (n_syncs & 15), n_dev, 4, cudaMemcpyDeviceToHost, st));
+        VC_CUDA(cudaStreamSynchronize(st));        // the one data-dependent size per strided conv
+        const int n_out = pinned_host[n_syncs & 15];
+        ++n_syncs;
+        R.K = rb_K[o[F_C]]; R.n_in = I.n; R.n_out = n_out; R.subm = 0; R.unique = 1;
+        O.n = n_out; O.ndim = I.ndim;
+        for (int d = 0; d < 3; ++d) O.shape[d] = oshape[d];
+        VC_ALLOC(oidx, int32_t*, (size_t)(n_out > 0 ? n_out : 1) * (1 + I.ndim) * 4);
+        O.idx = oidx;
+        VC_TRY(conv_rulebook_fill_phases(I.idx, I.n, I.ndim, batch_size, I.shape, o + F_KS, o + F_ST, o + F_PD, o + F_DL, n_out, O.idx,
+                                         nullptr, nullptr, nullptr, ws, wsb, st, 1));
+        O.prod = s;
+        O.ev = s == 1 ? (last_side_ev = record_on(C, 1)) : -1;
+        chain_ws[j] = ws; chain_wsb[j] = wsb; chain_done[j] = true;
+        return VC_OK;
+    };
 
     for (int i = 0; i < n_ops; ++i) {
         const int* o = C.op(i);
@@ -440,37 +477,31 @@ extern "C" int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_o
                 break;
             }
             case OP_CONV_RB: {
+                // First strided conv reached: run the count -> (host reads the row count) -> emit-indices chain of EVERY
+                // strided conv of the plan now, back to back.  Each link only needs the previous link's output indices,
+                // and it is the only part of the forward the host has to wait for; the neighbour tables, submanifold
+                // rulebooks and projections queue up behind it without further synchronisation.
+                if (!chain_done[i]) {
+                    for (int j = i; j < n_ops; ++j)
+                        if (C.op(j)[F_KIND] == OP_CONV_RB && S->iset[C.op(j)[F_A]].idx) VC_TRY(count_emit(j));
+                }
+                VC_CHECK_ARG(chain_done[i], "op %d: index set %d not built", i, o[F_A]);
                 ISet& I = S->iset[o[F_A]];
                 ISet& O = S->iset[o[F_B]];
                 RBk& R = S->rb[o[F_C]];
-                VC_CHECK_ARG(I.idx && I.ndim == o[F_NDIM], "op %d: index set %d not built / wrong ndim", i, o[F_A]);
                 VC_TRY(wait_for(C, I.ev, I.prod, s));
-                int32_t oshape[3] = {0, 0, 0};
-                VC_TRY(vc_conv_out_shape(I.ndim, I.shape, o + F_KS, o + F_ST, o + F_PD, o + F_DL, oshape));
-                const size_t wsb = vc_conv_rulebook_ws_bytes(I.ndim, batch_size, oshape);
-                VC_ALLOC(ws, void*, wsb);
-                VC_ALLOC(n_dev, int32_t*, 4);
-                VC_TRY(vc_conv_rulebook_count(I.idx, I.n, I.ndim, batch_size, I.shape, o + F_KS, o + F_ST, o + F_PD, o + F_DL, n_dev,
-                                              ws, wsb, st));
-                VC_CUDA(cudaMemcpyAsync(pinned_host + (n_syncs & 15), n_dev, 4, cudaMemcpyDeviceToHost, st));
-                VC_CUDA(cudaStreamSynchronize(st));        // the one data-dependent size per strided conv
-                const int n_out = pinned_host[n_syncs & 15];
-                ++n_syncs;
-                R.K = rb_K[o[F_C]]; R.n_in = I.n; R.n_out = n_out; R.subm = 0; R.unique = 1;
-                O.n = n_out; O.ndim = I.ndim;
-                for (int d = 0; d < 3; ++d) O.shape[d] = oshape[d];
-                VC_ALLOC(oidx, int32_t*, (size_t)(n_out > 0 ? n_out : 1) * (1 + I.ndim) * 4);
-                VC_ALLOC(nbr, int32_t*, (size_t)R.K * (n_out > 0 ? n_out : 1) * 4);
+                VC_TRY(wait_for(C, O.ev, O.prod, s));
+                VC_ALLOC(nbr, int32_t*, (size_t)R.K * (R.n_out > 0 ? R.n_out : 1) * 4);
                 VC_ALLOC(nbr_bwd, int32_t*, (size_t)R.K * I.n * 4);
-                O.idx = oidx; R.nbr = nbr; R.nbr_bwd = nbr_bwd;
+                R.nbr = nbr; R.nbr_bwd = nbr_bwd;
                 if (want_pair_num) {
                     VC_ALLOC(pn, int32_t*, (size_t)R.K * 4);
                     R.pair_num = pn;
                 }
-                VC_TRY(vc_conv_rulebook_fill(I.idx, I.n, I.ndim, batch_size, I.shape, o + F_KS, o + F_ST, o + F_PD, o + F_DL, n_out,
-                                             O.idx, R.nbr, R.nbr_bwd, R.pair_num, ws, wsb, st));
-                R.prod = O.prod = s;
-                R.ev = O.ev = s == 1 ? (last_side_ev = record_on(C, 1)) : -1;
+                VC_TRY(conv_rulebook_fill_phases(I.idx, I.n, I.ndim, batch_size, I.shape, o + F_KS, o + F_ST, o + F_PD, o + F_DL,
+                                                 R.n_out, O.idx, R.nbr, R.nbr_bwd, R.pair_num, chain_ws[i], chain_wsb[i], st, 2));
+                R.prod = s;
+                R.ev = s == 1 ? (last_side_ev = record_on(C, 1)) : -1;
                 break;
             }
             case OP_INDEX2UV: {

@@ -438,7 +438,17 @@ extern "C" int vc_conv_rulebook_fill(const int32_t* indices, int n, int ndim, in
                                      const int32_t* padding, const int32_t* dilation, int n_out, int32_t* out_indices,
                                      int32_t* nbr_fwd, int32_t* nbr_bwd, int32_t* pair_num, void* ws, size_t ws_bytes,
                                      vc_stream_t stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
+    return vc::conv_rulebook_fill_phases(indices, n, ndim, batch_size, spatial_shape, ksize, stride, padding, dilation, n_out,
+                                         out_indices, nbr_fwd, nbr_bwd, pair_num, ws, ws_bytes, (cudaStream_t)stream_, 3);
+}
+
+// phases: bit 0 = emit the output indices, bit 1 = build the neighbour tables.  The plan executor runs the emit phase of
+// every strided conv first (the next conv's row count depends on it and the host waits for that), the tables later.
+int vc::conv_rulebook_fill_phases(const int32_t* indices, int n, int ndim, int batch_size, const int32_t* spatial_shape,
+                                  const int32_t* ksize, const int32_t* stride, const int32_t* padding,
+                                  const int32_t* dilation, int n_out, int32_t* out_indices, int32_t* nbr_fwd,
+                                  int32_t* nbr_bwd, int32_t* pair_num, void* ws, size_t ws_bytes, cudaStream_t stream,
+                                  int phases) {
     Geom g;
     int rc = make_geom(g, ndim, spatial_shape, ksize, stride, padding, dilation);
     if (rc) return rc;
@@ -447,13 +457,17 @@ extern "C" int vc_conv_rulebook_fill(const int32_t* indices, int n, int ndim, in
         set_error("conv rulebook workspace %zu < %zu", ws_bytes, w.bytes);
         return VC_ERR_WORKSPACE;
     }
-    if (pair_num) VC_CUDA(cudaMemsetAsync(pair_num, 0, sizeof(int32_t) * g.K, stream));
-    if (n_out > 0) {
-        VC_CHECK_ARG(out_indices && nbr_fwd, "null output pointer");
-        VC_CUDA(cudaMemsetAsync(nbr_fwd, 0xFF, (size_t)g.K * n_out * 4, stream));
+    if ((phases & 1) && n_out > 0) {
+        VC_CHECK_ARG(out_indices, "null output pointer");
         conv_emit_indices_kernel<<<cdiv(w.n_words, 256), 256, 0, stream>>>(w.bitmap, w.word_rank, w.block_sum,
                                                                             w.n_words, g, out_indices);
         VC_LAUNCH_CHECK();
+    }
+    if (!(phases & 2)) return VC_OK;
+    if (pair_num) VC_CUDA(cudaMemsetAsync(pair_num, 0, sizeof(int32_t) * g.K, stream));
+    if (n_out > 0) {
+        VC_CHECK_ARG(nbr_fwd, "null output pointer");
+        VC_CUDA(cudaMemsetAsync(nbr_fwd, 0xFF, (size_t)g.K * n_out * 4, stream));
     }
     if (n > 0) {
         VC_CHECK_ARG(nbr_bwd, "null nbr_bwd");

@@ -392,7 +392,7 @@ def run_plan(plan, feats, coords_i32, spatial_shape, batch_size, proj, training,
     res = {}
     for (name, slot, iset), f in zip(plan.published, outs):
         idx, shape = (coords_i32, list(spatial_shape)) if iset == 0 else run.indices(iset)
-        res[name] = (f, idx, shape, run.feature_bf16(slot))
+        res[name] = (f, idx, shape, (lambda slot=slot: run.feature_bf16(slot)))    # shadow resolved on first use
     return run, res
 
 

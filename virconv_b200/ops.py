@@ -532,8 +532,15 @@ def projection_params(calib, trans_param, batch_size, device, stream=None):
         tp = tp.astype(np.float32)
     out = np.zeros((batch_size, 28), dtype=np.float32)
     for b in range(batch_size):
-        out[b, 0:12] = compose_lidar_to_rect(calib[b].V2C, calib[b].R0).reshape(-1)
-        out[b, 12:20] = np.asarray(calib[b].P2, dtype=np.float32).T[:, :2].reshape(-1)
+        cached = getattr(calib[b], '_vc_proj20', None)      # a Calibration object is immutable after construction
+        if cached is None:
+            cached = np.concatenate([compose_lidar_to_rect(calib[b].V2C, calib[b].R0).reshape(-1),
+                                     np.asarray(calib[b].P2, dtype=np.float32).T[:, :2].reshape(-1)])
+            try:
+                calib[b]._vc_proj20 = cached
+            except AttributeError:
+                pass
+        out[b, 0:20] = cached
         if tp is not None:
             rot, flip, scale = tp[b]
             out[b, 20] = 1.0

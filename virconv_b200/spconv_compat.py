@@ -37,7 +37,18 @@ class SparseConvTensor:
         self.grid = grid
         self.voxel_num = voxel_num
         self.benchmark = benchmark
-        self.features_bf16 = None            # optional bf16 shadow of `features` (tensor-core operand), see ops.py
+        self._features_bf16 = None           # optional bf16 shadow of `features` (tensor-core operand), see ops.py
+
+    @property
+    def features_bf16(self):
+        v = self._features_bf16
+        if callable(v):                      # plan-executor tensors resolve their shadow on first use
+            v = self._features_bf16 = v()
+        return v
+
+    @features_bf16.setter
+    def features_bf16(self, val):
+        self._features_bf16 = val
 
     @property
     def features(self):
