@@ -256,10 +256,10 @@ scatter_gemm_kernel(const float* __restrict__ in, const float* __restrict__ wt, 
             int dst = nbr_s[k * TM + row0 + r];
             if (dst >= 0) {
                 float* p = out + (size_t)dst * CO + tx * 4;
-                atomicAdd(p + 0, acc[r][0]);
-                atomicAdd(p + 1, acc[r][1]);
-                atomicAdd(p + 2, acc[r][2]);
-                atomicAdd(p + 3, acc[r][3]);
+                // one 16-byte vector reduction (sm_90+) instead of four scalar atomics: a quarter of the L2 atomic operations
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(acc[r][0]), "f"(acc[r][1]),
+                             "f"(acc[r][2]), "f"(acc[r][3])
+                             : "memory");
             }
         }
     }
