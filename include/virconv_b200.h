@@ -47,6 +47,9 @@ int vc_version(void);
 const char* vc_last_error(void);
 /* number of kernels this library has launched so far in this process (bench.py's gpu_launches) */
 long long vc_launch_count(void);
+/* Programmatic dependent launch for the kernels of the conv / BN chain (default on): each starts while its predecessor
+ * drains and blocks in `griddepcontrol.wait` before touching dependent data.  0 = plain stream-ordered launches. */
+int vc_set_pdl(int enable);
 
 /* ------------------------------------------------------------------------------------------------
  * Rulebooks.  Replaces spconv `ops.get_indice_pairs`, reached from every conv call site:
@@ -200,6 +203,24 @@ int vc_voxelize_mean(const float* points, int n_points, int c, int batch_size, c
                      const float* voxel_size, int max_points, int max_voxels, int vfe_max_last, float* out_features,
                      int32_t* out_coords, int32_t* out_num, float* out_voxels /*may be NULL*/, int32_t* n_out_dev,
                      void* ws, size_t ws_bytes, vc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * StVD input point discard.  Replaces `DatasetTemplate.partition` + `DatasetTemplate.input_point_discard`
+ * (pcdet/datasets/dataset.py:120-189; applied to the virtual points of every frame at :275-290): bin_num range bins
+ * along x of width max_dis/bin_num (last bin open-ended, x < 0 / NaN in no bin), emitted far -> near, the nearest bins
+ * randomly subsampled.  The random draws stay on the host so that they come from the same numpy generator, in the same
+ * order, as the reference's (virconv_b200/preprocess.py); the device does the order-preserving partition and the gather.
+ *   vc_stvd_partition: points [n, c] fp32 (x in column 0) -> totals_dev[16] = points per bin, and in ws the per-bin point
+ *                      lists (original order inside a bin).
+ *   vc_stvd_gather   : segs host [n_seg][4] = (bin, out_base, count, sel_base): output rows [out_base, out_base+count)
+ *                      are the bin's points with in-bin ranks sel_dev[sel_base + r] (sel_base < 0: rank r itself).
+ * ws >= vc_stvd_ws_bytes(n), the same buffer for both calls.
+ * ---------------------------------------------------------------------------------------------- */
+size_t vc_stvd_ws_bytes(int n_points);
+int vc_stvd_partition(const float* points, int n, int c, int bin_num, double max_dis, int32_t* totals_dev /*[16]*/,
+                      void* ws, size_t ws_bytes, vc_stream_t stream);
+int vc_stvd_gather(const float* points, int n, int c, const int32_t* segs /*host*/, int n_seg, const int32_t* sel_dev,
+                   float* out /*[n_out, c]*/, int n_out, void* ws, size_t ws_bytes, vc_stream_t stream);
 
 /* `generate_voxel2pinds` (pcdet/utils/spconv_utils.py:13-21): dense [B, *spatial_shape] int32 map voxel -> row, -1 where
  * empty (the RoI head's look-up table, ted_head.py:527,625). */

@@ -51,6 +51,64 @@ def import_reference():
     return bb, calib, vfe
 
 
+def import_reference_dataset():
+    """`pcdet/datasets/dataset.py` with its dataloader-side imports (augmentor, spconv voxel generator) stubbed: only the
+    two pure-numpy StVD methods of DatasetTemplate are used."""
+    for stub, names in (('pcdet.datasets.augmentor.data_augmentor', ['DataAugmentor']),
+                        ('pcdet.datasets.processor', []),
+                        ('pcdet.datasets.processor.data_processor', ['DataProcessor']),
+                        ('pcdet.datasets.processor.point_feature_encoder', ['PointFeatureEncoder'])):
+        m = types.ModuleType(stub)
+        for n in names:
+            setattr(m, n, object)
+        sys.modules.setdefault(stub, m)
+    return importlib.import_module('pcdet.datasets.dataset')
+
+
+def stvd_cases():
+    """(name, points [N, 8] float32, bin_num, rate, seed): virtual points of synthetic scenes + adversarial clouds."""
+    from virconv_b200 import scenes
+    cases = []
+    for sid, nv in ((3, 20000), (4, 5000)):
+        pts = scenes.make_points(sid, n_lidar=2048, n_virtual=nv)
+        virt = np.ascontiguousarray(pts[pts[:, -1] == 1]).astype(np.float32)
+        for bn, seed in ((2, 10 + sid), (10, 20 + sid)):
+            cases.append((f'scene{sid}_bins{bn}', virt, bn, 0.8, seed))
+    rng = np.random.default_rng(99)
+    wide = rng.uniform(-10, 90, (4000, 8)).astype(np.float32)          # x < 0 (dropped) and x > 60 (last bin) present
+    wide[::97, 0] = np.nan
+    cases.append(('wide_bins10', wide, 10, 0.8, 31))
+    cases.append(('wide_bins2_rate05', wide, 2, 0.5, 32))
+    cases.append(('wide_bins7', wide, 7, 0.8, 33))                      # 60/7 is not exactly representable
+    near = rng.uniform(0, 6, (1500, 8)).astype(np.float32)              # everything in the nearest bin
+    cases.append(('near_bins10', near, 10, 0.8, 34))
+    far = rng.uniform(55, 70, (1200, 8)).astype(np.float32)             # everything in the farthest bin
+    cases.append(('far_bins10', far, 10, 0.8, 35))
+    cases.append(('tiny_bins2', rng.uniform(0, 60, (7, 8)).astype(np.float32), 2, 0.8, 36))
+    return cases
+
+
+def stvd_golden():
+    from . import stvd as o_stvd
+    ds_mod = import_reference_dataset()
+    ds = ds_mod.DatasetTemplate.__new__(ds_mod.DatasetTemplate)
+    out, report = {}, []
+    for name, pts, bn, rate, seed in stvd_cases():
+        np.random.seed(seed)
+        ref = ds.input_point_discard(pts.copy(), bin_num=bn, rate=rate)
+        np.random.seed(seed)
+        mine = o_stvd.input_point_discard(pts.copy(), bin_num=bn, rate=rate, rng=np.random)
+        same = ref.shape == mine.shape and np.array_equal(ref, mine, equal_nan=True)
+        report.append(f'StVD input discard {name}: N={pts.shape[0]} -> {ref.shape[0]} rows, restated == reference: {same}')
+        assert same, name
+        out[f'{name}:points'] = pts
+        out[f'{name}:out'] = ref
+        out[f'{name}:meta'] = np.array([bn, seed], dtype=np.int64)
+        out[f'{name}:rate'] = np.float64(rate)
+    np.savez_compressed(os.path.join(OUT, 'stvd_input.npz'), **out)
+    return report
+
+
 def main():
     from virconv_b200 import scenes
     from . import index2uv as o_uv
@@ -212,6 +270,9 @@ def main():
             report.append(f'VirConv8x[{mode}]: scenes ({first_scene},{first_scene + 1}) skipped (pixel-cell flip or mismatch: '
                           f'same_idx={same} err={worst:.2e})')
     np.savez_compressed(os.path.join(OUT, 'virconv_t_small.npz'), seed=np.int32(667), **gold8)
+
+    # ---- StVD input point discard (dataset.py:120-189), the reference's own methods under a seeded np.random --------
+    report += stvd_golden()
 
     with open(os.path.join(OUT, 'REPORT.txt'), 'w') as f:
         f.write('\n'.join(report) + '\n')

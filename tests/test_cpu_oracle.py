@@ -181,3 +181,54 @@ def test_oracle_virconv8x_matches_reference_flow_golden(mode):
         assert np.array_equal(t.features.numpy(), g[k])
         n += 1
     assert n == (9 if mode == 'train' else 21)
+
+
+# ---------------------------------------------------------------------------------------- StVD input point discard
+def _stvd_cases():
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'stvd_input.npz'))
+    names = sorted({k.split(':')[0] for k in g.files})
+    return g, names
+
+
+def test_stvd_input_discard_oracle_matches_reference_golden():
+    """tests/golden/stvd_input.npz holds outputs of the reference's OWN `DatasetTemplate.input_point_discard`
+    (dataset.py:168-189) under seeded np.random (oracle/make_golden.py): the restatement must reproduce every row."""
+    from oracle import stvd
+    g, names = _stvd_cases()
+    assert len(names) >= 10
+    for name in names:
+        bn, seed = (int(v) for v in g[f'{name}:meta'])
+        out = stvd.input_point_discard(g[f'{name}:points'].copy(), bin_num=bn, rate=float(g[f'{name}:rate']),
+                                       rng=np.random.RandomState(seed))
+        assert np.array_equal(out, g[f'{name}:out'], equal_nan=True), name
+
+
+def test_stvd_host_plan_of_the_product_matches_oracle():
+    """The product's host-side half (position / per_bin arithmetic + RNG draws from the bin sizes alone) against the
+    oracle's, including the python-slice corner (per_bin < 0) and empty bins."""
+    from oracle import stvd
+    from virconv_b200 import preprocess
+    rng = np.random.default_rng(5)
+    for trial in range(200):
+        bn = int(rng.integers(1, 11))
+        counts = rng.integers(0, 400, bn) * (rng.random(bn) > 0.2)
+        n_all = int(counts.sum() + rng.integers(0, 50))        # points outside every bin still count in the total
+        if n_all == 0:
+            continue
+        rate = float(rng.choice([0.8, 0.5, 0.95, 0.1]))
+        seed = int(rng.integers(0, 1 << 30))
+        far_to_near = [int(counts[bn - 1 - it]) for it in range(bn)]
+        want = stvd.plan(far_to_near, n_all, bn, rate, np.random.RandomState(seed))
+        segs, sel, n_out = preprocess._discard_plan(counts, n_all, bn, rate, np.random.RandomState(seed))
+        assert [s[0] for s in segs] == [b for b, _ in want]
+        total = 0
+        for (b, base, cnt, sbase), (_, wsel) in zip(segs, want):
+            assert base == total
+            if wsel is None:
+                assert sbase < 0 and cnt == int(counts[b])
+            elif len(wsel) == 0:
+                assert cnt == 0
+            else:
+                assert sbase >= 0 and np.array_equal(sel[sbase:sbase + cnt], wsel)
+            total += cnt
+        assert total == n_out

@@ -24,6 +24,7 @@ SIGNATURES = {
     'vc_version': (_I, []),
     'vc_last_error': (c_char_p, []),
     'vc_launch_count': (ctypes.c_longlong, []),
+    'vc_set_pdl': (_I, [_I]),
     'vc_subm_rulebook_ws_bytes': (_Z, [_I]),
     'vc_subm_rulebook': (_I, [_P, _I, _I, _I, _HOST, _HOST, _HOST, _P, _P, _P, _Z, _P]),
     'vc_conv_rulebook_ws_bytes': (_Z, [_I, _I, _HOST]),
@@ -53,6 +54,9 @@ SIGNATURES = {
     'vc_voxel2pinds': (_I, [_P, _I, _I, _I, _HOST, _P, _P]),
     'vc_cat2_f32': (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     'vc_gather_rows': (_I, [_P, _P, _P, _I, _I, _P]),
+    'vc_stvd_ws_bytes': (_Z, [_I]),
+    'vc_stvd_partition': (_I, [_P, _I, _I, _I, ctypes.c_double, _P, _P, _Z, _P]),
+    'vc_stvd_gather': (_I, [_P, _I, _I, _HOST, _I, _P, _P, _I, _P, _Z, _P]),
     'vc_exec_state_bytes': (_Z, []),
     'vc_exec_forward': (_I, [_P, _P, _I, _P, _P, _I, _P, _I, _P, _I, _HOST, _I, _P, _I, _I, _I, _P, _Z, _P, _P, _P, _Z, _P, _P, _I]),
     'vc_exec_backward': (_I, [_P, _P, _I, _P, _P, _I, _P, _P, _I, _P, _Z, _P, _P, _P, _P]),
@@ -83,6 +87,9 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
+    # programmatic dependent launch of the conv / BN chain: implemented and parity-tested, but measured no faster on
+    # B200 (3.18-3.24 ms/step with, 3.24 without; e2e 0.1 ms worse) -> off unless asked for
+    lib.vc_set_pdl(1 if os.environ.get('VIRCONV_PDL', '0') == '1' else 0)
     _lib = lib
     return lib
 

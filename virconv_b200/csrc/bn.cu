@@ -30,6 +30,8 @@ __global__ void __launch_bounds__(256) bn_apply_relu_kernel(
     const float* __restrict__ beta, float* running_mean, float* running_var, long long* num_batches_tracked,
     float momentum, float eps, int training, float4* __restrict__ y, uint2* __restrict__ y_bf16,
     float* __restrict__ stats_out, int relu) {
+    pdl_wait();                 // the conv's output and channel sums
+    pdl_launch_dependents();
     const int c4 = c / 4;
     const size_t n4 = (size_t)n_rows * c4;
     const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -94,6 +96,8 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float4* __rest
                                                             const float* __restrict__ stats, int n, int c,
                                                             double* __restrict__ bsums) {
     extern __shared__ float shf[];  // [rowlanes][2][c]
+    pdl_wait();
+    pdl_launch_dependents();
     const int c4 = c / 4;
     const int cg = threadIdx.x % c4, rl = threadIdx.x / c4, rowlanes = blockDim.x / c4;
     const float4 m = reinterpret_cast<const float4*>(stats + 2 * c)[cg];
@@ -129,6 +133,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float4* __restr
                                                            const double* __restrict__ bsums, int n_rows, int c, int training,
                                                            float4* __restrict__ dx, uint2* __restrict__ dx_bf16,
                                                            float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    pdl_wait();                 // bsums from the reduce kernel
+    pdl_launch_dependents();
     const int c4 = c / 4;
     const size_t n4 = (size_t)n_rows * c4;
     const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -196,10 +202,9 @@ extern "C" int vc_bn_apply_relu_f32(const float* x, const double* sums, int n_ro
     VC_CHECK_ARG(!training || sums, "training-mode BN needs the conv's channel sums");
     VC_CHECK_ARG(!training || n_rows > 0, "training-mode BN over zero rows");
     VC_CHECK_ARG(n_rows == 0 || (x && y), "null pointer");
-    bn_apply_relu_kernel<<<ew_blocks((size_t)n_rows * c / 4), 256, 0, stream>>>(
-        (const float4*)x, sums, n_rows, c, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps,
-        training, (float4*)y, (uint2*)y_bf16, stats_out, relu);
-    VC_LAUNCH_CHECK();
+    VC_LAUNCH_CHAIN(bn_apply_relu_kernel, dim3(ew_blocks((size_t)n_rows * c / 4)), dim3(256), 0, stream, (const float4*)x, sums,
+                    n_rows, c, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, training, (float4*)y,
+                    (uint2*)y_bf16, stats_out, relu);
     return VC_OK;
 }
 
@@ -216,13 +221,11 @@ extern "C" int vc_bn_relu_bwd_f32(const float* dy, const float* x, const float* 
         int blocks = (n + rowlanes - 1) / rowlanes;
         if (blocks > 296) blocks = 296;
         size_t smem = (size_t)rowlanes * 2 * c * sizeof(float);
-        bn_bwd_reduce_kernel<<<blocks, 256, smem, stream>>>((const float4*)dy, (const float4*)x, (const float4*)y, stats, n, c,
-                                                            bsums);
-        VC_LAUNCH_CHECK();
+        VC_LAUNCH_CHAIN(bn_bwd_reduce_kernel, dim3(blocks), dim3(256), smem, stream, (const float4*)dy, (const float4*)x,
+                        (const float4*)y, stats, n, c, bsums);
     }
-    bn_bwd_apply_kernel<<<ew_blocks((size_t)n * c / 4), 256, 0, stream>>>((const float4*)dy, (const float4*)x,
-                                                                          (const float4*)y, gamma, stats, bsums, n, c, training,
-                                                                          (float4*)dx, (uint2*)dx_bf16, dgamma, dbeta);
-    VC_LAUNCH_CHECK();
+    VC_LAUNCH_CHAIN(bn_bwd_apply_kernel, dim3(ew_blocks((size_t)n * c / 4)), dim3(256), 0, stream, (const float4*)dy,
+                    (const float4*)x, (const float4*)y, gamma, stats, bsums, n, c, training, (float4*)dx, (uint2*)dx_bf16, dgamma,
+                    dbeta);
     return VC_OK;
 }

@@ -96,6 +96,38 @@ __device__ __forceinline__ void stage_nbr_tile(const int32_t* __restrict__ nbr, 
     }
 }
 
+// ---- programmatic dependent launch (PDL) for the kernels of the main-stream chain ----
+// Every step is ~160 small dependent kernels on one stream; a plain launch starts only after the previous grid has
+// drained AND been flushed (2-3 us each, 0.4-0.6 ms per step).  Launched with the programmatic-stream-serialisation
+// attribute a kernel may start (block scheduling, prologue) as soon as every CTA of its predecessor has issued
+// `griddepcontrol.launch_dependents`, and blocks in `griddepcontrol.wait` until the predecessor has completed and its
+// writes are visible.  Kernels using this call pdl_wait() before their first global read or write of dependent data;
+// both instructions are no-ops for a normally launched grid.  vc_set_pdl(0) turns the attribute off.
+extern int g_pdl;
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KP, typename... A>
+static inline cudaError_t launch_chain(void (*kern)(KP...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, A... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at{};
+    at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &at;
+    cfg.numAttrs = g_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KP>(args)...);
+}
+
+#define VC_LAUNCH_CHAIN(...)                      \
+    do {                                          \
+        vc::count_launch();                       \
+        VC_CUDA(vc::launch_chain(__VA_ARGS__));   \
+    } while (0)
+
 // ---- shared between rulebook.cu and executor.cu ----
 int conv_rulebook_fill_phases(const int32_t* indices, int n, int ndim, int batch_size, const int32_t* spatial_shape,
                               const int32_t* ksize, const int32_t* stride, const int32_t* padding, const int32_t* dilation,

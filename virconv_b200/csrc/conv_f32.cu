@@ -38,6 +38,8 @@ struct Cfg {
 //             mode 1 (dgrad)    wt[k][co][ci] = w[co][kk][ci], kk = mirror ? K-1-k : k
 __global__ void prep_weights_kernel(const float* __restrict__ w, float* __restrict__ wt, int cin, int cout, int K,
                                     int mode, int mirror) {
+    pdl_wait();
+    pdl_launch_dependents();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int total = K * cin * cout;
     if (i >= total) return;
@@ -136,6 +138,8 @@ gather_gemm_kernel(const float* __restrict__ in, const float* __restrict__ wt, c
     __shared__ unsigned kmask;
     __shared__ float red[NTHREADS / 32][2][CO];
 
+    pdl_wait();
+    pdl_launch_dependents();
     const int base = blockIdx.x * TM;
     const int nk = stage_nbr(nbr, n_out, K, base, nbr_s, klist, &kmask);
 
@@ -221,6 +225,8 @@ scatter_gemm_kernel(const float* __restrict__ in, const float* __restrict__ wt, 
     __shared__ int klist[MAXK];
     __shared__ unsigned kmask;
 
+    pdl_wait();
+    pdl_launch_dependents();
     const int base = blockIdx.x * TM;
     const int nk = stage_nbr(nbr, n_rows, K, base, nbr_s, klist, &kmask);
     if (nk == 0) return;
@@ -391,8 +397,7 @@ static int launch_gather(const float* in, const float* wt, const int32_t* nbr, f
     size_t smem = Cfg<CI, CO>::smem_gather(K);
     auto kern = gather_gemm_kernel<CI, CO>;
     VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<cdiv(n_out, TM), NTHREADS, smem, stream>>>(in, wt, nbr, out, n_out, K, bn_sums);
-    VC_LAUNCH_CHECK();
+    VC_LAUNCH_CHAIN(kern, dim3(cdiv(n_out, TM)), dim3(NTHREADS), smem, stream, in, wt, nbr, out, n_out, K, bn_sums);
     return VC_OK;
 }
 template <int CI, int CO>
@@ -401,8 +406,7 @@ static int launch_scatter(const float* in, const float* wt, const int32_t* nbr, 
     size_t smem = Cfg<CI, CO>::smem_scatter(K);
     auto kern = scatter_gemm_kernel<CI, CO>;
     VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<cdiv(n_rows, TM), NTHREADS, smem, stream>>>(in, wt, nbr, out, n_rows, K);
-    VC_LAUNCH_CHECK();
+    VC_LAUNCH_CHAIN(kern, dim3(cdiv(n_rows, TM)), dim3(NTHREADS), smem, stream, in, wt, nbr, out, n_rows, K);
     return VC_OK;
 }
 template <int CI, int CO>
@@ -454,8 +458,7 @@ extern "C" size_t vc_conv_ws_bytes(int cin, int cout, int K) { return (size_t)K 
 
 static int prep(const float* w, float* wt, int cin, int cout, int K, int mode, int mirror, cudaStream_t stream) {
     int total = K * cin * cout;
-    prep_weights_kernel<<<cdiv(total, 256), 256, 0, stream>>>(w, wt, cin, cout, K, mode, mirror);
-    VC_LAUNCH_CHECK();
+    VC_LAUNCH_CHAIN(prep_weights_kernel, dim3(cdiv(total, 256)), dim3(256), 0, stream, w, wt, cin, cout, K, mode, mirror);
     return VC_OK;
 }
 

@@ -194,6 +194,9 @@ tc_gather_gemm_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16*
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         kmask = 0u;
     }
+    // on-chip set-up above overlaps the previous kernel's tail (PDL); everything below reads global memory
+    pdl_wait();
+    pdl_launch_dependents();
     // stage the tile's slice of the neighbour table
     stage_nbr_tile<TC_THREADS, 24>(nbr, n_out, 0, K, base, nbr_s);   // all of a thread's loads in one round trip
     tc_fence_before();
@@ -376,8 +379,7 @@ static int launch_tc(const __nv_bfloat16* in, const __nv_bfloat16* wimg, const i
     size_t smem = TcCfg<KC, NR>::smem(K);
     auto kern = tc_gather_gemm_kernel<KC, NR>;
     VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<cdiv(n_out, TCM), TC_THREADS, smem, stream>>>(in, wimg, nbr, out, n_out, K, bn_sums, err);
-    VC_LAUNCH_CHECK();
+    VC_LAUNCH_CHAIN(kern, dim3(cdiv(n_out, TCM)), dim3(TC_THREADS), smem, stream, in, wimg, nbr, out, n_out, K, bn_sums, err);
     return VC_OK;
 }
 

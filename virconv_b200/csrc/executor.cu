@@ -132,6 +132,8 @@ struct Timed {
 };
 
 __global__ void __launch_bounds__(256) add_kernel(const float4* a, const float4* b, float4* c, size_t n4) {   // c may alias a or b
+    pdl_wait();
+    pdl_launch_dependents();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (; i < n4; i += stride) {
@@ -144,6 +146,8 @@ __global__ void __launch_bounds__(256) add_kernel(const float4* a, const float4*
 // the outputs (in-place accumulation) or be NULL
 __global__ void __launch_bounds__(256) cat2_bwd_kernel(const float4* __restrict__ dcat, int n, int ca4, int cb4,
                                                        float4* da, const float4* a_add, float4* db, const float4* b_add) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int c4 = ca4 + cb4;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t total = (size_t)n * c4, stride = (size_t)gridDim.x * blockDim.x;
@@ -171,8 +175,7 @@ int ew_grid(size_t n4) {
 
 int launch_add(const float* a, const float* b, float* c, size_t n, cudaStream_t st) {
     if (n == 0) return VC_OK;
-    add_kernel<<<ew_grid(n / 4), 256, 0, st>>>((const float4*)a, (const float4*)b, (float4*)c, n / 4);
-    VC_LAUNCH_CHECK();
+    VC_LAUNCH_CHAIN(add_kernel, dim3(ew_grid(n / 4)), dim3(256), 0, st, (const float4*)a, (const float4*)b, (float4*)c, n / 4);
     return VC_OK;
 }
 
@@ -659,10 +662,8 @@ extern "C" int vc_exec_backward(const int32_t* ops_i, const float* ops_f, int n_
             if (Bb.grad_state == G_OWN) { db = Bb.grad; b_add = Bb.grad; }
             else { VC_ALLOC(t, float*, (size_t)Bb.rows * Bb.c * 4); db = t; b_add = Bb.grad_state == G_EXT ? Bb.grad : nullptr; }
             if (O.rows > 0) {
-                cat2_bwd_kernel<<<ew_grid((size_t)O.rows * O.c / 4), 256, 0, st>>>((const float4*)O.grad, O.rows, Aa.c / 4, Bb.c / 4,
-                                                                                   (float4*)da, (const float4*)a_add, (float4*)db,
-                                                                                   (const float4*)b_add);
-                VC_LAUNCH_CHECK();
+                VC_LAUNCH_CHAIN(cat2_bwd_kernel, dim3(ew_grid((size_t)O.rows * O.c / 4)), dim3(256), 0, st, (const float4*)O.grad,
+                                O.rows, Aa.c / 4, Bb.c / 4, (float4*)da, (const float4*)a_add, (float4*)db, (const float4*)b_add);
             }
             Aa.grad = da; Aa.grad_state = G_OWN;
             Bb.grad = db; Bb.grad_state = G_OWN;
