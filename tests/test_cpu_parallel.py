@@ -19,7 +19,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, flat_grads=False):
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
@@ -28,19 +28,29 @@ def _worker(rank, world, port, q):
     torch.manual_seed(100 + rank)                           # different data per rank (different scenes)
     x = torch.randn(32, 8)
     model(x).square().mean().backward()
+    if flat_grads:
+        # what the plan executor hands autograd: every .grad is a slice of ONE flat buffer -> reduced in place
+        params = list(model.parameters())
+        buf = torch.cat([p.grad.reshape(-1) for p in params])
+        for p, v in zip(params, buf.split([p.numel() for p in params])):
+            p.grad = v.view_as(p)
+        assert parallel._as_one_buffer([p.grad for p in params]) is not None
     local = [p.grad.clone() for p in model.parameters()]
     nbytes = parallel.allreduce_gradients(list(model.parameters()), average=True)
+    if flat_grads:
+        assert all(p.grad.untyped_storage().data_ptr() == buf.untyped_storage().data_ptr() for p in params)
     q.put((rank, [g.numpy() for g in local], [p.grad.clone().numpy() for p in model.parameters()], nbytes))
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_gradient_allreduce_two_ranks_gloo():
+@pytest.mark.parametrize('flat_grads', [False, True])
+def test_gradient_allreduce_two_ranks_gloo(flat_grads):
     world = 2
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, flat_grads)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])

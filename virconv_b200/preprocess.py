@@ -96,7 +96,9 @@ def split_and_discard(points, training, input_discard_rate=0.8, later_fusion=Fal
     if later_fusion:
         return {'points': lidar, 'points_mm': kept}
     fused = torch.cat([lidar, kept])
-    fused[:, 3] /= 10
+    # IEEE division like numpy's `points[:, 3] /= 10` (:294); torch's tensor / python-scalar on CUDA multiplies by the
+    # rounded reciprocal instead, which is 1 ulp off for some values
+    fused[:, 3] = torch.div(fused[:, 3], torch.full((), 10.0, dtype=torch.float32, device=fused.device))
     return {'points': fused}
 
 
