@@ -242,6 +242,29 @@ int vc_cat2_f32(const float* a, const float* b, float* out, void* out_bf16 /*may
 int vc_gather_rows(const void* in, const int32_t* rows, void* out, int n_rows, int row_bytes, vc_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Voxel-RoI pooling primitives: the stacked pointnet2 ops the RoI head runs on x_conv3 / x_conv4 (ted_head.py:496-552).
+ * Same arguments, layouts and results as the reference launchers they replace:
+ *   vc_voxel_query       <- voxel_query_kernel_launcher_stack (pointnet2_stack/src/voxel_query_gpu.cu:92-113) plus the
+ *                           `idx[empty_ball_mask] = 0` of VoxelQuery.forward (voxel_query_utils.py:38-39): idx [M, nsample]
+ *                           = the first nsample rows found scanning the (2r+1)^3 cells around new_coords (b,z,y,x) in
+ *                           z-major order whose centre xyz lies within `radius` of new_xyz, padded with the first hit;
+ *                           empty_mask [M] uint8 = 1 and idx row = 0 where nothing was found.  point_indices: dense
+ *                           [B, R1, R2, R3] voxel -> row map (vc_voxel2pinds).
+ *   vc_group_points      <- group_points_kernel_launcher_stack (group_points_gpu.cu:106-125): out [M, C, nsample] =
+ *                           features[start(batch of m) + idx[m, s], c], idx batch-local.
+ *   vc_group_points_grad <- group_points_grad_kernel_launcher_stack (:47-68): grad_features (zeroed by the caller)
+ *                           += grad_out, float atomics.
+ * ---------------------------------------------------------------------------------------------- */
+int vc_voxel_query(int M, int R1, int R2, int R3, int nsample, float radius, int z_range, int y_range, int x_range,
+                   const float* new_xyz, const float* xyz, const int32_t* new_coords, const int32_t* point_indices,
+                   int32_t* idx, unsigned char* empty_mask, vc_stream_t stream);
+int vc_group_points(int B, int M, int C, int nsample, const float* features, const int32_t* features_batch_cnt,
+                    const int32_t* idx, const int32_t* idx_batch_cnt, float* out, vc_stream_t stream);
+int vc_group_points_grad(int B, int M, int C, int N, int nsample, const float* grad_out, const int32_t* idx,
+                         const int32_t* idx_batch_cnt, const int32_t* features_batch_cnt, float* grad_features,
+                         vc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Plan executor: a whole backbone forward / backward in ONE call.  Replaces the Python layer loop of
  * `VirConvL8x.forward` (spconv_backbone.py:609-699), `NRConvBlock.forward` (:207-229) and the two streams of
  * `VirConv8x.forward` (:339-535) together with autograd's reverse walk over them: the host side of ~100 operator
