@@ -30,7 +30,7 @@ def _scene(seed, n_per=(5000, 4200), shape=(21, 400, 352), n_query=(3000, 3000),
         coords.append(np.stack([np.full_like(z, b), z, y, x], 1))
         cnt.append(n)
     coords = np.concatenate(coords).astype(np.int32)
-    xyz = ((coords[:, [3, 2, 1]].astype(np.float32) + 0.5) * vs + lo).astype(np.float32)
+    xyz = np.ascontiguousarray(((coords[:, [3, 2, 1]].astype(np.float32) + 0.5) * vs + lo).astype(np.float32))
     v2p = -np.ones((len(n_per),) + tuple(shape), dtype=np.int32)
     v2p[coords[:, 0], coords[:, 1], coords[:, 2], coords[:, 3]] = np.arange(len(coords), dtype=np.int32)
     new_xyz, new_coords = [], []
@@ -38,12 +38,12 @@ def _scene(seed, n_per=(5000, 4200), shape=(21, 400, 352), n_query=(3000, 3000),
     for b, (n, m) in enumerate(zip(cnt, n_query)):
         pick = rng.integers(0, n, m) + start
         p = xyz[pick] + rng.normal(0, jitter, (m, 3)).astype(np.float32)
-        c = np.floor((p - lo) / vs).astype(np.int32)[:, [2, 1, 0]]
+        c = np.ascontiguousarray(np.floor((p - lo) / vs).astype(np.int32)[:, [2, 1, 0]])
         new_xyz.append(p)
         new_coords.append(np.concatenate([np.full((m, 1), b, np.int32), c], 1))
         start += n
-    return (xyz, np.array(cnt, np.int32), np.concatenate(new_xyz).astype(np.float32), np.array(n_query, np.int32),
-            np.concatenate(new_coords).astype(np.int32), v2p)
+    return (xyz, np.array(cnt, np.int32), np.ascontiguousarray(np.concatenate(new_xyz).astype(np.float32)),
+            np.array(n_query, np.int32), np.ascontiguousarray(np.concatenate(new_coords).astype(np.int32)), v2p)
 
 
 def _ref():
