@@ -137,6 +137,10 @@ int vc_cast_f32_bf16(const float* in, void* out_bf16, long long n_elements /* mu
 size_t vc_conv_tc_ws_bytes(int cin, int cout, int K);
 int vc_conv_fwd_tc(const void* in_bf16, const float* w, const int32_t* nbr, float* out, int n_out, int cin, int cout,
                    int K, double* bn_sums, void* ws, size_t ws_bytes, int32_t* err_flag, vc_stream_t stream);
+/* din[nbr[k,o], :] += dout[o, :] @ w[:, k, :] on tensor cores, for many-to-one tables (image branch); din zeroed by the
+ * caller; the dout tile is contiguous, the result is scattered with 16-byte vector reductions. */
+int vc_conv_dgrad_scatter_tc(const void* dout_bf16, const float* w, const int32_t* nbr, float* din, int n_out, int cin,
+                             int cout, int K, void* ws, size_t ws_bytes, int32_t* err_flag, vc_stream_t stream);
 int vc_conv_dgrad_tc(const void* dout_bf16, const float* w, const int32_t* nbr_t, float* din, int n_in, int cin,
                      int cout, int K, int mirror, void* ws, size_t ws_bytes, int32_t* err_flag, vc_stream_t stream);
 /* dw[co,k,ci] = sum_o in[nbr[k,o],ci] * dout[o,co] on tensor cores: both operands bf16 (MN-major UMMA), 128/cin

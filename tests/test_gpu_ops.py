@@ -375,7 +375,7 @@ def test_tc_strided_conv_fwd_dgrad(lib_built, cin, cout, geo):
 
 
 def test_tc_subm2d_duplicates_and_tails(lib_built):
-    """image-branch table (forward on tensor cores, dgrad falls back to the fp32 scatter kernel) + ragged tiles"""
+    """image-branch table (forward and the scatter-form dgrad on tensor cores) + ragged tiles"""
     from virconv_b200 import ops
     for n_req, cch in ((1, 16), (127, 32), (129, 32), (5000, 32)):
         rng = np.random.default_rng(n_req)
@@ -394,10 +394,12 @@ def test_tc_subm2d_duplicates_and_tails(lib_built):
         nbr = orb.subm_rulebook(co, shape, 3)
         ro, _, _ = _oracle_conv(_bf(feats), _bf(weight), nbr, n, True, dout)
         assert rel_err(out.detach().cpu(), ro) < TOL
-        _, rdf, _ = _oracle_conv(feats, weight, nbr, n, True, dout)
+        _, rdf, _ = _oracle_conv(feats, _bf(weight), nbr, n, True, _bf(dout))       # scatter dgrad: bf16 operands
         assert rel_err(f.grad.cpu(), rdf) < TOL
         _, _, rdw = _oracle_conv(_bf(feats), weight, nbr, n, True, _bf(dout))
         assert rel_err(w.grad.cpu(), rdw) < TOL
+        _, rdf32, _ = _oracle_conv(feats, weight, nbr, n, True, dout)
+        assert rel_err(f.grad.cpu(), rdf32) < 2e-2
 
 
 def test_tc_backbone_bf16_vs_fp32_oracle(lib_built):

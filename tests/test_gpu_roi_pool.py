@@ -88,17 +88,18 @@ def test_voxel_query_and_grouping_vs_compiled_reference(lib_built, max_range, ra
     rgf = torch.empty((M, 32, nsample), device='cuda')
     rgx = torch.empty((M, 3, nsample), device='cuda')
     fc = feats.detach().contiguous()
+    cnt_f, cnt_q = d(xyz_cnt), d(new_cnt)          # kept alive: the raw pointers below must not dangle
     torch.cuda.synchronize()
-    lib.ref_group_points(len(xyz_cnt), M, 32, nsample, _p(fc), _p(d(xyz_cnt)), _p(lidx), _p(d(new_cnt)), _p(rgf))
-    lib.ref_group_points(len(xyz_cnt), M, 3, nsample, _p(t_xyz), _p(d(xyz_cnt)), _p(lidx), _p(d(new_cnt)), _p(rgx))
+    lib.ref_group_points(len(xyz_cnt), M, 32, nsample, _p(fc), _p(cnt_f), _p(lidx), _p(cnt_q), _p(rgf))
+    lib.ref_group_points(len(xyz_cnt), M, 3, nsample, _p(t_xyz), _p(cnt_f), _p(lidx), _p(cnt_q), _p(rgx))
     torch.cuda.synchronize()
     assert torch.equal(em, rempty) and torch.equal(gf, rgf) and torch.equal(gx, rgx)
     go = torch.randn_like(gf)
     gf.backward(go)
     rg = torch.zeros_like(fc)
-    cnt_f, cnt_q = d(xyz_cnt), d(new_cnt)
+    go_c = go.contiguous()
     torch.cuda.synchronize()
-    lib.ref_group_points_grad(len(xyz_cnt), M, 32, xyz.shape[0], nsample, _p(go.contiguous()), _p(lidx), _p(cnt_q), _p(cnt_f), _p(rg))
+    lib.ref_group_points_grad(len(xyz_cnt), M, 32, xyz.shape[0], nsample, _p(go_c), _p(lidx), _p(cnt_q), _p(cnt_f), _p(rg))
     torch.cuda.synchronize()
     assert torch.allclose(feats.grad, rg, rtol=1e-5, atol=1e-5)       # float atomics: order differs
 

@@ -42,6 +42,7 @@ SIGNATURES = {
     'vc_conv_tc_ws_bytes': (_Z, [_I, _I, _I]),
     'vc_conv_fwd_tc': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _Z, _P, _P]),
     'vc_conv_dgrad_tc': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _Z, _P, _P]),
+    'vc_conv_dgrad_scatter_tc': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _Z, _P, _P]),
     'vc_conv_wgrad_tc_ws_bytes': (_Z, [_I, _I, _I, _I]),
     'vc_conv_wgrad_tc': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _Z, _P, _P]),
     'vc_bn_apply_relu_f32': (_I, [_P, _P, _I, _I, _P, _P, _P, _P, _P, _F, _F, _I, _P, _P, _P, _I, _P]),

@@ -397,6 +397,140 @@ static int dispatch_tc(int kc, int nr, const __nv_bfloat16* in, const __nv_bfloa
     return VC_ERR_UNSUPPORTED;
 }
 
+// ------------------------------------------------------------------------------------------------
+// dgrad of a MANY-TO-ONE table (the image branch: several rows share a pixel, so the transposed relation is not a
+// table and the gradient has to be scattered):  din[nbr[k,o], :] += dout[o, :] @ W_k.
+// The fp32 kernel this replaces (conv_f32.cu scatter_gemm_kernel) spent its time in the CUDA-core tile GEMM.  Here the
+// GEMM is free: the dout tile [128 x C_out] is CONTIGUOUS (no gather) and is loaded once, all K weight images arrive
+// through one bulk copy, and for each offset one tcgen05.mma chain writes dout_tile @ W_k into its own TMEM column
+// range (128 / C_in offsets per pass in 128 columns); the epilogue reads a row's 16 values with tcgen05.ld and adds
+// them to the destination row with 16-byte vector reductions (red.global.add.v4.f32).  What is left is the atomic
+// traffic itself: P * C_in * 4 bytes.
+// ------------------------------------------------------------------------------------------------
+template <int KC, int NR>
+__global__ void __launch_bounds__(128)
+tc_scatter_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ wimg,
+                  const int32_t* __restrict__ nbr, float* __restrict__ din, int n_out, int K, int* __restrict__ err) {
+    using C = TcCfg<KC, NR>;
+    constexpr int TM_COLS = 128;
+    constexpr int KPASS = TM_COLS / NR;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* A = smem_raw;                               // [128 x KC] bf16, UMMA K-major core-matrix image
+    unsigned char* B = smem_raw + C::A_BYTES;                  // [K] weight images, as laid out by the prep kernel
+    int* nbr_s = reinterpret_cast<int*>(B + (size_t)K * C::B_BYTES);   // [K][128]
+    __shared__ __align__(8) uint64_t load_bar;
+    __shared__ __align__(8) uint64_t mma_bar;
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int base = blockIdx.x * TCM;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                     "r"((uint32_t)TM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    if (tid == 0) {
+        mbar_init(&load_bar, 1);
+        mbar_init(&mma_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    stage_nbr_tile<128, 8>(nbr, n_out, 0, K, base, nbr_s);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    if (tid == 0) {
+        const uint32_t bar = smem_u32(&load_bar);
+        const uint32_t bytes = (uint32_t)K * C::B_BYTES;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(B)),
+                     "l"(wimg), "r"(bytes), "r"(bar)
+                     : "memory");
+    }
+    // the dout tile: consecutive threads -> consecutive 16-byte chunks of consecutive rows (fully coalesced)
+    for (int q = tid; q < TCM * C::CPR; q += 128) {
+        const int r = q / C::CPR, c = q % C::CPR;
+        const bool v = base + r < n_out;
+        cp_async16(A + ((r >> 3) * C::CPR + c) * 128 + (r & 7) * 16, dout + (size_t)(v ? base + r : 0) * KC + c * 8, v);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    fence_async_smem();
+    __syncthreads();
+    bool ok = mbar_wait(&load_bar, 0u, err);
+    constexpr uint32_t IDESC = umma_idesc(TCM, NR);
+    const int r = warp * 32 + lane;
+    int pass = 0;
+    for (int k0 = 0; k0 < K; k0 += KPASS, ++pass) {
+        const int kn = min(KPASS, K - k0);
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t a0 = smem_u32(A), b0 = smem_u32(B);
+            for (int j = 0; j < kn; ++j) {
+#pragma unroll
+                for (int m = 0; m < KC / 16; ++m) {
+                    const uint64_t ad = umma_desc(a0 + m * 256, 128, C::CPR * 128);
+                    const uint64_t bd = umma_desc(b0 + (uint32_t)(k0 + j) * C::B_BYTES + m * 256, 128, C::CPR * 128);
+                    umma_f16(tmem_base + (uint32_t)(j * NR), ad, bd, IDESC, m > 0 ? 1u : 0u);
+                }
+            }
+            umma_commit(&mma_bar);
+        }
+        ok &= mbar_wait(&mma_bar, (uint32_t)(pass & 1), err);
+        tc_fence_after();
+        for (int j = 0; j < kn; ++j) {
+            const int dst = nbr_s[(k0 + j) * TCM + r];
+            if (!__any_sync(0xffffffffu, dst >= 0)) continue;          // warp-uniform: tcgen05.ld is warp-collective
+#pragma unroll
+            for (int c0 = 0; c0 < NR; c0 += 16) {
+                float v[16];
+                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(j * NR + c0), v);
+                if (dst >= 0) {
+                    float* p = din + (size_t)dst * NR + c0;
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4)
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p + i), "f"(v[i]), "f"(v[i + 1]),
+                                     "f"(v[i + 2]), "f"(v[i + 3])
+                                     : "memory");
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();      // every warp has read its TMEM lanes: the next pass may overwrite the columns
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TM_COLS));
+    }
+    (void)ok;
+}
+
+template <int KC, int NR>
+static int launch_tc_scatter(const __nv_bfloat16* dout, const __nv_bfloat16* wimg, const int32_t* nbr, float* din, int n_out,
+                             int K, int* err, cudaStream_t stream) {
+    size_t smem = (size_t)TcCfg<KC, NR>::A_BYTES + (size_t)K * TcCfg<KC, NR>::B_BYTES + (size_t)K * TCM * 4;
+    auto kern = tc_scatter_kernel<KC, NR>;
+    VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<cdiv(n_out, TCM), 128, smem, stream>>>(dout, wimg, nbr, din, n_out, K, err);
+    VC_LAUNCH_CHECK();
+    return VC_OK;
+}
+
+// kc = C_out (reduction), nr = C_in (gradient channels); wimg = the K dgrad images (prep mode 1, no mirror)
+int tc_scatter_with_image(int kc, int nr, const void* dout_bf16, const void* wimg, const int32_t* nbr, float* din, int n_out,
+                          int K, int* err, cudaStream_t stream) {
+    if (n_out == 0) return VC_OK;
+    const __nv_bfloat16* a = (const __nv_bfloat16*)dout_bf16;
+    const __nv_bfloat16* b = (const __nv_bfloat16*)wimg;
+#define VC_TS_CASE(A, B) \
+    if (kc == A && nr == B) return launch_tc_scatter<A, B>(a, b, nbr, din, n_out, K, err, stream);
+    VC_TS_CASE(16, 16) VC_TS_CASE(16, 32) VC_TS_CASE(16, 64)
+    VC_TS_CASE(32, 16) VC_TS_CASE(32, 32) VC_TS_CASE(32, 64)
+    VC_TS_CASE(64, 16) VC_TS_CASE(64, 32) VC_TS_CASE(64, 64)
+#undef VC_TS_CASE
+    set_error("tensor-core scatter dgrad: unsupported channel pair (%d, %d), need 16/32/64", kc, nr);
+    return VC_ERR_UNSUPPORTED;
+}
+
 // ---- entry points for the plan executor (executor.cu): pre-built weight images, one batched prep launch ----
 int tc_conv_with_image(int kc, int nr, const void* in_bf16, const void* wimg, const int32_t* nbr, float* out, int n_rows,
                        int K, double* bn_sums, int* err, cudaStream_t stream) {
@@ -488,6 +622,29 @@ extern "C" int vc_conv_fwd_tc(const void* in_bf16, const float* w, const int32_t
                               int cout, int K, double* bn_sums, void* ws, size_t ws_bytes, int32_t* err_flag,
                               vc_stream_t stream_) {
     return tc_common(in_bf16, w, nbr, out, n_out, cin, cout, K, 0, 0, bn_sums, ws, ws_bytes, err_flag, (cudaStream_t)stream_);
+}
+
+/* din[nbr[k,o], :] += dout[o, :] @ w[:, k, :] on tensor cores (many-to-one tables; din zeroed by the caller) */
+extern "C" int vc_conv_dgrad_scatter_tc(const void* dout_bf16, const float* w, const int32_t* nbr, float* din, int n_out,
+                                        int cin, int cout, int K, void* ws, size_t ws_bytes, int32_t* err_flag,
+                                        vc_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    VC_CHECK_ARG(n_out >= 0 && K >= 1 && K <= MAXK_TC, "bad n=%d or K=%d", n_out, K);
+    if (!tc_ch_ok(cin) || !tc_ch_ok(cout)) {
+        set_error("tensor-core scatter dgrad: unsupported channels cin=%d cout=%d (need 16/32/64)", cin, cout);
+        return VC_ERR_UNSUPPORTED;
+    }
+    if (n_out == 0) return VC_OK;
+    VC_CHECK_ARG(dout_bf16 && w && nbr && din && ws, "null pointer");
+    if (ws_bytes < vc_conv_tc_ws_bytes(cin, cout, K)) {
+        set_error("tensor-core conv workspace %zu < %zu", ws_bytes, vc_conv_tc_ws_bytes(cin, cout, K));
+        return VC_ERR_WORKSPACE;
+    }
+    __nv_bfloat16* img = (__nv_bfloat16*)ws;
+    int total = K * cin * cout;
+    prep_weights_tc_kernel<<<cdiv(total, 256), 256, 0, stream>>>(w, img, cin, cout, K, 1, 0);
+    VC_LAUNCH_CHECK();
+    return tc_scatter_with_image(cout, cin, dout_bf16, img, nbr, din, n_out, K, err_flag, stream);
 }
 
 extern "C" int vc_conv_dgrad_tc(const void* dout_bf16, const float* w, const int32_t* nbr_t, float* din, int n_in, int cin,

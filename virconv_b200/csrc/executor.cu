@@ -105,7 +105,7 @@ int ev_init() {
 // optional per-kernel timing (bench.py's roofline pass): event pairs around the conv launches
 struct TimeRec {
     cudaEvent_t a, b;
-    int kind, layer;   // kind: 0 conv fwd f32, 1 conv fwd tc, 2 dgrad f32, 3 dgrad tc, 4 dgrad scatter, 5 wgrad f32, 6 wgrad tc
+    int kind, layer;   // kind: 0 conv fwd f32, 1 conv fwd tc, 2 dgrad f32, 3 dgrad tc, 4 dgrad scatter, 5 wgrad f32, 6 wgrad tc, 7 scatter tc
 };
 constexpr int T_MAX = 4096;
 TimeRec g_t[T_MAX];
@@ -390,7 +390,10 @@ extern "C" int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_o
             if (!L.use_tc) continue;
             const int K = rb_K[L.rb];
             const size_t bytes = (size_t)K * L.cin * L.cout * 2;
-            const bool dgrad_tc = training && L.need_dgrad && !(rb_subm[L.rb] && !rb_unique[L.rb]);
+            // dgrad image: mirrored for a submanifold table used as its own transpose, plain for a strided conv's
+            // nbr_bwd table and for the many-to-one image-branch table (tensor-core scatter)
+            const bool many_to_one = rb_subm[L.rb] && !rb_unique[L.rb];
+            const bool dgrad_tc = training && L.need_dgrad;
             for (int mode = 0; mode < (dgrad_tc ? 2 : 1); ++mode) {
                 VC_ALLOC(img, void*, bytes);
                 (mode == 0 ? L.wimg_fwd : L.wimg_dgrad) = img;
@@ -400,7 +403,7 @@ extern "C" int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_o
                 }
                 TcPrepEntry& e = T.e[T.n++];
                 e.w = C.P<const float>(o[F_LAYER], P_W); e.img = img; e.cin = L.cin; e.cout = L.cout; e.K = K; e.mode = mode;
-                e.mirror = mode == 1 && rb_subm[L.rb];
+                e.mirror = mode == 1 && rb_subm[L.rb] && !many_to_one;
             }
         }
         VC_TRY(tc_prep_images(T, C.st[0]));
@@ -713,7 +716,13 @@ extern "C" int vc_exec_backward(const int32_t* ops_i, const float* ops_f, int n_
         if (two) last_w_ev = record_on(C, 1);
         // dgrad
         if (!L.need_dgrad || L.in_slot == 0) continue;
-        if (R.subm && !R.unique) {
+        if (R.subm && !R.unique && L.use_tc && L.wimg_dgrad) {
+            VC_TRY(contribute(C, X, st, [&](float* dst) -> int {
+                VC_CUDA(cudaMemsetAsync(dst, 0, (size_t)X.rows * X.c * 4, st));
+                Timed t(7, li, st);
+                return tc_scatter_with_image(L.cout, L.cin, dxb, L.wimg_dgrad, R.nbr, dst, R.n_out, R.K, C.err, st);
+            }));
+        } else if (R.subm && !R.unique) {
             const size_t wsb = vc_conv_ws_bytes(L.cin, L.cout, R.K);
             VC_ALLOC(ws, void*, wsb);
             VC_TRY(contribute(C, X, st, [&](float* dst) -> int {

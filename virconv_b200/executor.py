@@ -48,7 +48,7 @@ OP_SUBM_RB, OP_CONV_RB, OP_INDEX2UV, OP_CBR, OP_CAT = 1, 2, 3, 4, 5
 VC_ERR_WORKSPACE = -3
 OPI, OPF, PCOLS = 24, 8, 9
 KIND_NAMES = {0: 'conv_fwd', 1: 'conv_fwd_tc', 2: 'conv_dgrad', 3: 'conv_dgrad_tc', 4: 'conv_dgrad_scatter',
-              5: 'conv_wgrad', 6: 'conv_wgrad_tc'}
+              5: 'conv_wgrad', 6: 'conv_wgrad_tc', 7: 'conv_dgrad_scatter_tc'}
 
 
 def _t3(v, nd, fill):
@@ -428,7 +428,7 @@ def alg_bytes_flops(run, kind, layer):
     w = K * cin * cout
     if kind == 'conv_fwd_tc':
         b = n_in * cin * 2 + n_out * cout * 4 + w * 2
-    elif kind == 'conv_dgrad_tc':
+    elif kind in ('conv_dgrad_tc', 'conv_dgrad_scatter_tc'):
         b = n_out * cout * 2 + n_in * cin * 4 + w * 2
     elif kind == 'conv_wgrad_tc':
         b = (n_in * cin + n_out * cout) * 2 + w * 4

@@ -335,6 +335,18 @@ def conv_dgrad(dout, weight, rb: Rulebook, precision='fp32', dout_bf16=None):
                                                   _p(ws), ws.numel(), _p(tc_error_flag(dout.device)), _stream()),
                              'vc_conv_dgrad_tc'))
         return din
+    if rb.subm and not rb.unique_coords and precision == 'bf16' and tc_supported(cin, cout) and rb.n_out > 0:
+        # image branch (many-to-one table): GEMM on the tensor cores, result scattered with vector reductions
+        db = dout_bf16 if dout_bf16 is not None else cast_bf16(dout)
+        din = torch.zeros((rb.n_in, cin), dtype=torch.float32, device=dout.device)
+        ws = _ws(lib.vc_conv_tc_ws_bytes(cin, cout, rb.K), dout.device)
+        _timed('conv_dgrad_scatter_tc',
+               lambda: rb.n_out * cout * 2 + rb.n_in * cin * 4 + rb.K * cin * cout * 2 + rb.n_pairs() * 8,
+               lambda: 2 * rb.n_pairs() * cin * cout,
+               lambda: check(lib.vc_conv_dgrad_scatter_tc(_p(db), _p(weight), _p(rb.nbr), _p(din), rb.n_out, cin, cout, rb.K,
+                                                          _p(ws), ws.numel(), _p(tc_error_flag(dout.device)), _stream()),
+                             'vc_conv_dgrad_scatter_tc'))
+        return din
     ws = _ws(lib.vc_conv_ws_bytes(cin, cout, rb.K), dout.device)
     if rb.subm and not rb.unique_coords:
         din = torch.zeros((rb.n_in, cin), dtype=torch.float32, device=dout.device)
