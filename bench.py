@@ -299,10 +299,10 @@ def run_ours(args):
     # allocator priming (untimed, after the W warm-up steps): the timed loop below never synchronises, so the host runs
     # several steps ahead of the GPU and that many per-step arenas are in flight at once; let the caching allocator create
     # those blocks now rather than with cudaMalloc calls inside the timed region (seen as 5-10 ms/step outliers)
+    sampler = ClockSampler(local) if rank == 0 else None      # samples the priming burst too (same load, more samples)
     timed(args.steps, False)
     barrier()
     dev_allocs0 = torch.cuda.memory_stats(dev).get('num_device_alloc', 0)
-    sampler = ClockSampler(local) if rank == 0 else None
     l0 = lib.vc_launch_count()
     t_wall = time.time()
     ms_list = timed(args.steps, False)

@@ -101,7 +101,8 @@ def test_voxel_query_and_grouping_vs_compiled_reference(lib_built, max_range, ra
     torch.cuda.synchronize()
     lib.ref_group_points_grad(len(xyz_cnt), M, 32, xyz.shape[0], nsample, _p(go_c), _p(lidx), _p(cnt_q), _p(cnt_f), _p(rg))
     torch.cuda.synchronize()
-    assert torch.allclose(feats.grad, rg, rtol=1e-5, atol=1e-5)       # float atomics: order differs
+    # float atomics in a different order; row 0 of every sample collects the gradient of all empty balls (thousands of terms)
+    assert float((feats.grad - rg).abs().max()) <= 1e-5 * float(rg.abs().max())
 
 
 def test_voxel_query_and_grouping_vs_numpy_restatement(lib_built):

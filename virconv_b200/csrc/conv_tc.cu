@@ -37,7 +37,11 @@ static constexpr int TC_NPW = VC_TC_NPW;               // gather-producer warps 
 static constexpr int TC_PRODUCERS = 32 * TC_NPW;       // (warp w < 4 owns TMEM lanes [32w, 32w+32))
 static constexpr int TC_THREADS = TC_PRODUCERS + 32;   // + the last warp: MMA issuer
 #ifndef VC_TC_STAGES
-#define VC_TC_STAGES 4
+// ring depth.  Measured on the bench workload (profiles/microbench_stages_r1.txt, sum over the 15 layers, us):
+//   stages   2: fwd 757 dgrad 837 | 3: 783 / 871 | 4: 789 / 878 | 6: 864 / 974
+// a shallower ring wins: less shared memory per CTA -> more CTAs per SM, and CTA-level parallelism hides the gather
+// latency better than a deeper pipeline inside one CTA
+#define VC_TC_STAGES 2
 #endif
 static constexpr int TC_STAGES = VC_TC_STAGES;
 static constexpr int TC_LAG = TC_STAGES - 1;   // stages a producer thread keeps in flight before it signals `full`

@@ -169,6 +169,31 @@ def _arena_bytes(plan, n0, device):
     return want
 
 
+_RESERVED = {}
+ARENAS_IN_FLIGHT = 8
+
+
+def _alloc_arena(plan, nbytes, dev, stream):
+    """One arena for this step.  The host may run several steps ahead of the GPU (no per-step synchronisation), so that
+    many arenas are alive at once; a fresh multi-GB block costs a cudaMalloc of tens of milliseconds when it lands in
+    the middle of training (seen as 5-10 ms/step outliers).  The first time a (plan, size) is used, ARENAS_IN_FLIGHT
+    blocks are therefore allocated and released at once, which parks them in the caching allocator's pool of `stream`;
+    every later request is served from there."""
+    key = (id(plan), dev.index, stream.cuda_stream if stream is not None else 0)
+    ctx = torch.cuda.stream(stream) if stream is not None else None
+    if ctx is not None:
+        ctx.__enter__()
+    try:
+        if _RESERVED.get(key) != nbytes:
+            hold = [torch.empty(nbytes, dtype=torch.uint8, device=dev) for _ in range(ARENAS_IN_FLIGHT)]
+            del hold
+            _RESERVED[key] = nbytes
+        return torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    finally:
+        if ctx is not None:
+            ctx.__exit__(None, None, None)
+
+
 def _view(arena, ptr, shape, dtype):
     """A tensor over arena memory at device address `ptr` that is NOT an autograd view of the arena (Tensor.set_ on the
     shared storage), so it can be returned from an autograd Function and outlive the arena tensor object."""
@@ -323,11 +348,10 @@ class PlanFn(torch.autograd.Function):
             # The arena belongs to the SIDE stream (its index kernels are the first writers, possibly while main still
             # runs the previous step); main's uses are registered with record_stream, so the caching allocator recycles
             # the block only after both streams are done with it.
-            with torch.cuda.stream(side_obj):
-                arena = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            arena = _alloc_arena(plan, nbytes, dev, side_obj)
             arena.record_stream(torch.cuda.current_stream(dev))
         else:
-            arena = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            arena = _alloc_arena(plan, nbytes, dev, None)
         state = np.zeros(lib.vc_exec_state_bytes(), dtype=np.uint8)
         tab = _layer_ptrs(plan)
         rc = lib.vc_exec_forward(oi.ctypes.data, of.ctypes.data, oi.shape[0], tab.ctypes.data, lf.ctypes.data, len(plan.layers),
