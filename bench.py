@@ -310,7 +310,7 @@ def run_ours(args):
     wall = time.time() - t_wall
     launches = (lib.vc_launch_count() - l0) / max(args.steps, 1)
     dev_allocs = torch.cuda.memory_stats(dev).get('num_device_alloc', 0) - dev_allocs0
-    timed(2, True)
+    timed(max(2, min(args.steps, 10)), True)      # warm-up + allocator priming of the e2e loop
     barrier()
     e2e_list = timed(args.steps, True)
     barrier()
