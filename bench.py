@@ -312,8 +312,12 @@ def run_ours(args):
     dev_allocs = torch.cuda.memory_stats(dev).get('num_device_alloc', 0) - dev_allocs0
     timed(max(2, min(args.steps, 10)), True)      # warm-up + allocator priming of the e2e loop
     barrier()
+    st0 = torch.cuda.memory_stats(dev)
     e2e_list = timed(args.steps, True)
     barrier()
+    st1 = torch.cuda.memory_stats(dev)
+    e2e_allocs = {k: int(st1.get(k, 0) - st0.get(k, 0)) for k in ('num_device_alloc', 'num_device_free', 'num_alloc_retries',
+                                                                   'num_sync_all_streams')}
     clocks = sampler.stop() if sampler else None
 
     tot = torch.tensor([sum(ms_list), sum(e2e_list)], dtype=torch.float64, device=dev)
@@ -414,7 +418,7 @@ def run_ours(args):
                        'precision': ('bf16 operands on tcgen05 for conv forward/dgrad (C>=16), fp32 accumulate, fp32 features, '
                                      'fp32 wgrad/BN' if args.precision == 'bf16' else 'fp32 storage, fp32 accumulate (parity path)')},
             'e2e': {'value': scenes_per_step / (ms_e2e * 1e-3), 'unit': 'scenes/s', 'ms_per_step': ms_e2e,
-                    'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': 4 + 4 * 4},
+                    'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': 4 + 4 * 4, 'allocator_events_in_timed_region': e2e_allocs},
             'gpu_launches': launches, 'wall_s_timed_region': wall, 'cuda_mallocs_in_timed_region': int(dev_allocs), 'clocks': clocks, 'roofline': roof,
             'cpu_baseline': cpu_base}
     print(json.dumps(line), flush=True)

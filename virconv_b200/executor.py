@@ -24,7 +24,7 @@ TWO_STREAMS = os.environ.get('VIRCONV_EXEC_STREAMS', '2') != '1'
 # (measured, profiles/sweep_wgrad_r1.txt: 3.91 ms/step without, 3.29-3.31 with 96-112 CTAs; the shared-memory floor that
 # keeps gather CTAs off the wgrad SMs made no difference at 96 CTAs, so it is off)
 WGRAD_STREAM = os.environ.get('VIRCONV_WGRAD_STREAM', '1') != '0'
-WGRAD_CTAS = int(os.environ.get('VIRCONV_WGRAD_CTAS', '96'))
+WGRAD_CTAS = int(os.environ.get('VIRCONV_WGRAD_CTAS', '128'))     # re-swept after the dgrad chain got faster: sweep_wgrad_r1b.txt
 WGRAD_SMEM_KB = int(os.environ.get('VIRCONV_WGRAD_SMEM_KB', '0'))
 _WSTREAM = {}
 _WCFG = [None]
@@ -171,6 +171,20 @@ def _arena_bytes(plan, n0, device):
 
 _RESERVED = {}
 ARENAS_IN_FLIGHT = 8
+MAX_STEPS_AHEAD = 4          # the host never enqueues more than this many forwards of a plan beyond the GPU
+_INFLIGHT = {}
+
+
+def _throttle(plan, dev):
+    """Bound how far the host runs ahead of the GPU.  Without a per-step synchronisation the only brake is the driver's
+    launch-queue depth, and with the step's work spread over four streams that allowed more steps in flight than
+    ARENAS_IN_FLIGHT — the next arena then cost a multi-GB cudaMalloc (a 30-100 ms stall once every few runs).  Each
+    forward leaves an event at its tail; before a new forward starts, the host waits for the one MAX_STEPS_AHEAD steps
+    back (free when the GPU is the bottleneck: the host would otherwise sit in a full launch queue anyway)."""
+    q = _INFLIGHT.setdefault((id(plan), dev.index), [])
+    while len(q) >= MAX_STEPS_AHEAD:
+        q.pop(0).synchronize()
+    return q
 
 
 def _alloc_arena(plan, nbytes, dev, stream):
@@ -341,6 +355,7 @@ class PlanFn(torch.autograd.Function):
         feats = feats.contiguous()
         n0 = feats.shape[0]
         nbytes = _arena_bytes(plan, n0, dev)
+        inflight = _throttle(plan, dev)
         main = ops._stream()
         side_obj = ops.side(dev).stream if TWO_STREAMS else None
         side = side_obj.cuda_stream if side_obj is not None else None
@@ -363,6 +378,9 @@ class PlanFn(torch.autograd.Function):
         if rc == VC_ERR_WORKSPACE:
             _ARENA_BYTES[(id(plan), dev.index)] = 2 * arena.numel()     # the next call gets twice as much
         check(rc, 'vc_exec_forward')
+        tail = torch.cuda.Event()
+        tail.record()
+        inflight.append(tail)
         run = _Run(plan, arena, state, precision)
         holder.append(run)
         if TIMING:
