@@ -245,6 +245,13 @@ def run_ours(args):
         parallel.allreduce_gradients(params, average=True)     # one flat fp32 bucket over NCCL/NVLink; no-op at N=1
         return float(loss.detach()) if sync_loss else loss
 
+    # e2e upload targets: a ring of device buffers (what a prefetching loader keeps), so the timed loop allocates nothing
+    # (a cudaMalloc landing inside it costs 30-60 ms: profiles/e2e_repeat_r1.txt).  Slot reuse is safe: the executor never
+    # lets the host run more than 4 forwards ahead of the GPU.
+    RING = 8
+    n_max = max(h[0].shape[0] for h in host)
+    ring = [(torch.empty((n_max, host[0][0].shape[1]), dtype=torch.float32, device=dev),
+             torch.empty((n_max, host[0][1].shape[1]), dtype=host[0][1].dtype, device=dev)) for _ in range(RING)]
     copy_stream = torch.cuda.Stream(device=dev)
     main_stream = torch.cuda.current_stream(dev)
     loss_host = torch.zeros(4096, dtype=torch.float32).pin_memory()
@@ -262,15 +269,15 @@ def run_ours(args):
             a.record()
             if from_host:
                 hv, hc, b = host[s % POOL]
+                rf, rc = ring[s % RING]
+                vf, vc = rf[:hv.shape[0]], rc[:hc.shape[0]]
                 with torch.cuda.stream(copy_stream):
-                    vf, vc = hv.to(dev, non_blocking=True), hc.to(dev, non_blocking=True)
+                    vf.copy_(hv, non_blocking=True)
+                    vc.copy_(hc, non_blocking=True)
                     up = torch.cuda.Event()
                     up.record(copy_stream)
                 main_stream.wait_event(up)
                 ops.side(dev).stream.wait_event(up)        # the executor's rulebook stream reads the coordinates
-                for t in (vf, vc):
-                    t.record_stream(main_stream)
-                    t.record_stream(ops.side(dev).stream)
                 loss = step(vf, vc, b, False, resident=True)
                 loss_host[s % loss_host.numel()].copy_(loss.detach(), non_blocking=True)
             else:

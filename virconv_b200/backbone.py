@@ -225,6 +225,7 @@ class VirConvL8x(nn.Module):
                 side = ops.side(feats.device).stream if executor.TWO_STREAMS else None
                 ready = side is not None and bool(batch_dict.get('virconv_inputs_ready', False))
                 if ready and (coords.dtype != torch.int32 or not coords.is_contiguous()):
+                    executor.reserve_blocks('coords_i32', 4 * coords.numel(), feats.device, side)
                     with torch.cuda.stream(side):
                         ci = spconv._as_i32(coords)
                     ci.record_stream(torch.cuda.current_stream(feats.device))   # published as x_conv1's indices

@@ -208,6 +208,29 @@ def _alloc_arena(plan, nbytes, dev, stream):
             ctx.__exit__(None, None, None)
 
 
+_POOLED = {}
+
+
+def reserve_blocks(tag, nbytes, dev, stream=None, count=16):
+    """Park `count` blocks of `nbytes` in the caching allocator's pool of `stream` (once per tag/size).  For the few
+    per-step tensors that are used on more than one stream (`record_stream` defers their reuse, so how many are alive at
+    once depends on timing): without this the pool occasionally grows by a cudaMalloc in the middle of training, which
+    stalls the busy GPU for tens of milliseconds."""
+    key = (tag, dev.index, stream.cuda_stream if stream is not None else 0)
+    if _POOLED.get(key, 0) >= nbytes:
+        return
+    ctx = torch.cuda.stream(stream) if stream is not None else None
+    if ctx is not None:
+        ctx.__enter__()
+    try:
+        hold = [torch.empty(nbytes, dtype=torch.uint8, device=dev) for _ in range(count)]
+        del hold
+    finally:
+        if ctx is not None:
+            ctx.__exit__(None, None, None)
+    _POOLED[key] = nbytes
+
+
 def _view(arena, ptr, shape, dtype):
     """A tensor over arena memory at device address `ptr` that is NOT an autograd view of the arena (Tensor.set_ on the
     shared storage), so it can be returned from an autograd Function and outlive the arena tensor object."""
@@ -396,6 +419,7 @@ class PlanFn(torch.autograd.Function):
         plan = run.plan
         oi, of, lf, sizes, offs = plan.finalize()
         dev = run.arena.device
+        reserve_blocks(('flat_grad', id(plan)), 4 * int(offs[-1]), dev)
         flat = torch.empty(int(offs[-1]), dtype=torch.float32, device=dev)
         tab = _layer_ptrs(plan, flat.data_ptr())
         gs = [None if g is None else g.contiguous() for g in grads]
