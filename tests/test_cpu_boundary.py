@@ -177,3 +177,26 @@ def test_executor_plan_layout_and_host_side_validation(lib_built):
     assert rc == -1 and b'unknown kind' in lib.vc_last_error()
     out = (ctypes.c_longlong * 8)()
     assert lib.vc_exec_query(state.ctypes.data, 0, 0, out) == -1        # not a valid state blob
+
+
+def test_model_with_a_built_plan_can_be_copied_and_pickled():
+    """The executor plan is a cache: deepcopy / torch.save of the owning model drop it (it may hold CUDA events) and the
+    copy rebuilds its own on first use; state_dict keys are unaffected."""
+    import copy
+    import io
+    import torch
+    from virconv_b200.backbone import VirConv8x
+    cfg = dict(RETURN_NUM_FEATURES_AS_DICT=True, OUT_FEATURES=64, LAYER_DISCARD_RATE=0.15, NUM_FILTERS=[16, 32, 64, 64], MM=True)
+    m = VirConv8x(cfg, 8, [1408, 1600, 80])
+    keys = set(m.state_dict())
+    m._plan_lidar().inflight[0] = [object()]
+    m._plan_mm()
+    twin = copy.deepcopy(m)
+    assert twin._plan_lidar_cache is None and len(twin._plan_lidar().layers) == 12 and len(twin._plan_mm().layers) == 19
+    assert twin._plan_lidar().layers[0][0] is twin.conv_input[0]            # bound to the COPY's modules
+    buf = io.BytesIO()
+    torch.save(m, buf)
+    buf.seek(0)
+    again = torch.load(buf, weights_only=False)
+    assert again._plan_mm_cache is None and again._plan_mm().eligible()
+    assert set(m.state_dict()) == keys == set(again.state_dict())

@@ -68,6 +68,17 @@ class Plan:
         self.published = []           # (name, feature slot, index set)
         self.rb_keys = {}             # rulebook id -> (indice_keys, ndim, in index set, out index set)
         self._final = None
+        # per-device run-time state (dies with the plan, i.e. with the model that owns it)
+        self.arena_bytes = {}         # device index -> arena size handed out (monotone)
+        self.reserved = {}            # (device, stream) -> arena size already parked in the allocator pool
+        self.inflight = {}            # device index -> tail events of the forwards still in flight
+
+    # a plan is a cache derived from the modules: copies / pickles of the owning model drop it and rebuild it lazily
+    def __deepcopy__(self, memo):
+        return None
+
+    def __reduce__(self):
+        return (type(None), ())
 
     def _row(self, kind, stream, a=0, b=0, c=0, ndim=0, ks=(0, 0, 0), st=(1, 1, 1), pd=(0, 0, 0), dl=(1, 1, 1), cin=0,
              cout=0, layer=0, x0=0, x1=0, x2=0, f=()):
@@ -147,7 +158,6 @@ class Plan:
 
 
 _PINNED = {}
-_ARENA_BYTES = {}
 
 
 def _pinned(device):
@@ -161,18 +171,15 @@ def _arena_bytes(plan, n0, device):
     """Arena size for a step: generous (rows * 24 KB + 256 MB, rounded up to 256 MB; VirConv-L uses ~16 KB per input
     voxel, forward + backward), grown from what earlier steps of the same plan actually used, never shrunk — so the
     caching allocator hands back the same block every step."""
-    key = (id(plan), device.index)
     want = int(n0) * 24576 + (256 << 20)
-    want = max(want, _ARENA_BYTES.get(key, 0))
+    want = max(want, plan.arena_bytes.get(device.index, 0))
     want = (want + (256 << 20) - 1) // (256 << 20) * (256 << 20)
-    _ARENA_BYTES[key] = want
+    plan.arena_bytes[device.index] = want
     return want
 
 
-_RESERVED = {}
 ARENAS_IN_FLIGHT = 8
 MAX_STEPS_AHEAD = 4          # the host never enqueues more than this many forwards of a plan beyond the GPU
-_INFLIGHT = {}
 
 
 def _throttle(plan, dev):
@@ -181,7 +188,7 @@ def _throttle(plan, dev):
     ARENAS_IN_FLIGHT — the next arena then cost a multi-GB cudaMalloc (a 30-100 ms stall once every few runs).  Each
     forward leaves an event at its tail; before a new forward starts, the host waits for the one MAX_STEPS_AHEAD steps
     back (free when the GPU is the bottleneck: the host would otherwise sit in a full launch queue anyway)."""
-    q = _INFLIGHT.setdefault((id(plan), dev.index), [])
+    q = plan.inflight.setdefault(dev.index, [])
     while len(q) >= MAX_STEPS_AHEAD:
         q.pop(0).synchronize()
     return q
@@ -193,15 +200,15 @@ def _alloc_arena(plan, nbytes, dev, stream):
     the middle of training (seen as 5-10 ms/step outliers).  The first time a (plan, size) is used, ARENAS_IN_FLIGHT
     blocks are therefore allocated and released at once, which parks them in the caching allocator's pool of `stream`;
     every later request is served from there."""
-    key = (id(plan), dev.index, stream.cuda_stream if stream is not None else 0)
+    key = (dev.index, stream.cuda_stream if stream is not None else 0)
     ctx = torch.cuda.stream(stream) if stream is not None else None
     if ctx is not None:
         ctx.__enter__()
     try:
-        if _RESERVED.get(key) != nbytes:
+        if plan.reserved.get(key) != nbytes:
             hold = [torch.empty(nbytes, dtype=torch.uint8, device=dev) for _ in range(ARENAS_IN_FLIGHT)]
             del hold
-            _RESERVED[key] = nbytes
+            plan.reserved[key] = nbytes
         return torch.empty(nbytes, dtype=torch.uint8, device=dev)
     finally:
         if ctx is not None:
@@ -399,7 +406,7 @@ class PlanFn(torch.autograd.Function):
                                  _pinned(dev).data_ptr(), ops.tc_error_flag(dev).data_ptr(), state.ctypes.data, state.size,
                                  main, side, 0 if (inputs_ready and side is not None) else 1)
         if rc == VC_ERR_WORKSPACE:
-            _ARENA_BYTES[(id(plan), dev.index)] = 2 * arena.numel()     # the next call gets twice as much
+            plan.arena_bytes[dev.index] = 2 * arena.numel()     # the next call gets twice as much
         check(rc, 'vc_exec_forward')
         tail = torch.cuda.Event()
         tail.record()
@@ -433,11 +440,11 @@ class PlanFn(torch.autograd.Function):
                                   slots.ctypes.data, ext.ctypes.data, len(gs), run.arena.data_ptr(), run.arena.numel(),
                                   ops.tc_error_flag(dev).data_ptr(), run.state.ctypes.data, ops._stream(),
                                   ws.cuda_stream if ws is not None else None)
-        key = (id(plan), dev.index)
         if rc == VC_ERR_WORKSPACE:
-            _ARENA_BYTES[key] = 2 * run.arena.numel()
+            plan.arena_bytes[dev.index] = 2 * run.arena.numel()
         check(rc, 'vc_exec_backward')
-        _ARENA_BYTES[key] = max(_ARENA_BYTES.get(key, 0), int(1.5 * run.query(0, 0)[0]))   # keep ahead of what steps really use
+        # keep ahead of what steps really use
+        plan.arena_bytes[dev.index] = max(plan.arena_bytes.get(dev.index, 0), int(1.5 * run.query(0, 0)[0]))
         run.flat_grad = flat
         views = flat.split(sizes)
         out = [v.view_as(p) for v, p in zip(views, plan.params())]
