@@ -195,8 +195,8 @@ class VirConvL8x(nn.Module):
         return self._plan_cache
 
     def _use_plan(self, feats):
-        if not executor.ENABLED or not feats.is_cuda or feats.shape[0] == 0:
-            return False
+        if not executor.ENABLED or not feats.is_cuda or feats.shape[0] == 0 or feats.requires_grad:
+            return False             # (the plan does not propagate a gradient into the voxel features; the module path does)
         if self.training and self.discard_mode == 'paper' and self.layer_discard_rate != 0:
             return False             # row-dropping StVD between the blocks is only on the module path
         plan = self._plan()
@@ -359,7 +359,7 @@ class VirConv8x(nn.Module):
 
     @staticmethod
     def _plan_usable(plan, feats):
-        if not executor.ENABLED or not feats.is_cuda or feats.shape[0] == 0 or not plan.eligible():
+        if not executor.ENABLED or not feats.is_cuda or feats.shape[0] == 0 or feats.requires_grad or not plan.eligible():
             return False
         mode = plan.layers[0][1].training
         return all(bn.training == mode for _, bn in plan.layers)

@@ -9,7 +9,7 @@
 //     offset is a pre-formatted image copied linearly — no register staging, no re-layout pass;
 //   * one elected thread issues C_in/16 `tcgen05.mma.cta_group::1.kind::f16` (M=128, N=C_out, K=16) per offset,
 //     accumulating all offsets of the tile in TMEM (fp32, C_out columns); `tcgen05.commit` onto an mbarrier
-//     frees the operand stage; a 3-deep ring keeps 2 gathers in flight behind the MMA;
+//     frees the operand stage; a ring of TC_STAGES operand stages keeps the next gather in flight behind the MMA;
 //   * epilogue: `tcgen05.ld` 32x32b (thread = output row) -> smem -> coalesced fp32 stores + per-tile BN sums.
 // Replaces spconv `ops.indice_conv` behind spconv_backbone.py:89,92-93,113,563-564 in the bf16 (benchmark)
 // precision mode; the fp32 kernels in conv_f32.cu stay the 1e-4 parity path.
