@@ -152,6 +152,6 @@ int tc_prep_images(TcPrepTable& t, cudaStream_t stream);
 int tc_scatter_with_image(int kc, int nr, const void* dout_bf16, const void* wimg, const int32_t* nbr, float* din, int n_out,
                           int K, int* err, cudaStream_t stream);
 int tc_conv_with_image(int kc, int nr, const void* in_bf16, const void* wimg, const int32_t* nbr, float* out, int n_rows,
-                       int K, double* bn_sums, int* err, cudaStream_t stream);
+                       int K, double* bn_sums, int* err, cudaStream_t stream, const float* addend = nullptr);
 
 }  // namespace vc

@@ -164,8 +164,10 @@ __global__ void prep_weights_tc_kernel(const float* __restrict__ w, __nv_bfloat1
 template <int KC, int NR>
 __global__ void __launch_bounds__(TC_THREADS)
 tc_gather_gemm_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __restrict__ wimg,
-                      const int32_t* __restrict__ nbr, float* __restrict__ out, int n_out, int K,
-                      double* __restrict__ bn_sums, int* __restrict__ err) {
+                      const int32_t* __restrict__ nbr, float* out, int n_out, int K, double* __restrict__ bn_sums,
+                      int* __restrict__ err, const float* addend) {
+    // addend (may be NULL, may alias `out`): a [n_out, NR] fp32 matrix added to the result in the epilogue — the plan
+    // executor's gradient accumulation (an earlier contribution to the same feature slot) without a separate add kernel
     using C = TcCfg<KC, NR>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* ring = smem_raw;                                          // [stages][A | B]
@@ -345,7 +347,13 @@ tc_gather_gemm_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16*
         const int r = q / (NR / 4), c4 = q % (NR / 4);
         if (base + r < n_out) {
             const float* s = stg + r * (NR + 1) + c4 * 4;
-            *reinterpret_cast<float4*>(out + (size_t)(base + r) * NR + c4 * 4) = make_float4(s[0], s[1], s[2], s[3]);
+            float4 v = make_float4(s[0], s[1], s[2], s[3]);
+            const size_t o = (size_t)(base + r) * NR + c4 * 4;
+            if (addend != nullptr) {       // same element read and written by this thread only: aliasing `out` is safe
+                const float4 a = *reinterpret_cast<const float4*>(addend + o);
+                v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+            }
+            *reinterpret_cast<float4*>(out + o) = v;
         }
     }
     if (bn_sums != nullptr) {
@@ -379,20 +387,21 @@ tc_gather_gemm_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16*
 
 template <int KC, int NR>
 static int launch_tc(const __nv_bfloat16* in, const __nv_bfloat16* wimg, const int32_t* nbr, float* out, int n_out, int K,
-                     double* bn_sums, int* err, cudaStream_t stream) {
+                     double* bn_sums, int* err, cudaStream_t stream, const float* addend = nullptr) {
     size_t smem = TcCfg<KC, NR>::smem(K);
     auto kern = tc_gather_gemm_kernel<KC, NR>;
     VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    VC_LAUNCH_CHAIN(kern, dim3(cdiv(n_out, TCM)), dim3(TC_THREADS), smem, stream, in, wimg, nbr, out, n_out, K, bn_sums, err);
+    VC_LAUNCH_CHAIN(kern, dim3(cdiv(n_out, TCM)), dim3(TC_THREADS), smem, stream, in, wimg, nbr, out, n_out, K, bn_sums, err,
+                    addend);
     return VC_OK;
 }
 
 static bool tc_ch_ok(int c) { return c == 16 || c == 32 || c == 64; }
 
 static int dispatch_tc(int kc, int nr, const __nv_bfloat16* in, const __nv_bfloat16* wimg, const int32_t* nbr, float* out,
-                       int n_out, int K, double* bn_sums, int* err, cudaStream_t stream) {
+                       int n_out, int K, double* bn_sums, int* err, cudaStream_t stream, const float* addend = nullptr) {
 #define VC_TC_CASE(A, B) \
-    if (kc == A && nr == B) return launch_tc<A, B>(in, wimg, nbr, out, n_out, K, bn_sums, err, stream);
+    if (kc == A && nr == B) return launch_tc<A, B>(in, wimg, nbr, out, n_out, K, bn_sums, err, stream, addend);
     VC_TC_CASE(16, 16) VC_TC_CASE(16, 32) VC_TC_CASE(16, 64)
     VC_TC_CASE(32, 16) VC_TC_CASE(32, 32) VC_TC_CASE(32, 64)
     VC_TC_CASE(64, 16) VC_TC_CASE(64, 32) VC_TC_CASE(64, 64)
@@ -537,10 +546,10 @@ int tc_scatter_with_image(int kc, int nr, const void* dout_bf16, const void* wim
 
 // ---- entry points for the plan executor (executor.cu): pre-built weight images, one batched prep launch ----
 int tc_conv_with_image(int kc, int nr, const void* in_bf16, const void* wimg, const int32_t* nbr, float* out, int n_rows,
-                       int K, double* bn_sums, int* err, cudaStream_t stream) {
+                       int K, double* bn_sums, int* err, cudaStream_t stream, const float* addend) {
     if (n_rows == 0) return VC_OK;
     return dispatch_tc(kc, nr, (const __nv_bfloat16*)in_bf16, (const __nv_bfloat16*)wimg, nbr, out, n_rows, K, bn_sums, err,
-                       stream);
+                       stream, addend);
 }
 
 // every layer's forward / dgrad weight image in ONE launch: thread i -> (entry, element) by binary search over the

@@ -616,6 +616,39 @@ int contribute(Ctx& C, FSlot& F, cudaStream_t st, W&& write) {
     return VC_OK;
 }
 
+// contribution by a kernel that can ADD an existing [rows, c] matrix in its epilogue (the tensor-core gather dgrad):
+// `write(dst, addend)` overwrites dst with result + addend (addend may be NULL or alias dst) — no add kernel, no temporary
+template <class W>
+int contribute_fused(Ctx& C, FSlot& F, W&& write) {
+    const size_t n = (size_t)F.rows * F.c;
+    if (F.grad_state == G_OWN) {
+        VC_TRY(write(F.grad, (const float*)F.grad));
+    } else {
+        VC_ALLOC(buf, float*, n * 4);
+        VC_TRY(write(buf, F.grad_state == G_EXT ? (const float*)F.grad : nullptr));
+        F.grad = buf;
+    }
+    F.grad_state = G_OWN;
+    return VC_OK;
+}
+
+// contribution by a kernel that ACCUMULATES with atomics (the scatter dgrads): `scatter(dst)` adds into dst, which must
+// hold the sum so far — zeros, a copy of the outside gradient, or the slot's own buffer (then nothing is staged at all)
+template <class W>
+int contribute_scatter(Ctx& C, FSlot& F, cudaStream_t st, W&& scatter) {
+    const size_t n = (size_t)F.rows * F.c;
+    if (F.grad_state != G_OWN) {
+        VC_ALLOC(buf, float*, n * 4);
+        if (F.grad_state == G_EXT)
+            VC_CUDA(cudaMemcpyAsync(buf, F.grad, n * 4, cudaMemcpyDeviceToDevice, st));
+        else
+            VC_CUDA(cudaMemsetAsync(buf, 0, n * 4, st));
+        F.grad = buf;
+        F.grad_state = G_OWN;
+    }
+    return scatter(F.grad);
+}
+
 }  // namespace
 }  // namespace vc
 
@@ -717,24 +750,22 @@ extern "C" int vc_exec_backward(const int32_t* ops_i, const float* ops_f, int n_
         // dgrad
         if (!L.need_dgrad || L.in_slot == 0) continue;
         if (R.subm && !R.unique && L.use_tc && L.wimg_dgrad) {
-            VC_TRY(contribute(C, X, st, [&](float* dst) -> int {
-                VC_CUDA(cudaMemsetAsync(dst, 0, (size_t)X.rows * X.c * 4, st));
+            VC_TRY(contribute_scatter(C, X, st, [&](float* dst) -> int {
                 Timed t(7, li, st);
                 return tc_scatter_with_image(L.cout, L.cin, dxb, L.wimg_dgrad, R.nbr, dst, R.n_out, R.K, C.err, st);
             }));
         } else if (R.subm && !R.unique) {
             const size_t wsb = vc_conv_ws_bytes(L.cin, L.cout, R.K);
             VC_ALLOC(ws, void*, wsb);
-            VC_TRY(contribute(C, X, st, [&](float* dst) -> int {
-                VC_CUDA(cudaMemsetAsync(dst, 0, (size_t)X.rows * X.c * 4, st));
+            VC_TRY(contribute_scatter(C, X, st, [&](float* dst) -> int {
                 Timed t(4, li, st);
                 return vc_conv_dgrad_scatter_f32(dx, C.P<const float>(li, P_W), R.nbr, dst, R.n_out, L.cin, L.cout, R.K, ws, wsb, st);
             }));
         } else if (L.use_tc && L.wimg_dgrad) {
             const int32_t* table = R.subm ? R.nbr : R.nbr_bwd;
-            VC_TRY(contribute(C, X, st, [&](float* dst) -> int {
+            VC_TRY(contribute_fused(C, X, [&](float* dst, const float* addend) -> int {
                 Timed t(3, li, st);
-                return tc_conv_with_image(L.cout, L.cin, dxb, L.wimg_dgrad, table, dst, R.n_in, R.K, nullptr, C.err, st);
+                return tc_conv_with_image(L.cout, L.cin, dxb, L.wimg_dgrad, table, dst, R.n_in, R.K, nullptr, C.err, st, addend);
             }));
         } else {
             const size_t wsb = vc_conv_ws_bytes(L.cin, L.cout, R.K);
