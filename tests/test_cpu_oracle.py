@@ -232,3 +232,67 @@ def test_stvd_host_plan_of_the_product_matches_oracle():
                 assert sbase >= 0 and np.array_equal(sel[sbase:sbase + cnt], wsel)
             total += cnt
         assert total == n_out
+
+
+# ---------------------------------------------------------------------------------------- voxel-RoI pooling primitives
+def test_pointnet2_restatement_against_a_vectorised_definition():
+    """oracle/pointnet2.py walks cells like the reference kernel (voxel_query_gpu.cu:40-87); here the same answer from a
+    definition that does not share its control flow: all neighbours of a query cell sorted by (dz, dy, dx), filtered by
+    radius, first nsample kept, padded with the first."""
+    from oracle import pointnet2 as o_pn
+    rng = np.random.default_rng(4)
+    B, shape = 2, (4, 12, 10)
+    n = 150
+    lin = np.sort(rng.choice(B * shape[0] * shape[1] * shape[2], n, replace=False))
+    b, rem = lin // (shape[0] * shape[1] * shape[2]), lin % (shape[0] * shape[1] * shape[2])
+    coords = np.stack([b, rem // (shape[1] * shape[2]), (rem // shape[2]) % shape[1], rem % shape[2]], 1).astype(np.int32)
+    xyz = np.ascontiguousarray((coords[:, [3, 2, 1]] + 0.5).astype(np.float32) * np.float32(0.4))
+    v2p = -np.ones((B,) + shape, np.int32)
+    v2p[coords[:, 0], coords[:, 1], coords[:, 2], coords[:, 3]] = np.arange(n)
+    m = 60
+    pick = rng.integers(0, n, m)
+    new_xyz = (xyz[pick] + rng.normal(0, 0.3, (m, 3))).astype(np.float32)
+    new_coords = np.concatenate([coords[pick, :1], np.floor(new_xyz[:, [2, 1, 0]] / np.float32(0.4)).astype(np.int32)], 1)
+    for rngs, radius, ns in (((1, 1, 1), 0.55, 4), ((2, 3, 1), 0.9, 8)):
+        idx, empty = o_pn.voxel_query(rngs, radius, ns, xyz, new_xyz, new_coords, v2p)
+        for q in range(m):
+            d = coords[:, 1:].astype(np.int64) - new_coords[q, 1:].astype(np.int64)
+            cand = np.nonzero((coords[:, 0] == new_coords[q, 0]) & (np.abs(d[:, 0]) <= rngs[0]) & (np.abs(d[:, 1]) <= rngs[1])
+                              & (np.abs(d[:, 2]) <= rngs[2]))[0]
+            cand = cand[np.lexsort((d[cand, 2], d[cand, 1], d[cand, 0]))]
+            dist2 = ((xyz[cand].astype(np.float64) - new_xyz[q].astype(np.float64)) ** 2).sum(1)
+            hits = cand[dist2 <= np.float64(np.float32(radius) * np.float32(radius))][:ns]
+            if len(hits) == 0:
+                assert empty[q] and not idx[q].any()
+            else:
+                want = np.full(ns, hits[0])
+                want[:len(hits)] = hits
+                assert not empty[q] and np.array_equal(idx[q], want), q
+    # grouping and its gradient are transposes of each other:  <group(f), g> == <f, group_grad(g)>
+    feats = rng.normal(size=(n, 6)).astype(np.float32)
+    cnt_f = np.array([(coords[:, 0] == i).sum() for i in range(B)], np.int32)
+    order = np.argsort(new_coords[:, 0], kind='stable')
+    qb = new_coords[order, 0]
+    cnt_q = np.array([(qb == i).sum() for i in range(B)], np.int32)
+    starts = np.concatenate([[0], np.cumsum(cnt_f)[:-1]])
+    lidx = (idx[order] - starts[qb][:, None]).astype(np.int32)
+    lidx[empty[order]] = 0
+    out = o_pn.group_points(feats, cnt_f, lidx, cnt_q)
+    g = rng.normal(size=out.shape).astype(np.float32)
+    back = o_pn.group_points_grad(g, lidx, cnt_q, cnt_f, n)
+    assert abs(float((out.astype(np.float64) * g).sum()) - float((feats.astype(np.float64) * back).sum())) < 1e-3
+
+
+def test_reference_pointnet2_kernels_build_into_oracle_ref():
+    """oracle/ref_build.py compiles the reference's stand-alone CUDA sources where they lie; on a box without
+    /root/reference the prebuilt library (if it travelled) is used as is."""
+    import ctypes
+    from oracle import ref_build
+    lib = ref_build.build()
+    if lib is None:
+        pytest.skip('no /root/reference and no prebuilt oracle/_ref library')
+    assert os.path.exists(lib)
+    if torch.cuda.is_available() or os.path.exists('/usr/local/cuda/lib64/libcudart.so'):
+        h = ctypes.CDLL(lib)
+        for sym in ('ref_voxel_query', 'ref_group_points', 'ref_group_points_grad'):
+            assert hasattr(h, sym)
