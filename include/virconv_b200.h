@@ -50,6 +50,10 @@ long long vc_launch_count(void);
 /* Programmatic dependent launch for the kernels of the conv / BN chain (default on): each starts while its predecessor
  * drains and blocks in `griddepcontrol.wait` before touching dependent data.  0 = plain stream-ordered launches. */
 int vc_set_pdl(int enable);
+/* Tensor-core conv forward / gather-dgrad kernel: 1 (default) = persistent kernel with a deep cp.async operand ring
+ * (csrc/conv_tc2.cu; C in {8,16,32,64}); 0 = the round-1 one-tile-per-CTA kernel (csrc/conv_tc.cu; C in {16,32,64}).
+ * A/B measurements only — weight images built under one variant are not valid under the other. */
+int vc_set_tc_variant(int variant);
 
 /* ------------------------------------------------------------------------------------------------
  * Rulebooks.  Replaces spconv `ops.get_indice_pairs`, reached from every conv call site:
@@ -296,6 +300,13 @@ int vc_group_points_grad(int B, int M, int C, int N, int nsample, const float* g
  * main_stream (always safe).  0: the caller guarantees idx0 / proj_params are valid in side_stream order and that the
  * arena may be written from side_stream right away (e.g. it was allocated there) — the index ops of this step then
  * overlap the previous step's backward.
+ * Static mode (n0_dev != NULL): nothing in the call reads a device value on the host, so the whole forward (and the
+ * backward that follows it) can be captured into a CUDA graph (SURVEY §8b "CUDA-graph-capturable").  n0 is then the
+ * CAPACITY of feats0 / idx0, *n0_dev the number of valid rows; caps[i] (host, indexed by index-set id) is the row
+ * capacity of the strided convs' output sets; every data-dependent row count stays in device memory
+ * (vc_exec_query(state, 2, id)[6] = its address), published buffers have capacity rows with a zero / -1 tail, and a row
+ * count that does not fit its capacity is clamped and reported as max() into *overflow_flag (device int32; zero it
+ * before the step, re-run with larger capacities when it is non-zero afterwards).  Use side_waits_main = 1 under capture.
  * ---------------------------------------------------------------------------------------------- */
 size_t vc_exec_state_bytes(void);
 int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_ops, const uint64_t* layer_ptrs, const float* layer_f,
@@ -303,7 +314,8 @@ int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_ops, const u
                     int batch_size, const float* proj_params /*device [B,28], may be NULL without INDEX2UV ops*/,
                     int training, int precision, int want_pair_num, void* arena, size_t arena_bytes,
                     int32_t* pinned_host, int32_t* err_flag, void* state, size_t state_bytes, vc_stream_t main_stream,
-                    vc_stream_t side_stream, int side_waits_main);
+                    vc_stream_t side_stream, int side_waits_main, const int32_t* caps /*host, may be NULL*/,
+                    const int32_t* n0_dev /*device, NULL = exact mode*/, int32_t* overflow_flag /*device*/);
 /* Reverse walk.  pub_slots [n_pub]: feature slots whose gradients come from outside (the published tensors), ext_grads
  * [n_pub]: device pointers to those gradients ([rows, c] fp32 contiguous, read only) or 0.  Writes d_weight / d_gamma /
  * d_beta of every layer (zeros where nothing flowed back).  Same arena as the forward (it continues allocating).

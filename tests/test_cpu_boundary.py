@@ -173,7 +173,7 @@ def test_executor_plan_layout_and_host_side_validation(lib_built):
     bad[3, 0] = 99
     state = np.zeros(lib.vc_exec_state_bytes(), dtype=np.uint8)
     rc = lib.vc_exec_forward(bad.ctypes.data, of.ctypes.data, 40, None, None, 20, None, 8, None, 1, _lib.host_i32([41, 1600, 1408]),
-                             2, None, 1, 0, 1, None, 0, None, None, state.ctypes.data, state.size, None, None, 1)
+                             2, None, 1, 0, 1, None, 0, None, None, state.ctypes.data, state.size, None, None, 1, None, None, None)
     assert rc == -1 and b'unknown kind' in lib.vc_last_error()
     out = (ctypes.c_longlong * 8)()
     assert lib.vc_exec_query(state.ctypes.data, 0, 0, out) == -1        # not a valid state blob

@@ -1,0 +1,167 @@
+"""GPU tests of the configuration bench.py measures: bf16 tensor-core kernels + plan executor in STATIC mode (device
+row counts, capacity-sized buffers) + whole-step CUDA graph replay over rotating batches, against the exact-shape,
+host-synchronised execution of the same step (which the other test files pin against the oracle)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.testing import fill_module, rel_err
+
+pytestmark = pytest.mark.gpu
+CFG = dict(RETURN_NUM_FEATURES_AS_DICT=True, OUT_FEATURES=64, LAYER_DISCARD_RATE=0.1, NUM_FILTERS=[16, 32, 64, 64])
+KEYS = ('x_conv1', 'x_conv2', 'x_conv3', 'x_conv4', 'out')
+
+
+def _model(precision):
+    from virconv_b200.backbone import VirConvL8x
+    m = VirConvL8x(CFG, 8, [1408, 1600, 80], precision=precision)
+    fill_module(m, 666)
+    return m.to('cuda:0').train()
+
+
+def _batch(ids, n_lidar=4096, n_virtual=9000, max_voxels=7000):
+    from virconv_b200 import scenes
+    b = scenes.make_batch(ids, n_lidar=n_lidar, n_virtual=n_virtual, max_voxels=max_voxels, training=True)
+    return {'voxel_features': torch.from_numpy(b.voxel_features.copy()).cuda(),
+            'voxel_coords': torch.from_numpy(b.voxel_coords.copy()).cuda(), 'batch_size': b.batch_size, 'calib': b.calib,
+            'aug_param': torch.from_numpy(b.aug_param.copy())}
+
+
+def _named(out):
+    named = dict(out['multi_scale_3d_features'])
+    named['out'] = out['encoded_spconv_tensor']
+    return named
+
+
+def _loss(out):
+    from virconv_b200.graph import masked_mean
+    return sum(masked_mean(t) for t in _named(out).values())
+
+
+def _exact(model, batch):
+    for p in model.parameters():
+        p.grad = None
+    out = model(dict(batch))
+    loss = _loss(out)
+    loss.backward()
+    torch.cuda.synchronize()
+    return float(loss), {k: v.grad.clone() for k, v in model.named_parameters()}, _named(out)
+
+
+def _err_flag():
+    from virconv_b200 import ops
+    return int(ops.tc_error_flag(torch.device('cuda:0')).item())
+
+
+@pytest.mark.parametrize('precision', ['bf16', 'fp32'])
+def test_static_mode_matches_exact_mode(lib_built, precision):
+    """Same batch, same weights: the static (capacity + device count) execution publishes the exact mode's tensors on
+    the valid rows, zero / -1 tails beyond them, the same row counts, loss and parameter gradients."""
+    from virconv_b200 import executor, ops
+    model = _model(precision)
+    batch = _batch([11, 12])
+    l0, g0, n0 = _exact(model, batch)
+    run = executor.last_run(model)
+    caps = executor.measured_caps(run, 1.3, 256)
+    n = batch['voxel_features'].shape[0]
+    cap0 = (int(n * 1.25) + 255) // 256 * 256
+    dev = torch.device('cuda:0')
+    vf = torch.zeros((cap0, 8), device=dev)
+    vc = torch.full((cap0, 4), -1.0, device=dev)
+    vf[:n] = batch['voxel_features']
+    vc[:n] = batch['voxel_coords']
+    vf[n:] = float('nan')                 # whatever is beyond the count must never be read into a result
+    spec = executor.StaticSpec(torch.tensor([n], dtype=torch.int32, device=dev), caps,
+                               torch.zeros(1, dtype=torch.int32, device=dev))
+    proj = ops.projection_params(batch['calib'], batch['aug_param'], 2, dev)
+    for p in model.parameters():
+        p.grad = None
+    bd = {'voxel_features': vf, 'voxel_coords': vc, 'batch_size': 2, 'calib': batch['calib'], 'aug_param': batch['aug_param'],
+          'virconv_static': spec, 'virconv_proj': proj}
+    out = model(bd)
+    loss = _loss(out)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert _err_flag() == 0
+    assert int(spec.overflow.item()) == 0
+    named = _named(out)
+    for k in KEYS:
+        t, e = named[k], n0[k]
+        rows = int(t.num_rows.item())
+        assert rows == e.features.shape[0], k
+        assert t.features.shape[0] >= rows and t.features.shape[0] % 256 == 0, k
+        assert torch.equal(t.indices[:rows].int(), e.indices.int()), k
+        assert rel_err(t.features[:rows].detach().cpu(), e.features.detach().cpu()) < 1e-5, k
+        assert float(t.features[rows:].abs().max()) == 0.0 if t.features.shape[0] > rows else True, k
+        if k != 'x_conv1':
+            assert bool((t.indices[rows:] == -1).all()), k
+    assert abs(float(loss) - l0) < 1e-5 * max(1.0, abs(l0))
+    tol = 1e-2 if precision == 'bf16' else 2e-4        # order of the scatter / float64 atomics differs run to run
+    for name, p in model.named_parameters():
+        assert p.grad is not None and bool(torch.isfinite(p.grad).all()), name
+        assert rel_err(p.grad.cpu(), g0[name].cpu()) < tol, name
+
+
+def test_static_mode_reports_overflow(lib_built):
+    from virconv_b200 import executor, ops
+    model = _model('bf16')
+    batch = _batch([11, 12])
+    _exact(model, batch)
+    caps = executor.measured_caps(executor.last_run(model), 1.0, 1)
+    k = sorted(caps)[0]
+    true_rows = caps[k]
+    caps[k] = caps[k] - 300                # one strided conv's output set does not fit
+    n = batch['voxel_features'].shape[0]
+    dev = torch.device('cuda:0')
+    spec = executor.StaticSpec(torch.tensor([n], dtype=torch.int32, device=dev), caps, torch.zeros(1, dtype=torch.int32, device=dev))
+    bd = dict(batch)
+    bd.update(virconv_static=spec, virconv_proj=ops.projection_params(batch['calib'], batch['aug_param'], 2, dev))
+    with torch.no_grad():
+        out = model(bd)
+    torch.cuda.synchronize()
+    assert int(spec.overflow.item()) == true_rows          # the row count that did not fit
+    assert bool(torch.isfinite(out['encoded_spconv_tensor'].features).all())
+
+
+def test_graph_replay_matches_eager_over_rotating_batches(lib_built):
+    """What bench.py times: >= 8 back-to-back replays of the captured step (bf16, wgrad stream, index stream, no host
+    synchronisation between steps) over rotating batches; every step's loss and parameter gradients against a
+    synchronous exact-mode execution of the same batch with the same weights."""
+    from virconv_b200.graph import GraphedStep
+    model = _model('bf16')
+    batches = [_batch([20 + 2 * i, 21 + 2 * i]) for i in range(4)]
+    ref = []
+    for b in batches:
+        l, g, _ = _exact(model, b)
+        ref.append((l, g))
+    step = GraphedStep(model, _loss, margin=1.35, grain=256)
+    params = dict(model.named_parameters())
+    losses, grads = [], []
+    for s in range(9):
+        loss = step(batches[s % 4])
+        losses.append(loss.detach().clone())                       # device-side copies, no synchronisation
+        grads.append({k: v.grad.detach().clone() for k, v in params.items()})
+    torch.cuda.synchronize()
+    assert _err_flag() == 0
+    assert step.recaptures == 1
+    for s in range(9):
+        l0, g0 = ref[s % 4]
+        assert abs(float(losses[s]) - l0) < 1e-5 * max(1.0, abs(l0)), s
+        for k in params:
+            assert rel_err(grads[s][k].cpu(), g0[k].cpu()) < 1e-2, (s, k)
+
+
+def test_graph_recaptures_when_a_batch_does_not_fit(lib_built):
+    from virconv_b200.graph import GraphedStep
+    model = _model('bf16')
+    small = _batch([31, 32], n_lidar=2048, n_virtual=3000, max_voxels=2500)
+    big = _batch([33, 34], n_lidar=4096, n_virtual=9000, max_voxels=7000)
+    step = GraphedStep(model, _loss, margin=1.05, grain=64)
+    step(small)
+    torch.cuda.synchronize()
+    assert step.recaptures == 1
+    l_big, g_big, _ = _exact(model, big)
+    loss = step(big)                                                # more input rows than the buffers hold -> re-capture
+    torch.cuda.synchronize()
+    assert step.recaptures == 2
+    assert abs(float(loss) - l_big) < 1e-5 * max(1.0, abs(l_big))

@@ -25,6 +25,7 @@ SIGNATURES = {
     'vc_last_error': (c_char_p, []),
     'vc_launch_count': (ctypes.c_longlong, []),
     'vc_set_pdl': (_I, [_I]),
+    'vc_set_tc_variant': (_I, [_I]),
     'vc_subm_rulebook_ws_bytes': (_Z, [_I]),
     'vc_subm_rulebook': (_I, [_P, _I, _I, _I, _HOST, _HOST, _HOST, _P, _P, _P, _Z, _P]),
     'vc_conv_rulebook_ws_bytes': (_Z, [_I, _I, _HOST]),
@@ -62,7 +63,8 @@ SIGNATURES = {
     'vc_group_points': (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     'vc_group_points_grad': (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     'vc_exec_state_bytes': (_Z, []),
-    'vc_exec_forward': (_I, [_P, _P, _I, _P, _P, _I, _P, _I, _P, _I, _HOST, _I, _P, _I, _I, _I, _P, _Z, _P, _P, _P, _Z, _P, _P, _I]),
+    'vc_exec_forward': (_I, [_P, _P, _I, _P, _P, _I, _P, _I, _P, _I, _HOST, _I, _P, _I, _I, _I, _P, _Z, _P, _P, _P, _Z, _P, _P, _I,
+                             _P, _P, _P]),
     'vc_exec_backward': (_I, [_P, _P, _I, _P, _P, _I, _P, _P, _I, _P, _Z, _P, _P, _P, _P]),
     'vc_conv_wgrad_tc_config': (_I, [_I, _I]),
     'vc_exec_query': (_I, [_P, _I, _I, _P]),

@@ -122,9 +122,10 @@ def plan_nrconv(plan, block, f, iset, proj_stride):
 
 
 def _published_tensor(res, name, batch_size, indice_dict):
-    f, idx, shape, fb = res[name]
+    f, idx, shape, fb, cnt = res[name]
     t = spconv.SparseConvTensor(f, idx, shape, batch_size, indice_dict=indice_dict)
     t.features_bf16 = fb
+    t.num_rows = cnt          # static mode: device int32[1] row count (features / indices are capacity sized, zero / -1 tail)
     return t
 
 
@@ -223,7 +224,8 @@ class VirConvL8x(nn.Module):
                 # batch) -> the index pipeline of this step (starting with the .int() of the coordinates, :641) runs on
                 # the side stream without waiting for main, i.e. it may overlap the previous step's backward
                 side = ops.side(feats.device).stream if executor.TWO_STREAMS else None
-                ready = side is not None and bool(batch_dict.get('virconv_inputs_ready', False))
+                static = batch_dict.get('virconv_static')
+                ready = side is not None and static is None and bool(batch_dict.get('virconv_inputs_ready', False))
                 if ready and (coords.dtype != torch.int32 or not coords.is_contiguous()):
                     executor.reserve_blocks('coords_i32', 4 * coords.numel(), feats.device, side)
                     with torch.cuda.stream(side):
@@ -231,9 +233,16 @@ class VirConvL8x(nn.Module):
                     ci.record_stream(torch.cuda.current_stream(feats.device))   # published as x_conv1's indices
                 else:
                     ci = spconv._as_i32(coords)
-                proj = ops.projection_params(calib, trans, batch_size, feats.device, side)
+                # static mode ('virconv_static': executor.StaticSpec): capacity-sized inputs + device row count, projection
+                # block already on the device ('virconv_proj', [B,28], ops.projection_params) — nothing below reads a
+                # device value or uploads from pageable memory, so the call can be captured into a CUDA graph
+                proj = batch_dict.get('virconv_proj')
+                if proj is None:
+                    assert static is None, "static mode needs batch_dict['virconv_proj'] (ops.projection_params on the device)"
+                    proj = ops.projection_params(calib, trans, batch_size, feats.device, side)
                 run, res = executor.run_plan(self._plan(), feats, ci, self.sparse_shape, batch_size, proj, bn_training,
-                                             self.conv_out[0].precision, inputs_ready=ready)
+                                             self.conv_out[0].precision, inputs_ready=ready, static=static)
+                executor.note_last_run(self, run)   # (graph.GraphedStep sizes its capacities from an exact-mode run)
                 idict = executor.LazyIndiceDict(run, ci, self.sparse_shape)
                 x1, x2, x3, x4, out = (_published_tensor(res, k, batch_size, idict)
                                        for k in ('x_conv1', 'x_conv2', 'x_conv3', 'x_conv4', 'out'))

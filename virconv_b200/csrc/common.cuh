@@ -129,10 +129,30 @@ static inline cudaError_t launch_chain(void (*kern)(KP...), dim3 grid, dim3 bloc
     } while (0)
 
 // ---- shared between rulebook.cu and executor.cu ----
-int conv_rulebook_fill_phases(const int32_t* indices, int n, int ndim, int batch_size, const int32_t* spatial_shape,
-                              const int32_t* ksize, const int32_t* stride, const int32_t* padding, const int32_t* dilation,
-                              int n_out, int32_t* out_indices, int32_t* nbr_fwd, int32_t* nbr_bwd, int32_t* pair_num,
-                              void* ws, size_t ws_bytes, cudaStream_t stream, int phases);
+// `n_dev` (optional): the row count lives in device memory and `n` / `n_out` are capacities (static mode, graph capturable)
+int subm_rulebook_dev(const int32_t* indices, int n, const int* n_dev, int ndim, int batch_size, const int32_t* spatial_shape,
+                      const int32_t* ksize, const int32_t* dilation, int32_t* nbr, int32_t* pair_num, void* ws, size_t ws_bytes,
+                      cudaStream_t stream);
+int conv_rulebook_count_dev(const int32_t* indices, int n, const int* n_dev, int ndim, int batch_size,
+                            const int32_t* spatial_shape, const int32_t* ksize, const int32_t* stride, const int32_t* padding,
+                            const int32_t* dilation, int32_t* n_out_dev, int cap_out, int* overflow, void* ws, size_t ws_bytes,
+                            cudaStream_t stream);
+int conv_rulebook_fill_phases(const int32_t* indices, int n, const int* n_dev, int ndim, int batch_size,
+                              const int32_t* spatial_shape, const int32_t* ksize, const int32_t* stride, const int32_t* padding,
+                              const int32_t* dilation, int n_out, int32_t* out_indices, int32_t* nbr_fwd, int32_t* nbr_bwd,
+                              int32_t* pair_num, void* ws, size_t ws_bytes, cudaStream_t stream, int phases);
+
+// ---- bn.cu / misc.cu internals used by the plan executor (device row counts, strided outputs) ----
+int bn_apply_relu_dev(const float* x, const double* sums, int n_rows, const int* n_dev, int c, const float* gamma,
+                      const float* beta, float* running_mean, float* running_var, long long* num_batches_tracked, float momentum,
+                      float eps, int training, float* y, int y_ld, void* y_bf16, int yb_ld, float* stats_out, int relu,
+                      int tail_zero, cudaStream_t stream);
+int bn_relu_bwd_dev(const float* dy, int dy_ld, const float* x, const float* gamma, const float* stats, float* dx, void* dx_bf16,
+                    float* dgamma, float* dbeta, int n, const int* n_dev, int c, int training, double* bsums, int tail_zero,
+                    cudaStream_t stream);
+int cat2_dev(const float* a, const float* b, float* out, void* out_bf16, int n, const int* n_dev, int ca, int cb, cudaStream_t stream);
+int index2uv_dev(const int32_t* indices, int n, const int* n_dev, int batch_size, const float* params, const float* grid,
+                 int stride, int u_max, int v_max, int32_t* uv_out, cudaStream_t stream);
 
 // ---- shared between conv_tc.cu and executor.cu ----
 struct TcPrepEntry {
@@ -141,6 +161,7 @@ struct TcPrepEntry {
     int cin, cout, K;
     int mode;         // 0 forward image, 1 dgrad image
     int mirror;       // dgrad: kernel offsets mirrored (submanifold table re-used as its own transpose)
+    int layout;       // 0: round-1 core-matrix image (tc_scatter_kernel, legacy gather kernel); 1: swizzled + padded to 16 (conv_tc2.cu)
     int first;        // element prefix (filled by tc_prep_images)
 };
 static constexpr int TC_PREP_MAX = 64;
@@ -151,7 +172,16 @@ struct TcPrepTable {
 int tc_prep_images(TcPrepTable& t, cudaStream_t stream);
 int tc_scatter_with_image(int kc, int nr, const void* dout_bf16, const void* wimg, const int32_t* nbr, float* din, int n_out,
                           int K, int* err, cudaStream_t stream);
-int tc_conv_with_image(int kc, int nr, const void* in_bf16, const void* wimg, const int32_t* nbr, float* out, int n_rows,
-                       int K, double* bn_sums, int* err, cudaStream_t stream, const float* addend = nullptr);
+int tc_conv_with_image(int kc, int nr, const void* in_bf16, const void* wimg, const int32_t* nbr, long long pitch, float* out,
+                       int n_rows, const int* n_dev, int K, double* bn_sums, int* err, cudaStream_t stream, const float* addend,
+                       int* tile_counter = nullptr);
+bool tc_conv_ch_ok(int c);
+// ---- conv_tc2.cu (persistent tensor-core conv) ----
+extern int g_tc_variant;
+size_t tc_image_bytes(int cin, int cout, int K, int layout);
+bool tc2_ch_ok(int c);
+int tc2_conv(int kc, int nr, const void* in_bf16, const void* wimg, const int32_t* nbr, long long pitch, float* out, int n_rows,
+             const int* n_dev, int K, double* bn_sums, int* err, cudaStream_t stream, const float* addend,
+             int* tile_counter = nullptr);
 
 }  // namespace vc

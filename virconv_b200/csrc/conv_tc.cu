@@ -17,7 +17,7 @@
 //   N_in*C_in*2 + N_out*C_out*4 + P*8 + K*C_in*C_out*2;  FLOPs 2*P*C_in*C_out.
 #include <cuda_bf16.h>
 
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace vc {
 
@@ -29,7 +29,6 @@ __device__ long long* g_trace = nullptr;
 #define VC_TRACE(slot) do { } while (0)
 #endif
 
-static constexpr int TCM = 128;        // rows per tile == UMMA M
 #ifndef VC_TC_NPW
 #define VC_TC_NPW 4
 #endif
@@ -45,70 +44,6 @@ static constexpr int TC_THREADS = TC_PRODUCERS + 32;   // + the last warp: MMA i
 #endif
 static constexpr int TC_STAGES = VC_TC_STAGES;
 static constexpr int TC_LAG = TC_STAGES - 1;   // stages a producer thread keeps in flight before it signals `full`
-static constexpr int MAXK_TC = 32;
-static constexpr unsigned SPIN_LIMIT = 1u << 24;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-// bounded spin: a wedged pipeline must not hang the GPU (sets *err and returns false instead)
-__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* err) {
-    uint32_t addr = smem_u32(bar), done = 0;
-    for (unsigned spin = 0; spin < SPIN_LIMIT; ++spin) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(addr), "r"(parity)
-            : "memory");
-        if (done) return true;
-    }
-    if (err) atomicExch(err, 1);
-    return false;
-}
-
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-// UMMA shared-memory descriptor, K-major, SWIZZLE_NONE (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
-//   [0,14) start>>4   [16,30) LBO>>4 (between the two 16-byte K chunks of one MMA)   [32,46) SBO>>4 (between 8-row groups)
-//   [46,48) version = 1   [61,64) layout type = 0
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ULL << 46);
-}
-// instruction descriptor (InstrDescriptor): D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), K-major both,
-// N>>3 at bit 17, M>>4 at bit 24
-__host__ __device__ constexpr uint32_t umma_idesc(int m, int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
 template <int KC, int NR>
 struct TcCfg {
     static constexpr int CPR = KC / 8;                       // 16-byte chunks per gathered row
@@ -133,27 +68,6 @@ __global__ void cast_bf16_kernel(const float4* __restrict__ in, uint2* __restric
         o.y = *reinterpret_cast<uint32_t*>(&b);
         out[i] = o;
     }
-}
-
-// weight images: per offset k a [NR rows][KC] bf16 matrix in the UMMA K-major core-matrix layout.
-//   mode 0 (forward): B[n=co][kk=ci] = w[co][k][ci]
-//   mode 1 (dgrad)  : B[n=ci][kk=co] = w[co][k'][ci],  k' = mirror ? K-1-k : k
-__global__ void prep_weights_tc_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ img, int cin, int cout,
-                                       int K, int mode, int mirror) {
-    int NRr = mode == 0 ? cout : cin, KCc = mode == 0 ? cin : cout;
-    int total = K * NRr * KCc;
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    int kk = i % KCc, n = (i / KCc) % NRr, k = i / (KCc * NRr);
-    float v;
-    if (mode == 0) {
-        v = w[((size_t)n * K + k) * cin + kk];
-    } else {
-        int ks = mirror ? (K - 1 - k) : k;
-        v = w[((size_t)kk * K + ks) * cin + n];
-    }
-    size_t off = (size_t)k * NRr * KCc + ((size_t)((n >> 3) * (KCc >> 3) + (kk >> 3)) * 64) + (n & 7) * 8 + (kk & 7);
-    img[off] = __float2bfloat16_rn(v);
 }
 
 // Warp-specialised: warps 0-3 are gather producers (each owns 32 rows of the tile and streams its 16-byte chunks of
@@ -544,52 +458,24 @@ int tc_scatter_with_image(int kc, int nr, const void* dout_bf16, const void* wim
     return VC_ERR_UNSUPPORTED;
 }
 
-// ---- entry points for the plan executor (executor.cu): pre-built weight images, one batched prep launch ----
-int tc_conv_with_image(int kc, int nr, const void* in_bf16, const void* wimg, const int32_t* nbr, float* out, int n_rows,
-                       int K, double* bn_sums, int* err, cudaStream_t stream, const float* addend) {
+// ---- entry point for the plan executor (executor.cu) and the per-operator C ABI: pre-built weight images ----
+// variant 1 (default): the persistent kernel of conv_tc2.cu (swizzled images, C = 8 supported, optional device row count);
+// variant 0: the round-1 kernel above (core-matrix images, C >= 16, host row count, dense table pitch)
+int tc_conv_with_image(int kc, int nr, const void* in_bf16, const void* wimg, const int32_t* nbr, long long pitch, float* out,
+                       int n_rows, const int* n_dev, int K, double* bn_sums, int* err, cudaStream_t stream, const float* addend,
+                       int* tile_counter) {
     if (n_rows == 0) return VC_OK;
+    if (g_tc_variant == 1)
+        return tc2_conv(kc, nr, in_bf16, wimg, nbr, pitch, out, n_rows, n_dev, K, bn_sums, err, stream, addend, tile_counter);
+    if (n_dev != nullptr || pitch != n_rows) {
+        set_error("round-1 tensor-core conv kernel needs a host row count and a dense table");
+        return VC_ERR_UNSUPPORTED;
+    }
     return dispatch_tc(kc, nr, (const __nv_bfloat16*)in_bf16, (const __nv_bfloat16*)wimg, nbr, out, n_rows, K, bn_sums, err,
                        stream, addend);
 }
 
-// every layer's forward / dgrad weight image in ONE launch: thread i -> (entry, element) by binary search over the
-// entries' element prefix
-__global__ void __launch_bounds__(256) prep_weights_tc_batch_kernel(TcPrepTable t) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= t.total) return;
-    int lo = 0, hi = t.n - 1;
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (t.e[mid].first <= i) lo = mid; else hi = mid - 1;
-    }
-    const TcPrepEntry& e = t.e[lo];
-    const int j = i - e.first;
-    const int cin = e.cin, cout = e.cout, K = e.K;
-    const int NRr = e.mode == 0 ? cout : cin, KCc = e.mode == 0 ? cin : cout;
-    const int kk = j % KCc, n = (j / KCc) % NRr, k = j / (KCc * NRr);
-    float v;
-    if (e.mode == 0) {
-        v = e.w[((size_t)n * K + k) * cin + kk];
-    } else {
-        const int ks = e.mirror ? (K - 1 - k) : k;
-        v = e.w[((size_t)kk * K + ks) * cin + n];
-    }
-    const size_t off = (size_t)k * NRr * KCc + ((size_t)((n >> 3) * (KCc >> 3) + (kk >> 3)) * 64) + (n & 7) * 8 + (kk & 7);
-    reinterpret_cast<__nv_bfloat16*>(e.img)[off] = __float2bfloat16_rn(v);
-}
-
-int tc_prep_images(TcPrepTable& t, cudaStream_t stream) {
-    if (t.n == 0) return VC_OK;
-    int total = 0;
-    for (int i = 0; i < t.n; ++i) {
-        t.e[i].first = total;
-        total += t.e[i].K * t.e[i].cin * t.e[i].cout;
-    }
-    t.total = total;
-    prep_weights_tc_batch_kernel<<<cdiv(total, 256), 256, 0, stream>>>(t);
-    VC_LAUNCH_CHECK();
-    return VC_OK;
-}
+bool tc_conv_ch_ok(int c) { return g_tc_variant == 1 ? tc2_ch_ok(c) : tc_ch_ok(c); }
 
 }  // namespace vc
 
@@ -608,13 +494,21 @@ extern "C" int vc_cast_f32_bf16(const float* in, void* out, long long n, vc_stre
     return VC_OK;
 }
 
-extern "C" size_t vc_conv_tc_ws_bytes(int cin, int cout, int K) { return (size_t)K * cin * cout * 2; }
+extern "C" size_t vc_conv_tc_ws_bytes(int cin, int cout, int K) { return vc::tc_image_bytes(cin, cout, K, 1); }   // >= either layout
+
+static int tc_one_image(const float* w, void* img, int cin, int cout, int K, int mode, int mirror, int layout, cudaStream_t stream) {
+    TcPrepTable T;
+    T.n = 1;
+    TcPrepEntry& e = T.e[0];
+    e.w = w; e.img = img; e.cin = cin; e.cout = cout; e.K = K; e.mode = mode; e.mirror = mirror; e.layout = layout; e.first = 0;
+    return tc_prep_images(T, stream);
+}
 
 static int tc_common(const void* feats_bf16, const float* w, const int32_t* nbr, float* out, int n_rows, int cin, int cout,
                      int K, int mode, int mirror, double* bn_sums, void* ws, size_t ws_bytes, int32_t* err, cudaStream_t stream) {
     VC_CHECK_ARG(n_rows >= 0 && K >= 1 && K <= MAXK_TC, "bad n=%d or K=%d", n_rows, K);
-    if (!tc_ch_ok(cin) || !tc_ch_ok(cout)) {
-        set_error("tensor-core conv: unsupported channels cin=%d cout=%d (need 16/32/64)", cin, cout);
+    if (!tc_conv_ch_ok(cin) || !tc_conv_ch_ok(cout)) {
+        set_error("tensor-core conv: unsupported channels cin=%d cout=%d", cin, cout);
         return VC_ERR_UNSUPPORTED;
     }
     if (n_rows == 0) return VC_OK;
@@ -623,12 +517,10 @@ static int tc_common(const void* feats_bf16, const float* w, const int32_t* nbr,
         set_error("tensor-core conv workspace %zu < %zu", ws_bytes, vc_conv_tc_ws_bytes(cin, cout, K));
         return VC_ERR_WORKSPACE;
     }
-    __nv_bfloat16* img = (__nv_bfloat16*)ws;
-    int total = K * cin * cout;
-    prep_weights_tc_kernel<<<cdiv(total, 256), 256, 0, stream>>>(w, img, cin, cout, K, mode, mirror);
-    VC_LAUNCH_CHECK();
+    int rc = tc_one_image(w, ws, cin, cout, K, mode, mirror, g_tc_variant, stream);
+    if (rc) return rc;
     int kc = mode == 0 ? cin : cout, nr = mode == 0 ? cout : cin;
-    return dispatch_tc(kc, nr, (const __nv_bfloat16*)feats_bf16, img, nbr, out, n_rows, K, bn_sums, err, stream);
+    return tc_conv_with_image(kc, nr, feats_bf16, ws, nbr, n_rows, out, n_rows, nullptr, K, bn_sums, err, stream, nullptr);
 }
 
 extern "C" int vc_conv_fwd_tc(const void* in_bf16, const float* w, const int32_t* nbr, float* out, int n_out, int cin,
@@ -653,11 +545,9 @@ extern "C" int vc_conv_dgrad_scatter_tc(const void* dout_bf16, const float* w, c
         set_error("tensor-core conv workspace %zu < %zu", ws_bytes, vc_conv_tc_ws_bytes(cin, cout, K));
         return VC_ERR_WORKSPACE;
     }
-    __nv_bfloat16* img = (__nv_bfloat16*)ws;
-    int total = K * cin * cout;
-    prep_weights_tc_kernel<<<cdiv(total, 256), 256, 0, stream>>>(w, img, cin, cout, K, 1, 0);
-    VC_LAUNCH_CHECK();
-    return tc_scatter_with_image(cout, cin, dout_bf16, img, nbr, din, n_out, K, err_flag, stream);
+    int rc = tc_one_image(w, ws, cin, cout, K, 1, 0, 0, stream);
+    if (rc) return rc;
+    return tc_scatter_with_image(cout, cin, dout_bf16, ws, nbr, din, n_out, K, err_flag, stream);
 }
 
 extern "C" int vc_conv_dgrad_tc(const void* dout_bf16, const float* w, const int32_t* nbr_t, float* din, int n_in, int cin,

@@ -1,0 +1,588 @@
+// bf16 tensor-core sparse convolution, forward and dgrad — PERSISTENT variant (round 2), tcgen05 / TMEM, sm_100a only.
+//
+// Same contraction as conv_tc.cu (output-stationary 128-row tiles, per kernel offset one [128 x C_in] x [C_in x C_out]
+// UMMA accumulating in TMEM), restructured around what the round-1 profiles and profiles/exp_gather4_r2.txt measured:
+//   * a launch of the old kernel was ONE wave of short-lived CTAs, each a chain of <= 27 dependent
+//     {table read -> gather round trip -> MMA -> commit} links on a 2-deep ring: latency bound at 6-9 % of the HBM peak;
+//   * the gather throughput of an SM is set by how many independent 16-byte cp.async a producer warp can keep in flight
+//     (1.2+ row slots/clk/SM with 16 warps and a deep ring); TMA tile::gather4 tops out at 0.35 row slots/clk/SM with all
+//     rows in bounds and 0.11 with the rulebooks' 57 % missing neighbours, so the gather stays on cp.async and the TMA
+//     engine carries the weight slices.
+// One CTA per SM lives for the whole launch and walks its tiles (tile = blockIdx.x + i * gridDim.x):
+//   warps 0-3   epilogue: TMEM -> registers -> shared staging -> coalesced fp32 stores (+ addend), BatchNorm channel sums
+//               kept in registers across ALL tiles of the CTA (one set of float64 atomics per CTA, not per tile);
+//   warp  4     table loader: the NEXT tile's slice of the neighbour table (K x 128 int32) into a double-buffered shared
+//               copy, plus the list of kernel offsets that touch the tile — producers never wait for global memory;
+//   warp  5     MMA issuer: C_in/16 tcgen05.mma per (tile, offset) into one of TWO TMEM accumulators, so the epilogue of
+//               tile i overlaps the main loop of tile i+1; tcgen05.commit frees the operand stage;
+//   warps 6-13  gather producers: 16 rows each, 16-byte cp.async (zero fill for missing neighbours and for the padded
+//               channels of the C = 8 layers) straight into the 32/64/128-byte-swizzled K-major operand image, completion
+//               through cp.async.mbarrier.arrive.noinc on the stage's `full` barrier; the ring is as deep as shared memory
+//               allows (6-32 stages) and runs ACROSS tile boundaries, so there is no per-tile pipeline fill or drain.
+// The row count may come from device memory (n_dev): the grid is sized from a host-side capacity and every role derives
+// its tile list from *n_dev, which is what makes the plan executor CUDA-graph capturable (no host read of a row count).
+// Replaces spconv `ops.indice_conv` / `indice_conv_backward` (input gradient) behind spconv_backbone.py:89,92-93,113,563-564.
+// Algorithmic bytes per launch: N_in*C_in*2 + N_out*C_out*4 + P*8 + K*C_in*C_out*2;  FLOPs 2*P*C_in*C_out.
+#include "tc_common.cuh"
+
+namespace vc {
+
+int g_tc_variant = 1;   // 1: this kernel; 0: the round-1 kernel (conv_tc.cu) — vc_set_tc_variant, A/B runs only
+
+namespace {
+
+constexpr int P_WARP_LOADER = 4, P_WARP_MMA = 5, P_WARP_PROD0 = 6, P_PROD_WARPS = 8;
+constexpr int P_THREADS = 32 * (P_WARP_PROD0 + P_PROD_WARPS);   // 448
+constexpr int P_MAX_STAGES = 16;
+constexpr int P_NTB = 4;                                        // neighbour-table buffers (the loader runs 2 tiles ahead)
+constexpr int P_AHEAD = 2;                                      // table loads in flight
+constexpr int P_ROWS_PER_PROD = TCM / P_PROD_WARPS;             // 16
+constexpr int SMEM_BUDGET = 227 * 1024 - 3072;                  // dynamic shared memory per CTA (static part is small)
+
+template <int KC, int NR>
+struct PCfg {
+    static constexpr int ROWB = KC * 2;                      // bytes per gathered operand row == swizzle span
+    static constexpr int CPR = KC / 8;                       // 16-byte chunks per row
+    static constexpr int G = 64 / KC;                        // kernel offsets per ring stage: 16 KB of gathered rows per stage
+    static constexpr int A_BYTES = TCM * ROWB;               // one offset's gathered tile
+    static constexpr int B_BYTES = NR * ROWB;                // one offset's weight slice
+    static constexpr int STAGE = G * (A_BYTES + B_BYTES);    // [G x A | G x B]
+    static constexpr int TMEM_COLS = 2 * NR < 32 ? 32 : 2 * NR;   // two accumulators
+    static constexpr int STG_LD = NR + 1;                    // staging row pitch (floats)
+    static constexpr int STG_BYTES = TCM * STG_LD * 4;
+};
+
+struct PArgs {
+    const __nv_bfloat16* in;   // gathered operand rows, row pitch in_c elements
+    int in_c;                  // real channels of a row (8 or KC)
+    const unsigned char* wimg; // K swizzled [NR][KC] images
+    const int32_t* nbr;        // [K][pitch]
+    long long pitch;
+    float* out;                // [n, out_c]
+    int out_c;                 // real output channels (8 or NR)
+    const float* addend;       // optional [n, out_c], may alias out
+    double* bn_sums;           // optional [2, out_c]
+    const int* n_dev;          // optional device row count (n_host is then the capacity of the buffers)
+    int n_host;
+    int* tile_counter;         // optional (zeroed by the caller): dynamic tile scheduling; NULL: tile = blockIdx.x + i * gridDim.x
+    int K, S;
+    int* err;
+};
+
+#ifdef VC_TC_TRACE
+// debug build only (profiles/trace_tc2.py): globaltimer stamps of CTA 0's pipeline events, 256 slots per role
+// role 0 loader (table published), 1 producer leader (stage issued), 2 MMA (stage consumed), 3 MMA (tile committed),
+// 4 epilogue (tile start), 5 epilogue (tile end), 6 misc (kernel start / roles start / end)
+__device__ long long* g_trace2 = nullptr;
+__device__ __forceinline__ void ptrace(int role, int& idx) {
+    if (g_trace2 != nullptr && blockIdx.x == 0 && idx < 256) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        g_trace2[role * 256 + idx] = (long long)t;
+        ++idx;
+    }
+}
+#define P_TRACE(role, idx) ptrace(role, idx)
+#else
+#define P_TRACE(role, idx) do { } while (0)
+#endif
+
+#define P_WAIT(bar, parity)                                   \
+    do {                                                      \
+        if (!mbar_wait_t((bar), (parity), a.err)) goto done;  \
+    } while (0)
+
+template <int KC, int NR>
+__global__ void __launch_bounds__(P_THREADS, 1) tc_conv_persist_kernel(const PArgs a) {
+    using C = PCfg<KC, NR>;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int S = a.S, K = a.K;
+    unsigned char* ring = smem_raw;                                              // [S][G x A | G x B]
+    int* nbr_s = reinterpret_cast<int*>(smem_raw + (size_t)S * C::STAGE);        // [P_NTB][K][128]
+    float* stg = reinterpret_cast<float*>(nbr_s + (size_t)P_NTB * K * TCM);      // [128][STG_LD]
+    __shared__ __align__(8) uint64_t full_bar[P_MAX_STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[P_MAX_STAGES];
+    __shared__ __align__(8) uint64_t tbl_full[P_NTB], tbl_empty[P_NTB];
+    __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
+    __shared__ int klist_s[P_NTB][MAXK_TC];
+    __shared__ int nk_s[P_NTB], tile_s[P_NTB];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ double red_s[2][TCM];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int tr = 0, tr2 = 0;      // trace cursors (debug build)
+    (void)tr; (void)tr2;
+    if (tid == 0) P_TRACE(6, tr);
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                     "r"((uint32_t)C::TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    if (tid == P_WARP_MMA * 32) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(&full_bar[s], 32 * P_PROD_WARPS + 1);    // every producer thread (cp.async arrive) + the weight expect_tx
+            mbar_init(&empty_bar[s], 1);                       // tcgen05.commit
+        }
+        for (int b = 0; b < P_NTB; ++b) {
+            mbar_init(&tbl_full[b], 1);                        // loader
+            mbar_init(&tbl_empty[b], P_PROD_WARPS + 1 + 4);    // producers + MMA warp + epilogue warps
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&acc_full[b], 1);                        // tcgen05.commit
+            mbar_init(&acc_empty[b], 4);                       // epilogue warps
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    pdl_wait();                 // everything below reads what the previous kernel of the chain wrote
+    pdl_launch_dependents();
+    const int n = a.n_dev != nullptr ? min(__ldg(a.n_dev), a.n_host) : a.n_host;
+    const int n_tiles = (n + TCM - 1) / TCM;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    if (tid == 0) P_TRACE(6, tr);
+    // epilogue threads: BatchNorm partial sums over all tiles of this CTA.  Every tile contributes fp32 partials over fixed
+    // row groups, summed in float64 — the result does not depend on which CTA processed which tile (dynamic scheduling)
+    double bs = 0.0, bq = 0.0;
+
+    if (warp == P_WARP_LOADER) {
+        // ------------------------------------------------------------ tile scheduler + neighbour-table loader
+        // Table slices travel global -> shared with cp.async (no register staging), P_AHEAD tiles in flight: producers
+        // never wait for global memory, and the loader's own latency is pipelined across tiles.
+        const bool vec_ok = (reinterpret_cast<uintptr_t>(a.nbr) & 15u) == 0 && (a.pitch & 3) == 0;
+        int my_tile[P_AHEAD + 1];       // tiles of the loads in flight (ring indexed by it % (P_AHEAD + 1))
+        bool stop = false;
+        int issued = 0;
+        auto issue = [&](int it) -> bool {           // returns false on a pipeline timeout
+            const int tb = it % P_NTB;
+            if (it >= P_NTB && !mbar_wait_t(&tbl_empty[tb], (uint32_t)(((it / P_NTB) - 1) & 1), a.err)) return false;
+            int tile;
+            if (a.tile_counter != nullptr) {
+                tile = lane == 0 ? atomicAdd(a.tile_counter, 1) : 0;
+                tile = __shfl_sync(0xffffffffu, tile, 0);
+            } else {
+                tile = blockIdx.x + it * gridDim.x;
+            }
+            if (tile >= n_tiles) tile = -1;
+            my_tile[it % (P_AHEAD + 1)] = tile;
+            if (tile >= 0) {
+                int* dst = nbr_s + (size_t)tb * K * TCM;
+                const int base = tile * TCM;
+                if (vec_ok && (long long)base + TCM <= a.pitch) {
+                    const uint32_t d0 = smem_u32(dst) + lane * 16;
+                    const int32_t* s0 = a.nbr + base + lane * 4;
+                    for (int k = 0; k < K; ++k) cp_async16_s(d0 + k * (TCM * 4), s0 + (size_t)k * a.pitch, true);
+                } else {
+                    for (int k = 0; k < K; ++k) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int row = base + q * 32 + lane;
+                            if (row < n) {
+                                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_u32(dst + k * TCM + q * 32 + lane)),
+                                             "l"(a.nbr + (size_t)k * a.pitch + row));
+                            } else {
+                                dst[k * TCM + q * 32 + lane] = -1;
+                            }
+                        }
+                    }
+                }
+            }
+            cp_async_commit();
+            return true;
+        };
+        for (int it = 0;; ++it) {
+            // keep P_AHEAD table loads in flight
+            while (!stop && issued <= it + P_AHEAD - 1) {
+                if (!issue(issued)) goto done;
+                if (my_tile[issued % (P_AHEAD + 1)] < 0) stop = true;
+                ++issued;
+            }
+            const int tb = it % P_NTB;
+            const int tile = my_tile[it % (P_AHEAD + 1)];
+            // groups are committed in order: allow (issued - it - 1) younger ones to stay in flight
+            if (issued - it - 1 >= 1) cp_async_wait<1>(); else cp_async_wait<0>();
+            __syncwarp();
+            if (tile < 0) {
+                if (lane == 0) {
+                    tile_s[tb] = -1;
+                    mbar_arrive(&tbl_full[tb]);
+                }
+                break;
+            }
+            int* dst = nbr_s + (size_t)tb * K * TCM;
+            const int base = tile * TCM;
+            unsigned km = 0u;
+            const bool partial = base + TCM > n;
+            for (int k = 0; k < K; ++k) {
+                int4 v = reinterpret_cast<const int4*>(dst + k * TCM)[lane];
+                if (partial) {          // rows beyond the count (static mode / last tile): no neighbour
+                    const int r0 = base + lane * 4;
+                    bool ch = false;
+                    if (r0 + 0 >= n && v.x != -1) { v.x = -1; ch = true; }
+                    if (r0 + 1 >= n && v.y != -1) { v.y = -1; ch = true; }
+                    if (r0 + 2 >= n && v.z != -1) { v.z = -1; ch = true; }
+                    if (r0 + 3 >= n && v.w != -1) { v.w = -1; ch = true; }
+                    if (ch) reinterpret_cast<int4*>(dst + k * TCM)[lane] = v;
+                }
+                const bool any = (v.x >= 0) | (v.y >= 0) | (v.z >= 0) | (v.w >= 0);
+                if (__any_sync(0xffffffffu, any)) km |= 1u << k;
+            }
+            if (lane == 0) {
+                int c = 0;
+                for (int k = 0; k < K; ++k)
+                    if (km >> k & 1u) klist_s[tb][c++] = k;
+                nk_s[tb] = c;
+                tile_s[tb] = tile;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&tbl_full[tb]);
+                P_TRACE(0, tr);
+            }
+        }
+    } else if (warp >= P_WARP_PROD0) {
+        // ------------------------------------------------------------ gather producers
+        const int pw = warp - P_WARP_PROD0;
+        constexpr int CW = C::CPR < 4 ? C::CPR : 4;         // chunks of one row handled by adjacent lanes (full sectors)
+        constexpr int RPI = 32 / CW;                        // rows per warp instruction
+        constexpr int NIT = P_ROWS_PER_PROD / RPI;          // row groups per offset and warp
+        constexpr int NCG = C::CPR / CW;                    // chunk groups per row
+        static_assert(P_ROWS_PER_PROD % RPI == 0, "producer rows must be a multiple of the rows per instruction");
+        const int c_sub = lane % CW, r_sub = lane / CW;
+        int rows[NIT];
+        uint32_t dst_off[NIT][NCG];
+        bool ch_ok[NCG];
+#pragma unroll
+        for (int i = 0; i < NIT; ++i) {
+            rows[i] = pw * P_ROWS_PER_PROD + i * RPI + r_sub;
+#pragma unroll
+            for (int cg = 0; cg < NCG; ++cg) dst_off[i][cg] = swz_off<C::ROWB>(rows[i], cg * CW + c_sub);
+        }
+#pragma unroll
+        for (int cg = 0; cg < NCG; ++cg) ch_ok[cg] = (cg * CW + c_sub) * 8 < a.in_c;
+        const uint32_t ring_s = smem_u32(ring);
+        const bool leader = pw == 0 && lane == 0;
+        int s = 0;
+        uint32_t ph = 0;       // parity of the `empty` phase to wait for once the ring has wrapped
+        bool wrapped = false;
+        for (int it = 0;; ++it) {
+            const int tb = it % P_NTB;
+            P_WAIT(&tbl_full[tb], (uint32_t)((it / P_NTB) & 1));
+            if (tile_s[tb] < 0) break;
+            const int nk = nk_s[tb];
+            const int* tbl = nbr_s + (size_t)tb * K * TCM;
+            for (int t0 = 0; t0 < nk; t0 += C::G) {
+                const int cnt = min(C::G, nk - t0);
+                int kk[C::G];
+                int src[C::G][NIT];
+#pragma unroll
+                for (int g = 0; g < C::G; ++g) {
+                    kk[g] = g < cnt ? klist_s[tb][t0 + g] : 0;
+#pragma unroll
+                    for (int i = 0; i < NIT; ++i) src[g][i] = g < cnt ? tbl[kk[g] * TCM + rows[i]] : -1;
+                }
+                if (wrapped) P_WAIT(&empty_bar[s], ph);
+                const uint32_t st_s = ring_s + (uint32_t)s * C::STAGE;
+#pragma unroll
+                for (int g = 0; g < C::G; ++g) {
+                    if (g < cnt) {
+                        const uint32_t a_s = st_s + (uint32_t)g * C::A_BYTES;
+#pragma unroll
+                        for (int i = 0; i < NIT; ++i) {
+                            const bool v = src[g][i] >= 0;
+                            const __nv_bfloat16* srow = a.in + (size_t)(v ? src[g][i] : 0) * a.in_c + c_sub * 8;
+#pragma unroll
+                            for (int cg = 0; cg < NCG; ++cg) {
+                                const bool vc = v && ch_ok[cg];
+                                cp_async16_s(a_s + dst_off[i][cg], vc ? srow + cg * CW * 8 : a.in, vc);
+                            }
+                        }
+                    }
+                }
+                if (leader) {
+                    mbar_expect_tx(&full_bar[s], (uint32_t)(cnt * C::B_BYTES));
+                    for (int g = 0; g < cnt; ++g)
+                        bulk_g2s(st_s + C::G * C::A_BYTES + (uint32_t)g * C::B_BYTES, a.wimg + (size_t)kk[g] * C::B_BYTES,
+                                 (uint32_t)C::B_BYTES, &full_bar[s]);
+                }
+                cp_async_arrive_noinc(&full_bar[s]);
+                if (leader) P_TRACE(1, tr);
+                if (++s == S) {
+                    s = 0;
+                    if (wrapped) ph ^= 1u;
+                    wrapped = true;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tbl_empty[tb]);
+        }
+    } else if (warp == P_WARP_MMA) {
+        // ------------------------------------------------------------ MMA issuer
+        constexpr uint32_t IDESC = umma_idesc(TCM, NR);
+        int s = 0;
+        uint32_t ph = 0;
+        for (int it = 0;; ++it) {
+            const int tb = it % P_NTB, ab = it & 1;
+            P_WAIT(&tbl_full[tb], (uint32_t)((it / P_NTB) & 1));
+            if (tile_s[tb] < 0) break;
+            const int nk = nk_s[tb];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tbl_empty[tb]);
+            if (it >= 2) P_WAIT(&acc_empty[ab], (uint32_t)(((it >> 1) - 1) & 1));
+            tc_fence_after();
+            const uint32_t acc = tmem_base + (uint32_t)(ab * NR);
+            for (int t0 = 0; t0 < nk; t0 += C::G) {
+                const int cnt = min(C::G, nk - t0);
+                P_WAIT(&full_bar[s], ph);
+                fence_async_smem();     // generic-proxy (cp.async) writes -> visible to the tensor core's async proxy
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t st_s = smem_u32(ring) + (uint32_t)s * C::STAGE;
+                    for (int g = 0; g < cnt; ++g) {
+                        const uint32_t a0 = st_s + (uint32_t)g * C::A_BYTES;
+                        const uint32_t b0 = st_s + C::G * C::A_BYTES + (uint32_t)g * C::B_BYTES;
+#pragma unroll
+                        for (int m = 0; m < KC / 16; ++m)
+                            umma_f16(acc, umma_desc_sw<C::ROWB>(a0 + m * 32), umma_desc_sw<C::ROWB>(b0 + m * 32), IDESC,
+                                     (t0 > 0 || g > 0 || m > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[s]);
+                    P_TRACE(2, tr);
+                    if (t0 + cnt >= nk) {
+                        umma_commit(&acc_full[ab]);
+                        P_TRACE(3, tr2);
+                    }
+                }
+                __syncwarp();
+                if (++s == S) {
+                    s = 0;
+                    ph ^= 1u;
+                }
+            }
+            if (nk == 0 && lane == 0) umma_commit(&acc_full[ab]);   // (cannot happen for a valid tile; keeps the epilogue live)
+            __syncwarp();
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue (warps 0-3 == TMEM lane quarters)
+        const int e = tid;                       // 0..127
+        const int oc = a.out_c;
+        const int ch = e % oc, rg = e / oc, n_rg = TCM / oc;
+        for (int it = 0;; ++it) {
+            const int tb = it % P_NTB, ab = it & 1;
+            P_WAIT(&tbl_full[tb], (uint32_t)((it / P_NTB) & 1));
+            const int tile = tile_s[tb];
+            if (tile < 0) break;
+            const int nk = nk_s[tb];
+            const int base = tile * TCM;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tbl_empty[tb]);
+            P_WAIT(&acc_full[ab], (uint32_t)((it >> 1) & 1));
+            tc_fence_after();
+            if (tid == 0) P_TRACE(4, tr);
+            const int r = warp * 32 + lane;
+#pragma unroll
+            for (int c0 = 0; c0 < NR; c0 += 16) {
+                float v[16];
+                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(ab * NR + c0), v);
+                if (c0 < oc) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (c0 + i < oc) stg[r * C::STG_LD + c0 + i] = nk > 0 ? v[i] : 0.f;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[ab]);      // the accumulator may be overwritten by tile it + 2
+            named_bar_sync(1, 128);
+            // coalesced fp32 stores: consecutive threads -> consecutive float4 of the [128, out_c] tile
+            const int oc4 = oc >> 2;
+            for (int q = e; q < TCM * oc4; q += 128) {
+                const int rr = q / oc4, c4 = q % oc4;
+                if (base + rr < n) {
+                    const float* sp = stg + rr * C::STG_LD + c4 * 4;
+                    float4 v = make_float4(sp[0], sp[1], sp[2], sp[3]);
+                    const size_t o = (size_t)(base + rr) * oc + c4 * 4;
+                    if (a.addend != nullptr) {      // same element read and written by this thread only: aliasing `out` is safe
+                        const float4 w = *reinterpret_cast<const float4*>(a.addend + o);
+                        v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+                    }
+                    *reinterpret_cast<float4*>(a.out + o) = v;
+                }
+            }
+            if (a.bn_sums != nullptr) {
+                const int rows_valid = min(TCM, n - base);
+                float ts = 0.f, tq = 0.f;
+                for (int rr = rg; rr < rows_valid; rr += n_rg) {
+                    const float x = stg[rr * C::STG_LD + ch];
+                    ts += x;
+                    tq = fmaf(x, x, tq);
+                }
+                bs += (double)ts;
+                bq += (double)tq;
+            }
+            named_bar_sync(1, 128);
+            if (tid == 0) P_TRACE(5, tr2);
+        }
+    }
+done:
+    cp_async_wait<0>();
+    if (warp < 4 && a.bn_sums != nullptr) {
+        // (after a pipeline timeout the sums are garbage like everything else; the error flag says so)
+        const int e = tid, oc = a.out_c, n_rg = TCM / oc;
+        red_s[0][e] = bs;
+        red_s[1][e] = bq;
+        named_bar_sync(2, 128);
+        if (e < 2 * oc) {
+            const int which = e / oc, c = e % oc;
+            double v = 0.0;
+            for (int g = 0; g < n_rg; ++g) v += red_s[which][g * oc + c];
+            atomicAdd(a.bn_sums + which * oc + c, v);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS));
+    }
+}
+
+// weight images for the kernel above: per offset k a [NRp rows][KCp] bf16 matrix, K-major, rows = one swizzle span,
+// zero padded to NRp / KCp = max(16, .)
+//   mode 0 (forward): B[n=co][kk=ci] = w[co][k][ci]
+//   mode 1 (dgrad)  : B[n=ci][kk=co] = w[co][k'][ci],  k' = mirror ? K-1-k : k
+template <int ROWB>
+__device__ __forceinline__ size_t img_off(int k, int n, int kk, int NRp) {
+    return (size_t)k * NRp * ROWB + swz_off<ROWB>(n, kk >> 3) + (size_t)(kk & 7) * 2;
+}
+
+int num_sms() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+template <int KC, int NR>
+int launch_persist(const PArgs& a0, int n_cap, cudaStream_t stream) {
+    using C = PCfg<KC, NR>;
+    PArgs a = a0;
+    const size_t fixed = (size_t)P_NTB * a.K * TCM * 4 + C::STG_BYTES;
+    int S = (int)((SMEM_BUDGET - fixed) / C::STAGE);
+    if (S > P_MAX_STAGES) S = P_MAX_STAGES;
+    if (S < 2) {
+        set_error("tensor-core conv: no room for the operand ring (K=%d, %d->%d)", a.K, KC, NR);
+        return VC_ERR_UNSUPPORTED;
+    }
+    a.S = S;
+    const size_t smem = (size_t)S * C::STAGE + fixed;
+    auto kern = tc_conv_persist_kernel<KC, NR>;
+    static bool attr_done = false;            // per instantiation
+    if (!attr_done) {
+        VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
+        attr_done = true;
+    }
+    const int tiles = cdiv(n_cap, TCM);
+    const int grid = tiles < num_sms() ? (tiles < 1 ? 1 : tiles) : num_sms();
+    VC_LAUNCH_CHAIN(kern, dim3(grid), dim3(P_THREADS), smem, stream, a);
+    return VC_OK;
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(256) prep_weights_tc_batch_kernel(TcPrepTable t) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= t.total) return;
+    int lo = 0, hi = t.n - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (t.e[mid].first <= i) lo = mid; else hi = mid - 1;
+    }
+    const TcPrepEntry& e = t.e[lo];
+    const int j = i - e.first;
+    const int cin = e.cin, cout = e.cout, K = e.K;
+    const int NRr = e.mode == 0 ? cout : cin, KCc = e.mode == 0 ? cin : cout;     // real dims
+    const int NRp = e.layout ? tc_pad16(NRr) : NRr, KCp = e.layout ? tc_pad16(KCc) : KCc;
+    const int kk = j % KCp, n = (j / KCp) % NRp, k = j / (KCp * NRp);
+    float v = 0.f;
+    if (n < NRr && kk < KCc) {
+        if (e.mode == 0) {
+            v = e.w[((size_t)n * K + k) * cin + kk];
+        } else {
+            const int ks = e.mirror ? (K - 1 - k) : k;
+            v = e.w[((size_t)kk * K + ks) * cin + n];
+        }
+    }
+    const __nv_bfloat16 b = __float2bfloat16_rn(v);
+    if (e.layout == 0) {      // round-1 image: 8-row x 16-byte core matrices, no swizzle (tc_scatter_kernel, legacy gather kernel)
+        const size_t off = (size_t)k * NRr * KCc + ((size_t)((n >> 3) * (KCc >> 3) + (kk >> 3)) * 64) + (n & 7) * 8 + (kk & 7);
+        reinterpret_cast<__nv_bfloat16*>(e.img)[off] = b;
+    } else {
+        unsigned char* p = reinterpret_cast<unsigned char*>(e.img);
+        const size_t off = KCp == 64 ? img_off<128>(k, n, kk, NRp) : KCp == 32 ? img_off<64>(k, n, kk, NRp) : img_off<32>(k, n, kk, NRp);
+        *reinterpret_cast<__nv_bfloat16*>(p + off) = b;
+    }
+}
+
+size_t tc_image_bytes(int cin, int cout, int K, int layout) {
+    return layout ? (size_t)K * tc_pad16(cin) * tc_pad16(cout) * 2 : (size_t)K * cin * cout * 2;
+}
+
+int tc_prep_images(TcPrepTable& t, cudaStream_t stream) {
+    if (t.n == 0) return VC_OK;
+    int total = 0;
+    for (int i = 0; i < t.n; ++i) {
+        t.e[i].first = total;
+        total += (int)(tc_image_bytes(t.e[i].cin, t.e[i].cout, t.e[i].K, t.e[i].layout) / 2);
+    }
+    t.total = total;
+    prep_weights_tc_batch_kernel<<<cdiv(total, 256), 256, 0, stream>>>(t);
+    VC_LAUNCH_CHECK();
+    return VC_OK;
+}
+
+bool tc2_ch_ok(int c) { return c == 8 || c == 16 || c == 32 || c == 64; }
+
+// kc = channels of the gathered operand rows (reduction), nr = channels of the result; wimg = K swizzled images
+// (layout 1).  n_dev (optional) overrides n_rows on the device; n_rows is then the capacity the grid is sized for.
+int tc2_conv(int kc, int nr, const void* in_bf16, const void* wimg, const int32_t* nbr, long long pitch, float* out,
+             int n_rows, const int* n_dev, int K, double* bn_sums, int* err, cudaStream_t stream, const float* addend,
+             int* tile_counter) {
+    if (n_rows == 0) return VC_OK;
+    if (!tc2_ch_ok(kc) || !tc2_ch_ok(nr) || K < 1 || K > MAXK_TC) {
+        set_error("tensor-core conv: unsupported shape (%d -> %d channels, K=%d)", kc, nr, K);
+        return VC_ERR_UNSUPPORTED;
+    }
+    PArgs a;
+    a.in = (const __nv_bfloat16*)in_bf16; a.in_c = kc; a.wimg = (const unsigned char*)wimg; a.nbr = nbr; a.pitch = pitch;
+    a.out = out; a.out_c = nr; a.addend = addend; a.bn_sums = bn_sums; a.n_dev = n_dev; a.n_host = n_rows; a.tile_counter = tile_counter;
+    a.K = K; a.S = 0;
+    a.err = err;
+    const int kcp = tc_pad16(kc), nrp = tc_pad16(nr);
+#define VC_P_CASE(A, B) \
+    if (kcp == A && nrp == B) return launch_persist<A, B>(a, n_rows, stream);
+    VC_P_CASE(16, 16) VC_P_CASE(16, 32) VC_P_CASE(16, 64)
+    VC_P_CASE(32, 16) VC_P_CASE(32, 32) VC_P_CASE(32, 64)
+    VC_P_CASE(64, 16) VC_P_CASE(64, 32) VC_P_CASE(64, 64)
+#undef VC_P_CASE
+    return VC_ERR_UNSUPPORTED;
+}
+
+}  // namespace vc
+
+#ifdef VC_TC_TRACE
+extern "C" int vc_debug_set_trace2(long long* buf) {
+    return cudaMemcpyToSymbol(vc::g_trace2, &buf, sizeof(buf)) == cudaSuccess ? 0 : -2;
+}
+#endif
+
+extern "C" int vc_set_tc_variant(int variant) {
+    VC_CHECK_ARG(variant == 0 || variant == 1, "tensor-core conv variant must be 0 (round-1 kernel) or 1 (persistent)");
+    vc::g_tc_variant = variant;
+    return VC_OK;
+}

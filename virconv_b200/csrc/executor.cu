@@ -37,6 +37,7 @@ enum { P_W = 0, P_GAMMA, P_BETA, P_RM, P_RV, P_NBT, P_DW, P_DGAMMA, P_DBETA, P_C
 
 struct ISet {
     int32_t* idx;
+    const int* n_dev;      // static mode: the row count lives on the device and `n` is the capacity of the buffers
     int n, ndim, shape[3];
     int ev;  // event to wait on when consumed from the other stream (-1: none), stream that produced it
     int prod;
@@ -45,22 +46,25 @@ struct FSlot {
     float* f32;
     void* bf16;
     float* grad;
+    const int* n_dev;      // static mode (see ISet)
     int rows, c, grad_state, ev, prod;
 };
 struct RBk {
     int32_t *nbr, *nbr_bwd, *pair_num;
+    const int *n_in_dev, *n_out_dev;   // static mode (see ISet); table pitches are n_out (nbr) and n_in (nbr_bwd)
     int K, n_in, n_out, subm, unique, ev, prod;
 };
 struct Layer {
     float *x, *y, *stats;
     double* sums;          // [4*cout]: forward sums, backward sums
+    int* tile_ctr;         // [2] tile-scheduler counters of the persistent conv kernels (forward, dgrad), zeroed with the sums
     void *wimg_fwd, *wimg_dgrad;
-    int in_slot, out_slot, rb, use_tc, cin, cout, need_dgrad;
+    int in_slot, out_slot, rb, use_tc, use_tc_w, cin, cout, need_dgrad;   // use_tc: conv fwd / gather dgrad; use_tc_w: wgrad / scatter dgrad
 };
 struct State {
     uint64_t magic;
     size_t used;           // arena bytes in use after the last call
-    int n_ops, n_layers, training, precision, batch_size;
+    int n_ops, n_layers, training, precision, batch_size, is_static;
     ISet iset[MAX_I];
     FSlot f[MAX_F];
     RBk rb[MAX_RB];
@@ -294,7 +298,7 @@ extern "C" int vc_exec_query(const void* state, int what, int id, long long* out
             VC_CHECK_ARG(id >= 0 && id < MAX_I, "index-set id");
             const ISet& s = S->iset[id];
             out[0] = (long long)(uintptr_t)s.idx; out[1] = s.n; out[2] = s.ndim; out[3] = s.shape[0]; out[4] = s.shape[1];
-            out[5] = s.shape[2];
+            out[5] = s.shape[2]; out[6] = (long long)(uintptr_t)s.n_dev;
             return VC_OK;
         }
         case 3: {
@@ -322,7 +326,13 @@ extern "C" int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_o
                                const int32_t* shape0, int batch_size, const float* proj_params, int training, int precision,
                                int want_pair_num, void* arena, size_t arena_bytes, int32_t* pinned_host, int32_t* err_flag,
                                void* state, size_t state_bytes, vc_stream_t main_stream, vc_stream_t side_stream,
-                               int side_waits_main) {
+                               int side_waits_main, const int32_t* caps, const int32_t* n0_dev, int32_t* overflow_flag) {
+    // Static mode (n0_dev != NULL; CUDA-graph capturable: no host read of a device value, every buffer sized from host-side
+    // capacities): n0 is the capacity of the input buffers, *n0_dev the number of valid rows, caps[i] the row capacity of
+    // index set i (the strided convs' outputs); every data-dependent row count stays in device memory, kernels clamp to the
+    // capacities and report an overflow through *overflow_flag (the largest row count that did not fit).
+    const bool is_static = n0_dev != nullptr;
+    VC_CHECK_ARG(!is_static || (caps && overflow_flag), "static mode needs capacities and an overflow flag");
     VC_TRY(check_plan(ops_i, n_ops, n_layers));
     VC_CHECK_ARG(state && state_bytes >= sizeof(State), "state blob too small (%zu < %zu)", state_bytes, sizeof(State));
     VC_CHECK_ARG(feats0 && idx0 && n0 > 0 && shape0 && batch_size > 0 && arena && pinned_host && ops_f && layer_ptrs && layer_f,
@@ -332,6 +342,7 @@ extern "C" int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_o
     State* S = new (state) State();
     memset(S, 0, sizeof(State));
     S->n_ops = n_ops; S->n_layers = n_layers; S->training = training; S->precision = precision; S->batch_size = batch_size;
+    S->is_static = is_static;
     for (int i = 0; i < MAX_I; ++i) S->iset[i].ev = -1;
     for (int i = 0; i < MAX_F; ++i) S->f[i].ev = -1;
     for (int i = 0; i < MAX_RB; ++i) S->rb[i].ev = -1;
@@ -344,9 +355,9 @@ extern "C" int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_o
     C.err = err_flag;
     const bool two = C.st[0] != C.st[1];
 
-    S->iset[0].idx = const_cast<int32_t*>(idx0); S->iset[0].n = n0; S->iset[0].ndim = 3;
+    S->iset[0].idx = const_cast<int32_t*>(idx0); S->iset[0].n = n0; S->iset[0].ndim = 3; S->iset[0].n_dev = n0_dev;
     for (int d = 0; d < 3; ++d) S->iset[0].shape[d] = shape0[d];
-    S->f[0].f32 = const_cast<float*>(feats0); S->f[0].rows = n0; S->f[0].c = c0;
+    S->f[0].f32 = const_cast<float*>(feats0); S->f[0].rows = n0; S->f[0].c = c0; S->f[0].n_dev = n0_dev;
 
     // rulebook meta known from the plan alone (needed to choose the dgrad weight images)
     int rb_subm[MAX_RB] = {0}, rb_unique[MAX_RB] = {0}, rb_K[MAX_RB] = {0};
@@ -361,13 +372,17 @@ extern "C" int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_o
         }
     }
 
-    // BatchNorm accumulators of every layer: one region, one memset
-    size_t sums_doubles = 0;
+    // BatchNorm accumulators + tile-scheduler counters of every layer: one region, one memset
+    size_t sums_doubles = 0, n_cbr = 0;
     for (int i = 0; i < n_ops; ++i)
-        if (C.op(i)[F_KIND] == OP_CBR) sums_doubles += 4 * (size_t)C.op(i)[F_COUT];
-    VC_ALLOC(sums_all, double*, sums_doubles * 8);
-    if (sums_doubles) VC_CUDA(cudaMemsetAsync(sums_all, 0, sums_doubles * 8, C.st[0]));
-    size_t sums_cur = 0;
+        if (C.op(i)[F_KIND] == OP_CBR) {
+            sums_doubles += 4 * (size_t)C.op(i)[F_COUT];
+            ++n_cbr;
+        }
+    VC_ALLOC(sums_all, double*, sums_doubles * 8 + n_cbr * 2 * sizeof(int));
+    int* ctr_all = reinterpret_cast<int*>(sums_all + sums_doubles);
+    if (sums_doubles) VC_CUDA(cudaMemsetAsync(sums_all, 0, sums_doubles * 8 + n_cbr * 2 * sizeof(int), C.st[0]));
+    size_t sums_cur = 0, ctr_cur = 0;
 
     // tensor-core weight images of every layer, one launch
     for (int i = 0; i < n_ops; ++i) {
@@ -376,9 +391,11 @@ extern "C" int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_o
         Layer& L = S->layer[o[F_LAYER]];
         L.cin = o[F_CIN]; L.cout = o[F_COUT]; L.in_slot = o[F_A]; L.out_slot = o[F_B]; L.rb = o[F_C];
         L.need_dgrad = o[F_X0];
-        L.use_tc = precision == 1 && tc_ok(L.cin) && tc_ok(L.cout);
+        L.use_tc = precision == 1 && tc_conv_ch_ok(L.cin) && tc_conv_ch_ok(L.cout);
+        L.use_tc_w = precision == 1 && tc_ok(L.cin) && tc_ok(L.cout);
         L.sums = sums_all + sums_cur;
         sums_cur += 4 * (size_t)L.cout;
+        L.tile_ctr = ctr_all + 2 * ctr_cur++;
     }
     if (precision == 1) {
         TcPrepTable T;
@@ -389,13 +406,13 @@ extern "C" int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_o
             Layer& L = S->layer[o[F_LAYER]];
             if (!L.use_tc) continue;
             const int K = rb_K[L.rb];
-            const size_t bytes = (size_t)K * L.cin * L.cout * 2;
             // dgrad image: mirrored for a submanifold table used as its own transpose, plain for a strided conv's
-            // nbr_bwd table and for the many-to-one image-branch table (tensor-core scatter)
+            // nbr_bwd table and for the many-to-one image-branch table (tensor-core scatter, round-1 image layout)
             const bool many_to_one = rb_subm[L.rb] && !rb_unique[L.rb];
-            const bool dgrad_tc = training && L.need_dgrad;
+            const bool dgrad_tc = training && L.need_dgrad && (!many_to_one || L.use_tc_w);
             for (int mode = 0; mode < (dgrad_tc ? 2 : 1); ++mode) {
-                VC_ALLOC(img, void*, bytes);
+                const int layout = (mode == 1 && many_to_one) ? 0 : g_tc_variant;
+                VC_ALLOC(img, void*, tc_image_bytes(L.cin, L.cout, K, layout));
                 (mode == 0 ? L.wimg_fwd : L.wimg_dgrad) = img;
                 if (T.n == TC_PREP_MAX) {
                     VC_TRY(tc_prep_images(T, C.st[0]));
@@ -404,6 +421,7 @@ extern "C" int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_o
                 TcPrepEntry& e = T.e[T.n++];
                 e.w = C.P<const float>(o[F_LAYER], P_W); e.img = img; e.cin = L.cin; e.cout = L.cout; e.K = K; e.mode = mode;
                 e.mirror = mode == 1 && rb_subm[L.rb] && !many_to_one;
+                e.layout = layout;
             }
         }
         VC_TRY(tc_prep_images(T, C.st[0]));
@@ -438,18 +456,28 @@ extern "C" int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_o
         const size_t wsb = vc_conv_rulebook_ws_bytes(I.ndim, batch_size, oshape);
         VC_ALLOC(ws, void*, wsb);
         VC_ALLOC(n_dev, int32_t*, 4);
-        VC_TRY(vc_conv_rulebook_count(I.idx, I.n, I.ndim, batch_size, I.shape, o + F_KS, o + F_ST, o + F_PD, o + F_DL, n_dev, ws, wsb,
-                                      st));
-        VC_CUDA(cudaMemcpyAsync(pinned_host + (n_syncs & 15), n_dev, 4, cudaMemcpyDeviceToHost, st));
-        VC_CUDA(cudaStreamSynchronize(st));        // the one data-dependent size per strided conv
-        const int n_out = pinned_host[n_syncs & 15];
-        ++n_syncs;
+        int n_out;
+        if (is_static) {
+            n_out = caps[o[F_B]];
+            VC_CHECK_ARG(n_out > 0, "op %d: static mode needs a capacity for index set %d", j, o[F_B]);
+            VC_TRY(conv_rulebook_count_dev(I.idx, I.n, I.n_dev, I.ndim, batch_size, I.shape, o + F_KS, o + F_ST, o + F_PD, o + F_DL,
+                                           n_dev, n_out, overflow_flag, ws, wsb, st));
+        } else {
+            VC_TRY(conv_rulebook_count_dev(I.idx, I.n, nullptr, I.ndim, batch_size, I.shape, o + F_KS, o + F_ST, o + F_PD, o + F_DL,
+                                           n_dev, 0, nullptr, ws, wsb, st));
+            VC_CUDA(cudaMemcpyAsync(pinned_host + (n_syncs & 15), n_dev, 4, cudaMemcpyDeviceToHost, st));
+            VC_CUDA(cudaStreamSynchronize(st));        // the one data-dependent size per strided conv
+            n_out = pinned_host[n_syncs & 15];
+            ++n_syncs;
+        }
         R.K = rb_K[o[F_C]]; R.n_in = I.n; R.n_out = n_out; R.subm = 0; R.unique = 1;
-        O.n = n_out; O.ndim = I.ndim;
+        R.n_in_dev = I.n_dev; R.n_out_dev = is_static ? n_dev : nullptr;
+        O.n = n_out; O.ndim = I.ndim; O.n_dev = R.n_out_dev;
         for (int d = 0; d < 3; ++d) O.shape[d] = oshape[d];
         VC_ALLOC(oidx, int32_t*, (size_t)(n_out > 0 ? n_out : 1) * (1 + I.ndim) * 4);
         O.idx = oidx;
-        VC_TRY(conv_rulebook_fill_phases(I.idx, I.n, I.ndim, batch_size, I.shape, o + F_KS, o + F_ST, o + F_PD, o + F_DL, n_out, O.idx,
+        if (is_static) VC_CUDA(cudaMemsetAsync(oidx, 0xFF, (size_t)n_out * (1 + I.ndim) * 4, st));   // defined tail (-1) for the published indices
+        VC_TRY(conv_rulebook_fill_phases(I.idx, I.n, I.n_dev, I.ndim, batch_size, I.shape, o + F_KS, o + F_ST, o + F_PD, o + F_DL, n_out, O.idx,
                                          nullptr, nullptr, nullptr, ws, wsb, st, 1));
         O.prod = s;
         O.ev = s == 1 ? (last_side_ev = record_on(C, 1)) : -1;
@@ -469,6 +497,7 @@ extern "C" int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_o
                 VC_CHECK_ARG(I.idx && I.ndim == o[F_NDIM], "op %d: index set %d not built / wrong ndim", i, o[F_A]);
                 VC_TRY(wait_for(C, I.ev, I.prod, s));
                 R.K = rb_K[o[F_C]]; R.n_in = R.n_out = I.n; R.subm = 1; R.unique = o[F_X0];
+                R.n_in_dev = R.n_out_dev = I.n_dev;
                 VC_ALLOC(nbr, int32_t*, (size_t)R.K * I.n * 4);
                 R.nbr = nbr;
                 if (want_pair_num) {
@@ -477,7 +506,7 @@ extern "C" int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_o
                 }
                 const size_t wsb = vc_subm_rulebook_ws_bytes(I.n);
                 VC_ALLOC(ws, void*, wsb);
-                VC_TRY(vc_subm_rulebook(I.idx, I.n, I.ndim, batch_size, I.shape, o + F_KS, o + F_DL, R.nbr, R.pair_num, ws, wsb, st));
+                VC_TRY(subm_rulebook_dev(I.idx, I.n, I.n_dev, I.ndim, batch_size, I.shape, o + F_KS, o + F_DL, R.nbr, R.pair_num, ws, wsb, st));
                 R.prod = s;
                 R.ev = s == 1 ? (last_side_ev = record_on(C, 1)) : -1;
                 break;
@@ -504,7 +533,7 @@ extern "C" int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_o
                     VC_ALLOC(pn, int32_t*, (size_t)R.K * 4);
                     R.pair_num = pn;
                 }
-                VC_TRY(conv_rulebook_fill_phases(I.idx, I.n, I.ndim, batch_size, I.shape, o + F_KS, o + F_ST, o + F_PD, o + F_DL,
+                VC_TRY(conv_rulebook_fill_phases(I.idx, I.n, I.n_dev, I.ndim, batch_size, I.shape, o + F_KS, o + F_ST, o + F_PD, o + F_DL,
                                                  R.n_out, O.idx, R.nbr, R.nbr_bwd, R.pair_num, chain_ws[i], chain_wsb[i], st, 2));
                 R.prod = s;
                 R.ev = s == 1 ? (last_side_ev = record_on(C, 1)) : -1;
@@ -516,8 +545,8 @@ extern "C" int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_o
                 VC_CHECK_ARG(I.idx && I.ndim == 3 && proj_params, "op %d: index2uv needs a built 3-D index set and projection params", i);
                 VC_TRY(wait_for(C, I.ev, I.prod, s));
                 VC_ALLOC(uv, int32_t*, (size_t)I.n * 3 * 4);
-                O.idx = uv; O.n = I.n; O.ndim = 2; O.shape[0] = o[F_KS]; O.shape[1] = o[F_KS + 1]; O.shape[2] = 0;
-                VC_TRY(vc_index2uv(I.idx, I.n, batch_size, proj_params, fo, o[F_X0], o[F_X1], o[F_X2], uv, st));
+                O.idx = uv; O.n = I.n; O.ndim = 2; O.shape[0] = o[F_KS]; O.shape[1] = o[F_KS + 1]; O.shape[2] = 0; O.n_dev = I.n_dev;
+                VC_TRY(index2uv_dev(I.idx, I.n, I.n_dev, batch_size, proj_params, fo, o[F_X0], o[F_X1], o[F_X2], uv, st));
                 O.prod = s;
                 O.ev = s == 1 ? (last_side_ev = record_on(C, 1)) : -1;
                 break;
@@ -550,17 +579,18 @@ extern "C" int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_o
                         X.bf16 = xb;
                     }
                     Timed t(1, li, st);
-                    VC_TRY(tc_conv_with_image(L.cin, L.cout, X.bf16, L.wimg_fwd, R.nbr, x, R.n_out, R.K, sums, C.err, st));
+                    VC_TRY(tc_conv_with_image(L.cin, L.cout, X.bf16, L.wimg_fwd, R.nbr, R.n_out, x, R.n_out, R.n_out_dev, R.K, sums, C.err, st,
+                                              nullptr, L.tile_ctr));
                 } else {
                     const size_t wsb = vc_conv_ws_bytes(L.cin, L.cout, R.K);
                     VC_ALLOC(ws, void*, wsb);
                     Timed t(0, li, st);
                     VC_TRY(vc_conv_fwd_f32(X.f32, C.P<const float>(li, P_W), R.nbr, x, R.n_out, L.cin, L.cout, R.K, sums, ws, wsb, st));
                 }
-                VC_TRY(vc_bn_apply_relu_f32(x, L.sums, R.n_out, L.cout, C.P<const float>(li, P_GAMMA), C.P<const float>(li, P_BETA),
-                                            C.P<float>(li, P_RM), C.P<float>(li, P_RV), C.P<long long>(li, P_NBT),
-                                            C.lf[2 * li + 1], C.lf[2 * li], training, y, yb, stats, 1, st));
-                Y.f32 = y; Y.bf16 = yb; Y.rows = R.n_out; Y.c = L.cout; Y.prod = s;
+                VC_TRY(bn_apply_relu_dev(x, L.sums, R.n_out, R.n_out_dev, L.cout, C.P<const float>(li, P_GAMMA), C.P<const float>(li, P_BETA),
+                                         C.P<float>(li, P_RM), C.P<float>(li, P_RV), C.P<long long>(li, P_NBT), C.lf[2 * li + 1],
+                                         C.lf[2 * li], training, y, L.cout, yb, L.cout, stats, 1, is_static, st));
+                Y.f32 = y; Y.bf16 = yb; Y.rows = R.n_out; Y.c = L.cout; Y.prod = s; Y.n_dev = R.n_out_dev;
                 Y.ev = s == 1 ? (last_side_ev = record_on(C, 1)) : -1;
                 break;
             }
@@ -578,8 +608,8 @@ extern "C" int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_o
                     VC_ALLOC(ob_, void*, elems * 2);
                     ob = ob_;
                 }
-                VC_TRY(vc_cat2_f32(Aa.f32, Bb.f32, out, ob, Aa.rows, Aa.c, Bb.c, st));
-                O.f32 = out; O.bf16 = ob; O.rows = Aa.rows; O.c = Aa.c + Bb.c; O.prod = s;
+                VC_TRY(cat2_dev(Aa.f32, Bb.f32, out, ob, Aa.rows, Aa.n_dev, Aa.c, Bb.c, st));
+                O.f32 = out; O.bf16 = ob; O.rows = Aa.rows; O.c = Aa.c + Bb.c; O.prod = s; O.n_dev = Aa.n_dev;
                 O.ev = s == 1 ? (last_side_ev = record_on(C, 1)) : -1;
                 break;
             }
@@ -724,18 +754,18 @@ extern "C" int vc_exec_backward(const int32_t* ops_i, const float* ops_f, int n_
         const size_t elems = (size_t)R.n_out * L.cout;
         VC_ALLOC(dx, float*, elems * 4);
         void* dxb = nullptr;
-        if (L.use_tc) {
+        if (S->precision == 1) {
             VC_ALLOC(t, void*, elems * 2);
             dxb = t;
         }
-        VC_TRY(vc_bn_relu_bwd_f32(Y.grad, L.x, L.y, C.P<const float>(li, P_GAMMA), L.stats, dx, dxb, dgamma, dbeta, R.n_out, L.cout,
-                                  training, L.sums + 2 * L.cout, st));
+        VC_TRY(bn_relu_bwd_dev(Y.grad, L.cout, L.x, C.P<const float>(li, P_GAMMA), L.stats, dx, dxb, dgamma, dbeta, R.n_out, R.n_out_dev,
+                               L.cout, training, L.sums + 2 * L.cout, S->is_static, st));
         // wgrad (needs dx / its bf16 shadow: ordered after the BN backward through an event when on its own stream)
         if (two) {
             int e = record_on(C, 0);
             if (e >= 0) VC_CUDA(cudaStreamWaitEvent(wst, g_ev[e], 0));
         }
-        if (L.use_tc) {
+        if (L.use_tc_w) {
             const size_t wsb = vc_conv_wgrad_tc_ws_bytes(R.n_out, L.cin, L.cout, R.K);
             VC_ALLOC(ws, void*, wsb);
             Timed t(6, li, wst);
@@ -749,7 +779,7 @@ extern "C" int vc_exec_backward(const int32_t* ops_i, const float* ops_f, int n_
         if (two) last_w_ev = record_on(C, 1);
         // dgrad
         if (!L.need_dgrad || L.in_slot == 0) continue;
-        if (R.subm && !R.unique && L.use_tc && L.wimg_dgrad) {
+        if (R.subm && !R.unique && L.use_tc_w && L.wimg_dgrad) {
             VC_TRY(contribute_scatter(C, X, st, [&](float* dst) -> int {
                 Timed t(7, li, st);
                 return tc_scatter_with_image(L.cout, L.cin, dxb, L.wimg_dgrad, R.nbr, dst, R.n_out, R.K, C.err, st);
@@ -765,7 +795,8 @@ extern "C" int vc_exec_backward(const int32_t* ops_i, const float* ops_f, int n_
             const int32_t* table = R.subm ? R.nbr : R.nbr_bwd;
             VC_TRY(contribute_fused(C, X, [&](float* dst, const float* addend) -> int {
                 Timed t(3, li, st);
-                return tc_conv_with_image(L.cout, L.cin, dxb, L.wimg_dgrad, table, dst, R.n_in, R.K, nullptr, C.err, st, addend);
+                return tc_conv_with_image(L.cout, L.cin, dxb, L.wimg_dgrad, table, R.n_in, dst, R.n_in, R.n_in_dev, R.K, nullptr, C.err, st,
+                                          addend, L.tile_ctr + 1);
             }));
         } else {
             const size_t wsb = vc_conv_ws_bytes(L.cin, L.cout, R.K);

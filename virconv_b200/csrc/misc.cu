@@ -25,9 +25,10 @@ struct UVGrid {
 // Voxel index -> pixel cell.  Every float op is an explicitly rounded fp32 multiply / add / divide in the
 // order oracle/index2uv.py fixes (no FMA contraction), so the integer result is bit-identical to it.
 // Reference arithmetic: spconv_backbone.py:8-24,54-83; X_transform.py:139-154; calibration_kitti.py:120-153.
-__global__ void __launch_bounds__(256) index2uv_kernel(const int4* __restrict__ idx, int n, int batch_size,
-                                                       const float* __restrict__ params, UVGrid g, int stride,
+__global__ void __launch_bounds__(256) index2uv_kernel(const int4* __restrict__ idx, int n, const int* __restrict__ n_dev,
+                                                       int batch_size, const float* __restrict__ params, UVGrid g, int stride,
                                                        int u_max, int v_max, int32_t* __restrict__ uv) {
+    if (n_dev != nullptr) n = min(n, __ldg(n_dev));
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int4 v = idx[i];  // (b, z, y, x)
@@ -108,15 +109,18 @@ __global__ void gather_rows4_kernel(const uint32_t* __restrict__ in, const int32
 }
 
 // out[:, :ca] = a, out[:, ca:] = b (fp32) plus an optional bf16 shadow of the same matrix; float4 granularity
+// (n_dev: device row count, n = capacity; rows [count, capacity) are written as zeros — the concat is a published tensor)
 __global__ void cat2_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float4* __restrict__ out,
-                            uint2* __restrict__ out_bf16, int n, int ca4, int cb4) {
+                            uint2* __restrict__ out_bf16, int n, const int* __restrict__ n_dev, int ca4, int cb4) {
     pdl_wait();
     pdl_launch_dependents();
+    const int cnt = n_dev != nullptr ? min(n, __ldg(n_dev)) : n;
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     int w = ca4 + cb4;
     if (t >= (long long)n * w) return;
     int r = (int)(t / w), c = (int)(t % w);
-    float4 v = c < ca4 ? a[(size_t)r * ca4 + c] : b[(size_t)r * cb4 + (c - ca4)];
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < cnt) v = c < ca4 ? a[(size_t)r * ca4 + c] : b[(size_t)r * cb4 + (c - ca4)];
     out[t] = v;
     if (out_bf16 != nullptr) {
         __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
@@ -131,16 +135,20 @@ __global__ void cat2_kernel(const float4* __restrict__ a, const float4* __restri
 
 using namespace vc;
 
-extern "C" int vc_cat2_f32(const float* a, const float* b, float* out, void* out_bf16, int n, int ca, int cb,
-                           vc_stream_t stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
+int vc::cat2_dev(const float* a, const float* b, float* out, void* out_bf16, int n, const int* n_dev, int ca, int cb,
+                 cudaStream_t stream) {
     VC_CHECK_ARG(n >= 0 && ca > 0 && cb > 0 && ca % 4 == 0 && cb % 4 == 0, "bad cat2 arguments");
     if (n == 0) return VC_OK;
     VC_CHECK_ARG(a && b && out, "null pointer");
     long long total = (long long)n * (ca + cb) / 4;
     VC_LAUNCH_CHAIN(cat2_kernel, dim3(cdiv(total, 256)), dim3(256), 0, stream, (const float4*)a, (const float4*)b, (float4*)out,
-                    (uint2*)out_bf16, n, ca / 4, cb / 4);
+                    (uint2*)out_bf16, n, n_dev, ca / 4, cb / 4);
     return VC_OK;
+}
+
+extern "C" int vc_cat2_f32(const float* a, const float* b, float* out, void* out_bf16, int n, int ca, int cb,
+                           vc_stream_t stream_) {
+    return vc::cat2_dev(a, b, out, out_bf16, n, nullptr, ca, cb, (cudaStream_t)stream_);
 }
 
 extern "C" int vc_version(void) { return 100; }
@@ -151,17 +159,21 @@ extern "C" int vc_set_pdl(int enable) {
     return VC_OK;
 }
 
-extern "C" int vc_index2uv(const int32_t* indices, int n, int batch_size, const float* params, const float* grid,
-                           int stride, int u_max, int v_max, int32_t* uv_out, vc_stream_t stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
+int vc::index2uv_dev(const int32_t* indices, int n, const int* n_dev, int batch_size, const float* params, const float* grid,
+                     int stride, int u_max, int v_max, int32_t* uv_out, cudaStream_t stream) {
     VC_CHECK_ARG(n >= 0 && batch_size > 0 && stride > 0 && u_max > 0 && v_max > 0 && grid, "bad index2uv arguments");
     if (n == 0) return VC_OK;
     VC_CHECK_ARG(indices && params && uv_out, "null pointer");
     UVGrid g{grid[0], grid[1], grid[2], grid[3], grid[4], grid[5]};
-    index2uv_kernel<<<cdiv(n, 256), 256, 0, stream>>>((const int4*)indices, n, batch_size, params, g, stride, u_max, v_max,
+    index2uv_kernel<<<cdiv(n, 256), 256, 0, stream>>>((const int4*)indices, n, n_dev, batch_size, params, g, stride, u_max, v_max,
                                                       uv_out);
     VC_LAUNCH_CHECK();
     return VC_OK;
+}
+
+extern "C" int vc_index2uv(const int32_t* indices, int n, int batch_size, const float* params, const float* grid,
+                           int stride, int u_max, int v_max, int32_t* uv_out, vc_stream_t stream_) {
+    return vc::index2uv_dev(indices, n, nullptr, batch_size, params, grid, stride, u_max, v_max, uv_out, (cudaStream_t)stream_);
 }
 
 static int dense_common(const float* features, const int32_t* indices, int n, int c, int ndim, int batch_size,

@@ -40,8 +40,11 @@ __device__ __forceinline__ void load_index(const int32_t* __restrict__ idx, int 
 // ------------------------------------------------------------------------------------------------
 // hash table
 // ------------------------------------------------------------------------------------------------
-__global__ void hash_insert_kernel(const int32_t* __restrict__ idx, int n, Geom g, unsigned long long* table,
-                                   uint32_t mask) {
+// (every kernel below that takes a row count `n` also takes `n_dev`: when non-NULL the count is read from device memory
+// and `n` is the capacity the grid / buffers were sized for — the plan executor's static mode, CUDA-graph capturable)
+__global__ void hash_insert_kernel(const int32_t* __restrict__ idx, int n, const int* __restrict__ n_dev, Geom g,
+                                   unsigned long long* table, uint32_t mask) {
+    if (n_dev != nullptr) n = min(n, __ldg(n_dev));
     int row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= n) return;
     int b, c[VC_MAX_NDIM];
@@ -78,11 +81,14 @@ __device__ __forceinline__ int hash_lookup(const unsigned long long* __restrict_
 // One thread per (output row, kernel offset): grid (ceil(n/256), K).  Every probe chain is independent, so the
 // hash look-ups of all K offsets are in flight together (the per-row loop this replaced was latency bound);
 // nbr[k, row] writes stay fully coalesced.  Pair counts: warp ballot -> shared counter -> one atomic per block.
-__global__ void __launch_bounds__(256) subm_probe_kernel(const int32_t* __restrict__ idx, int n, Geom g,
+__global__ void __launch_bounds__(256) subm_probe_kernel(const int32_t* __restrict__ idx, int n,
+                                                         const int* __restrict__ n_dev, Geom g,
                                                          const unsigned long long* __restrict__ table,
                                                          uint32_t mask, int32_t* __restrict__ nbr,
                                                          int32_t* __restrict__ pair_num) {
     __shared__ int cnt;
+    const int pitch = n;                  // table rows are [K][capacity]
+    if (n_dev != nullptr) n = min(n, __ldg(n_dev));
     if (threadIdx.x == 0) cnt = 0;
     __syncthreads();
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
@@ -107,7 +113,9 @@ __global__ void __launch_bounds__(256) subm_probe_kernel(const int32_t* __restri
             }
             if (ok) res = hash_lookup(table, mask, key);
         }
-        nbr[(size_t)k * n + row] = res;
+        nbr[(size_t)k * pitch + row] = res;
+    } else if (row < pitch) {
+        nbr[(size_t)k * pitch + row] = -1;    // static mode: rows between the count and the capacity have no neighbours
     }
     unsigned m = __ballot_sync(0xffffffffu, res >= 0);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(&cnt, __popc(m));
@@ -135,7 +143,9 @@ __device__ __forceinline__ long long out_cell(const Geom& g, int b, const int* c
     return lin;
 }
 
-__global__ void conv_mark_kernel(const int32_t* __restrict__ idx, int n, Geom g, uint32_t* bitmap) {   // grid (rows, K)
+__global__ void conv_mark_kernel(const int32_t* __restrict__ idx, int n, const int* __restrict__ n_dev, Geom g,
+                                 uint32_t* bitmap) {   // grid (rows, K)
+    if (n_dev != nullptr) n = min(n, __ldg(n_dev));
     int row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= n) return;
     int b, c[VC_MAX_NDIM];
@@ -182,7 +192,9 @@ __global__ void __launch_bounds__(256) scan_local_kernel(const uint32_t* __restr
 }
 
 // single block: exclusive scan of block sums in place; total -> n_out
-__global__ void __launch_bounds__(1024) scan_blocks_kernel(uint32_t* block_sum, int n_blocks, int32_t* n_out) {
+// (cap > 0: the output buffers hold `cap` rows; a larger total is clamped and reported through *overflow)
+__global__ void __launch_bounds__(1024) scan_blocks_kernel(uint32_t* block_sum, int n_blocks, int32_t* n_out, int cap,
+                                                           int* overflow) {
     __shared__ uint32_t warp_tot[32];
     __shared__ uint32_t carry_s;
     if (threadIdx.x == 0) carry_s = 0;
@@ -206,7 +218,14 @@ __global__ void __launch_bounds__(1024) scan_blocks_kernel(uint32_t* block_sum, 
         if (threadIdx.x == 1023) carry_s = carry + woff + incl;
         __syncthreads();
     }
-    if (threadIdx.x == 0) *n_out = (int32_t)carry_s;
+    if (threadIdx.x == 0) {
+        int total = (int)carry_s;
+        if (cap > 0 && total > cap) {
+            if (overflow != nullptr) atomicMax(overflow, total);
+            total = cap;
+        }
+        *n_out = total;
+    }
 }
 
 __device__ __forceinline__ int cell_rank(const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ word_rank,
@@ -218,7 +237,7 @@ __device__ __forceinline__ int cell_rank(const uint32_t* __restrict__ bitmap, co
 
 __global__ void conv_emit_indices_kernel(const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ word_rank,
                                          const uint32_t* __restrict__ block_sum, long long n_words, Geom g,
-                                         int32_t* __restrict__ out_idx) {
+                                         int32_t* __restrict__ out_idx, int cap) {
     long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= n_words) return;
     uint32_t word = bitmap[w];
@@ -227,6 +246,7 @@ __global__ void conv_emit_indices_kernel(const uint32_t* __restrict__ bitmap, co
     while (word) {
         int bit = __ffs(word) - 1;
         word &= word - 1;
+        if (row >= cap) return;           // capacity overflow (flagged by scan_blocks_kernel)
         long long lin = (w << 5) + bit;
         int c[VC_MAX_NDIM];
         for (int d = g.ndim - 1; d >= 0; --d) {
@@ -240,13 +260,16 @@ __global__ void conv_emit_indices_kernel(const uint32_t* __restrict__ bitmap, co
     }
 }
 
-__global__ void __launch_bounds__(256) conv_tables_kernel(const int32_t* __restrict__ idx, int n, int n_out, Geom g,
+__global__ void __launch_bounds__(256) conv_tables_kernel(const int32_t* __restrict__ idx, int n, const int* __restrict__ n_dev,
+                                                          int n_out, Geom g,
                                                           const uint32_t* __restrict__ bitmap,
                                                           const uint32_t* __restrict__ word_rank,
                                                           const uint32_t* __restrict__ block_sum,
                                                           int32_t* __restrict__ nbr_fwd, int32_t* __restrict__ nbr_bwd,
                                                           int32_t* __restrict__ pair_num) {   // grid (rows, K)
     __shared__ int cnt;
+    const int pitch_in = n;               // nbr_bwd rows are [K][input capacity], nbr_fwd rows [K][n_out = output capacity]
+    if (n_dev != nullptr) n = min(n, __ldg(n_dev));
     if (threadIdx.x == 0) cnt = 0;
     __syncthreads();
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
@@ -258,9 +281,12 @@ __global__ void __launch_bounds__(256) conv_tables_kernel(const int32_t* __restr
         long long lin = out_cell(g, b, c, k);
         if (lin >= 0) {
             orow = cell_rank(bitmap, word_rank, block_sum, lin);
-            nbr_fwd[(size_t)k * n_out + orow] = row;  // unique writer: (o,k) determines the input cell
+            if (orow < n_out) nbr_fwd[(size_t)k * n_out + orow] = row;  // unique writer: (o,k) determines the input cell
+            else orow = -1;                                             // beyond the output capacity (overflow flagged)
         }
-        nbr_bwd[(size_t)k * n + row] = orow;
+        nbr_bwd[(size_t)k * pitch_in + row] = orow;
+    } else if (row < pitch_in) {
+        nbr_bwd[(size_t)k * pitch_in + row] = -1;   // static mode: rows between the count and the capacity
     }
     unsigned m = __ballot_sync(0xffffffffu, orow >= 0);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(&cnt, __popc(m));
@@ -341,10 +367,9 @@ using namespace vc;
 
 extern "C" size_t vc_subm_rulebook_ws_bytes(int n) { return (size_t)table_slots(n) * sizeof(unsigned long long); }
 
-extern "C" int vc_subm_rulebook(const int32_t* indices, int n, int ndim, int batch_size, const int32_t* spatial_shape,
-                                const int32_t* ksize, const int32_t* dilation, int32_t* nbr, int32_t* pair_num,
-                                void* ws, size_t ws_bytes, vc_stream_t stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
+int vc::subm_rulebook_dev(const int32_t* indices, int n, const int* n_dev, int ndim, int batch_size,
+                          const int32_t* spatial_shape, const int32_t* ksize, const int32_t* dilation, int32_t* nbr,
+                          int32_t* pair_num, void* ws, size_t ws_bytes, cudaStream_t stream) {
     Geom g;
     int rc = make_geom(g, ndim, spatial_shape, ksize, nullptr, nullptr, dilation);
     if (rc) return rc;
@@ -362,11 +387,18 @@ extern "C" int vc_subm_rulebook(const int32_t* indices, int n, int ndim, int bat
     }
     unsigned long long* table = (unsigned long long*)ws;
     VC_CUDA(cudaMemsetAsync(table, 0xFF, (size_t)slots * 8, stream));
-    hash_insert_kernel<<<cdiv(n, 256), 256, 0, stream>>>(indices, n, g, table, slots - 1);
+    hash_insert_kernel<<<cdiv(n, 256), 256, 0, stream>>>(indices, n, n_dev, g, table, slots - 1);
     VC_LAUNCH_CHECK();
-    subm_probe_kernel<<<dim3(cdiv(n, 256), g.K), 256, 0, stream>>>(indices, n, g, table, slots - 1, nbr, pair_num);
+    subm_probe_kernel<<<dim3(cdiv(n, 256), g.K), 256, 0, stream>>>(indices, n, n_dev, g, table, slots - 1, nbr, pair_num);
     VC_LAUNCH_CHECK();
     return VC_OK;
+}
+
+extern "C" int vc_subm_rulebook(const int32_t* indices, int n, int ndim, int batch_size, const int32_t* spatial_shape,
+                                const int32_t* ksize, const int32_t* dilation, int32_t* nbr, int32_t* pair_num,
+                                void* ws, size_t ws_bytes, vc_stream_t stream_) {
+    return vc::subm_rulebook_dev(indices, n, nullptr, ndim, batch_size, spatial_shape, ksize, dilation, nbr, pair_num, ws, ws_bytes,
+                                 (cudaStream_t)stream_);
 }
 
 extern "C" int vc_conv_out_shape(int ndim, const int32_t* spatial_shape, const int32_t* ksize, const int32_t* stride,
@@ -406,11 +438,11 @@ extern "C" size_t vc_conv_rulebook_ws_bytes(int ndim, int batch_size, const int3
     return conv_ws_layout(ndim, batch_size, out_shape, nullptr).bytes;
 }
 
-extern "C" int vc_conv_rulebook_count(const int32_t* indices, int n, int ndim, int batch_size,
-                                      const int32_t* spatial_shape, const int32_t* ksize, const int32_t* stride,
-                                      const int32_t* padding, const int32_t* dilation, int32_t* n_out_dev, void* ws,
-                                      size_t ws_bytes, vc_stream_t stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
+// cap_out > 0: the caller's output buffers hold cap_out rows (static mode): the count is clamped, *overflow gets the real total
+int vc::conv_rulebook_count_dev(const int32_t* indices, int n, const int* n_dev, int ndim, int batch_size,
+                                const int32_t* spatial_shape, const int32_t* ksize, const int32_t* stride,
+                                const int32_t* padding, const int32_t* dilation, int32_t* n_out_dev, int cap_out, int* overflow,
+                                void* ws, size_t ws_bytes, cudaStream_t stream) {
     Geom g;
     int rc = make_geom(g, ndim, spatial_shape, ksize, stride, padding, dilation);
     if (rc) return rc;
@@ -423,14 +455,22 @@ extern "C" int vc_conv_rulebook_count(const int32_t* indices, int n, int ndim, i
     }
     VC_CUDA(cudaMemsetAsync(w.bitmap, 0, (size_t)w.n_words * 4, stream));
     if (n > 0) {
-        conv_mark_kernel<<<dim3(cdiv(n, 256), g.K), 256, 0, stream>>>(indices, n, g, w.bitmap);
+        conv_mark_kernel<<<dim3(cdiv(n, 256), g.K), 256, 0, stream>>>(indices, n, n_dev, g, w.bitmap);
         VC_LAUNCH_CHECK();
     }
     scan_local_kernel<<<w.n_blocks, 256, 0, stream>>>(w.bitmap, w.n_words, w.word_rank, w.block_sum);
     VC_LAUNCH_CHECK();
-    scan_blocks_kernel<<<1, 1024, 0, stream>>>(w.block_sum, w.n_blocks, n_out_dev);
+    scan_blocks_kernel<<<1, 1024, 0, stream>>>(w.block_sum, w.n_blocks, n_out_dev, cap_out, overflow);
     VC_LAUNCH_CHECK();
     return VC_OK;
+}
+
+extern "C" int vc_conv_rulebook_count(const int32_t* indices, int n, int ndim, int batch_size,
+                                      const int32_t* spatial_shape, const int32_t* ksize, const int32_t* stride,
+                                      const int32_t* padding, const int32_t* dilation, int32_t* n_out_dev, void* ws,
+                                      size_t ws_bytes, vc_stream_t stream_) {
+    return vc::conv_rulebook_count_dev(indices, n, nullptr, ndim, batch_size, spatial_shape, ksize, stride, padding, dilation,
+                                       n_out_dev, 0, nullptr, ws, ws_bytes, (cudaStream_t)stream_);
 }
 
 extern "C" int vc_conv_rulebook_fill(const int32_t* indices, int n, int ndim, int batch_size,
@@ -438,13 +478,14 @@ extern "C" int vc_conv_rulebook_fill(const int32_t* indices, int n, int ndim, in
                                      const int32_t* padding, const int32_t* dilation, int n_out, int32_t* out_indices,
                                      int32_t* nbr_fwd, int32_t* nbr_bwd, int32_t* pair_num, void* ws, size_t ws_bytes,
                                      vc_stream_t stream_) {
-    return vc::conv_rulebook_fill_phases(indices, n, ndim, batch_size, spatial_shape, ksize, stride, padding, dilation, n_out,
+    return vc::conv_rulebook_fill_phases(indices, n, nullptr, ndim, batch_size, spatial_shape, ksize, stride, padding, dilation, n_out,
                                          out_indices, nbr_fwd, nbr_bwd, pair_num, ws, ws_bytes, (cudaStream_t)stream_, 3);
 }
 
 // phases: bit 0 = emit the output indices, bit 1 = build the neighbour tables.  The plan executor runs the emit phase of
 // every strided conv first (the next conv's row count depends on it and the host waits for that), the tables later.
-int vc::conv_rulebook_fill_phases(const int32_t* indices, int n, int ndim, int batch_size, const int32_t* spatial_shape,
+// (n_dev != NULL: n / n_out are the capacities of the input / output index sets, the real input count is *n_dev)
+int vc::conv_rulebook_fill_phases(const int32_t* indices, int n, const int* n_dev, int ndim, int batch_size, const int32_t* spatial_shape,
                                   const int32_t* ksize, const int32_t* stride, const int32_t* padding,
                                   const int32_t* dilation, int n_out, int32_t* out_indices, int32_t* nbr_fwd,
                                   int32_t* nbr_bwd, int32_t* pair_num, void* ws, size_t ws_bytes, cudaStream_t stream,
@@ -460,7 +501,7 @@ int vc::conv_rulebook_fill_phases(const int32_t* indices, int n, int ndim, int b
     if ((phases & 1) && n_out > 0) {
         VC_CHECK_ARG(out_indices, "null output pointer");
         conv_emit_indices_kernel<<<cdiv(w.n_words, 256), 256, 0, stream>>>(w.bitmap, w.word_rank, w.block_sum,
-                                                                            w.n_words, g, out_indices);
+                                                                            w.n_words, g, out_indices, n_out);
         VC_LAUNCH_CHECK();
     }
     if (!(phases & 2)) return VC_OK;
@@ -471,7 +512,7 @@ int vc::conv_rulebook_fill_phases(const int32_t* indices, int n, int ndim, int b
     }
     if (n > 0) {
         VC_CHECK_ARG(nbr_bwd, "null nbr_bwd");
-        conv_tables_kernel<<<dim3(cdiv(n, 256), g.K), 256, 0, stream>>>(indices, n, n_out, g, w.bitmap, w.word_rank, w.block_sum,
+        conv_tables_kernel<<<dim3(cdiv(n, 256), g.K), 256, 0, stream>>>(indices, n, n_dev, n_out, g, w.bitmap, w.word_rank, w.block_sum,
                                                              nbr_fwd, nbr_bwd, pair_num);
         VC_LAUNCH_CHECK();
     }

@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import weakref
 
 import numpy as np
 import torch
@@ -69,7 +70,8 @@ class Plan:
         self.rb_keys = {}             # rulebook id -> (indice_keys, ndim, in index set, out index set)
         self._final = None
         # per-device run-time state (dies with the plan, i.e. with the model that owns it)
-        self.arena_bytes = {}         # device index -> arena size handed out (monotone)
+        self.arena_bytes = {}         # (device index, training) -> arena size handed out (monotone)
+        self.arena_used = {}          # (device index, training) -> largest number of arena bytes a step really used
         self.reserved = {}            # (device, stream) -> arena size already parked in the allocator pool
         self.inflight = {}            # device index -> tail events of the forwards still in flight
 
@@ -167,19 +169,34 @@ def _pinned(device):
     return _PINNED[key]
 
 
-def _arena_bytes(plan, n0, device):
-    """Arena size for a step: generous (rows * 24 KB + 256 MB, rounded up to 256 MB; VirConv-L uses ~16 KB per input
-    voxel, forward + backward), grown from what earlier steps of the same plan actually used, never shrunk — so the
-    caching allocator hands back the same block every step."""
-    want = int(n0) * 24576 + (256 << 20)
-    want = max(want, plan.arena_bytes.get(device.index, 0))
-    want = (want + (256 << 20) - 1) // (256 << 20) * (256 << 20)
-    plan.arena_bytes[device.index] = want
+ARENA_GRAIN = 64 << 20
+
+
+def _arena_bytes(plan, n0, device, training=True):
+    """Arena size for a step.  First use of a plan: a generous guess from the input row count (VirConv-L uses ~16 KB per
+    input voxel, forward + backward; a forward alone about half).  Afterwards: the largest bytes-per-input-row an earlier
+    step of the same plan really used (recorded by the backward / the eval forward) times this step's rows plus 30 %
+    head-room — monotone per plan, so the caching allocator keeps handing back the same block, and an eval-only or
+    small-batch user does not reserve the training worst case (rows*24 KB + 256 MB over-reserved ~2x)."""
+    key = (device.index, bool(training))
+    per_row = plan.arena_used.get(key, 0.0)
+    if per_row:
+        want = int(1.3 * per_row * int(n0)) + (32 << 20)
+    else:
+        want = int(n0) * (24576 if training else 12288) + (128 << 20)
+    want = max(want, plan.arena_bytes.get(key, 0))
+    want = (want + ARENA_GRAIN - 1) // ARENA_GRAIN * ARENA_GRAIN
+    plan.arena_bytes[key] = want
     return want
 
 
-ARENAS_IN_FLIGHT = 8
+def _note_arena_use(plan, device, training, used, n0):
+    key = (device.index, bool(training))
+    plan.arena_used[key] = max(plan.arena_used.get(key, 0.0), float(used) / max(int(n0), 1))
+
+
 MAX_STEPS_AHEAD = 4          # the host never enqueues more than this many forwards of a plan beyond the GPU
+ARENAS_IN_FLIGHT = MAX_STEPS_AHEAD + 1
 
 
 def _throttle(plan, dev):
@@ -281,6 +298,11 @@ class _Run:
         p, n, ndim, s0, s1, s2 = self.query(2, iset)[:6]
         return _view(self.arena, p, (n, 1 + ndim), torch.int32), [s0, s1, s2][:ndim]
 
+    def count(self, iset):
+        """Static mode: the device int32[1] row count of an index set (a view into the arena)."""
+        p = self.query(2, iset)[6]
+        return _view(self.arena, p, (1,), torch.int32) if p else None
+
     def rulebook(self, rb):
         """(nbr [K, n_out] int32, nbr_bwd or None, pair_num or None, meta dict) — tests compare these with the oracle."""
         p, pbw, ppn, K, n_in, n_out, subm, unique = self.query(3, rb)
@@ -373,46 +395,85 @@ def _layer_ptrs(plan, grad_base=0):
     return tab
 
 
+class StaticSpec:
+    """Static (CUDA-graph capturable) execution of a plan: `n_dev` int32[1] device tensor = number of valid input rows
+    (the feature / coordinate tensors passed to the plan are then CAPACITY sized), `caps` {index-set id: row capacity} for
+    the strided convs' output sets, `overflow` int32[1] device tensor receiving the largest row count that did not fit."""
+
+    def __init__(self, n_dev, caps, overflow):
+        self.n_dev, self.caps, self.overflow = n_dev, dict(caps), overflow
+        self._arr = None
+
+    def caps_array(self):
+        if self._arr is None:
+            a = np.zeros(64, dtype=np.int32)
+            for k, v in self.caps.items():
+                a[int(k)] = int(v)
+            self._arr = a
+        return self._arr
+
+
 class PlanFn(torch.autograd.Function):
     """forward: (features of the published slots..., ) ; backward: gradients of every layer's weight / gamma / beta."""
 
     @staticmethod
-    def forward(ctx, plan, holder, feats, coords, spatial_shape, batch_size, proj, training, precision, inputs_ready, *params):
+    def forward(ctx, plan, holder, feats, coords, spatial_shape, batch_size, proj, training, precision, inputs_ready, static,
+                *params):
         lib = _lib.load()
         ctx.set_materialize_grads(False)     # published tensors the loss does not touch arrive as None, not as zeros
         dev = feats.device
         oi, of, lf, sizes, offs = plan.finalize()
         feats = feats.contiguous()
         n0 = feats.shape[0]
-        nbytes = _arena_bytes(plan, n0, dev)
-        inflight = _throttle(plan, dev)
         main = ops._stream()
         side_obj = ops.side(dev).stream if TWO_STREAMS else None
         side = side_obj.cuda_stream if side_obj is not None else None
-        if side_obj is not None:
-            # The arena belongs to the SIDE stream (its index kernels are the first writers, possibly while main still
-            # runs the previous step); main's uses are registered with record_stream, so the caching allocator recycles
-            # the block only after both streams are done with it.
-            arena = _alloc_arena(plan, nbytes, dev, side_obj)
-            arena.record_stream(torch.cuda.current_stream(dev))
+        inflight = None
+        if static is not None:
+            inputs_ready = False             # under capture the side stream must fork from the capturing stream
         else:
-            arena = _alloc_arena(plan, nbytes, dev, None)
-        state = np.zeros(lib.vc_exec_state_bytes(), dtype=np.uint8)
+            inflight = _throttle(plan, dev)
         tab = _layer_ptrs(plan)
-        rc = lib.vc_exec_forward(oi.ctypes.data, of.ctypes.data, oi.shape[0], tab.ctypes.data, lf.ctypes.data, len(plan.layers),
-                                 feats.data_ptr(), feats.shape[1], coords.data_ptr(), n0, _lib.host_i32(spatial_shape),
-                                 int(batch_size), proj.data_ptr() if proj is not None else None, int(training),
-                                 int(precision == 'bf16'), 1, arena.data_ptr(), arena.numel(),
-                                 _pinned(dev).data_ptr(), ops.tc_error_flag(dev).data_ptr(), state.ctypes.data, state.size,
-                                 main, side, 0 if (inputs_ready and side is not None) else 1)
-        if rc == VC_ERR_WORKSPACE:
-            plan.arena_bytes[dev.index] = 2 * arena.numel()     # the next call gets twice as much
+        for attempt in range(3):
+            nbytes = _arena_bytes(plan, n0, dev, training)
+            if static is not None:
+                # (inside a capture: the graph's own pool.  No record_stream: the side / wgrad streams are forked from and
+                #  joined back into the calling stream inside vc_exec_forward / vc_exec_backward, so every later use of the
+                #  block in the calling stream's order comes after all of this step's uses)
+                arena = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            elif side_obj is not None:
+                # The arena belongs to the SIDE stream (its index kernels are the first writers, possibly while main still
+                # runs the previous step); main's uses are registered with record_stream, so the caching allocator recycles
+                # the block only after both streams are done with it.
+                arena = _alloc_arena(plan, nbytes, dev, side_obj)
+                arena.record_stream(torch.cuda.current_stream(dev))
+            else:
+                arena = _alloc_arena(plan, nbytes, dev, None)
+            state = np.zeros(lib.vc_exec_state_bytes(), dtype=np.uint8)
+            rc = lib.vc_exec_forward(oi.ctypes.data, of.ctypes.data, oi.shape[0], tab.ctypes.data, lf.ctypes.data, len(plan.layers),
+                                     feats.data_ptr(), feats.shape[1], coords.data_ptr(), n0, _lib.host_i32(spatial_shape),
+                                     int(batch_size), proj.data_ptr() if proj is not None else None, int(training),
+                                     int(precision == 'bf16'), 1, arena.data_ptr(), arena.numel(),
+                                     _pinned(dev).data_ptr(), ops.tc_error_flag(dev).data_ptr(), state.ctypes.data, state.size,
+                                     main, side, 0 if (inputs_ready and side is not None) else 1,
+                                     static.caps_array().ctypes.data if static is not None else None,
+                                     static.n_dev.data_ptr() if static is not None else None,
+                                     static.overflow.data_ptr() if static is not None else None)
+            if rc != VC_ERR_WORKSPACE:
+                break
+            # too small (first use of a plan on an unusually dense batch): the call is restartable — nothing it enqueued is
+            # read by anyone — so take a bigger arena and run it again
+            plan.arena_bytes[(dev.index, bool(training))] = 2 * arena.numel()
         check(rc, 'vc_exec_forward')
-        tail = torch.cuda.Event()
-        tail.record()
-        inflight.append(tail)
+        if inflight is not None:
+            tail = torch.cuda.Event()
+            tail.record()
+            inflight.append(tail)
         run = _Run(plan, arena, state, precision)
+        run.static, run.n0, run.training = static, n0, bool(training)
         holder.append(run)
+        if not training:
+            _note_arena_use(plan, dev, False, run.query(0, 0)[0], n0)
         if TIMING:
             global LAST_RUN
             LAST_RUN = run
@@ -426,14 +487,15 @@ class PlanFn(torch.autograd.Function):
         plan = run.plan
         oi, of, lf, sizes, offs = plan.finalize()
         dev = run.arena.device
-        reserve_blocks(('flat_grad', id(plan)), 4 * int(offs[-1]), dev)
+        if run.static is None:
+            reserve_blocks(('flat_grad', id(plan)), 4 * int(offs[-1]), dev)
         flat = torch.empty(int(offs[-1]), dtype=torch.float32, device=dev)
         tab = _layer_ptrs(plan, flat.data_ptr())
         gs = [None if g is None else g.contiguous() for g in grads]
         slots = np.array([slot for _, slot, _ in plan.published], dtype=np.int32)
         ext = np.array([0 if g is None else g.data_ptr() for g in gs], dtype=np.uint64)
         ws = _wgrad_stream(dev)
-        if ws is not None:
+        if ws is not None and run.static is None:
             flat.record_stream(ws)
             run.arena.record_stream(ws)
         rc = lib.vc_exec_backward(oi.ctypes.data, of.ctypes.data, oi.shape[0], tab.ctypes.data, lf.ctypes.data, len(plan.layers),
@@ -441,32 +503,58 @@ class PlanFn(torch.autograd.Function):
                                   ops.tc_error_flag(dev).data_ptr(), run.state.ctypes.data, ops._stream(),
                                   ws.cuda_stream if ws is not None else None)
         if rc == VC_ERR_WORKSPACE:
-            plan.arena_bytes[dev.index] = 2 * run.arena.numel()
+            plan.arena_bytes[(dev.index, run.training)] = 2 * run.arena.numel()
         check(rc, 'vc_exec_backward')
-        # keep ahead of what steps really use
-        plan.arena_bytes[dev.index] = max(plan.arena_bytes.get(dev.index, 0), int(1.5 * run.query(0, 0)[0]))
+        _note_arena_use(plan, dev, run.training, run.query(0, 0)[0], run.n0)
         run.flat_grad = flat
         views = flat.split(sizes)
         out = [v.view_as(p) for v, p in zip(views, plan.params())]
-        return (None,) * 10 + tuple(out)
+        return (None,) * 11 + tuple(out)
 
 
-def run_plan(plan, feats, coords_i32, spatial_shape, batch_size, proj, training, precision, inputs_ready=False):
-    """-> (run record, {name: (features, indices, spatial_shape, bf16 shadow)}).  `coords_i32` [N,4] int32 contiguous
-    (b,z,y,x).  inputs_ready: the caller vouches that `coords_i32` and `proj` are complete in the SIDE stream's order
-    (resident from an earlier step, or produced on / synchronised with ops.side(device).stream): the index pipeline then
-    does not wait for the main stream and overlaps the previous step's backward."""
+def run_plan(plan, feats, coords_i32, spatial_shape, batch_size, proj, training, precision, inputs_ready=False, static=None):
+    """-> (run record, {name: (features, indices, spatial_shape, bf16 shadow, device row count or None)}).  `coords_i32`
+    [N,4] int32 contiguous (b,z,y,x).  inputs_ready: the caller vouches that `coords_i32` and `proj` are complete in the
+    SIDE stream's order (resident from an earlier step, or produced on / synchronised with ops.side(device).stream): the
+    index pipeline then does not wait for the main stream and overlaps the previous step's backward.  static: a StaticSpec
+    (capacity-sized tensors, device row counts, no host synchronisation: CUDA-graph capturable)."""
     ops._require_cuda(feats, coords_i32)
     assert coords_i32.dtype == torch.int32 and coords_i32.is_contiguous()
     holder = []
     outs = PlanFn.apply(plan, holder, feats, coords_i32, list(spatial_shape), batch_size, proj, training, precision,
-                        bool(inputs_ready), *plan.params())
+                        bool(inputs_ready), static, *plan.params())
     run = holder[0]
     res = {}
     for (name, slot, iset), f in zip(plan.published, outs):
         idx, shape = (coords_i32, list(spatial_shape)) if iset == 0 else run.indices(iset)
-        res[name] = (f, idx, shape, (lambda slot=slot: run.feature_bf16(slot)))    # shadow resolved on first use
+        cnt = None
+        if static is not None:
+            cnt = static.n_dev if iset == 0 else run.count(iset)
+        res[name] = (f, idx, shape, (lambda slot=slot: run.feature_bf16(slot)), cnt)    # shadow resolved on first use
     return run, res
+
+
+_LAST_RUNS = weakref.WeakKeyDictionary()     # model -> weak reference to its most recent run record
+
+
+def note_last_run(model, run):
+    _LAST_RUNS[model] = weakref.ref(run)
+
+
+def last_run(model):
+    r = _LAST_RUNS.get(model)
+    return r() if r is not None else None
+
+
+def measured_caps(run, margin=1.3, grain=1024):
+    """{index-set id: capacity} for a StaticSpec from an EXACT-mode run of the same plan on a representative batch: the
+    observed row count of every strided conv's output set times `margin`, rounded up to `grain` rows."""
+    caps = {}
+    for rb, (keys, ndim, i_in, i_out) in run.plan.rb_keys.items():
+        if i_out != i_in and i_out != 0:
+            n = run.query(2, i_out)[1]
+            caps[i_out] = (int(n * margin) + grain - 1) // grain * grain
+    return caps
 
 
 def timing_start():

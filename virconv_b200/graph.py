@@ -1,0 +1,169 @@
+"""Whole training step (backbone forward + loss + backward) as ONE CUDA graph.
+
+The reference drives every step from Python (`tools/train_utils/train_utils.py:27-57`: `model(batch)`, `loss.backward()`):
+~200 kernel launches whose enqueue cost (3 ms of host time per step in round 1) exceeds the kernels' run time on a B200.
+The plan executor's static mode (`executor.StaticSpec`, `vc_exec_forward(..., caps, n0_dev, overflow)`) keeps every
+data-dependent row count in device memory and sizes every buffer from host-side capacities, so nothing in a step reads a
+device value on the host; `GraphedStep` captures such a step once and replays it:
+
+    step = GraphedStep(model, loss_fn, params)          # model: VirConvL8x in train / eval mode
+    for batch in loader:
+        loss = step(batch)                              # copies the batch into the graph's input buffers, replays
+        optimizer.step()                                # parameter .grad tensors are rewritten in place by every replay
+
+Published tensors inside the graph are capacity sized: `t.features` [cap, C] with a zero tail, `t.indices` [cap, 4] with a
+-1 tail, `t.num_rows` a device int32[1]; `loss_fn(batch_dict)` must use `num_rows` where the reference uses `shape[0]`.
+A batch whose row counts exceed the captured capacities is detected through the executor's overflow flag (read back
+asynchronously, one step late) and handled by re-capturing with larger capacities and re-running that batch.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import executor, ops
+
+
+def masked_mean(t):
+    """Mean over the valid rows of a published tensor: static mode (zero tail, device row count) or exact mode."""
+    if getattr(t, 'num_rows', None) is None:
+        return t.features.mean()
+    return t.features.sum() / (t.num_rows.to(torch.float32) * t.features.shape[1]).squeeze(0)
+
+
+class GraphedStep:
+    def __init__(self, model, loss_fn, params=None, margin=1.3, grain=1024, warmup=2, check_overflow=True):
+        self.model, self.loss_fn = model, loss_fn
+        self.params = list(model.parameters()) if params is None else list(params)
+        self.margin, self.grain, self.warmup = margin, grain, warmup
+        self.check_overflow = check_overflow
+        self.graph = None
+        self.cap0 = 0
+        self.caps = {}
+        self.recaptures = 0
+        self._pending = []        # (event, pinned slot) of the replays whose overflow flag has not been looked at yet
+        self._slot = 0
+
+    # ------------------------------------------------------------------------------------------------
+    def _round(self, n):
+        return (int(n * self.margin) + self.grain - 1) // self.grain * self.grain
+
+    def _exact_step(self, batch):
+        """One ordinary (exact-shape, host-synchronised) step; also measures the row counts of this batch."""
+        for p in self.params:
+            p.grad = None
+        bd = dict(batch)
+        out = self.model(bd)
+        loss = self.loss_fn(out)
+        loss.backward()
+        return loss.detach(), executor.last_run(self.model)
+
+    def _make_buffers(self, batch, run):
+        dev = batch['voxel_features'].device
+        vf, vc = batch['voxel_features'], batch['voxel_coords']
+        self.cap0 = max(self.cap0, self._round(vf.shape[0]))
+        for k, v in executor.measured_caps(run, self.margin, self.grain).items():
+            self.caps[k] = max(self.caps.get(k, 0), v)
+        B = int(batch['batch_size'])
+        self.dev, self.B = dev, B
+        self.vf = torch.zeros((self.cap0, vf.shape[1]), dtype=torch.float32, device=dev)
+        self.vc = torch.full((self.cap0, vc.shape[1]), -1, dtype=vc.dtype, device=dev)
+        self.n_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.proj = torch.zeros((B, 28), dtype=torch.float32, device=dev)
+        self.proj_host = torch.zeros((B, 28), dtype=torch.float32).pin_memory()
+        self.n_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.ovf_host = torch.zeros(8, dtype=torch.int32).pin_memory()
+        self._pending, self._slot = [], 0
+        self.spec = executor.StaticSpec(self.n_dev, self.caps, self.overflow)
+
+    def _load(self, batch):
+        """Copy one batch into the graph's input buffers (asynchronous, current stream)."""
+        vf, vc = batch['voxel_features'], batch['voxel_coords']
+        n = vf.shape[0]
+        if n > self.cap0:
+            return False
+        self.vf[:n].copy_(vf, non_blocking=True)
+        self.vc[:n].copy_(vc, non_blocking=True)
+        self.n_host[0] = n
+        self.n_dev.copy_(self.n_host, non_blocking=True)
+        trans = batch.get('aug_param')
+        self.proj_host.copy_(torch.from_numpy(ops.projection_params_host(batch['calib'], trans, self.B)))
+        self.proj.copy_(self.proj_host, non_blocking=True)
+        return True
+
+    def _static_batch(self, batch):
+        bd = {k: v for k, v in batch.items() if k not in ('voxel_features', 'voxel_coords')}
+        bd.update(voxel_features=self.vf, voxel_coords=self.vc, virconv_static=self.spec, virconv_proj=self.proj)
+        return bd
+
+    def _static_step(self, batch):
+        out = self.model(self._static_batch(batch))
+        loss = self.loss_fn(out)
+        loss.backward()
+        return loss
+
+    def _capture(self, batch):
+        torch.cuda.synchronize(self.dev)
+        loss_e, run = self._exact_step(batch)
+        assert run is not None, 'GraphedStep needs a backbone running through the plan executor'
+        self._make_buffers(batch, run)
+        assert self._load(batch)
+        # warm-up of the static path on a side stream (allocator pools, lazy kernel attributes), as torch.cuda.graphs asks for
+        s = torch.cuda.Stream(device=self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(s):
+            for _ in range(max(self.warmup, 1)):
+                for p in self.params:
+                    p.grad = None
+                self._static_step(batch)
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        torch.cuda.synchronize(self.dev)
+        for p in self.params:
+            p.grad = None
+        self.overflow.zero_()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._static_step(batch)
+        self.recaptures += 1
+        torch.cuda.synchronize(self.dev)
+
+    # ------------------------------------------------------------------------------------------------
+    def _overflowed(self):
+        """Largest overflow reported by the replays that have COMPLETED so far (never blocks: the flag of a step is read
+        back asynchronously and looked at when its event has fired, typically one or two calls later)."""
+        worst = 0
+        while self._pending and self._pending[0][0].query():
+            ev, slot = self._pending.pop(0)
+            worst = max(worst, int(self.ovf_host[slot]))
+        return worst
+
+    def __call__(self, batch):
+        """-> the step's loss (a device tensor owned by the graph: read or copy it before the next call)."""
+        if self.graph is None:
+            self._capture(batch)
+        if self.check_overflow and self._overflowed():
+            # an EARLIER batch did not fit: its gradients were computed on clamped row sets.  Grow and re-capture; the
+            # caller sees the event through `recaptures` (a training loop may want to discard those optimizer steps).
+            self.margin *= 1.25
+            self._capture(batch)
+        if not self._load(batch):
+            self.margin *= 1.25
+            self._capture(batch)            # more input rows than the input buffers hold
+            assert self._load(batch)
+        self.graph.replay()
+        if self.check_overflow:
+            if len(self._pending) >= self.ovf_host.numel():     # (host far ahead of the GPU: wait for the oldest read-back)
+                self._pending[0][0].synchronize()
+                if self._overflowed():
+                    self.margin *= 1.25
+                    self._capture(batch)
+                    return self(batch)
+            slot = self._slot
+            self._slot = (slot + 1) % self.ovf_host.numel()
+            self.ovf_host[slot:slot + 1].copy_(self.overflow, non_blocking=True)
+            self.overflow.zero_()
+            ev = torch.cuda.Event()
+            ev.record()
+            self._pending.append((ev, slot))
+        return self.loss

@@ -187,7 +187,14 @@ def tc_error_flag(device):
 
 
 def tc_supported(cin, cout):
+    """Channel pairs of the tensor-core wgrad / scatter-dgrad kernels."""
     return cin in (16, 32, 64) and cout in (16, 32, 64)
+
+
+def tc_conv_supported(cin, cout):
+    """Channel pairs of the tensor-core conv forward / gather-dgrad kernel (persistent kernel, csrc/conv_tc2.cu): the
+    C = 8 layers run with K and N padded to 16 (zero-filled by the gather / the weight image)."""
+    return cin in (8, 16, 32, 64) and cout in (8, 16, 32, 64)
 
 
 def cast_bf16(t):
@@ -294,7 +301,7 @@ def conv_forward(feats, weight, rb: Rulebook, bn_sums=None, precision='fp32', fe
     feats = feats.contiguous()
     weight = weight.contiguous()
     out = torch.empty((rb.n_out, cout), dtype=torch.float32, device=feats.device)
-    if precision == 'bf16' and tc_supported(cin, cout) and rb.n_out > 0:
+    if precision == 'bf16' and tc_conv_supported(cin, cout) and rb.n_out > 0:
         fb = feats_bf16 if feats_bf16 is not None else cast_bf16(feats)
         if keep is not None:
             keep['feats_bf16'] = fb
@@ -323,7 +330,7 @@ def conv_dgrad(dout, weight, rb: Rulebook, precision='fp32', dout_bf16=None):
     cout, cin = weight.shape[0], weight.shape[-1]
     dout = dout.contiguous()
     weight = weight.contiguous()
-    if precision == 'bf16' and tc_supported(cin, cout) and rb.n_in > 0 and not (rb.subm and not rb.unique_coords):
+    if precision == 'bf16' and tc_conv_supported(cin, cout) and rb.n_in > 0 and not (rb.subm and not rb.unique_coords):
         db = dout_bf16 if dout_bf16 is not None else cast_bf16(dout)
         din = torch.empty((rb.n_in, cin), dtype=torch.float32, device=dout.device)
         table, mirror = (rb.nbr, 1) if rb.subm else (rb.nbr_bwd, 0)
@@ -414,7 +421,7 @@ class SparseConvFn(torch.autograd.Function):
         rb = ctx.rb
         dout = dout.contiguous()
         cout, cin = weight.shape[0], weight.shape[-1]
-        db = cast_bf16(dout) if (ctx.precision == 'bf16' and tc_supported(cin, cout) and rb.n_out > 0) else None
+        db = cast_bf16(dout) if (ctx.precision == 'bf16' and tc_conv_supported(cin, cout) and rb.n_out > 0) else None
         din = conv_dgrad(dout, weight, rb, ctx.precision, db) if ctx.needs_input_grad[0] else None
         dw = conv_wgrad(feats, dout, weight.shape, rb, ctx.precision, ctx.fb, db) if ctx.needs_input_grad[1] else None
         return din, dw, None, None
@@ -459,7 +466,7 @@ class ConvBNReLUFn(torch.autograd.Function):
         cout, cin = weight.shape[0], weight.shape[-1]
         dy = dy.contiguous()
         dx = torch.empty_like(x)
-        use_tc = ctx.precision == 'bf16' and tc_supported(cin, cout) and rb.n_out > 0
+        use_tc = ctx.precision == 'bf16' and tc_conv_supported(cin, cout) and rb.n_out > 0
         db = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device) if use_tc else None
         dgamma = torch.empty_like(gamma)
         dbeta = torch.empty_like(gamma)
@@ -535,9 +542,8 @@ def compose_lidar_to_rect(V2C, R0):
     return m
 
 
-def projection_params(calib, trans_param, batch_size, device, stream=None):
-    """[B, 28] float32 parameter block of vc_index2uv (layout: include/virconv_b200.h).  `stream`: upload on that
-    torch stream (the plan executor consumes the block on its side stream only)."""
+def projection_params_host(calib, trans_param, batch_size):
+    """[B, 28] float32 parameter block of vc_index2uv (layout: include/virconv_b200.h) as a numpy array."""
     tp = None
     if trans_param is not None:
         tp = trans_param.detach().cpu().numpy() if torch.is_tensor(trans_param) else np.asarray(trans_param)
@@ -560,6 +566,13 @@ def projection_params(calib, trans_param, batch_size, device, stream=None):
             out[b, 22] = flip
             out[b, 23] = np.cos(_f32(-rot))
             out[b, 24] = np.sin(_f32(-rot))
+    return out
+
+
+def projection_params(calib, trans_param, batch_size, device, stream=None):
+    """The block of projection_params_host on the device.  `stream`: upload on that torch stream (the plan executor
+    consumes the block on its side stream only)."""
+    out = projection_params_host(calib, trans_param, batch_size)
     if stream is not None:
         with torch.cuda.stream(stream):
             return torch.from_numpy(out).to(device, non_blocking=True)

@@ -38,6 +38,7 @@ class SparseConvTensor:
         self.voxel_num = voxel_num
         self.benchmark = benchmark
         self._features_bf16 = None           # optional bf16 shadow of `features` (tensor-core operand), see ops.py
+        self.num_rows = None                 # static (graph) mode only: device row count of capacity-sized features / indices
 
     @property
     def features_bf16(self):
