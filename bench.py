@@ -51,6 +51,10 @@ def parse():
                     help='bf16 = tcgen05 tensor-core contractions (BASELINE configs[1] dtype); fp32 = 1e-4 parity kernels')
     ap.add_argument('--ref-budget-s', type=float, default=150.0)
     ap.add_argument('--cpu-worker', action='store_true', help=argparse.SUPPRESS)
+    ap.add_argument('--mode', default=os.environ.get('VIRCONV_BENCH_MODE', 'graph'), choices=['graph', 'eager'],
+                    help='graph = the whole step (forward + loss + backward) replayed as one CUDA graph (plan executor static '
+                         'mode: device row counts, no host synchronisation); eager = exact-shape execution, one C-ABI call per '
+                         'forward / backward, 4 data-dependent row counts read on the host')
     ap.add_argument('--ncu-step', action='store_true',
                     help='profiling aid: W warm-up steps, then exactly one step between cudaProfilerStart/Stop; no JSON')
     return ap.parse_args()
@@ -234,7 +238,16 @@ def run_ours(args):
         h2d = hv.numel() * 4 + hc.numel() * 4 + b.batch_size * 28 * 4
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
+    from virconv_b200.graph import GraphedStep, masked_mean
+
+    def loss_of(out):
+        loss = masked_mean(out['encoded_spconv_tensor'])
+        for t in out['multi_scale_3d_features'].values():
+            loss = loss + masked_mean(t)
+        return loss
+
     def step(vf, vc, b, sync_loss, resident=False):
+        """exact-shape (eager) step: one C-ABI call per forward / backward"""
         for p in params:
             p.grad = None
         bd = {'voxel_features': vf, 'voxel_coords': vc, 'batch_size': b.batch_size, 'calib': b.calib,
@@ -243,16 +256,23 @@ def run_ours(args):
               # step's backward; the e2e loop uploads on the main stream every step and makes no such promise
               'virconv_inputs_ready': resident}
         out = model(bd)
-        loss = out['encoded_spconv_tensor'].features.mean()
-        for t in out['multi_scale_3d_features'].values():
-            loss = loss + t.features.mean()
+        loss = loss_of(out)
         loss.backward()
         parallel.allreduce_gradients(params, average=True)     # one flat fp32 bucket over NCCL/NVLink; no-op at N=1
         return float(loss.detach()) if sync_loss else loss
 
+    graphed = GraphedStep(model, loss_of, params, margin=1.3) if args.mode == 'graph' else None
+
+    def gstep(vf, vc, b):
+        """graph step: inputs (device or pinned-host tensors) are copied into the graph's buffers, then ONE graph launch"""
+        loss = graphed({'voxel_features': vf, 'voxel_coords': vc, 'batch_size': b.batch_size, 'calib': b.calib,
+                        'aug_param': b.aug_param})
+        parallel.allreduce_gradients(params, average=True)
+        return loss
+
     # e2e upload targets: a ring of device buffers (what a prefetching loader keeps), so the timed loop allocates nothing
     # (a cudaMalloc landing inside it costs 30-60 ms: profiles/e2e_repeat_r1.txt).  Slot reuse is safe: the executor never
-    # lets the host run more than 4 forwards ahead of the GPU.
+    # lets the host run more than 4 forwards ahead of the GPU.  (graph mode copies straight into the graph's input buffers)
     RING = 8
     n_max = max(h[0].shape[0] for h in host)
     ring = [(torch.empty((n_max, host[0][0].shape[1]), dtype=torch.float32, device=dev),
@@ -264,9 +284,9 @@ def run_ours(args):
     def timed(n_steps, from_host):
         """from_host (the e2e loop): every step uploads its inputs from PINNED host memory and reads its loss back into
         pinned host memory, both inside the timed region — the way a training loop with a prefetching loader and lagged
-        loss logging does it: the upload runs on a copy stream (the main and rulebook streams wait for its event), the
-        loss read-back is an asynchronous D2H copy; nothing blocks the host per step, all copies have completed when the
-        timed region ends (synchronize below)."""
+        loss logging does it; nothing blocks the host per step, all copies have completed when the timed region ends
+        (synchronize below).  eager mode: the upload runs on a copy stream (the main and rulebook streams wait for its
+        event); graph mode: the upload goes straight into the graph's input buffers on the main stream."""
         evs = []
         for s in range(n_steps):
             flush_buf.zero_()
@@ -274,25 +294,33 @@ def run_ours(args):
             a.record()
             if from_host:
                 hv, hc, b = host[s % POOL]
-                rf, rc = ring[s % RING]
-                vf, vc = rf[:hv.shape[0]], rc[:hc.shape[0]]
-                with torch.cuda.stream(copy_stream):
-                    vf.copy_(hv, non_blocking=True)
-                    vc.copy_(hc, non_blocking=True)
-                    up = torch.cuda.Event()
-                    up.record(copy_stream)
-                main_stream.wait_event(up)
-                ops.side(dev).stream.wait_event(up)        # the executor's rulebook stream reads the coordinates
-                loss = step(vf, vc, b, False, resident=True)
+                if graphed is not None:
+                    loss = gstep(hv, hc, b)
+                else:
+                    rf, rc = ring[s % RING]
+                    vf, vc = rf[:hv.shape[0]], rc[:hc.shape[0]]
+                    with torch.cuda.stream(copy_stream):
+                        vf.copy_(hv, non_blocking=True)
+                        vc.copy_(hc, non_blocking=True)
+                        up = torch.cuda.Event()
+                        up.record(copy_stream)
+                    main_stream.wait_event(up)
+                    ops.side(dev).stream.wait_event(up)        # the executor's rulebook stream reads the coordinates
+                    loss = step(vf, vc, b, False, resident=True)
                 loss_host[s % loss_host.numel()].copy_(loss.detach(), non_blocking=True)
             else:
                 vf, vc, b = devb[s % POOL]
-                step(vf, vc, b, False, resident=True)
+                if graphed is not None:
+                    gstep(vf, vc, b)
+                else:
+                    step(vf, vc, b, False, resident=True)
             e.record()
             evs.append((a, e))
         torch.cuda.synchronize()
         if from_host:
             assert bool(torch.isfinite(loss_host[:min(n_steps, loss_host.numel())]).all()), 'non-finite loss read back'
+        err = int(ops.tc_error_flag(dev).item())
+        assert err == 0, 'a tensor-core pipeline wait timed out (error flag %d): results are invalid' % err
         return [a.elapsed_time(e) for a, e in evs]
 
     def barrier():
@@ -321,6 +349,8 @@ def run_ours(args):
     barrier()
     wall = time.time() - t_wall
     launches = (lib.vc_launch_count() - l0) / max(args.steps, 1)
+    if graphed is not None:
+        launches = graphed.launches_per_replay        # kernels of this library inside the captured step (counted at capture)
     dev_allocs = torch.cuda.memory_stats(dev).get('num_device_alloc', 0) - dev_allocs0
     timed(max(2, min(args.steps, 10)), True)      # warm-up + allocator priming of the e2e loop
     barrier()
@@ -422,7 +452,10 @@ def run_ours(args):
             'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_step,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'scenes_per_step': scenes_per_step, 'parallelism': f'dp{world}',
-                       'host_path': ('native plan executor: one C-ABI call per forward / backward, index ops on a side stream'
+                       'host_path': ('whole step (forward + loss + backward) replayed as ONE CUDA graph: plan executor static mode, '
+                                     'device row counts, no host synchronisation; %d capture(s)' % graphed.recaptures
+                                     if graphed is not None else
+                                     'native plan executor: one C-ABI call per forward / backward, index ops on a side stream'
                                      if executor.ENABLED else 'per-operator C-ABI calls from Python autograd'),
                        'l2': 'flushed between timed steps (256 MiB write)', 'timing': 'per-step CUDA events, max over ranks',
                        'e2e_loop': ('inputs uploaded from pinned host memory on a copy stream every step, loss copied back to '

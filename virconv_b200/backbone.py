@@ -108,7 +108,7 @@ def plan_nrconv(plan, block, f, iset, proj_stride):
     if block.stride > 1:
         conv = block.down_layer[0]
         iset, rb = plan.conv_rb(iset, 3, conv.kernel_size, conv.stride, conv.padding, conv.dilation, keys=[conv.indice_key])
-        f = plan.cbr(f, rb, conv, block.down_layer[1])
+        f = plan.cbr(f, rb, conv, block.down_layer[1], seq=block.down_layer)
     c3, c2 = block.d3_conv1[0], block.d2_conv1[0]
     assert (block.d3_conv2[0].kernel_size, block.d3_conv2[0].dilation) == (c3.kernel_size, c3.dilation)
     assert (block.d2_conv2[0].kernel_size, block.d2_conv2[0].dilation) == (c2.kernel_size, c2.dilation)
@@ -116,8 +116,10 @@ def plan_nrconv(plan, block, f, iset, proj_stride):
     uv = plan.index2uv(iset, proj_stride)
     rb2 = plan.subm_rb(uv, 2, c2.kernel_size, c2.dilation, unique=False,      # projected pixels collide
                        keys=[c2.indice_key, block.d2_conv2[0].indice_key])
-    d3 = plan.cbr(plan.cbr(f, rb3, c3, block.d3_conv1[1]), rb3, block.d3_conv2[0], block.d3_conv2[1])
-    d2 = plan.cbr(plan.cbr(d3, rb2, c2, block.d2_conv1[1]), rb2, block.d2_conv2[0], block.d2_conv2[1])
+    d3 = plan.cbr(plan.cbr(f, rb3, c3, block.d3_conv1[1], seq=block.d3_conv1), rb3, block.d3_conv2[0], block.d3_conv2[1],
+                  seq=block.d3_conv2)
+    d2 = plan.cbr(plan.cbr(d3, rb2, c2, block.d2_conv1[1], seq=block.d2_conv1), rb2, block.d2_conv2[0], block.d2_conv2[1],
+                  seq=block.d2_conv2)
     return plan.cat(d3, d2), iset
 
 
@@ -191,7 +193,7 @@ class VirConvL8x(nn.Module):
                 plan.publish('x_conv%d' % (i + 1), f, iset)
             conv = self.conv_out[0]
             iset, rb = plan.conv_rb(iset, 3, conv.kernel_size, conv.stride, conv.padding, conv.dilation, keys=[conv.indice_key])
-            plan.publish('out', plan.cbr(f, rb, conv, self.conv_out[1]), iset)
+            plan.publish('out', plan.cbr(f, rb, conv, self.conv_out[1], seq=self.conv_out), iset)
             self._plan_cache = plan
         return self._plan_cache
 
@@ -201,10 +203,13 @@ class VirConvL8x(nn.Module):
         if self.training and self.discard_mode == 'paper' and self.layer_discard_rate != 0:
             return False             # row-dropping StVD between the blocks is only on the module path
         plan = self._plan()
-        if getattr(self, '_plan_ok', None) is None:
-            self._plan_ok = plan.eligible()
+        if not plan.is_current():          # a sub-module was replaced after the plan was built (e.g. SyncBatchNorm conversion)
+            self._plan_cache = None
+            plan = self._plan()
+        if not plan.eligible():            # (checked every forward: dtype / layout / module type may change under .half(), .to())
+            return False
         mode = plan.layers[0][1].training
-        return self._plan_ok and all(bn.training == mode for _, bn in plan.layers)
+        return all(bn.training == mode for _, bn in plan.layers)
 
     def forward(self, batch_dict):
         rot_num = batch_dict['transform_param'].shape[1] if 'transform_param' in batch_dict else 1
@@ -337,8 +342,8 @@ class VirConv8x(nn.Module):
             plan = executor.Plan(self.conv_input[0].in_channels)
             c0 = self.conv_input[0]
             rb = plan.subm_rb(0, 3, c0.kernel_size, c0.dilation, unique=True, keys=[c0.indice_key])
-            f = plan.cbr(0, rb, c0, self.conv_input[1])
-            f = plan.cbr(f, rb, self.conv1[0][0], self.conv1[0][1])
+            f = plan.cbr(0, rb, c0, self.conv_input[1], seq=self.conv_input)
+            f = plan.cbr(f, rb, self.conv1[0][0], self.conv1[0][1], seq=self.conv1[0])
             iset = 0
             plan.publish('x_conv1', f, iset)
             for name, stage in (('x_conv2', self.conv2), ('x_conv3', self.conv3), ('x_conv4', self.conv4)):
@@ -346,13 +351,13 @@ class VirConv8x(nn.Module):
                 iset, rbd = plan.conv_rb(iset, 3, down.kernel_size, down.stride, down.padding, down.dilation, keys=[down.indice_key])
                 c1 = stage[1][0]
                 rb = plan.subm_rb(iset, 3, c1.kernel_size, c1.dilation, unique=True, keys=[c1.indice_key])
-                f = plan.cbr(f, rbd, down, stage[0][1])
-                f = plan.cbr(f, rb, c1, stage[1][1])
-                f = plan.cbr(f, rb, stage[2][0], stage[2][1])
+                f = plan.cbr(f, rbd, down, stage[0][1], seq=stage[0])
+                f = plan.cbr(f, rb, c1, stage[1][1], seq=stage[1])
+                f = plan.cbr(f, rb, stage[2][0], stage[2][1], seq=stage[2])
                 plan.publish(name, f, iset)
             co = self.conv_out[0]
             iset, rbo = plan.conv_rb(iset, 3, co.kernel_size, co.stride, co.padding, co.dilation, keys=[co.indice_key])
-            plan.publish('out', plan.cbr(f, rbo, co, self.conv_out[1]), iset)
+            plan.publish('out', plan.cbr(f, rbo, co, self.conv_out[1], seq=self.conv_out), iset)
             self._plan_lidar_cache = plan
         return self._plan_lidar_cache
 
@@ -368,7 +373,8 @@ class VirConv8x(nn.Module):
 
     @staticmethod
     def _plan_usable(plan, feats):
-        if not executor.ENABLED or not feats.is_cuda or feats.shape[0] == 0 or feats.requires_grad or not plan.eligible():
+        if (not executor.ENABLED or not feats.is_cuda or feats.shape[0] == 0 or feats.requires_grad or not plan.is_current()
+                or not plan.eligible()):
             return False
         mode = plan.layers[0][1].training
         return all(bn.training == mode for _, bn in plan.layers)
@@ -382,6 +388,9 @@ class VirConv8x(nn.Module):
 
     def _lidar_stream(self, feats, coords, shape, batch_size):
         plan = self._plan_lidar()
+        if not plan.is_current():          # a sub-module was replaced after the plan was built
+            self._plan_lidar_cache = None
+            plan = self._plan_lidar()
         if self._plan_usable(plan, feats):
             return self._run(plan, feats, coords, shape, batch_size, None, ('x_conv1', 'x_conv2', 'x_conv3', 'x_conv4', 'out'))
         x = spconv.SparseConvTensor(feats, coords.int(), shape, batch_size)
@@ -437,6 +446,8 @@ class VirConv8x(nn.Module):
                 if 'transform_param' in batch_dict:
                     trans = batch_dict['transform_param'][:, i, :]
                 discarding = self.training and self.discard_mode == 'paper' and self.layer_discard_rate != 0
+                if not self._plan_mm().is_current():
+                    self._plan_mm_cache = None
                 if not discarding and self._plan_usable(self._plan_mm(), feats):
                     side = ops.side(feats.device).stream if executor.TWO_STREAMS else None
                     proj = ops.projection_params(calib, trans, batch_size, feats.device, side)

@@ -40,6 +40,7 @@ static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b)
 struct Geom {  // conv geometry, passed by value to kernels
     int ndim;
     int K;
+    int batch;                   // batch size: rows with a batch index outside [0, batch) or coordinates outside `shape` are ignored
     int shape[VC_MAX_NDIM];      // input spatial shape
     int oshape[VC_MAX_NDIM];     // output spatial shape
     int ksize[VC_MAX_NDIM];

@@ -26,6 +26,14 @@ __device__ __forceinline__ void decode_k(const Geom& g, int k, int* off) {
     }
 }
 
+// a row takes part in a rulebook only if its batch index and coordinates lie inside the grid (a padding row with b = -1 or
+// a wrong `batch_size` must not write outside the bitmap / alias hash keys — ADVICE r1)
+__device__ __forceinline__ bool index_ok(const Geom& g, int b, const int* c) {
+    bool ok = b >= 0 && b < g.batch;
+    for (int d = 0; d < g.ndim; ++d) ok &= (c[d] >= 0) & (c[d] < g.shape[d]);
+    return ok;
+}
+
 __device__ __forceinline__ void load_index(const int32_t* __restrict__ idx, int row, int ndim, int& b, int* c) {
     if (ndim == 3) {
         int4 v = __ldg(reinterpret_cast<const int4*>(idx) + row);
@@ -49,6 +57,7 @@ __global__ void hash_insert_kernel(const int32_t* __restrict__ idx, int n, const
     if (row >= n) return;
     int b, c[VC_MAX_NDIM];
     load_index(idx, row, g.ndim, b, c);
+    if (!index_ok(g, b, c)) return;
     unsigned long long key = (unsigned long long)b;
     for (int d = 0; d < g.ndim; ++d) key = key * (unsigned long long)g.shape[d] + (unsigned long long)c[d];
     unsigned long long packed = (key << ROW_BITS) | (unsigned long long)row;
@@ -104,7 +113,7 @@ __global__ void __launch_bounds__(256) subm_probe_kernel(const int32_t* __restri
             load_index(idx, row, g.ndim, b, c);
             int off[VC_MAX_NDIM];
             decode_k(g, k, off);
-            bool ok = true;
+            bool ok = index_ok(g, b, c);
             unsigned long long key = (unsigned long long)b;
             for (int d = 0; d < g.ndim; ++d) {
                 int v = c[d] + (off[d] - g.ksize[d] / 2) * g.dil[d];
@@ -130,6 +139,7 @@ static constexpr int SCAN_WORDS = 2048;  // words per scan block (256 threads x 
 
 // returns output linear cell (batch major) for (input coords c, offset k), or -1
 __device__ __forceinline__ long long out_cell(const Geom& g, int b, const int* c, int k) {
+    if (!index_ok(g, b, c)) return -1;
     int off[VC_MAX_NDIM];
     decode_k(g, k, off);
     long long lin = b;
@@ -333,11 +343,13 @@ __global__ void __launch_bounds__(1024) pairs_kernel(const int32_t* __restrict__
     if (threadIdx.x == 0) pair_num[k] = total;
 }
 
-static int make_geom(Geom& g, int ndim, const int32_t* shape, const int32_t* ksize, const int32_t* stride,
+static int make_geom(Geom& g, int ndim, int batch_size, const int32_t* shape, const int32_t* ksize, const int32_t* stride,
                      const int32_t* pad, const int32_t* dil) {
     VC_CHECK_ARG(ndim >= 1 && ndim <= VC_MAX_NDIM, "ndim %d not in [1,%d]", ndim, VC_MAX_NDIM);
+    VC_CHECK_ARG(batch_size > 0, "batch size %d", batch_size);
     memset(&g, 0, sizeof(g));
     g.ndim = ndim;
+    g.batch = batch_size;
     g.K = 1;
     for (int d = 0; d < ndim; ++d) {
         g.shape[d] = shape[d];
@@ -371,7 +383,7 @@ int vc::subm_rulebook_dev(const int32_t* indices, int n, const int* n_dev, int n
                           const int32_t* spatial_shape, const int32_t* ksize, const int32_t* dilation, int32_t* nbr,
                           int32_t* pair_num, void* ws, size_t ws_bytes, cudaStream_t stream) {
     Geom g;
-    int rc = make_geom(g, ndim, spatial_shape, ksize, nullptr, nullptr, dilation);
+    int rc = make_geom(g, ndim, batch_size, spatial_shape, ksize, nullptr, nullptr, dilation);
     if (rc) return rc;
     VC_CHECK_ARG(n >= 0 && n < (1 << ROW_BITS), "row count %d out of range", n);
     double cells = (double)batch_size;
@@ -404,7 +416,7 @@ extern "C" int vc_subm_rulebook(const int32_t* indices, int n, int ndim, int bat
 extern "C" int vc_conv_out_shape(int ndim, const int32_t* spatial_shape, const int32_t* ksize, const int32_t* stride,
                                  const int32_t* padding, const int32_t* dilation, int32_t* out_shape) {
     Geom g;
-    int rc = make_geom(g, ndim, spatial_shape, ksize, stride, padding, dilation);
+    int rc = make_geom(g, ndim, 1, spatial_shape, ksize, stride, padding, dilation);
     if (rc) return rc;
     for (int d = 0; d < ndim; ++d) out_shape[d] = g.oshape[d];
     return VC_OK;
@@ -444,7 +456,7 @@ int vc::conv_rulebook_count_dev(const int32_t* indices, int n, const int* n_dev,
                                 const int32_t* padding, const int32_t* dilation, int32_t* n_out_dev, int cap_out, int* overflow,
                                 void* ws, size_t ws_bytes, cudaStream_t stream) {
     Geom g;
-    int rc = make_geom(g, ndim, spatial_shape, ksize, stride, padding, dilation);
+    int rc = make_geom(g, ndim, batch_size, spatial_shape, ksize, stride, padding, dilation);
     if (rc) return rc;
     VC_CHECK_ARG(n >= 0 && n_out_dev && ws && batch_size > 0, "bad arguments");
     ConvWs w = conv_ws_layout(ndim, batch_size, g.oshape, ws);
@@ -491,7 +503,7 @@ int vc::conv_rulebook_fill_phases(const int32_t* indices, int n, const int* n_de
                                   int32_t* nbr_bwd, int32_t* pair_num, void* ws, size_t ws_bytes, cudaStream_t stream,
                                   int phases) {
     Geom g;
-    int rc = make_geom(g, ndim, spatial_shape, ksize, stride, padding, dilation);
+    int rc = make_geom(g, ndim, batch_size, spatial_shape, ksize, stride, padding, dilation);
     if (rc) return rc;
     ConvWs w = conv_ws_layout(ndim, batch_size, g.oshape, ws);
     if (ws_bytes < w.bytes) {

@@ -64,6 +64,7 @@ class Plan:
     def __init__(self, in_channels):
         self.rows_i, self.rows_f = [], []
         self.layers = []              # (conv module, bn module)
+        self.owners = []              # per layer: the SparseSequential the pair came from (or None)
         self.n_f, self.n_i, self.n_rb = 1, 1, 0
         self.f_channels = {0: in_channels}
         self.published = []           # (name, feature slot, index set)
@@ -114,11 +115,14 @@ class Plan:
                   x1=int(u_max), x2=int(v_max), f=[float(np.float32(g)) for g in grid])
         return out
 
-    def cbr(self, f_in, rb, conv, bn):
+    def cbr(self, f_in, rb, conv, bn, seq=None):
+        """`seq`: the container whose members [0], [1] the (conv, bn) pair was read from — lets is_current() notice a
+        swapped sub-module (e.g. SyncBatchNorm.convert_sync_batchnorm after the plan was built, tools/train.py:115-116)."""
         out = self.n_f
         self.n_f += 1
         layer = len(self.layers)
         self.layers.append((conv, bn))
+        self.owners.append(seq)
         assert self.f_channels[f_in] == conv.in_channels, (self.f_channels[f_in], conv.in_channels)
         self.f_channels[out] = conv.out_channels
         self._row(OP_CBR, 0, a=f_in, b=out, c=rb, cin=conv.in_channels, cout=conv.out_channels, layer=layer,
@@ -155,8 +159,21 @@ class Plan:
         return out
 
     def eligible(self):
-        """Every layer is conv(bias=False) + affine BatchNorm1d with running statistics (what the VirConv blocks build)."""
-        return all(conv.bias is None and bn.affine and bn.track_running_stats for conv, bn in self.layers)
+        """Every layer is conv(bias=False) + a plain affine BatchNorm1d with running statistics and a fixed momentum (what the
+        VirConv blocks build), all parameters / buffers fp32 and contiguous.  SyncBatchNorm (statistics across ranks), a
+        cumulative-average BatchNorm (momentum=None) or a half-precision model go through the module path instead."""
+        def f32(*ts):
+            return all(t is not None and t.dtype == torch.float32 and t.is_contiguous() for t in ts)
+        return all(conv.bias is None and type(bn) is torch.nn.BatchNorm1d and bn.affine and bn.track_running_stats
+                   and bn.momentum is not None and f32(conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var)
+                   for conv, bn in self.layers)
+
+    def is_current(self):
+        """The (conv, bn) objects recorded at build time are still the live members of their containers."""
+        for (conv, bn), seq in zip(self.layers, self.owners):
+            if seq is not None and (seq[0] is not conv or seq[1] is not bn):
+                return False
+        return True
 
 
 _PINNED = {}
@@ -375,7 +392,9 @@ def _layer_ptrs(plan, grad_base=0):
     only when a weight's address changes (module.to(), load of a new tensor object); the gradient columns are
     `grad_base` + fixed offsets into the step's flat gradient buffer."""
     oi, of, lf, sizes, offs = plan.finalize()
-    key = tuple(conv.weight.data_ptr() for conv, _ in plan.layers)
+    key = tuple((conv.weight.data_ptr(), bn.weight.data_ptr(), bn.bias.data_ptr(), bn.running_mean.data_ptr(),
+                 bn.running_var.data_ptr(), bn.num_batches_tracked.data_ptr() if bn.num_batches_tracked is not None else 0)
+                for conv, bn in plan.layers)
     cached = getattr(plan, '_ptr_cache', None)
     if cached is None or cached[0] != key:
         tab = np.zeros((len(plan.layers), PCOLS), dtype=np.uint64)

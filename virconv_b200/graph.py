@@ -21,7 +21,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from . import executor, ops
+from . import _lib, executor, ops
 
 
 def masked_mean(t):
@@ -41,6 +41,7 @@ class GraphedStep:
         self.cap0 = 0
         self.caps = {}
         self.recaptures = 0
+        self.launches_per_replay = 0
         self._pending = []        # (event, pinned slot) of the replays whose overflow flag has not been looked at yet
         self._slot = 0
 
@@ -123,8 +124,11 @@ class GraphedStep:
             p.grad = None
         self.overflow.zero_()
         self.graph = torch.cuda.CUDAGraph()
+        lib = _lib.load()
+        l0 = lib.vc_launch_count()
         with torch.cuda.graph(self.graph):
             self.loss = self._static_step(batch)
+        self.launches_per_replay = int(lib.vc_launch_count() - l0)     # this library's kernels inside one replay
         self.recaptures += 1
         torch.cuda.synchronize(self.dev)
 

@@ -20,6 +20,7 @@ import math
 import sys
 import types
 
+import numpy as np
 import torch
 import torch.nn as nn
 
@@ -106,6 +107,10 @@ class SparseConvolution(SparseModule):
         self.kernel_size, self.stride = tup(kernel_size), tup(stride)
         self.padding, self.dilation = tup(padding), tup(dilation)
         self.conv1x1 = all(k == 1 for k in self.kernel_size)
+        if subm and any(k % 2 == 0 for k in self.kernel_size):
+            # (spconv asserts the same; the dgrad of a submanifold conv reuses the forward table with mirrored offsets,
+            #  which is only its own transpose for odd, symmetric kernels)
+            raise ValueError(f'submanifold convolution needs odd kernel sizes, got {self.kernel_size}')
         self.subm, self.indice_key = subm, indice_key
         self.groups = groups
         self.precision = 'fp32'      # 'bf16' -> tcgen05 tensor-core kernels (see ops.py); set via set_precision()
@@ -172,7 +177,9 @@ class SparseConvolution(SparseModule):
         """conv + BatchNorm1d + ReLU in one autograd node (the SparseSequential fast path)."""
         rb = self.rulebook(x)
         training = bn.training or (bn.running_mean is None)
-        momentum = 0.0 if bn.momentum is None else bn.momentum
+        if bn.momentum is None:
+            raise ValueError('cumulative-average BatchNorm (momentum=None) is not fused; SparseSequential routes it through torch')
+        momentum = bn.momentum
         res = ops.ConvBNReLUFn.apply(x.features, self.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, rb,
                                      training, bn.eps, momentum, self.precision, x.features_bf16, bn.num_batches_tracked)
         if isinstance(res, tuple):
@@ -255,7 +262,7 @@ class SparseSequential(SparseModule):
         while i < len(mods):
             m = mods[i]
             if (isinstance(m, SparseConvolution) and m.bias is None and i + 2 < len(mods)
-                    and isinstance(mods[i + 1], nn.BatchNorm1d) and mods[i + 1].affine
+                    and type(mods[i + 1]) is nn.BatchNorm1d and mods[i + 1].affine and mods[i + 1].momentum is not None
                     and mods[i + 1].track_running_stats and isinstance(mods[i + 2], nn.ReLU)
                     and isinstance(x, SparseConvTensor) and x.indices.shape[0] > 0):
                 x = m.forward_bn_relu(x, mods[i + 1])
@@ -279,14 +286,75 @@ conv.SubMConv3d, conv.SubMConv2d = SubMConv3d, SubMConv2d
 conv.SparseConv3d, conv.SparseConv2d = SparseConv3d, SparseConv2d
 
 
+class _TVArray:
+    """Stand-in for a `cumm.tensorview` array on the dataloader path: the reference only wraps numpy arrays on the way
+    in (`tv.from_numpy`, data_processor.py:53) and calls `.numpy()` on the way out (:56-58)."""
+
+    def __init__(self, arr):
+        self._a = arr
+
+    def numpy(self):
+        return np.array(self._a, copy=True)       # "make copy with numpy()" (data_processor.py:55)
+
+    def numpy_view(self):
+        return self._a
+
+    @property
+    def shape(self):
+        return list(self._a.shape)
+
+
+class Point2VoxelCPU3d:
+    """`spconv.utils.Point2VoxelCPU3d` as the reference's dataloader uses it (data_processor.py:24,35-41,53-58): first-come
+    voxelisation on the host, coordinates emitted zyx.  The GPU path of this repo voxelises inside the model
+    (preprocess.PointsToVoxels -> vc_voxelize_mean); this class only keeps `tools/train.py`'s unmodified dataset code
+    importable and produces the same arrays (voxel order = first appearance, <= max_num_points_per_voxel points in point
+    order, zero padded) through scenes.voxelize_first_come."""
+
+    def __init__(self, vsize_xyz, coors_range_xyz, num_point_features, max_num_points_per_voxel, max_num_voxels):
+        self.vsize_xyz = [float(v) for v in vsize_xyz]
+        self.coors_range_xyz = [float(v) for v in coors_range_xyz]
+        self.num_point_features = int(num_point_features)
+        self.max_num_points_per_voxel = int(max_num_points_per_voxel)
+        self.max_num_voxels = int(max_num_voxels)
+        rng = np.asarray(self.coors_range_xyz, dtype=np.float64)
+        self.grid_size = np.round((rng[3:] - rng[:3]) / np.asarray(self.vsize_xyz, dtype=np.float64)).astype(np.int64).tolist()
+
+    def point_to_voxel(self, pc):
+        from . import scenes
+        pts = pc.numpy_view() if isinstance(pc, _TVArray) else np.asarray(pc)
+        assert pts.ndim == 2 and pts.shape[1] == self.num_point_features, (pts.shape, self.num_point_features)
+        voxels, coords, num = scenes.voxelize_first_come(pts, self.vsize_xyz, self.coors_range_xyz,
+                                                         self.max_num_points_per_voxel, self.max_num_voxels)
+        return _TVArray(voxels), _TVArray(coords), _TVArray(num)
+
+
 def install_as_spconv():
-    """Make `import spconv.pytorch as spconv` (pcdet/utils/spconv_utils.py:33-36) resolve to this module."""
+    """Make `import spconv.pytorch as spconv` (pcdet/utils/spconv_utils.py:33-36), `from spconv.utils import
+    Point2VoxelCPU3d` (data_processor.py:24) and `import cumm.tensorview as tv` (data_processor.py:10) resolve to this
+    module's implementations.  `cumm` is only registered when no real one is importable."""
     me = sys.modules[__name__]
     pkg = types.ModuleType('spconv')
     pkg.__path__ = []
     pkg.pytorch = me
     pkg.__version__ = '2.1.22+virconv_b200'
+    utils = types.ModuleType('spconv.utils')
+    utils.Point2VoxelCPU3d = Point2VoxelCPU3d
+    pkg.utils = utils
     sys.modules['spconv'] = pkg
     sys.modules['spconv.pytorch'] = me
     sys.modules['spconv.pytorch.conv'] = conv
+    sys.modules['spconv.utils'] = utils
+    if 'cumm' not in sys.modules:
+        try:
+            import cumm.tensorview  # noqa: F401
+        except Exception:           # noqa: BLE001
+            cumm = types.ModuleType('cumm')
+            cumm.__path__ = []
+            tvm = types.ModuleType('cumm.tensorview')
+            tvm.from_numpy = _TVArray
+            tvm.Tensor = _TVArray
+            cumm.tensorview = tvm
+            sys.modules['cumm'] = cumm
+            sys.modules['cumm.tensorview'] = tvm
     return pkg
