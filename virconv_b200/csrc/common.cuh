@@ -185,4 +185,20 @@ int tc2_conv(int kc, int nr, const void* in_bf16, const void* wimg, const int32_
              const int* n_dev, int K, double* bn_sums, int* err, cudaStream_t stream, const float* addend,
              int* tile_counter = nullptr);
 
+// ---- wgrad_tc2.cu (persistent tensor-core wgrad) ----
+struct WgradFinEntry {
+    const float* scratch;   // [K][cin][cout] accumulated by tc2_wgrad
+    float* dw;              // parameter layout [cout][K][cin]
+    int cin, cout, K, first;
+};
+static constexpr int WGRAD_FIN_MAX = 64;
+struct WgradFinTable {
+    WgradFinEntry e[WGRAD_FIN_MAX];
+    int n, total;
+};
+int wgrad_finalize(WgradFinTable& t, cudaStream_t stream);
+int tc2_wgrad(int cin, int cout, const void* in_bf16, const void* dout_bf16, const int32_t* nbr, long long pitch, float* scratch,
+              int n_rows, const int* n_dev, int K, int* err, cudaStream_t stream, int* tile_counter);
+int wgrad2_passes(int cin, int cout, int K);
+
 }  // namespace vc

@@ -867,7 +867,10 @@ extern "C" int vc_conv_wgrad_tc_config(int max_ctas, int smem_floor_bytes) {
 }
 
 extern "C" size_t vc_conv_wgrad_tc_ws_bytes(int n_out, int cin, int cout, int K) {
-    return (size_t)vc::wgrad_tc_grid(n_out) * K * cin * cout * sizeof(float);
+    // round-1 kernel: one [K, cin, cout] partial per CTA; persistent kernel (variant 1): one scratch image + 2 tile counters
+    const size_t v0 = (size_t)vc::wgrad_tc_grid(n_out) * K * cin * cout * sizeof(float);
+    const size_t v1 = (size_t)K * cin * cout * sizeof(float) + 64;
+    return v0 > v1 ? v0 : v1;
 }
 
 extern "C" int vc_conv_wgrad_tc(const void* in_bf16, const void* dout_bf16, const int32_t* nbr, float* dw, int n_out,
@@ -875,8 +878,8 @@ extern "C" int vc_conv_wgrad_tc(const void* in_bf16, const void* dout_bf16, cons
                                 vc_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     VC_CHECK_ARG(n_out >= 0 && K >= 1 && K <= MAXK_TC && dw, "bad arguments");
-    if (!tc_ch_ok(cin) || !tc_ch_ok(cout)) {
-        set_error("tensor-core wgrad: unsupported channels cin=%d cout=%d (need 16/32/64)", cin, cout);
+    if (!tc_conv_ch_ok(cin) || !tc_conv_ch_ok(cout)) {
+        set_error("tensor-core wgrad: unsupported channels cin=%d cout=%d", cin, cout);
         return VC_ERR_UNSUPPORTED;
     }
     if (n_out == 0) {
@@ -887,6 +890,18 @@ extern "C" int vc_conv_wgrad_tc(const void* in_bf16, const void* dout_bf16, cons
     if (ws_bytes < vc_conv_wgrad_tc_ws_bytes(n_out, cin, cout, K)) {
         set_error("tensor-core wgrad workspace %zu < %zu", ws_bytes, vc_conv_wgrad_tc_ws_bytes(n_out, cin, cout, K));
         return VC_ERR_WORKSPACE;
+    }
+    if (g_tc_variant == 1) {
+        // persistent kernel (wgrad_tc2.cu): accumulate into a zeroed scratch image, then one transposing pass
+        const size_t wbytes = (size_t)K * cin * cout * sizeof(float);
+        VC_CUDA(cudaMemsetAsync(ws, 0, wbytes + 64, stream));
+        int rc1 = tc2_wgrad(cin, cout, in_bf16, dout_bf16, nbr, n_out, (float*)ws, n_out, nullptr, K, err_flag, stream,
+                            reinterpret_cast<int*>((char*)ws + wbytes));
+        if (rc1) return rc1;
+        WgradFinTable T;
+        T.n = 1;
+        T.e[0].scratch = (const float*)ws; T.e[0].dw = dw; T.e[0].cin = cin; T.e[0].cout = cout; T.e[0].K = K; T.e[0].first = 0;
+        return wgrad_finalize(T, stream);
     }
     float* partial = (float*)ws;
     const __nv_bfloat16* a = (const __nv_bfloat16*)in_bf16;

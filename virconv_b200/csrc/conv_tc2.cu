@@ -35,9 +35,10 @@ constexpr int P_WARP_LOADER = 4, P_WARP_MMA = 5, P_WARP_PROD0 = 6, P_PROD_WARPS 
 constexpr int P_THREADS = 32 * (P_WARP_PROD0 + P_PROD_WARPS);   // 448
 constexpr int P_MAX_STAGES = 16;
 constexpr int P_NTB = 4;                                        // neighbour-table buffers (the loader runs 2 tiles ahead)
-constexpr int P_AHEAD = 2;                                      // table loads in flight
+constexpr int P_AHEAD = 2;                                      // table loads (global -> shared) in flight
+constexpr int P_PREF = 4;                                       // further tiles whose table rows are prefetched into L2
 constexpr int P_ROWS_PER_PROD = TCM / P_PROD_WARPS;             // 16
-constexpr int SMEM_BUDGET = 227 * 1024 - 3072;                  // dynamic shared memory per CTA (static part is small)
+constexpr int SMEM_BUDGET = 227 * 1024 - 4096;                  // dynamic shared memory per CTA (static part is small)
 
 template <int KC, int NR>
 struct PCfg {
@@ -152,21 +153,46 @@ __global__ void __launch_bounds__(P_THREADS, 1) tc_conv_persist_kernel(const PAr
         // Table slices travel global -> shared with cp.async (no register staging), P_AHEAD tiles in flight: producers
         // never wait for global memory, and the loader's own latency is pipelined across tiles.
         const bool vec_ok = (reinterpret_cast<uintptr_t>(a.nbr) & 15u) == 0 && (a.pitch & 3) == 0;
-        int my_tile[P_AHEAD + 1];       // tiles of the loads in flight (ring indexed by it % (P_AHEAD + 1))
-        bool stop = false;
+        // tiles are claimed P_AHEAD + P_PREF iterations ahead of their use; a claimed tile's table rows are pulled into L2
+        // right away (no shared memory needed for that), the copy into shared memory follows P_PREF iterations later:
+        // a DRAM-cold table (1-1.5 us under load) would otherwise make the loader the pipeline's bottleneck
+        constexpr int PQ = P_AHEAD + P_PREF + 1;
+        int my_tile[PQ];                // claimed tiles, ring indexed by it % PQ
+        int claimed = 0;
+        bool stop = false;              // a claim came back past the end
         int issued = 0;
-        auto issue = [&](int it) -> bool {           // returns false on a pipeline timeout
-            const int tb = it % P_NTB;
-            if (it >= P_NTB && !mbar_wait_t(&tbl_empty[tb], (uint32_t)(((it / P_NTB) - 1) & 1), a.err)) return false;
+        auto claim = [&]() {
             int tile;
             if (a.tile_counter != nullptr) {
                 tile = lane == 0 ? atomicAdd(a.tile_counter, 1) : 0;
                 tile = __shfl_sync(0xffffffffu, tile, 0);
             } else {
-                tile = blockIdx.x + it * gridDim.x;
+                tile = blockIdx.x + claimed * gridDim.x;
             }
-            if (tile >= n_tiles) tile = -1;
-            my_tile[it % (P_AHEAD + 1)] = tile;
+            if (tile >= n_tiles) {
+                tile = -1;
+                stop = true;
+            } else {
+                const int base = tile * TCM;
+                if (vec_ok && (long long)base + TCM <= a.pitch) {
+                    if (lane < K)
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.nbr + (size_t)lane * a.pitch + base), "r"(TCM * 4)
+                                     : "memory");
+                } else {
+                    for (int i = lane; i < K * 5; i += 32) {
+                        const int k = i / 5, seg = i % 5;
+                        const long long row = (long long)base + seg * 32;
+                        if (row < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.nbr + (size_t)k * a.pitch + row));
+                    }
+                }
+            }
+            my_tile[claimed % PQ] = tile;
+            ++claimed;
+        };
+        auto issue = [&](int it) -> bool {           // returns false on a pipeline timeout
+            const int tb = it % P_NTB;
+            if (it >= P_NTB && !mbar_wait_t(&tbl_empty[tb], (uint32_t)(((it / P_NTB) - 1) & 1), a.err)) return false;
+            const int tile = my_tile[it % PQ];
             if (tile >= 0) {
                 int* dst = nbr_s + (size_t)tb * K * TCM;
                 const int base = tile * TCM;
@@ -193,14 +219,14 @@ __global__ void __launch_bounds__(P_THREADS, 1) tc_conv_persist_kernel(const PAr
             return true;
         };
         for (int it = 0;; ++it) {
-            // keep P_AHEAD table loads in flight
-            while (!stop && issued <= it + P_AHEAD - 1) {
+            // keep the claims P_AHEAD + P_PREF and the shared-memory loads P_AHEAD iterations ahead
+            while (!stop && claimed <= it + P_AHEAD + P_PREF - 1) claim();
+            while (issued < claimed && issued <= it + P_AHEAD - 1) {
                 if (!issue(issued)) goto done;
-                if (my_tile[issued % (P_AHEAD + 1)] < 0) stop = true;
                 ++issued;
             }
             const int tb = it % P_NTB;
-            const int tile = my_tile[it % (P_AHEAD + 1)];
+            const int tile = my_tile[it % PQ];
             // groups are committed in order: allow (issued - it - 1) younger ones to stay in flight
             if (issued - it - 1 >= 1) cp_async_wait<1>(); else cp_async_wait<0>();
             __syncwarp();

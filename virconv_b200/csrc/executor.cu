@@ -57,7 +57,8 @@ struct RBk {
 struct Layer {
     float *x, *y, *stats;
     double* sums;          // [4*cout]: forward sums, backward sums
-    int* tile_ctr;         // [2] tile-scheduler counters of the persistent conv kernels (forward, dgrad), zeroed with the sums
+    int* tile_ctr;         // [4] tile-scheduler counters of the persistent kernels (forward, dgrad, wgrad pass 0 / 1), zeroed with the sums
+    float* wscratch;       // [K][cin][cout] fp32 accumulator of the persistent wgrad kernel (zeroed with the sums), or NULL
     void *wimg_fwd, *wimg_dgrad;
     int in_slot, out_slot, rb, use_tc, use_tc_w, cin, cout, need_dgrad;   // use_tc: conv fwd / gather dgrad; use_tc_w: wgrad / scatter dgrad
 };
@@ -372,16 +373,23 @@ extern "C" int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_o
         }
     }
 
-    // BatchNorm accumulators + tile-scheduler counters of every layer: one region, one memset
-    size_t sums_doubles = 0, n_cbr = 0;
+    // BatchNorm accumulators + tile-scheduler counters (+ the wgrad accumulators of a training step) of every layer: one
+    // region, one memset
+    size_t sums_doubles = 0, n_cbr = 0, wg_floats = 0;
     for (int i = 0; i < n_ops; ++i)
         if (C.op(i)[F_KIND] == OP_CBR) {
-            sums_doubles += 4 * (size_t)C.op(i)[F_COUT];
+            const int* o = C.op(i);
+            sums_doubles += 4 * (size_t)o[F_COUT];
             ++n_cbr;
+            if (training && precision == 1 && g_tc_variant == 1 && tc2_ch_ok(o[F_CIN]) && tc2_ch_ok(o[F_COUT]))
+                wg_floats += ((size_t)rb_K[o[F_C]] * o[F_CIN] * o[F_COUT] + 63) / 64 * 64;
         }
-    VC_ALLOC(sums_all, double*, sums_doubles * 8 + n_cbr * 2 * sizeof(int));
+    const size_t zero_bytes = sums_doubles * 8 + n_cbr * 4 * sizeof(int) + wg_floats * 4;
+    VC_ALLOC(sums_all, double*, zero_bytes);
     int* ctr_all = reinterpret_cast<int*>(sums_all + sums_doubles);
-    if (sums_doubles) VC_CUDA(cudaMemsetAsync(sums_all, 0, sums_doubles * 8 + n_cbr * 2 * sizeof(int), C.st[0]));
+    float* wg_all = reinterpret_cast<float*>(ctr_all + n_cbr * 4);
+    if (zero_bytes) VC_CUDA(cudaMemsetAsync(sums_all, 0, zero_bytes, C.st[0]));
+    size_t wg_cur = 0;
     size_t sums_cur = 0, ctr_cur = 0;
 
     // tensor-core weight images of every layer, one launch
@@ -395,7 +403,12 @@ extern "C" int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_o
         L.use_tc_w = precision == 1 && tc_ok(L.cin) && tc_ok(L.cout);
         L.sums = sums_all + sums_cur;
         sums_cur += 4 * (size_t)L.cout;
-        L.tile_ctr = ctr_all + 2 * ctr_cur++;
+        L.tile_ctr = ctr_all + 4 * ctr_cur++;
+        L.wscratch = nullptr;
+        if (training && precision == 1 && g_tc_variant == 1 && tc2_ch_ok(L.cin) && tc2_ch_ok(L.cout)) {
+            L.wscratch = wg_all + wg_cur;
+            wg_cur += ((size_t)rb_K[L.rb] * L.cin * L.cout + 63) / 64 * 64;
+        }
     }
     if (precision == 1) {
         TcPrepTable T;
@@ -702,6 +715,8 @@ extern "C" int vc_exec_backward(const int32_t* ops_i, const float* ops_f, int n_
     if (two) VC_TRY(ev_init());
     int last_w_ev = -1;
     const int training = S->training;
+    WgradFinTable fin;          // persistent wgrad kernels accumulate into scratch images; ONE transposing launch at the end
+    fin.n = 0;
 
     for (int i = 0; i < MAX_F; ++i) { S->f[i].grad = nullptr; S->f[i].grad_state = G_EMPTY; }
     for (int i = 0; i < n_pub; ++i) {
@@ -765,7 +780,17 @@ extern "C" int vc_exec_backward(const int32_t* ops_i, const float* ops_f, int n_
             int e = record_on(C, 0);
             if (e >= 0) VC_CUDA(cudaStreamWaitEvent(wst, g_ev[e], 0));
         }
-        if (L.use_tc_w) {
+        if (L.wscratch != nullptr) {
+            Timed t(6, li, wst);
+            VC_TRY(tc2_wgrad(L.cin, L.cout, X.bf16, dxb, R.nbr, R.n_out, L.wscratch, R.n_out, R.n_out_dev, R.K, C.err, wst,
+                             L.tile_ctr + 2));
+            if (fin.n == WGRAD_FIN_MAX) {
+                VC_TRY(wgrad_finalize(fin, wst));
+                fin.n = 0;
+            }
+            WgradFinEntry& fe = fin.e[fin.n++];
+            fe.scratch = L.wscratch; fe.dw = dw; fe.cin = L.cin; fe.cout = L.cout; fe.K = R.K; fe.first = 0;
+        } else if (L.use_tc_w) {
             const size_t wsb = vc_conv_wgrad_tc_ws_bytes(R.n_out, L.cin, L.cout, R.K);
             VC_ALLOC(ws, void*, wsb);
             Timed t(6, li, wst);
@@ -808,6 +833,10 @@ extern "C" int vc_exec_backward(const int32_t* ops_i, const float* ops_f, int n_
                                          st);
             }));
         }
+    }
+    if (fin.n > 0) {
+        VC_TRY(wgrad_finalize(fin, wst));
+        if (two) last_w_ev = record_on(C, 1);
     }
     if (two && last_w_ev >= 0) VC_CUDA(cudaStreamWaitEvent(st, g_ev[last_w_ev], 0));   // join: gradients complete on `stream`
     S->used = C.A.used;

@@ -381,7 +381,7 @@ def conv_wgrad(feats, dout, weight_shape, rb: Rulebook, precision='fp32', feats_
     feats = feats.contiguous()
     dout = dout.contiguous()
     dw = torch.empty(tuple(weight_shape), dtype=torch.float32, device=feats.device)
-    if precision == 'bf16' and tc_supported(cin, cout) and rb.n_out > 0:
+    if precision == 'bf16' and tc_conv_supported(cin, cout) and rb.n_out > 0:
         fb = feats_bf16 if feats_bf16 is not None else cast_bf16(feats)
         db = dout_bf16 if dout_bf16 is not None else cast_bf16(dout)
         ws = _ws(lib.vc_conv_wgrad_tc_ws_bytes(rb.n_out, cin, cout, rb.K), feats.device)

@@ -45,9 +45,13 @@ def allreduce_gradients(params, average: bool = True, group=None) -> int:
     if flat is not None:
         # the plan executor writes every gradient into ONE flat buffer (executor.PlanFn.backward): reduce it in place,
         # no flatten / scatter-back kernels
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-        if average:
-            flat.div_(world)
+        # (NCCL averages inside the collective: no separate divide kernel; gloo — the CPU tests — has no AVG)
+        if average and dist.get_backend(group) == 'nccl':
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)
+        else:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+            if average:
+                flat.div_(world)
         return flat.numel() * flat.element_size()
     flat = torch.cat([g.reshape(-1) for g in grads])
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
