@@ -51,6 +51,11 @@ def parse():
                     help='bf16 = tcgen05 tensor-core contractions (BASELINE configs[1] dtype); fp32 = 1e-4 parity kernels')
     ap.add_argument('--ref-budget-s', type=float, default=150.0)
     ap.add_argument('--cpu-worker', action='store_true', help=argparse.SUPPRESS)
+    ap.add_argument('--cpu-thread-sweep', action='store_true', help='CPU arm at several thread counts (profiles/ evidence)')
+    ap.add_argument('--model', default='L', choices=['L', 'T'],
+                    help='L = VirConv-L (VirConvL8x; the headline metric, BASELINE configs[1]); T = VirConv-T / -S backbone '
+                         '(VirConv8x, MM stream + LiDAR stream: BASELINE configs[2] and [4]) — training step and ROT_NUM=3 eval '
+                         'forward, gradient all-reduce timed separately (exposed time)')
     ap.add_argument('--mode', default=os.environ.get('VIRCONV_BENCH_MODE', 'graph'), choices=['graph', 'eager'],
                     help='graph = the whole step (forward + loss + backward) replayed as one CUDA graph (plan executor static '
                          'mode: device row counts, no host synchronisation); eager = exact-shape execution, one C-ABI call per '
@@ -129,8 +134,29 @@ def cpu_step(model, batch):
 
 def cpu_threads():
     """Threads for the CPU legs: the per-offset mm / index_add_ of the Native algorithm stop scaling (and then slow
-    down) beyond a few tens of threads, so 'all the threads it can use' is capped at 32."""
+    down) beyond a few tens of threads, so 'all the threads it can use' is capped at 32 (sweep on the B200 box's host:
+    profiles/cpu_thread_sweep_r2.txt, `python bench.py --cpu-thread-sweep`).  VIRCONV_CPU_THREADS overrides."""
+    env = os.environ.get('VIRCONV_CPU_THREADS')
+    if env:
+        return max(1, int(env))
     return max(1, min(os.cpu_count() or 1, 32))
+
+
+def run_cpu_thread_sweep():
+    """scenes/s of the CPU arm for a range of thread counts (one warm-up + 3 steps each)."""
+    from virconv_b200 import scenes
+    cm = make_cpu_model()
+    b = scenes.make_batch([0, 1], N_LIDAR, N_VIRTUAL, MAX_VOXELS, training=True)
+    n = os.cpu_count() or 1
+    for t in [c for c in (4, 8, 16, 32, 64, 128, 256) if c <= n] + ([n] if n not in (4, 8, 16, 32, 64, 128, 256) else []):
+        torch.set_num_threads(t)
+        cpu_step(cm, b)
+        ts = []
+        for _ in range(3):
+            t0 = time.time()
+            cpu_step(cm, b)
+            ts.append(time.time() - t0)
+        print(f'threads {t:4d}: {SCENES_PER_GPU / float(np.mean(ts)):.3f} scenes/s ({1e3 * float(np.mean(ts)):.0f} ms/step)', flush=True)
 
 
 def run_cpu_worker():
@@ -173,11 +199,15 @@ def run_reference(args):
     model = make_cpu_model()
     batches = [scenes.make_batch([2 * i, 2 * i + 1], N_LIDAR, N_VIRTUAL, MAX_VOXELS, training=True) for i in range(2)]
     t0 = time.time()
-    for w in range(min(args.warmup, 1)):
+    n_warm = 0
+    for w in range(max(args.warmup, 1)):
         cpu_step(model, batches[w % 2])
+        n_warm += 1
+        if time.time() - t0 > 0.4 * args.ref_budget_s:        # (a very slow host: keep most of the budget for timed steps)
+            break
     warm = time.time() - t0
-    per = max(warm, 1e-3)
-    k = max(1, min(args.steps, int(max(args.ref_budget_s - warm, per) / per))) if warm > 0 else args.steps
+    per = max(warm / n_warm, 1e-3)
+    k = max(1, min(args.steps, int(max(args.ref_budget_s - warm, per) / per)))
     times = []
     for s in range(k):
         t = time.time()
@@ -185,10 +215,10 @@ def run_reference(args):
         times.append(time.time() - t)
     ms = 1e3 * float(np.mean(times))
     val = SCENES_PER_GPU / (ms / 1e3)
-    sample = (f'{k} step(s) of one batch of {SCENES_PER_GPU} scenes (same workload), after {min(args.warmup, 1)} warm-up; '
+    sample = (f'{k} step(s) of one batch of {SCENES_PER_GPU} scenes (same workload), after {n_warm} warm-up step(s); '
               f'steps capped by a {args.ref_budget_s:.0f} s budget')
     line = {'impl': 'reference', 'metric': 'VirConv-L scenes/sec (fwd+bwd)', 'value': val, 'unit': 'scenes/s',
-            'n_gpus': args.gpus, 'steps': k, 'warmup': min(args.warmup, 1), 'ms_per_step': ms, 'higher_is_better': True,
+            'n_gpus': args.gpus, 'steps': k, 'warmup': n_warm, 'ms_per_step': ms, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'scenes_per_step': SCENES_PER_GPU,
                        'what': 'restated reference algorithm on CPU (spconv Native: C hash-map rulebook + per-offset '
@@ -200,9 +230,160 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------------
+# VirConv-T / VirConv-S backbone (BASELINE configs[2], [4]): separate arm, not the headline metric
+# ------------------------------------------------------------------------------------------------------
+CFG_T = dict(RETURN_NUM_FEATURES_AS_DICT=True, OUT_FEATURES=64, LAYER_DISCARD_RATE=0.15, NUM_FILTERS=[16, 32, 64, 64], MM=True)
+MAX_VOXELS_T_TRAIN, MAX_VOXELS_T_TEST = 16000, 40000      # VirConv-T.yaml:120-121
+
+
+def run_ours_t(args):
+    """VirConv8x (`spconv_backbone.py:232-535`): training step (one pass per stream, batch 2/GPU, random init — config 5
+    "VirConv-S training step": the two models share this backbone) with the gradient all-reduce timed on its own, and the
+    ROT_NUM=3 eval forward (LiDAR stream x-batched, MM stream looped — config 3).  Exact-shape executor path (one C-ABI call
+    per plan forward / backward); the CUDA-graph static mode covers VirConv-L only so far."""
+    import torch.distributed as dist
+    from virconv_b200 import _lib, ops, parallel, scenes
+    from virconv_b200.backbone import VirConv8x
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    lib = _lib.load()
+    torch.manual_seed(666)
+    model = VirConv8x(CFG_T, 8, [1408, 1600, 80], precision=args.precision).to(dev).train()
+    params = list(model.parameters())
+    if world > 1:
+        for p in params:
+            dist.broadcast(p.data, 0)
+
+    def to_dev(b, train):
+        bd = {k: torch.from_numpy(v).to(dev) for k, v in b.arrays.items()}
+        bd.update(batch_size=b.batch_size, calib=b.calib)
+        if train:
+            bd['aug_param'] = torch.from_numpy(b.aug_param)
+        else:
+            bd['transform_param'] = torch.from_numpy(b.transform_param)
+        return bd
+
+    train_b = [to_dev(scenes.make_batch_mm(parallel.shard_scene_ids(i, rank, world, SCENES_PER_GPU), N_LIDAR, N_VIRTUAL,
+                                           MAX_VOXELS_T_TRAIN, training=True), True) for i in range(POOL)]
+    test_b = [to_dev(scenes.make_batch_mm(parallel.shard_scene_ids(100 + i, rank, world, SCENES_PER_GPU), N_LIDAR, N_VIRTUAL,
+                                          MAX_VOXELS_T_TEST, training=False, rot_num=3), False) for i in range(2)]
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def loss_of(out, sfx=('',)):
+        loss = 0
+        for s_ in sfx:
+            loss = loss + out['encoded_spconv_tensor' + s_].features.mean()
+            for grp in ('multi_scale_3d_features', 'multi_scale_3d_features_mm'):
+                for t in out[grp + s_].values():
+                    if t is not None:
+                        loss = loss + t.features.mean()
+        return loss
+
+    def train_step(bd, reduce=True):
+        for p in params:
+            p.grad = None
+        out = model(dict(bd))
+        loss = loss_of(out)
+        loss.backward()
+        ar = None
+        if reduce and world > 1:
+            a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            parallel.allreduce_gradients(params, average=True)
+            e.record()
+            ar = (a, e)
+        return loss, ar
+
+    def timed_train(n, reduce=True):
+        evs, ars = [], []
+        for s_ in range(n):
+            flush_buf.zero_()
+            a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            _, ar = train_step(train_b[s_ % POOL], reduce)
+            e.record()
+            evs.append((a, e))
+            if ar:
+                ars.append(ar)
+        torch.cuda.synchronize()
+        return [a.elapsed_time(e) for a, e in evs], [a.elapsed_time(e) for a, e in ars]
+
+    def timed_eval(n):
+        model.eval()
+        evs = []
+        with torch.no_grad():
+            for s_ in range(n):
+                flush_buf.zero_()
+                a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                model(dict(test_b[s_ % 2]))
+                e.record()
+                evs.append((a, e))
+        torch.cuda.synchronize()
+        model.train()
+        return [a.elapsed_time(e) for a, e in evs]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    timed_train(max(args.warmup, 3))
+    barrier()
+    timed_train(args.steps)                  # allocator priming
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = lib.vc_launch_count()
+    ms_list, ar_list = timed_train(args.steps)
+    launches = (lib.vc_launch_count() - l0) / max(args.steps, 1)
+    barrier()
+    ms_nored, _ = timed_train(args.steps, reduce=False)
+    barrier()
+    timed_eval(3)
+    ev_list = timed_eval(max(args.steps // 2, 4))
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    tot = torch.tensor([sum(ms_list) / len(ms_list), sum(ms_nored) / len(ms_nored), sum(ev_list) / len(ev_list),
+                        (sum(ar_list) / len(ar_list)) if ar_list else 0.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    err = int(ops.tc_error_flag(dev).item())
+    assert err == 0, 'tensor-core pipeline timeout flag set'
+    if rank == 0:
+        ms_step, ms_step_nored, ms_eval, ms_ar = [float(x) for x in tot]
+        n_par = sum(p.numel() for p in params)
+        line = {'metric': 'VirConv-T/S backbone scenes/sec (fwd+bwd)', 'value': SCENES_PER_GPU * world / (ms_step * 1e-3),
+                'unit': 'scenes/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_step,
+                'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic', 'gpu_launches': launches,
+                'config': {'workload': 'VirConv-T / VirConv-S 3D backbone (VirConv8x: LiDAR stream + MM stream) fwd+bwd, synthetic KITTI '
+                                       'scenes 16k LiDAR + 80k virtual pts, 16000-voxel cap per stream and scene (train), grid '
+                                       '[81,1600,1408], batch 2/GPU, random init',
+                           'scenes_per_step': SCENES_PER_GPU * world, 'parallelism': f'dp{world}',
+                           'l2': 'flushed between timed steps (256 MiB write)', 'timing': 'per-step CUDA events, max over ranks'},
+                'allreduce': {'bytes': 4 * n_par, 'ms': ms_ar, 'exposed_ms': max(ms_step - ms_step_nored, 0.0),
+                              'ms_per_step_without_allreduce': ms_step_nored,
+                              'note': 'one flat fp32 bucket (NCCL AVG) after the backward: nothing overlaps it, exposed = its own time'},
+                'eval_rot3': {'ms_per_forward': ms_eval, 'scenes_per_s': SCENES_PER_GPU * world / (ms_eval * 1e-3),
+                              'what': 'ROT_NUM=3 test-mode forward: LiDAR stream x-batched [D,H,4W], MM stream 3 passes, 40000-voxel cap'},
+                'clocks': clocks}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------
 def run_ours(args):
+    if args.model == 'T':
+        return run_ours_t(args)
     import torch.distributed as dist
     from virconv_b200 import _lib, ops, parallel, scenes
     from virconv_b200.backbone import VirConvL8x
@@ -414,12 +595,14 @@ def run_ours(args):
         g_flops = sum(kern[k][3] for k in dom if k in kern)
         all_ms = sum(v[1] for v in kern.values())
         ach = g_bytes / (g_ms * 1e-3) / 1e9 if g_ms > 0 else 0.0
-        traffic = None
+        traffic, traffic_src = None, None
         tp = os.path.join(ROOT, 'profiles', 'traffic_tc_gather.json' if args.precision == 'bf16' else 'traffic_gather_f32.json')
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get('dram_bytes_per_launch')     # from the committed ncu --set full capture
+            traffic_src = 'profiles/' + os.path.basename(tp) + ' (ncu --set full capture of this kernel, not measured in this run)'
         roof = {'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'traffic': traffic,
-                'kernel': ('tc_gather_gemm_kernel<KC,NR> (tcgen05 conv forward + dgrad)'
+                'traffic_source': traffic_src,
+                'kernel': ('tc_conv_persist_kernel<KC,NR> (persistent tcgen05 conv forward + gather dgrad)'
                            if args.precision == 'bf16' else
                            'gather_gemm_kernel<CI,CO> (fp32 conv forward + dgrad), prep_weights included'),
                 'peak_source': how, 'launches_per_step': g_calls / nprof,
@@ -431,6 +614,16 @@ def run_ours(args):
                          '+ bf16 weights; CUDA events around each launch inside the plan executor, kernels timed alone (single stream)'
                          if args.precision == 'bf16' else
                          'fp32 CUDA-core parity path: FP32-FMA bound, HBM is the bound it is designed toward')}
+
+    roof_w = None
+    if rank == 0 and roof is not None and kern.get('conv_wgrad_tc'):
+        c, ms, by, fl = kern['conv_wgrad_tc']
+        peak, how = peaks()
+        roof_w = {'bound': 'hbm', 'kernel': 'tc_wgrad_persist_kernel<CI,CO> (persistent tcgen05 weight gradient)',
+                  'achieved': by / (ms * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s', 'frac': by / (ms * 1e-3) / 1e9 / peak,
+                  'launches_per_step': c / nprof, 'avg_launch_ms': ms / max(c, 1), 'alg_bytes_per_launch': by / max(c, 1),
+                  'achieved_tflops': fl / (ms * 1e-3) / 1e12, 'peak_source': how,
+                  'note': 'bytes = bf16 gathered rows + bf16 dout + P*8 + fp32 gradient; CUDA events inside the plan executor, kernels alone'}
 
     if rank != 0:
         if world > 1:
@@ -464,8 +657,9 @@ def run_ours(args):
                                      'fp32 wgrad/BN' if args.precision == 'bf16' else 'fp32 storage, fp32 accumulate (parity path)')},
             'e2e': {'value': scenes_per_step / (ms_e2e * 1e-3), 'unit': 'scenes/s', 'ms_per_step': ms_e2e,
                     'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': 4 + 4 * 4, 'allocator_events_in_timed_region': e2e_allocs},
-            'gpu_launches': launches, 'wall_s_timed_region': wall, 'cuda_mallocs_in_timed_region': int(dev_allocs), 'clocks': clocks, 'roofline': roof,
-            'cpu_baseline': cpu_base}
+            'gpu_launches': launches, 'wall_s_timed_region': wall,
+            'value_wall_clock': scenes_per_step * args.steps / wall,      # includes the L2 flushes and inter-step gaps 'cuda_mallocs_in_timed_region': int(dev_allocs), 'clocks': clocks, 'roofline': roof,
+            'roofline_wgrad': roof_w, 'cpu_baseline': cpu_base}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -475,6 +669,8 @@ if __name__ == '__main__':
     a = parse()
     if a.cpu_worker:
         run_cpu_worker()
+    elif a.cpu_thread_sweep:
+        run_cpu_thread_sweep()
     elif a.impl == 'reference':
         run_reference(a)
     else:

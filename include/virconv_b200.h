@@ -37,6 +37,7 @@ extern "C" {
 #define VC_ERR_CUDA (-2)         /* CUDA runtime error (launch / config) */
 #define VC_ERR_WORKSPACE (-3)    /* workspace too small */
 #define VC_ERR_UNSUPPORTED (-4)  /* channel count / ndim not compiled in */
+#define VC_ERR_PIPELINE (-5)     /* a tensor-core kernel's mbarrier wait timed out earlier (err_flag set): results invalid */
 
 #define VC_MAX_NDIM 3
 #define VC_TILE_ROWS 128         /* output rows per CTA tile in the conv kernels (BN partial granularity) */
@@ -318,7 +319,8 @@ int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_ops, const u
                     int training, int precision, int want_pair_num, void* arena, size_t arena_bytes,
                     int32_t* pinned_host, int32_t* err_flag, void* state, size_t state_bytes, vc_stream_t main_stream,
                     vc_stream_t side_stream, int side_waits_main, const int32_t* caps /*host, may be NULL*/,
-                    const int32_t* n0_dev /*device, NULL = exact mode*/, int32_t* overflow_flag /*device*/);
+                    const int32_t* n0_dev /*device, NULL = exact mode*/, int32_t* overflow_flag /*device*/,
+                    vc_stream_t side2_stream /*may be NULL: ops planned for stream 2 (image branch) then share side_stream*/);
 /* Reverse walk.  pub_slots [n_pub]: feature slots whose gradients come from outside (the published tensors), ext_grads
  * [n_pub]: device pointers to those gradients ([rows, c] fp32 contiguous, read only) or 0.  Writes d_weight / d_gamma /
  * d_beta of every layer (zeros where nothing flowed back).  Same arena as the forward (it continues allocating).

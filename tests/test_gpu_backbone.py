@@ -241,6 +241,54 @@ def test_full_size_properties(lib_built):
     assert float(dense.abs().sum()) == pytest.approx(float(named['out'].features.abs().sum()), rel=1e-5)
 
 
+def test_config1_full_size_vs_oracle(lib_built):
+    """BASELINE config 1 AT ITS STATED SIZE: one synthetic KITTI scene, 16 384 LiDAR returns, no virtual points, VirConv-L
+    forward in fp32 (train-mode BatchNorm): every layer's canonical rulebook bit-exact against the CPU oracle, the five
+    published feature maps within 1e-4 (north_star tolerance)."""
+    from virconv_b200 import scenes
+    batch = scenes.make_batch([7], n_lidar=16384, n_virtual=0, max_voxels=40000, training=False)
+    assert batch.voxel_features.shape[0] > 10000
+    model, ref = _models()
+    model.train()
+    ref.train()
+    with torch.no_grad():
+        named, _ = _run_gpu(model, batch.voxel_features, batch.voxel_coords, 1, batch.calib, None)
+        o = ref(torch.from_numpy(batch.voxel_features.copy()), torch.from_numpy(batch.voxel_coords.copy()), 1, batch.calib, None)
+    for k, t in named.items():
+        assert np.array_equal(t.indices.cpu().numpy(), o[k].indices.numpy()), k
+        assert rel_err(t.features.cpu(), o[k].features) < TOL, k
+    d, od = named['x_conv1'].indice_dict, o['x_conv1'].indice_dict
+    n_checked = 0
+    for key, rb in d.items():
+        if isinstance(key, str) and key in od:
+            assert np.array_equal(rb.nbr.cpu().numpy(), od[key]['nbr_np']), key
+            n_checked += 1
+    assert n_checked >= 8
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_bench_batch_forward_vs_oracle(lib_built, precision):
+    """The batch bench.py times (2 scenes x (16k LiDAR + 80k virtual), 40 000-voxel cap each: 80 000 input voxels),
+    forward against the CPU oracle: indices bit-exact; features 1e-4 on the fp32 kernels, 2e-2 on the bf16 tensor-core
+    kernels (operands rounded to bf16, fp32 accumulation)."""
+    from virconv_b200 import scenes
+    from virconv_b200 import spconv_compat as spc
+    batch = scenes.make_batch([0, 1], training=True)
+    assert batch.voxel_features.shape[0] == 80000
+    model, ref = _models()
+    spc.set_precision(model, precision)
+    model.train()
+    ref.train()
+    with torch.no_grad():
+        named, _ = _run_gpu(model, batch.voxel_features, batch.voxel_coords, 2, batch.calib, batch.aug_param)
+        o = ref(torch.from_numpy(batch.voxel_features.copy()), torch.from_numpy(batch.voxel_coords.copy()), 2, batch.calib,
+                batch.aug_param)
+    assert ops_err_flag() == 0
+    for k, t in named.items():
+        assert np.array_equal(t.indices.cpu().numpy(), o[k].indices.numpy()), k
+        assert rel_err(t.features.cpu(), o[k].features) < (TOL if precision == 'fp32' else 2e-2), k
+
+
 # ------------------------------------------------------------------------------------------------ VirConv-T / -S
 CFG8 = dict(RETURN_NUM_FEATURES_AS_DICT=True, OUT_FEATURES=64, LAYER_DISCARD_RATE=0.15, NUM_FILTERS=[16, 32, 64, 64], MM=True)
 

@@ -65,7 +65,7 @@ SIGNATURES = {
     'vc_group_points_grad': (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     'vc_exec_state_bytes': (_Z, []),
     'vc_exec_forward': (_I, [_P, _P, _I, _P, _P, _I, _P, _I, _P, _I, _HOST, _I, _P, _I, _I, _I, _P, _Z, _P, _P, _P, _Z, _P, _P, _I,
-                             _P, _P, _P]),
+                             _P, _P, _P, _P]),
     'vc_exec_backward': (_I, [_P, _P, _I, _P, _P, _I, _P, _P, _I, _P, _Z, _P, _P, _P, _P]),
     'vc_conv_wgrad_tc_config': (_I, [_I, _I]),
     'vc_exec_query': (_I, [_P, _I, _I, _P]),

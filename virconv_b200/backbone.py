@@ -113,9 +113,9 @@ def plan_nrconv(plan, block, f, iset, proj_stride):
     assert (block.d3_conv2[0].kernel_size, block.d3_conv2[0].dilation) == (c3.kernel_size, c3.dilation)
     assert (block.d2_conv2[0].kernel_size, block.d2_conv2[0].dilation) == (c2.kernel_size, c2.dilation)
     rb3 = plan.subm_rb(iset, 3, c3.kernel_size, c3.dilation, unique=True, keys=[c3.indice_key, block.d3_conv2[0].indice_key])
-    uv = plan.index2uv(iset, proj_stride)
+    uv = plan.index2uv(iset, proj_stride, stream=2)
     rb2 = plan.subm_rb(uv, 2, c2.kernel_size, c2.dilation, unique=False,      # projected pixels collide
-                       keys=[c2.indice_key, block.d2_conv2[0].indice_key])
+                       keys=[c2.indice_key, block.d2_conv2[0].indice_key], stream=2)
     d3 = plan.cbr(plan.cbr(f, rb3, c3, block.d3_conv1[1], seq=block.d3_conv1), rb3, block.d3_conv2[0], block.d3_conv2[1],
                   seq=block.d3_conv2)
     d2 = plan.cbr(plan.cbr(d3, rb2, c2, block.d2_conv1[1], seq=block.d2_conv1), rb2, block.d2_conv2[0], block.d2_conv2[1],

@@ -90,7 +90,7 @@ struct Arena {
 
 // library-owned event pool (cross-stream ordering only; timing disabled).  An event may be re-recorded as soon as the
 // wait on its previous recording has been ENQUEUED, so a small round-robin pool is enough.
-constexpr int EV_POOL = 64;
+constexpr int EV_POOL = 512;   // > the events of one forward / backward call: the cursor restarts at every call
 // (process-wide, not thread_local: autograd runs backward on its own thread; one process drives one device)
 cudaEvent_t g_ev[EV_POOL];
 int g_ev_dev = -1, g_ev_next = 0;
@@ -195,7 +195,7 @@ struct Ctx {
     int n_layers;
     State* S;
     Arena A;
-    cudaStream_t st[2];
+    cudaStream_t st[3];   // forward: main, index stream, second index stream (image branch); backward: main, wgrad
     int32_t* err;
     const int* op(int i) const { return oi + (size_t)i * OPI; }
     template <class T>
@@ -217,14 +217,11 @@ struct Ctx {
 
 // make `consumer` stream wait for a resource produced on the other stream
 int wait_for(Ctx& C, int& ev, int prod, int consumer) {
-    if (ev >= 0 && prod != consumer && C.st[0] != C.st[1]) {
-        VC_CUDA(cudaStreamWaitEvent(C.st[consumer], g_ev[ev], 0));
-        ev = -1;   // two streams only: the consumer stream is now ordered after the producer for good
-    }
+    if (ev >= 0 && C.st[prod] != C.st[consumer]) VC_CUDA(cudaStreamWaitEvent(C.st[consumer], g_ev[ev], 0));
     return VC_OK;
 }
 int record_on(Ctx& C, int s) {   // -> event id recorded at the current tail of stream s
-    if (C.st[0] == C.st[1]) return -1;
+    if (C.st[0] == C.st[1] && C.st[0] == C.st[2]) return -1;
     int e = g_ev_next;
     g_ev_next = (g_ev_next + 1) % EV_POOL;
     if (cudaEventRecord(g_ev[e], C.st[s]) != cudaSuccess) return -1;
@@ -236,7 +233,7 @@ int check_plan(const int32_t* oi, int n_ops, int n_layers) {
     for (int i = 0; i < n_ops; ++i) {
         const int* o = oi + (size_t)i * OPI;
         VC_CHECK_ARG(o[F_KIND] >= OP_SUBM_RB && o[F_KIND] <= OP_CAT, "op %d: unknown kind %d", i, o[F_KIND]);
-        VC_CHECK_ARG(o[F_STREAM] == 0 || o[F_STREAM] == 1, "op %d: bad stream", i);
+        VC_CHECK_ARG(o[F_STREAM] >= 0 && o[F_STREAM] <= 2, "op %d: bad stream", i);
         const int lim_a = (o[F_KIND] == OP_CBR || o[F_KIND] == OP_CAT) ? MAX_F : MAX_I;
         VC_CHECK_ARG(o[F_A] >= 0 && o[F_A] < lim_a, "op %d: slot a out of range", i);
         if (o[F_KIND] == OP_CBR) {
@@ -327,7 +324,8 @@ extern "C" int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_o
                                const int32_t* shape0, int batch_size, const float* proj_params, int training, int precision,
                                int want_pair_num, void* arena, size_t arena_bytes, int32_t* pinned_host, int32_t* err_flag,
                                void* state, size_t state_bytes, vc_stream_t main_stream, vc_stream_t side_stream,
-                               int side_waits_main, const int32_t* caps, const int32_t* n0_dev, int32_t* overflow_flag) {
+                               int side_waits_main, const int32_t* caps, const int32_t* n0_dev, int32_t* overflow_flag,
+                               vc_stream_t side2_stream) {
     // Static mode (n0_dev != NULL; CUDA-graph capturable: no host read of a device value, every buffer sized from host-side
     // capacities): n0 is the capacity of the input buffers, *n0_dev the number of valid rows, caps[i] the row capacity of
     // index set i (the strided convs' outputs); every data-dependent row count stays in device memory, kernels clamp to the
@@ -353,8 +351,10 @@ extern "C" int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_o
     C.A = Arena{(char*)arena, arena_bytes, 0, false};
     C.st[0] = (cudaStream_t)main_stream;
     C.st[1] = side_stream ? (cudaStream_t)side_stream : (cudaStream_t)main_stream;
+    C.st[2] = (side_stream && side2_stream) ? (cudaStream_t)side2_stream : C.st[1];   // image-branch index ops (index2uv + 2-D rulebooks)
     C.err = err_flag;
     const bool two = C.st[0] != C.st[1];
+    g_ev_next = 0;
 
     S->iset[0].idx = const_cast<int32_t*>(idx0); S->iset[0].n = n0; S->iset[0].ndim = 3; S->iset[0].n_dev = n0_dev;
     for (int d = 0; d < 3; ++d) S->iset[0].shape[d] = shape0[d];
@@ -446,9 +446,16 @@ extern "C" int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_o
     // previous step's backward)
     if (two && side_waits_main) {
         int e = record_on(C, 0);
-        if (e >= 0) VC_CUDA(cudaStreamWaitEvent(C.st[1], g_ev[e], 0));
+        if (e >= 0) {
+            VC_CUDA(cudaStreamWaitEvent(C.st[1], g_ev[e], 0));
+            if (C.st[2] != C.st[1]) VC_CUDA(cudaStreamWaitEvent(C.st[2], g_ev[e], 0));
+        }
     }
-    int last_side_ev = -1;
+    int last_ev[3] = {-1, -1, -1};     // latest event of each side stream (joined into main at the end)
+    auto side_ev = [&](int s_) -> int {
+        if (s_ == 0) return -1;
+        return last_ev[s_] = record_on(C, s_);
+    };
     int n_syncs = 0;
     static thread_local void* chain_ws[MAX_OPS];
     static thread_local size_t chain_wsb[MAX_OPS];
@@ -478,9 +485,17 @@ extern "C" int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_o
         } else {
             VC_TRY(conv_rulebook_count_dev(I.idx, I.n, nullptr, I.ndim, batch_size, I.shape, o + F_KS, o + F_ST, o + F_PD, o + F_DL,
                                            n_dev, 0, nullptr, ws, wsb, st));
-            VC_CUDA(cudaMemcpyAsync(pinned_host + (n_syncs & 15), n_dev, 4, cudaMemcpyDeviceToHost, st));
+            VC_CUDA(cudaMemcpyAsync(pinned_host + (n_syncs & 7), n_dev, 4, cudaMemcpyDeviceToHost, st));
+            // the tensor-core kernels' pipeline-timeout flag rides along with the first read-back of a step (it reports on the
+            // kernels of EARLIER steps: a wedged mbarrier wait must not go unnoticed in production — ADVICE r1)
+            if (n_syncs == 0 && C.err != nullptr) VC_CUDA(cudaMemcpyAsync(pinned_host + 15, C.err, 4, cudaMemcpyDeviceToHost, st));
             VC_CUDA(cudaStreamSynchronize(st));        // the one data-dependent size per strided conv
-            n_out = pinned_host[n_syncs & 15];
+            n_out = pinned_host[n_syncs & 7];
+            if (n_syncs == 0 && C.err != nullptr && pinned_host[15] != 0) {
+                set_error("a tensor-core kernel's pipeline wait timed out in an earlier step (error flag %d): its results are invalid",
+                          pinned_host[15]);
+                return VC_ERR_PIPELINE;
+            }
             ++n_syncs;
         }
         R.K = rb_K[o[F_C]]; R.n_in = I.n; R.n_out = n_out; R.subm = 0; R.unique = 1;
@@ -493,7 +508,7 @@ extern "C" int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_o
         VC_TRY(conv_rulebook_fill_phases(I.idx, I.n, I.n_dev, I.ndim, batch_size, I.shape, o + F_KS, o + F_ST, o + F_PD, o + F_DL, n_out, O.idx,
                                          nullptr, nullptr, nullptr, ws, wsb, st, 1));
         O.prod = s;
-        O.ev = s == 1 ? (last_side_ev = record_on(C, 1)) : -1;
+        O.ev = side_ev(s);
         chain_ws[j] = ws; chain_wsb[j] = wsb; chain_done[j] = true;
         return VC_OK;
     };
@@ -521,7 +536,7 @@ extern "C" int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_o
                 VC_ALLOC(ws, void*, wsb);
                 VC_TRY(subm_rulebook_dev(I.idx, I.n, I.n_dev, I.ndim, batch_size, I.shape, o + F_KS, o + F_DL, R.nbr, R.pair_num, ws, wsb, st));
                 R.prod = s;
-                R.ev = s == 1 ? (last_side_ev = record_on(C, 1)) : -1;
+                R.ev = side_ev(s);
                 break;
             }
             case OP_CONV_RB: {
@@ -549,7 +564,7 @@ extern "C" int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_o
                 VC_TRY(conv_rulebook_fill_phases(I.idx, I.n, I.n_dev, I.ndim, batch_size, I.shape, o + F_KS, o + F_ST, o + F_PD, o + F_DL,
                                                  R.n_out, O.idx, R.nbr, R.nbr_bwd, R.pair_num, chain_ws[i], chain_wsb[i], st, 2));
                 R.prod = s;
-                R.ev = s == 1 ? (last_side_ev = record_on(C, 1)) : -1;
+                R.ev = side_ev(s);
                 break;
             }
             case OP_INDEX2UV: {
@@ -561,7 +576,7 @@ extern "C" int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_o
                 O.idx = uv; O.n = I.n; O.ndim = 2; O.shape[0] = o[F_KS]; O.shape[1] = o[F_KS + 1]; O.shape[2] = 0; O.n_dev = I.n_dev;
                 VC_TRY(index2uv_dev(I.idx, I.n, I.n_dev, batch_size, proj_params, fo, o[F_X0], o[F_X1], o[F_X2], uv, st));
                 O.prod = s;
-                O.ev = s == 1 ? (last_side_ev = record_on(C, 1)) : -1;
+                O.ev = side_ev(s);
                 break;
             }
             case OP_CBR: {
@@ -604,7 +619,7 @@ extern "C" int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_o
                                          C.P<float>(li, P_RM), C.P<float>(li, P_RV), C.P<long long>(li, P_NBT), C.lf[2 * li + 1],
                                          C.lf[2 * li], training, y, L.cout, yb, L.cout, stats, 1, is_static, st));
                 Y.f32 = y; Y.bf16 = yb; Y.rows = R.n_out; Y.c = L.cout; Y.prod = s; Y.n_dev = R.n_out_dev;
-                Y.ev = s == 1 ? (last_side_ev = record_on(C, 1)) : -1;
+                Y.ev = side_ev(s);
                 break;
             }
             case OP_CAT: {
@@ -623,12 +638,13 @@ extern "C" int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_o
                 }
                 VC_TRY(cat2_dev(Aa.f32, Bb.f32, out, ob, Aa.rows, Aa.n_dev, Aa.c, Bb.c, st));
                 O.f32 = out; O.bf16 = ob; O.rows = Aa.rows; O.c = Aa.c + Bb.c; O.prod = s; O.n_dev = Aa.n_dev;
-                O.ev = s == 1 ? (last_side_ev = record_on(C, 1)) : -1;
+                O.ev = side_ev(s);
                 break;
             }
         }
     }
-    if (two && last_side_ev >= 0) VC_CUDA(cudaStreamWaitEvent(C.st[0], g_ev[last_side_ev], 0));   // join
+    for (int s_ = 1; s_ <= 2; ++s_)
+        if (two && last_ev[s_] >= 0) VC_CUDA(cudaStreamWaitEvent(C.st[0], g_ev[last_ev[s_]], 0));   // join
     S->used = C.A.used;
     S->magic = STATE_MAGIC;
     return VC_OK;
@@ -708,7 +724,9 @@ extern "C" int vc_exec_backward(const int32_t* ops_i, const float* ops_f, int n_
     C.A = Arena{(char*)arena, arena_bytes, S->used, false};
     C.st[0] = (cudaStream_t)stream_;
     C.st[1] = wgrad_stream_ ? (cudaStream_t)wgrad_stream_ : (cudaStream_t)stream_;
+    C.st[2] = C.st[1];
     C.err = err_flag;
+    g_ev_next = 0;
     cudaStream_t st = C.st[0];
     cudaStream_t wst = C.st[1];      // weight gradients: off the dgrad chain's critical path
     const bool two = st != wst;

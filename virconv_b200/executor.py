@@ -19,7 +19,8 @@ from . import _lib, ops
 from ._lib import check
 
 ENABLED = os.environ.get('VIRCONV_EXECUTOR', '1') != '0'
-TWO_STREAMS = os.environ.get('VIRCONV_EXEC_STREAMS', '2') != '1'
+TWO_STREAMS = os.environ.get('VIRCONV_EXEC_STREAMS', '3') != '1'
+THREE_STREAMS = os.environ.get('VIRCONV_EXEC_STREAMS', '3') == '3'
 # weight gradients on their own stream next to the BN-backward / dgrad chain (vc_exec_backward's wgrad_stream), with the
 # wgrad CTAs limited to WGRAD_CTAS SMs they keep to themselves (vc_conv_wgrad_tc_config)
 # (measured, profiles/sweep_wgrad_r1.txt: 3.91 ms/step without, 3.29-3.31 with 96-112 CTAs; the shared-memory floor that
@@ -89,11 +90,13 @@ class Plan:
         self.rows_f.append(list(f) + [0.0] * (OPF - len(f)))
         self._final = None
 
-    def subm_rb(self, iset, ndim, ksize, dilation=1, unique=True, keys=()):
+    def subm_rb(self, iset, ndim, ksize, dilation=1, unique=True, keys=(), stream=1):
+        """stream: 1 = index stream, 2 = second index stream (the image branch: its projection + 2-D rulebooks depend on a
+        stage's indices only, so they run beside the 3-D rulebooks of the same and the following stages)"""
         rb = self.n_rb
         self.n_rb += 1
         self.rb_keys[rb] = (tuple(keys), ndim, iset, iset)
-        self._row(OP_SUBM_RB, 1, a=iset, c=rb, ndim=ndim, ks=_t3(ksize, ndim, 1), dl=_t3(dilation, ndim, 1), x0=int(unique))
+        self._row(OP_SUBM_RB, stream, a=iset, c=rb, ndim=ndim, ks=_t3(ksize, ndim, 1), dl=_t3(dilation, ndim, 1), x0=int(unique))
         return rb
 
     def conv_rb(self, iset, ndim, ksize, stride, padding, dilation=1, keys=()):
@@ -106,12 +109,12 @@ class Plan:
         return out, rb
 
     def index2uv(self, iset, stride, pts_range=(0, -40, -3, 70.4, 40, 1), voxel_size=(0.05, 0.05, 0.05), u_max=1400,
-                 v_max=600, image_shape=(1600, 600)):
+                 v_max=600, image_shape=(1600, 600), stream=1):
         out = self.n_i
         self.n_i += 1
         vs = np.array(voxel_size, dtype=np.float64) * stride      # same host arithmetic as ops.index2uv
         grid = [vs[0], vs[1], vs[2], pts_range[0] + vs[0] / 2, pts_range[1] + vs[1] / 2, pts_range[2] + vs[2] / 2]
-        self._row(OP_INDEX2UV, 1, a=iset, b=out, ndim=3, ks=(int(image_shape[0]), int(image_shape[1]), 0), x0=int(stride),
+        self._row(OP_INDEX2UV, stream, a=iset, b=out, ndim=3, ks=(int(image_shape[0]), int(image_shape[1]), 0), x0=int(stride),
                   x1=int(u_max), x2=int(v_max), f=[float(np.float32(g)) for g in grid])
         return out
 
@@ -447,6 +450,11 @@ class PlanFn(torch.autograd.Function):
         main = ops._stream()
         side_obj = ops.side(dev).stream if TWO_STREAMS else None
         side = side_obj.cuda_stream if side_obj is not None else None
+        # second index stream (image-branch projection + 2-D rulebooks).  Only where the call's own fork / join orders it
+        # (static mode, or inputs the side streams must wait for anyway): with `inputs_ready` the index streams do not wait
+        # for main, and the arena / coordinate tensors are only registered with ONE side stream
+        side2_obj = ops.side2(dev) if (side_obj is not None and THREE_STREAMS and not inputs_ready) else None
+        side2 = side2_obj.cuda_stream if side2_obj is not None else None
         inflight = None
         if static is not None:
             inputs_ready = False             # under capture the side stream must fork from the capturing stream
@@ -477,7 +485,7 @@ class PlanFn(torch.autograd.Function):
                                      main, side, 0 if (inputs_ready and side is not None) else 1,
                                      static.caps_array().ctypes.data if static is not None else None,
                                      static.n_dev.data_ptr() if static is not None else None,
-                                     static.overflow.data_ptr() if static is not None else None)
+                                     static.overflow.data_ptr() if static is not None else None, side2)
             if rc != VC_ERR_WORKSPACE:
                 break
             # too small (first use of a plan on an unusually dense batch): the call is restartable — nothing it enqueued is

@@ -75,6 +75,7 @@ class GraphedStep:
         self.proj_host = torch.zeros((B, 28), dtype=torch.float32).pin_memory()
         self.n_host = torch.zeros(1, dtype=torch.int32).pin_memory()
         self.ovf_host = torch.zeros(8, dtype=torch.int32).pin_memory()
+        self.err_host = torch.zeros(8, dtype=torch.int32).pin_memory()
         self._pending, self._slot = [], 0
         self.spec = executor.StaticSpec(self.n_dev, self.caps, self.overflow)
 
@@ -140,6 +141,9 @@ class GraphedStep:
         while self._pending and self._pending[0][0].query():
             ev, slot = self._pending.pop(0)
             worst = max(worst, int(self.ovf_host[slot]))
+            if int(self.err_host[slot]) != 0:
+                raise _lib.VirConvLibraryError('a tensor-core kernel\'s pipeline wait timed out inside a replayed step '
+                                               '(error flag set): the results of that step are invalid')
         return worst
 
     def __call__(self, batch):
@@ -166,6 +170,7 @@ class GraphedStep:
             slot = self._slot
             self._slot = (slot + 1) % self.ovf_host.numel()
             self.ovf_host[slot:slot + 1].copy_(self.overflow, non_blocking=True)
+            self.err_host[slot:slot + 1].copy_(ops.tc_error_flag(self.dev), non_blocking=True)
             self.overflow.zero_()
             ev = torch.cuda.Event()
             ev.record()

@@ -88,6 +88,17 @@ def side(device) -> _Side:
     return _SIDE[key]
 
 
+_SIDE2 = {}
+
+
+def side2(device):
+    """Second index stream of the plan executor (image-branch projection + 2-D rulebooks)."""
+    key = (device.type, device.index)
+    if key not in _SIDE2:
+        _SIDE2[key] = torch.cuda.Stream(device=device)
+    return _SIDE2[key]
+
+
 def _keep_alive_on(stream, *tensors):
     for t in tensors:
         if t is not None:
