@@ -165,3 +165,36 @@ def test_graph_recaptures_when_a_batch_does_not_fit(lib_built):
     torch.cuda.synchronize()
     assert step.recaptures == 2
     assert abs(float(loss) - l_big) < 1e-5 * max(1.0, abs(l_big))
+
+
+def test_graph_with_in_graph_voxeliser(lib_built):
+    """bench.py's e2e path: raw collated points are the step's input, hash-grid voxelisation + MeanVFE run inside the
+    captured graph (capacity-sized point buffer with an out-of-range tail, device voxel count); result against the exact
+    execution on the host-voxelised batch of the same scenes."""
+    from virconv_b200 import scenes
+    from virconv_b200.graph import GraphedStep
+    model = _model('bf16')
+    ids = [[41, 42], [43, 44], [45, 46]]
+    kw = dict(n_lidar=4096, n_virtual=9000)
+    ref = []
+    for i in ids:
+        l, g, _ = _exact(model, _batch(i, max_voxels=7000, **kw))
+        ref.append((l, g))
+    vox = dict(point_cloud_range=(0, -40, -3, 70.4, 40, 1), voxel_size=(0.05, 0.05, 0.05), max_points_per_voxel=5,
+               max_voxels=7000, vfe_model='max')
+    step = GraphedStep(model, _loss, margin=1.35, grain=256, voxelizer=vox)
+    params = dict(model.named_parameters())
+    got = []
+    for s in range(6):
+        pb = scenes.make_points_batch(ids[s % 3], training=True, **kw)
+        b = {'points': torch.from_numpy(pb.points).cuda(), 'batch_size': pb.batch_size, 'calib': pb.calib,
+             'aug_param': torch.from_numpy(pb.aug_param)}
+        loss = step(b)
+        got.append((loss.detach().clone(), {k: v.grad.detach().clone() for k, v in params.items()}))
+    torch.cuda.synchronize()
+    assert _err_flag() == 0 and step.recaptures == 1
+    for s in range(6):
+        l0, g0 = ref[s % 3]
+        assert abs(float(got[s][0]) - l0) < 1e-5 * max(1.0, abs(l0)), s
+        for k in params:
+            assert rel_err(got[s][1][k].cpu(), g0[k].cpu()) < 1e-2, (s, k)

@@ -32,8 +32,12 @@ def masked_mean(t):
 
 
 class GraphedStep:
-    def __init__(self, model, loss_fn, params=None, margin=1.3, grain=1024, warmup=2, check_overflow=True):
+    def __init__(self, model, loss_fn, params=None, margin=1.3, grain=1024, warmup=2, check_overflow=True, voxelizer=None):
+        """voxelizer: None — batches carry `voxel_features` / `voxel_coords` (what the reference's dataloader + MeanVFE
+        deliver); or a dict(point_cloud_range, voxel_size, max_points_per_voxel, max_voxels, vfe_model) — batches carry the
+        collated raw `points` [N, 1+C] and the hash-grid voxelisation + VFE (vc_voxelize_mean) run INSIDE the graph."""
         self.model, self.loss_fn = model, loss_fn
+        self.vox = dict(voxelizer) if voxelizer is not None else None
         self.params = list(model.parameters()) if params is None else list(params)
         self.margin, self.grain, self.warmup = margin, grain, warmup
         self.check_overflow = check_overflow
@@ -54,21 +58,39 @@ class GraphedStep:
         for p in self.params:
             p.grad = None
         bd = dict(batch)
+        if self.vox is not None:
+            v = self.vox
+            f, c, _ = ops.voxelize_mean(batch['points'], int(batch['batch_size']), v['point_cloud_range'], v['voxel_size'],
+                                        v['max_points_per_voxel'], v['max_voxels'], v['vfe_model'])
+            bd.update(voxel_features=f, voxel_coords=c)
         out = self.model(bd)
         loss = self.loss_fn(out)
         loss.backward()
         return loss.detach(), executor.last_run(self.model)
 
     def _make_buffers(self, batch, run):
-        dev = batch['voxel_features'].device
-        vf, vc = batch['voxel_features'], batch['voxel_coords']
-        self.cap0 = max(self.cap0, self._round(vf.shape[0]))
         for k, v in executor.measured_caps(run, self.margin, self.grain).items():
             self.caps[k] = max(self.caps.get(k, 0), v)
         B = int(batch['batch_size'])
+        if self.vox is not None:
+            pts = batch['points']
+            dev = self.params[0].device
+            self.cap_pts = max(getattr(self, 'cap_pts', 0), self._round(pts.shape[0]))
+            # unused tail rows: last sample's batch index, coordinates far outside the range (dropped by the voxeliser)
+            row = torch.zeros(pts.shape[1], dtype=torch.float32)
+            row[0] = B - 1
+            row[1:4] = -1.0e6
+            self.sentinel = row.to(dev)
+            self.pts = self.sentinel.repeat(self.cap_pts, 1).contiguous()
+            self._prev_n = 0
+            self.cap0 = B * int(self.vox['max_voxels'])
+        else:
+            dev = batch['voxel_features'].device
+            vf, vc = batch['voxel_features'], batch['voxel_coords']
+            self.cap0 = max(self.cap0, self._round(vf.shape[0]))
+            self.vf = torch.zeros((self.cap0, vf.shape[1]), dtype=torch.float32, device=dev)
+            self.vc = torch.full((self.cap0, vc.shape[1]), -1, dtype=vc.dtype, device=dev)
         self.dev, self.B = dev, B
-        self.vf = torch.zeros((self.cap0, vf.shape[1]), dtype=torch.float32, device=dev)
-        self.vc = torch.full((self.cap0, vc.shape[1]), -1, dtype=vc.dtype, device=dev)
         self.n_dev = torch.zeros(1, dtype=torch.int32, device=dev)
         self.overflow = torch.zeros(1, dtype=torch.int32, device=dev)
         self.proj = torch.zeros((B, 28), dtype=torch.float32, device=dev)
@@ -81,22 +103,39 @@ class GraphedStep:
 
     def _load(self, batch):
         """Copy one batch into the graph's input buffers (asynchronous, current stream)."""
-        vf, vc = batch['voxel_features'], batch['voxel_coords']
-        n = vf.shape[0]
-        if n > self.cap0:
-            return False
-        self.vf[:n].copy_(vf, non_blocking=True)
-        self.vc[:n].copy_(vc, non_blocking=True)
-        self.n_host[0] = n
-        self.n_dev.copy_(self.n_host, non_blocking=True)
+        if self.vox is not None:
+            pts = batch['points']
+            n = pts.shape[0]
+            if n > self.cap_pts:
+                return False
+            self.pts[:n].copy_(pts, non_blocking=True)
+            if self._prev_n > n:                       # rows of the previous (larger) batch still sit behind this one
+                self.pts[n:self._prev_n] = self.sentinel
+            self._prev_n = n
+        else:
+            vf, vc = batch['voxel_features'], batch['voxel_coords']
+            n = vf.shape[0]
+            if n > self.cap0:
+                return False
+            self.vf[:n].copy_(vf, non_blocking=True)
+            self.vc[:n].copy_(vc, non_blocking=True)
+            self.n_host[0] = n
+            self.n_dev.copy_(self.n_host, non_blocking=True)
         trans = batch.get('aug_param')
         self.proj_host.copy_(torch.from_numpy(ops.projection_params_host(batch['calib'], trans, self.B)))
         self.proj.copy_(self.proj_host, non_blocking=True)
         return True
 
     def _static_batch(self, batch):
-        bd = {k: v for k, v in batch.items() if k not in ('voxel_features', 'voxel_coords')}
-        bd.update(voxel_features=self.vf, voxel_coords=self.vc, virconv_static=self.spec, virconv_proj=self.proj)
+        bd = {k: v for k, v in batch.items() if k not in ('voxel_features', 'voxel_coords', 'points')}
+        if self.vox is not None:
+            v = self.vox
+            f, c, num, n_dev = ops.voxelize_mean(self.pts, self.B, v['point_cloud_range'], v['voxel_size'], v['max_points_per_voxel'],
+                                                 v['max_voxels'], v['vfe_model'], static=True)
+            spec = executor.StaticSpec(n_dev, self.caps, self.overflow)
+            bd.update(voxel_features=f, voxel_coords=c, voxel_num_points=num, virconv_static=spec, virconv_proj=self.proj)
+        else:
+            bd.update(voxel_features=self.vf, voxel_coords=self.vc, virconv_static=self.spec, virconv_proj=self.proj)
         return bd
 
     def _static_step(self, batch):

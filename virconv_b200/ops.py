@@ -663,25 +663,35 @@ class GatherRowsFn(torch.autograd.Function):
 # voxelisation + MeanVFE, voxel -> row map
 # ------------------------------------------------------------------------------------------------
 def voxelize_mean(points, batch_size, pc_range=(0, -40, -3, 70.4, 40, 1), voxel_size=(0.05, 0.05, 0.05), max_points=5,
-                  max_voxels=40000, vfe_model='max', want_voxels=False):
+                  max_voxels=40000, vfe_model='max', want_voxels=False, static=False):
     """points [N, 1+C] f32 (b, x, y, z, ...), batch-contiguous -> (voxel_features [M,C], voxel_coords [M,4] int32
     (b,z,y,x), voxel_num_points [M] int32[, voxels [M,max_points,C]]): the dataloader's first-come voxeliser
-    (data_processor.py:43-59) fused with MeanVFE (mean_vfe.py:39-58), on the GPU."""
+    (data_processor.py:43-59) fused with MeanVFE (mean_vfe.py:39-58), on the GPU.
+    static=True (CUDA-graph capturable): no host read of the voxel count — returns capacity-sized tensors
+    (batch_size * max_voxels rows, zero / -1 tail) plus the count as a device int32[1] tensor; `points` may then be a
+    capacity-sized buffer whose unused tail rows carry out-of-range coordinates (they are dropped like any such point)."""
     _require_cuda(points)
     lib = _lib.load()
     points = points.contiguous()
     n, c = points.shape[0], points.shape[1] - 1
     cap = int(batch_size) * int(max_voxels)
     dev = points.device
-    feats = torch.empty((cap, c), dtype=torch.float32, device=dev)
-    coords = torch.empty((cap, 4), dtype=torch.int32, device=dev)
-    num = torch.empty((cap,), dtype=torch.int32, device=dev)
+    if static:
+        feats = torch.zeros((cap, c), dtype=torch.float32, device=dev)
+        coords = torch.full((cap, 4), -1, dtype=torch.int32, device=dev)
+        num = torch.zeros((cap,), dtype=torch.int32, device=dev)
+    else:
+        feats = torch.empty((cap, c), dtype=torch.float32, device=dev)
+        coords = torch.empty((cap, 4), dtype=torch.int32, device=dev)
+        num = torch.empty((cap,), dtype=torch.int32, device=dev)
     voxels = torch.zeros((cap, max_points, c), dtype=torch.float32, device=dev) if want_voxels else None
     n_out = torch.empty((1,), dtype=torch.int32, device=dev)
     ws = _ws(lib.vc_voxelize_ws_bytes(n, int(batch_size), int(max_points)), dev)
     check(lib.vc_voxelize_mean(_p(points), n, c, int(batch_size), host_f32(pc_range), host_f32(voxel_size), int(max_points),
                                int(max_voxels), int(vfe_model == 'max'), _p(feats), _p(coords), _p(num), _p(voxels),
                                _p(n_out), _p(ws), ws.numel(), _stream()), 'vc_voxelize_mean')
+    if static:
+        return (feats, coords, num, n_out) + ((voxels,) if want_voxels else ())
     m = int(n_out.item())
     out = (feats[:m], coords[:m], num[:m])
     return out + (voxels[:m],) if want_voxels else out

@@ -241,6 +241,40 @@ def make_batch(scene_ids, n_lidar=16384, n_virtual=80000, max_voxels=40000, trai
                       np.stack(augs) if training else None, tuple(int(g) for g in gs))
 
 
+@dataclass
+class PointsBatch:
+    """The same scenes as `make_batch`, one step EARLIER in the reference's pipeline: the collated `batch_dict['points']`
+    ([N, 1+8] f32 rows (b, x, y, z, intensity, r, g, b, indicator), samples contiguous in batch order, dataset.py:349-353)
+    before `transform_points_to_voxels` — the input of the model-side voxeliser (preprocess.PointsToVoxels,
+    graph.GraphedStep(voxelizer=...))."""
+    points: np.ndarray
+    batch_size: int
+    calib: list = field(default_factory=list)
+    aug_param: np.ndarray | None = None
+    grid_size: tuple = (1408, 1600, 80)
+
+
+def make_points_batch(scene_ids, n_lidar=16384, n_virtual=80000, training=False, pc_range=POINT_CLOUD_RANGE,
+                      voxel_size=VOXEL_SIZE) -> PointsBatch:
+    clouds, calibs, augs = [], [], []
+    for b, sid in enumerate(scene_ids):
+        calib = Calib()
+        pts = make_points(sid, n_lidar, n_virtual, calib)
+        if training:
+            rng = np.random.default_rng(10_000_019 * (sid + 1))
+            aug = np.array([rng.uniform(-0.78539816, 0.78539816), float(rng.integers(0, 2)),
+                            rng.uniform(0.95, 1.05)], dtype=np.float32)
+            pts = augment(pts, aug)
+            augs.append(aug)
+        pts = mask_points_by_range(pts, pc_range)
+        clouds.append(np.concatenate([np.full((pts.shape[0], 1), b, dtype=np.float32), pts.astype(np.float32)], axis=1))
+        calibs.append(calib)
+    gs = np.round((np.asarray(pc_range[3:], dtype=np.float64) - np.asarray(pc_range[:3], dtype=np.float64))
+                  / np.asarray(voxel_size, dtype=np.float64)).astype(np.int64)
+    return PointsBatch(np.ascontiguousarray(np.concatenate(clouds)), len(scene_ids), calibs,
+                       np.stack(augs) if training else None, tuple(int(g) for g in gs))
+
+
 # ------------------------------------------------------------------------------------------------------
 # VirConv-T / -S: LiDAR stream + virtual ("MM") stream (LATER_FUSION, dataset.py:270-281), optional test-time
 # transformed copies (X_TRANS.input_transform, X_transform.py:156-193)
