@@ -153,10 +153,11 @@ def test_executor_plan_layout_and_host_side_validation(lib_built):
     kinds = oi[:, 0].tolist()
     assert (kinds.count(executor.OP_SUBM_RB), kinds.count(executor.OP_CONV_RB), kinds.count(executor.OP_INDEX2UV),
             kinds.count(executor.OP_CBR), kinds.count(executor.OP_CAT)) == (8, 4, 4, 20, 4)
-    # feature ops on the main stream (0); 3-D index ops on the index stream (1); image branch (projection + 2-D rulebooks) on 2
+    # feature ops on the main stream (0); strided-conv rulebooks on the index stream (1); submanifold rulebooks + projection on 2
     assert all((oi[i, 1] == 0) == (oi[i, 0] in (executor.OP_CBR, executor.OP_CAT)) for i in range(40))
     assert all(oi[i, 1] == 2 for i in range(40) if oi[i, 0] == executor.OP_INDEX2UV)
-    assert sorted(oi[i, 1] for i in range(40) if oi[i, 0] == executor.OP_SUBM_RB) == [1] * 4 + [2] * 4
+    assert all(oi[i, 1] == 2 for i in range(40) if oi[i, 0] == executor.OP_SUBM_RB)
+    assert all(oi[i, 1] == 1 for i in range(40) if oi[i, 0] == executor.OP_CONV_RB)
     assert int(offs[-1]) == sum(p.numel() for p in m.parameters())
     assert [n for n, _, _ in plan.published] == ['x_conv1', 'x_conv2', 'x_conv3', 'x_conv4', 'out']
     keys = sorted(k for ks, *_ in plan.rb_keys.values() for k in ks)

@@ -112,7 +112,8 @@ def plan_nrconv(plan, block, f, iset, proj_stride):
     c3, c2 = block.d3_conv1[0], block.d2_conv1[0]
     assert (block.d3_conv2[0].kernel_size, block.d3_conv2[0].dilation) == (c3.kernel_size, c3.dilation)
     assert (block.d2_conv2[0].kernel_size, block.d2_conv2[0].dilation) == (c2.kernel_size, c2.dilation)
-    rb3 = plan.subm_rb(iset, 3, c3.kernel_size, c3.dilation, unique=True, keys=[c3.indice_key, block.d3_conv2[0].indice_key])
+    rb3 = plan.subm_rb(iset, 3, c3.kernel_size, c3.dilation, unique=True, keys=[c3.indice_key, block.d3_conv2[0].indice_key],
+                       stream=2)        # stream 1 keeps the strided convs' count -> indices -> tables chain to itself
     uv = plan.index2uv(iset, proj_stride, stream=2)
     rb2 = plan.subm_rb(uv, 2, c2.kernel_size, c2.dilation, unique=False,      # projected pixels collide
                        keys=[c2.indice_key, block.d2_conv2[0].indice_key], stream=2)

@@ -545,8 +545,14 @@ extern "C" int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_o
                 // and it is the only part of the forward the host has to wait for; the neighbour tables, submanifold
                 // rulebooks and projections queue up behind it without further synchronisation.
                 if (!chain_done[i]) {
-                    for (int j = i; j < n_ops; ++j)
-                        if (C.op(j)[F_KIND] == OP_CONV_RB && S->iset[C.op(j)[F_A]].idx) VC_TRY(count_emit(j));
+                    if (is_static) {
+                        // no host read to wait for: keep the natural order (count -> indices -> tables per stage), so the
+                        // tables of an early stage are not queued behind the counting kernels of all later ones
+                        VC_TRY(count_emit(i));
+                    } else {
+                        for (int j = i; j < n_ops; ++j)
+                            if (C.op(j)[F_KIND] == OP_CONV_RB && S->iset[C.op(j)[F_A]].idx) VC_TRY(count_emit(j));
+                    }
                 }
                 VC_CHECK_ARG(chain_done[i], "op %d: index set %d not built", i, o[F_A]);
                 ISet& I = S->iset[o[F_A]];
