@@ -31,13 +31,20 @@ int g_tc_variant = 1;   // 1: this kernel; 0: the round-1 kernel (conv_tc.cu) â€
 
 namespace {
 
-constexpr int P_WARP_LOADER = 4, P_WARP_MMA = 5, P_WARP_PROD0 = 6, P_PROD_WARPS = 8;
-constexpr int P_THREADS = 32 * (P_WARP_PROD0 + P_PROD_WARPS);   // 448
+#ifndef VC_P_GROUPS
+#define VC_P_GROUPS 2            // producer groups of 8 warps; consecutive ring stages go to consecutive groups
+#endif
+#ifndef VC_P_SKIP
+#define VC_P_SKIP 1              // 1: missing neighbours cost a shared-memory zero store, not a (zero-fill) cp.async
+#endif
+constexpr int P_WARP_LOADER = 4, P_WARP_MMA = 5, P_WARP_W = 6, P_WARP_PROD0 = 7;
+constexpr int P_GROUPS = VC_P_GROUPS, P_PROD_WARPS = 8;
+constexpr int P_THREADS = 32 * (P_WARP_PROD0 + P_GROUPS * P_PROD_WARPS);   // 736 with two groups
 constexpr int P_MAX_STAGES = 16;
-constexpr int P_NTB = 4;                                        // neighbour-table buffers (the loader runs 2 tiles ahead)
-constexpr int P_AHEAD = 2;                                      // table loads (global -> shared) in flight
-constexpr int P_PREF = 4;                                       // further tiles whose table rows are prefetched into L2
+constexpr int P_NTB = 4;                                        // neighbour-table buffers (<= 3 tiles loaded ahead)
 constexpr int P_ROWS_PER_PROD = TCM / P_PROD_WARPS;             // 16
+constexpr int P_W_CHUNK = 16384;                                // bytes per bulk copy of the resident weight image
+constexpr int P_W_RESIDENT_MAX = 56 * 1024;
 constexpr int SMEM_BUDGET = 227 * 1024 - 4096;                  // dynamic shared memory per CTA (static part is small)
 
 template <int KC, int NR>
@@ -47,7 +54,6 @@ struct PCfg {
     static constexpr int G = 64 / KC;                        // kernel offsets per ring stage: 16 KB of gathered rows per stage
     static constexpr int A_BYTES = TCM * ROWB;               // one offset's gathered tile
     static constexpr int B_BYTES = NR * ROWB;                // one offset's weight slice
-    static constexpr int STAGE = G * (A_BYTES + B_BYTES);    // [G x A | G x B]
     static constexpr int TMEM_COLS = 2 * NR < 32 ? 32 : 2 * NR;   // two accumulators
     static constexpr int STG_LD = NR + 1;                    // staging row pitch (floats)
     static constexpr int STG_BYTES = TCM * STG_LD * 4;
@@ -67,6 +73,7 @@ struct PArgs {
     int n_host;
     int* tile_counter;         // optional (zeroed by the caller): dynamic tile scheduling; NULL: tile = blockIdx.x + i * gridDim.x
     int K, S;
+    int w_resident;            // all K weight slices stay in shared memory for the whole launch (else: streamed with the ring)
     int* err;
 };
 
@@ -88,25 +95,33 @@ __device__ __forceinline__ void ptrace(int role, int& idx) {
 #define P_TRACE(role, idx) do { } while (0)
 #endif
 
-#define P_WAIT(bar, parity)                                   \
-    do {                                                      \
-        if (!mbar_wait_t((bar), (parity), a.err)) goto done;  \
+#define P_WAIT(bar, parity, code)                                     \
+    do {                                                              \
+        if (!mbar_wait_t((bar), (parity), a.err, (code))) goto done;  \
     } while (0)
+
+__device__ __forceinline__ void sts_zero16(uint32_t saddr) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(saddr), "r"(0u) : "memory");
+}
 
 template <int KC, int NR>
 __global__ void __launch_bounds__(P_THREADS, 1) tc_conv_persist_kernel(const PArgs a) {
     using C = PCfg<KC, NR>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int S = a.S, K = a.K;
-    unsigned char* ring = smem_raw;                                              // [S][G x A | G x B]
-    int* nbr_s = reinterpret_cast<int*>(smem_raw + (size_t)S * C::STAGE);        // [P_NTB][K][128]
+    const bool wres = a.w_resident != 0;
+    const uint32_t stage_bytes = (uint32_t)(C::G * C::A_BYTES + (wres ? 0 : C::G * C::B_BYTES));
+    const uint32_t wres_bytes = wres ? (uint32_t)((K * C::B_BYTES + 1023) & ~1023) : 0u;
+    unsigned char* ring = smem_raw;                                              // [S][G x A (| G x B)]
+    unsigned char* wimg_s = smem_raw + (size_t)S * stage_bytes;                  // [K][B] when resident
+    int* nbr_s = reinterpret_cast<int*>(wimg_s + wres_bytes);                    // [P_NTB][K][128]
     float* stg = reinterpret_cast<float*>(nbr_s + (size_t)P_NTB * K * TCM);      // [128][STG_LD]
     __shared__ __align__(8) uint64_t full_bar[P_MAX_STAGES];
     __shared__ __align__(8) uint64_t empty_bar[P_MAX_STAGES];
     __shared__ __align__(8) uint64_t tbl_full[P_NTB], tbl_empty[P_NTB];
     __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
-    __shared__ int klist_s[P_NTB][MAXK_TC];
-    __shared__ int nk_s[P_NTB], tile_s[P_NTB];
+    __shared__ __align__(8) uint64_t wres_bar;
+    __shared__ int tile_s[P_NTB];
     __shared__ uint32_t tmem_base_s;
     __shared__ double red_s[2][TCM];
 
@@ -122,23 +137,37 @@ __global__ void __launch_bounds__(P_THREADS, 1) tc_conv_persist_kernel(const PAr
     }
     if (tid == P_WARP_MMA * 32) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(&full_bar[s], 32 * P_PROD_WARPS + 1);    // every producer thread (cp.async arrive) + the weight expect_tx
+            // every producer thread of the stage's group (cp.async arrive) [+ one release arrive per producer warp for its
+            // zero stores] [+ the weight warp's expect_tx]
+            mbar_init(&full_bar[s], 32 * P_PROD_WARPS + (VC_P_SKIP ? P_PROD_WARPS : 0) + (wres ? 0 : 1));
             mbar_init(&empty_bar[s], 1);                       // tcgen05.commit
         }
         for (int b = 0; b < P_NTB; ++b) {
             mbar_init(&tbl_full[b], 1);                        // loader
-            mbar_init(&tbl_empty[b], P_PROD_WARPS + 1 + 4);    // producers + MMA warp + epilogue warps
+            mbar_init(&tbl_empty[b], P_GROUPS * P_PROD_WARPS + 1 + 4 + (wres ? 0 : 1));   // producers, MMA, epilogue, weights
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&acc_full[b], 1);                        // tcgen05.commit
             mbar_init(&acc_empty[b], 4);                       // epilogue warps
         }
+        mbar_init(&wres_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     pdl_wait();                 // everything below reads what the previous kernel of the chain wrote
     pdl_launch_dependents();
     const int n = a.n_dev != nullptr ? min(__ldg(a.n_dev), a.n_host) : a.n_host;
-    const int n_tiles = (n + TCM - 1) / TCM;
+    // a pipeline wait that timed out in an EARLIER launch left the (sticky) error flag set: do nothing, so that whatever went
+    // wrong costs one 2-second timeout, not one per launch
+    const bool dead = a.err != nullptr && *reinterpret_cast<volatile int*>(a.err) != 0;
+    const int n_tiles = dead ? 0 : (n + TCM - 1) / TCM;
+    // Table buffers in use == how many tiles a CTA holds claimed at once.  With dynamic scheduling a deep look-ahead
+    // unbalances short launches (the first CTAs would grab every tile), so it grows with the tiles per CTA.
+    int ntb = P_NTB;
+    if (a.tile_counter != nullptr) {
+        int d = n_tiles / (3 * (int)gridDim.x);
+        d = d < 1 ? 1 : (d > P_NTB - 1 ? P_NTB - 1 : d);
+        ntb = d + 1;
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -150,56 +179,46 @@ __global__ void __launch_bounds__(P_THREADS, 1) tc_conv_persist_kernel(const PAr
 
     if (warp == P_WARP_LOADER) {
         // ------------------------------------------------------------ tile scheduler + neighbour-table loader
-        // Table slices travel global -> shared with cp.async (no register staging), P_AHEAD tiles in flight: producers
-        // never wait for global memory, and the loader's own latency is pipelined across tiles.
+        // Table slices travel global -> shared with cp.async (no register staging), ntb - 1 tiles in flight: producers never
+        // wait for global memory, and the loader's own latency (DRAM-cold table rows: 1-1.5 us under load) is pipelined
+        // across tiles.  Every kernel offset of a tile is processed (no per-tile scan for empty offsets: a slice without a
+        // single neighbour costs the producers 128 zero stores and the tensor core one MMA group â€” cheaper than the scan,
+        // which was the pipeline's bottleneck at 3.3 us per tile, profiles/trace_tc2_r2_a.txt).
         const bool vec_ok = (reinterpret_cast<uintptr_t>(a.nbr) & 15u) == 0 && (a.pitch & 3) == 0;
-        // tiles are claimed P_AHEAD + P_PREF iterations ahead of their use; a claimed tile's table rows are pulled into L2
-        // right away (no shared memory needed for that), the copy into shared memory follows P_PREF iterations later:
-        // a DRAM-cold table (1-1.5 us under load) would otherwise make the loader the pipeline's bottleneck
-        constexpr int PQ = P_AHEAD + P_PREF + 1;
-        int my_tile[PQ];                // claimed tiles, ring indexed by it % PQ
+        const int lag = ntb - 1;
+        int tq0 = -1, tq1 = -1, tq2 = -1, tq3 = -1;      // tiles of the last four iterations (it & 3)
+        bool stop = false;
         int claimed = 0;
-        bool stop = false;              // a claim came back past the end
-        int issued = 0;
-        auto claim = [&]() {
-            int tile;
-            if (a.tile_counter != nullptr) {
-                tile = lane == 0 ? atomicAdd(a.tile_counter, 1) : 0;
-                tile = __shfl_sync(0xffffffffu, tile, 0);
-            } else {
-                tile = blockIdx.x + claimed * gridDim.x;
-            }
-            if (tile >= n_tiles) {
-                tile = -1;
-                stop = true;
-            } else {
-                const int base = tile * TCM;
-                if (vec_ok && (long long)base + TCM <= a.pitch) {
-                    if (lane < K)
-                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.nbr + (size_t)lane * a.pitch + base), "r"(TCM * 4)
-                                     : "memory");
+        for (int it = 0;; ++it) {
+            const int tb = it % ntb;
+            int tile = -1;
+            if (!stop) {
+                if (a.tile_counter != nullptr) {
+                    tile = lane == 0 ? atomicAdd(a.tile_counter, 1) : 0;
+                    tile = __shfl_sync(0xffffffffu, tile, 0);
                 } else {
-                    for (int i = lane; i < K * 5; i += 32) {
-                        const int k = i / 5, seg = i % 5;
-                        const long long row = (long long)base + seg * 32;
-                        if (row < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.nbr + (size_t)k * a.pitch + row));
-                    }
+                    tile = blockIdx.x + claimed * gridDim.x;
+                }
+                ++claimed;
+                if (tile >= n_tiles) {
+                    tile = -1;
+                    stop = true;
                 }
             }
-            my_tile[claimed % PQ] = tile;
-            ++claimed;
-        };
-        auto issue = [&](int it) -> bool {           // returns false on a pipeline timeout
-            const int tb = it % P_NTB;
-            if (it >= P_NTB && !mbar_wait_t(&tbl_empty[tb], (uint32_t)(((it / P_NTB) - 1) & 1), a.err)) return false;
-            const int tile = my_tile[it % PQ];
+            switch (it & 3) {
+                case 0: tq0 = tile; break;
+                case 1: tq1 = tile; break;
+                case 2: tq2 = tile; break;
+                default: tq3 = tile; break;
+            }
+            if (it >= ntb) P_WAIT(&tbl_empty[tb], (uint32_t)(((it / ntb) - 1) & 1), 0x101);
             if (tile >= 0) {
                 int* dst = nbr_s + (size_t)tb * K * TCM;
                 const int base = tile * TCM;
                 if (vec_ok && (long long)base + TCM <= a.pitch) {
-                    const uint32_t d0 = smem_u32(dst) + lane * 16;
-                    const int32_t* s0 = a.nbr + base + lane * 4;
-                    for (int k = 0; k < K; ++k) cp_async16_s(d0 + k * (TCM * 4), s0 + (size_t)k * a.pitch, true);
+                    uint32_t d = smem_u32(dst) + lane * 16;
+                    const int32_t* sp = a.nbr + base + lane * 4;
+                    for (int k = 0; k < K; ++k, d += TCM * 4, sp += a.pitch) cp_async16_s(d, sp, true);
                 } else {
                     for (int k = 0; k < K; ++k) {
 #pragma unroll
@@ -216,61 +235,37 @@ __global__ void __launch_bounds__(P_THREADS, 1) tc_conv_persist_kernel(const PAr
                 }
             }
             cp_async_commit();
-            return true;
-        };
-        for (int it = 0;; ++it) {
-            // keep the claims P_AHEAD + P_PREF and the shared-memory loads P_AHEAD iterations ahead
-            while (!stop && claimed <= it + P_AHEAD + P_PREF - 1) claim();
-            while (issued < claimed && issued <= it + P_AHEAD - 1) {
-                if (!issue(issued)) goto done;
-                ++issued;
-            }
-            const int tb = it % P_NTB;
-            const int tile = my_tile[it % PQ];
-            // groups are committed in order: allow (issued - it - 1) younger ones to stay in flight
-            if (issued - it - 1 >= 1) cp_async_wait<1>(); else cp_async_wait<0>();
-            __syncwarp();
-            if (tile < 0) {
+            if (it >= lag) {
+                const int pi = it - lag;             // publish the table issued `lag` iterations ago
+                if (lag == 3) cp_async_wait<3>(); else if (lag == 2) cp_async_wait<2>(); else cp_async_wait<1>();
+                __syncwarp();
+                const int ptb = pi % ntb;
+                const int ptile = (pi & 3) == 0 ? tq0 : (pi & 3) == 1 ? tq1 : (pi & 3) == 2 ? tq2 : tq3;
+                if (ptile >= 0 && ptile * TCM + TCM > n) {
+                    // rows beyond the count (static mode / last tile): no neighbour
+                    int* dst = nbr_s + (size_t)ptb * K * TCM;
+                    const int r0 = ptile * TCM + lane * 4;
+                    for (int k = 0; k < K; ++k) {
+                        int4 v = reinterpret_cast<const int4*>(dst + k * TCM)[lane];
+                        if (r0 + 0 >= n) v.x = -1;
+                        if (r0 + 1 >= n) v.y = -1;
+                        if (r0 + 2 >= n) v.z = -1;
+                        if (r0 + 3 >= n) v.w = -1;
+                        reinterpret_cast<int4*>(dst + k * TCM)[lane] = v;
+                    }
+                }
+                if (lane == 0) tile_s[ptb] = ptile;
+                __syncwarp();
                 if (lane == 0) {
-                    tile_s[tb] = -1;
-                    mbar_arrive(&tbl_full[tb]);
+                    mbar_arrive(&tbl_full[ptb]);
+                    P_TRACE(0, tr);
                 }
-                break;
-            }
-            int* dst = nbr_s + (size_t)tb * K * TCM;
-            const int base = tile * TCM;
-            unsigned km = 0u;
-            const bool partial = base + TCM > n;
-            for (int k = 0; k < K; ++k) {
-                int4 v = reinterpret_cast<const int4*>(dst + k * TCM)[lane];
-                if (partial) {          // rows beyond the count (static mode / last tile): no neighbour
-                    const int r0 = base + lane * 4;
-                    bool ch = false;
-                    if (r0 + 0 >= n && v.x != -1) { v.x = -1; ch = true; }
-                    if (r0 + 1 >= n && v.y != -1) { v.y = -1; ch = true; }
-                    if (r0 + 2 >= n && v.z != -1) { v.z = -1; ch = true; }
-                    if (r0 + 3 >= n && v.w != -1) { v.w = -1; ch = true; }
-                    if (ch) reinterpret_cast<int4*>(dst + k * TCM)[lane] = v;
-                }
-                const bool any = (v.x >= 0) | (v.y >= 0) | (v.z >= 0) | (v.w >= 0);
-                if (__any_sync(0xffffffffu, any)) km |= 1u << k;
-            }
-            if (lane == 0) {
-                int c = 0;
-                for (int k = 0; k < K; ++k)
-                    if (km >> k & 1u) klist_s[tb][c++] = k;
-                nk_s[tb] = c;
-                tile_s[tb] = tile;
-            }
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&tbl_full[tb]);
-                P_TRACE(0, tr);
+                if (ptile < 0) break;
             }
         }
     } else if (warp >= P_WARP_PROD0) {
         // ------------------------------------------------------------ gather producers
-        const int pw = warp - P_WARP_PROD0;
+        const int grp = (warp - P_WARP_PROD0) / P_PROD_WARPS, pw = (warp - P_WARP_PROD0) % P_PROD_WARPS;
         constexpr int CW = C::CPR < 4 ? C::CPR : 4;         // chunks of one row handled by adjacent lanes (full sectors)
         constexpr int RPI = 32 / CW;                        // rows per warp instruction
         constexpr int NIT = P_ROWS_PER_PROD / RPI;          // row groups per offset and warp
@@ -289,86 +284,128 @@ __global__ void __launch_bounds__(P_THREADS, 1) tc_conv_persist_kernel(const PAr
 #pragma unroll
         for (int cg = 0; cg < NCG; ++cg) ch_ok[cg] = (cg * CW + c_sub) * 8 < a.in_c;
         const uint32_t ring_s = smem_u32(ring);
-        const bool leader = pw == 0 && lane == 0;
-        int s = 0;
-        uint32_t ph = 0;       // parity of the `empty` phase to wait for once the ring has wrapped
-        bool wrapped = false;
+        const bool leader = grp == 0 && pw == 0 && lane == 0;
+        (void)leader;
+        int s = 0, wr = 0;     // ring slot and wrap count of the NEXT stage in sequence (all groups count every stage)
+        int turn = 0;          // whose stage it is: group `turn`
         for (int it = 0;; ++it) {
-            const int tb = it % P_NTB;
-            P_WAIT(&tbl_full[tb], (uint32_t)((it / P_NTB) & 1));
+            const int tb = it % ntb;
+            P_WAIT(&tbl_full[tb], (uint32_t)((it / ntb) & 1), 0x111);
             if (tile_s[tb] < 0) break;
-            const int nk = nk_s[tb];
             const int* tbl = nbr_s + (size_t)tb * K * TCM;
-            for (int t0 = 0; t0 < nk; t0 += C::G) {
-                const int cnt = min(C::G, nk - t0);
-                int kk[C::G];
-                int src[C::G][NIT];
+            for (int t0 = 0; t0 < K; t0 += C::G) {
+                if (turn == grp) {
+                    const int cnt = min(C::G, K - t0);
+                    int src[C::G][NIT];
 #pragma unroll
-                for (int g = 0; g < C::G; ++g) {
-                    kk[g] = g < cnt ? klist_s[tb][t0 + g] : 0;
+                    for (int g = 0; g < C::G; ++g) {
 #pragma unroll
-                    for (int i = 0; i < NIT; ++i) src[g][i] = g < cnt ? tbl[kk[g] * TCM + rows[i]] : -1;
-                }
-                if (wrapped) P_WAIT(&empty_bar[s], ph);
-                const uint32_t st_s = ring_s + (uint32_t)s * C::STAGE;
+                        for (int i = 0; i < NIT; ++i) src[g][i] = g < cnt ? tbl[(t0 + g) * TCM + rows[i]] : -1;
+                    }
+                    if (wr > 0) P_WAIT(&empty_bar[s], (uint32_t)((wr - 1) & 1), 0x112);
+                    const uint32_t st_s = ring_s + (uint32_t)s * stage_bytes;
 #pragma unroll
-                for (int g = 0; g < C::G; ++g) {
-                    if (g < cnt) {
-                        const uint32_t a_s = st_s + (uint32_t)g * C::A_BYTES;
+                    for (int g = 0; g < C::G; ++g) {
+                        if (g < cnt) {
+                            const uint32_t a_s = st_s + (uint32_t)g * C::A_BYTES;
 #pragma unroll
-                        for (int i = 0; i < NIT; ++i) {
-                            const bool v = src[g][i] >= 0;
-                            const __nv_bfloat16* srow = a.in + (size_t)(v ? src[g][i] : 0) * a.in_c + c_sub * 8;
+                            for (int i = 0; i < NIT; ++i) {
+                                const bool v = src[g][i] >= 0;
+                                const __nv_bfloat16* srow = a.in + (size_t)(v ? src[g][i] : 0) * a.in_c + c_sub * 8;
 #pragma unroll
-                            for (int cg = 0; cg < NCG; ++cg) {
-                                const bool vc = v && ch_ok[cg];
-                                cp_async16_s(a_s + dst_off[i][cg], vc ? srow + cg * CW * 8 : a.in, vc);
+                                for (int cg = 0; cg < NCG; ++cg) {
+                                    const bool vc = v && ch_ok[cg];
+#if VC_P_SKIP
+                                    if (vc) cp_async16_s(a_s + dst_off[i][cg], srow + cg * CW * 8, true);
+                                    else sts_zero16(a_s + dst_off[i][cg]);
+#else
+                                    cp_async16_s(a_s + dst_off[i][cg], vc ? srow + cg * CW * 8 : a.in, vc);
+#endif
+                                }
                             }
                         }
                     }
+                    cp_async_arrive_noinc(&full_bar[s]);
+#if VC_P_SKIP
+                    // the zero stores are ordinary shared-memory writes: published by a release arrive of the warp
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full_bar[s]);
+#endif
+                    if (leader) P_TRACE(1, tr);
                 }
-                if (leader) {
-                    mbar_expect_tx(&full_bar[s], (uint32_t)(cnt * C::B_BYTES));
-                    for (int g = 0; g < cnt; ++g)
-                        bulk_g2s(st_s + C::G * C::A_BYTES + (uint32_t)g * C::B_BYTES, a.wimg + (size_t)kk[g] * C::B_BYTES,
-                                 (uint32_t)C::B_BYTES, &full_bar[s]);
-                }
-                cp_async_arrive_noinc(&full_bar[s]);
-                if (leader) P_TRACE(1, tr);
+                if (++turn == P_GROUPS) turn = 0;
                 if (++s == S) {
                     s = 0;
-                    if (wrapped) ph ^= 1u;
-                    wrapped = true;
+                    ++wr;
                 }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&tbl_empty[tb]);
+        }
+    } else if (warp == P_WARP_W) {
+        // ------------------------------------------------------------ weight slices (TMA engine, linear bulk copies)
+        if (wres) {
+            if (lane == 0) {
+                const uint32_t total = (uint32_t)(K * C::B_BYTES);
+                mbar_expect_tx(&wres_bar, total);
+                for (uint32_t off = 0; off < total; off += P_W_CHUNK)
+                    bulk_g2s(smem_u32(wimg_s) + off, a.wimg + off, min((uint32_t)P_W_CHUNK, total - off), &wres_bar);
+            }
+        } else {
+            int s = 0, wr = 0;
+            for (int it = 0;; ++it) {
+                const int tb = it % ntb;
+                P_WAIT(&tbl_full[tb], (uint32_t)((it / ntb) & 1), 0x121);
+                if (tile_s[tb] < 0) break;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tbl_empty[tb]);
+                for (int t0 = 0; t0 < K; t0 += C::G) {
+                    const int cnt = min(C::G, K - t0);
+                    if (wr > 0) P_WAIT(&empty_bar[s], (uint32_t)((wr - 1) & 1), 0x122);
+                    if (lane == 0) {
+                        // the slices of consecutive offsets are contiguous in the image and in the stage: one copy
+                        mbar_expect_tx(&full_bar[s], (uint32_t)(cnt * C::B_BYTES));
+                        bulk_g2s(smem_u32(ring) + (uint32_t)s * stage_bytes + C::G * C::A_BYTES, a.wimg + (size_t)t0 * C::B_BYTES,
+                                 (uint32_t)(cnt * C::B_BYTES), &full_bar[s]);
+                    }
+                    __syncwarp();
+                    if (++s == S) {
+                        s = 0;
+                        ++wr;
+                    }
+                }
+            }
         }
     } else if (warp == P_WARP_MMA) {
         // ------------------------------------------------------------ MMA issuer
         constexpr uint32_t IDESC = umma_idesc(TCM, NR);
         int s = 0;
         uint32_t ph = 0;
+        bool w_ready = !wres;
         for (int it = 0;; ++it) {
-            const int tb = it % P_NTB, ab = it & 1;
-            P_WAIT(&tbl_full[tb], (uint32_t)((it / P_NTB) & 1));
+            const int tb = it % ntb, ab = it & 1;
+            P_WAIT(&tbl_full[tb], (uint32_t)((it / ntb) & 1), 0x131);
             if (tile_s[tb] < 0) break;
-            const int nk = nk_s[tb];
             __syncwarp();
             if (lane == 0) mbar_arrive(&tbl_empty[tb]);
-            if (it >= 2) P_WAIT(&acc_empty[ab], (uint32_t)(((it >> 1) - 1) & 1));
+            if (!w_ready) {
+                P_WAIT(&wres_bar, 0u, 0x132);
+                w_ready = true;
+            }
+            if (it >= 2) P_WAIT(&acc_empty[ab], (uint32_t)(((it >> 1) - 1) & 1), 0x133);
             tc_fence_after();
             const uint32_t acc = tmem_base + (uint32_t)(ab * NR);
-            for (int t0 = 0; t0 < nk; t0 += C::G) {
-                const int cnt = min(C::G, nk - t0);
-                P_WAIT(&full_bar[s], ph);
-                fence_async_smem();     // generic-proxy (cp.async) writes -> visible to the tensor core's async proxy
+            for (int t0 = 0; t0 < K; t0 += C::G) {
+                const int cnt = min(C::G, K - t0);
+                P_WAIT(&full_bar[s], ph, 0x134);
+                fence_async_smem();     // generic-proxy (cp.async, st.shared) writes -> visible to the tensor core's async proxy
                 tc_fence_after();
                 if (lane == 0) {
-                    const uint32_t st_s = smem_u32(ring) + (uint32_t)s * C::STAGE;
+                    const uint32_t st_s = smem_u32(ring) + (uint32_t)s * stage_bytes;
                     for (int g = 0; g < cnt; ++g) {
                         const uint32_t a0 = st_s + (uint32_t)g * C::A_BYTES;
-                        const uint32_t b0 = st_s + C::G * C::A_BYTES + (uint32_t)g * C::B_BYTES;
+                        const uint32_t b0 = wres ? smem_u32(wimg_s) + (uint32_t)((t0 + g) * C::B_BYTES)
+                                                 : st_s + C::G * C::A_BYTES + (uint32_t)g * C::B_BYTES;
 #pragma unroll
                         for (int m = 0; m < KC / 16; ++m)
                             umma_f16(acc, umma_desc_sw<C::ROWB>(a0 + m * 32), umma_desc_sw<C::ROWB>(b0 + m * 32), IDESC,
@@ -376,7 +413,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) tc_conv_persist_kernel(const PAr
                     }
                     umma_commit(&empty_bar[s]);
                     P_TRACE(2, tr);
-                    if (t0 + cnt >= nk) {
+                    if (t0 + cnt >= K) {
                         umma_commit(&acc_full[ab]);
                         P_TRACE(3, tr2);
                     }
@@ -387,8 +424,6 @@ __global__ void __launch_bounds__(P_THREADS, 1) tc_conv_persist_kernel(const PAr
                     ph ^= 1u;
                 }
             }
-            if (nk == 0 && lane == 0) umma_commit(&acc_full[ab]);   // (cannot happen for a valid tile; keeps the epilogue live)
-            __syncwarp();
         }
     } else {
         // ------------------------------------------------------------ epilogue (warps 0-3 == TMEM lane quarters)
@@ -396,15 +431,14 @@ __global__ void __launch_bounds__(P_THREADS, 1) tc_conv_persist_kernel(const PAr
         const int oc = a.out_c;
         const int ch = e % oc, rg = e / oc, n_rg = TCM / oc;
         for (int it = 0;; ++it) {
-            const int tb = it % P_NTB, ab = it & 1;
-            P_WAIT(&tbl_full[tb], (uint32_t)((it / P_NTB) & 1));
+            const int tb = it % ntb, ab = it & 1;
+            P_WAIT(&tbl_full[tb], (uint32_t)((it / ntb) & 1), 0x141);
             const int tile = tile_s[tb];
             if (tile < 0) break;
-            const int nk = nk_s[tb];
             const int base = tile * TCM;
             __syncwarp();
             if (lane == 0) mbar_arrive(&tbl_empty[tb]);
-            P_WAIT(&acc_full[ab], (uint32_t)((it >> 1) & 1));
+            P_WAIT(&acc_full[ab], (uint32_t)((it >> 1) & 1), 0x142);
             tc_fence_after();
             if (tid == 0) P_TRACE(4, tr);
             const int r = warp * 32 + lane;
@@ -415,7 +449,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) tc_conv_persist_kernel(const PAr
                 if (c0 < oc) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i)
-                        if (c0 + i < oc) stg[r * C::STG_LD + c0 + i] = nk > 0 ? v[i] : 0.f;
+                        if (c0 + i < oc) stg[r * C::STG_LD + c0 + i] = v[i];
                 }
             }
             tc_fence_before();
@@ -467,6 +501,10 @@ done:
             atomicAdd(a.bn_sums + which * oc + c, v);
         }
     }
+    if (wres && warp == P_WARP_MMA && lane == 0) {
+        // a CTA that was handed no tile must still see its weight copy land before it exits (the copy targets its smem)
+        mbar_wait_t(&wres_bar, 0u, a.err, 0x150);
+    }
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
@@ -499,14 +537,20 @@ int launch_persist(const PArgs& a0, int n_cap, cudaStream_t stream) {
     using C = PCfg<KC, NR>;
     PArgs a = a0;
     const size_t fixed = (size_t)P_NTB * a.K * TCM * 4 + C::STG_BYTES;
-    int S = (int)((SMEM_BUDGET - fixed) / C::STAGE);
+    const size_t wbytes = ((size_t)a.K * C::B_BYTES + 1023) & ~(size_t)1023;
+    // small weight sets stay in shared memory for the whole launch; large ones travel with the ring stages
+    const bool resident = wbytes <= (size_t)P_W_RESIDENT_MAX && (SMEM_BUDGET - fixed - wbytes) / (C::G * C::A_BYTES) >= 4;
+    const size_t stage = (size_t)C::G * C::A_BYTES + (resident ? 0 : (size_t)C::G * C::B_BYTES);
+    const size_t wres = resident ? wbytes : 0;
+    int S = (int)((SMEM_BUDGET - fixed - wres) / stage);
     if (S > P_MAX_STAGES) S = P_MAX_STAGES;
     if (S < 2) {
         set_error("tensor-core conv: no room for the operand ring (K=%d, %d->%d)", a.K, KC, NR);
         return VC_ERR_UNSUPPORTED;
     }
     a.S = S;
-    const size_t smem = (size_t)S * C::STAGE + fixed;
+    a.w_resident = resident ? 1 : 0;
+    const size_t smem = (size_t)S * stage + wres + fixed;
     auto kern = tc_conv_persist_kernel<KC, NR>;
     static bool attr_done = false;            // per instantiation
     if (!attr_done) {
@@ -587,7 +631,7 @@ int tc2_conv(int kc, int nr, const void* in_bf16, const void* wimg, const int32_
     PArgs a;
     a.in = (const __nv_bfloat16*)in_bf16; a.in_c = kc; a.wimg = (const unsigned char*)wimg; a.nbr = nbr; a.pitch = pitch;
     a.out = out; a.out_c = nr; a.addend = addend; a.bn_sums = bn_sums; a.n_dev = n_dev; a.n_host = n_rows; a.tile_counter = tile_counter;
-    a.K = K; a.S = 0;
+    a.K = K; a.S = 0; a.w_resident = 0;
     a.err = err;
     const int kcp = tc_pad16(kc), nrp = tc_pad16(nr);
 #define VC_P_CASE(A, B) \

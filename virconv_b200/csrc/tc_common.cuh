@@ -28,11 +28,12 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* e
             : "memory");
         if (done) return true;
     }
-    if (err) atomicExch(err, 1);
+    if (err) atomicCAS(err, 0, 0x300);
     return false;
 }
 // time-bounded wait (2 s of %globaltimer): used by the persistent kernels, whose roles abandon their loops on a timeout
-__device__ __forceinline__ bool mbar_wait_t(uint64_t* bar, uint32_t parity, int* err) {
+// `code` says which wait of which kernel gave up (0x1xx persistent conv, 0x2xx persistent wgrad; the first one sticks)
+__device__ __forceinline__ bool mbar_wait_t(uint64_t* bar, uint32_t parity, int* err, int code = 1) {
     uint32_t addr = smem_u32(bar), done = 0;
     unsigned long long t0 = 0;
     for (unsigned spin = 0;; ++spin) {
@@ -51,7 +52,7 @@ __device__ __forceinline__ bool mbar_wait_t(uint64_t* bar, uint32_t parity, int*
             else if (t - t0 > 2000000000ULL) break;
         }
     }
-    if (err) atomicExch(err, 1);
+    if (err) atomicCAS(err, 0, code);
     return false;
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {

@@ -23,11 +23,17 @@
 namespace vc {
 namespace {
 
-constexpr int W_WARP_LOADER = 4, W_WARP_MMA = 5, W_WARP_PROD0 = 6, W_PROD_WARPS = 8;
-constexpr int W_THREADS = 32 * (W_WARP_PROD0 + W_PROD_WARPS);   // 448
-constexpr int W_PROD_THREADS = 32 * W_PROD_WARPS;
+#ifndef VC_W_GROUPS
+#define VC_W_GROUPS 2            // producer groups of 8 warps; consecutive ring stages go to consecutive groups
+#endif
+#ifndef VC_P_SKIP
+#define VC_P_SKIP 1              // 1: missing neighbours cost a shared-memory zero store, not a (zero-fill) cp.async
+#endif
+constexpr int W_WARP_LOADER = 4, W_WARP_MMA = 5, W_WARP_PROD0 = 6, W_PROD_WARPS = 8, W_GROUPS = VC_W_GROUPS;
+constexpr int W_THREADS = 32 * (W_WARP_PROD0 + W_GROUPS * W_PROD_WARPS);   // 704 with two groups
+constexpr int W_PROD_THREADS = 32 * W_PROD_WARPS * W_GROUPS;
 constexpr int W_MAX_STAGES = 8;
-constexpr int W_NTB = 4, W_AHEAD = 2, W_PREF = 4;
+constexpr int W_NTB = 4;
 constexpr int W_ROWS_PER_PROD = TCM / W_PROD_WARPS;             // 16
 constexpr int W_SMEM_BUDGET = 227 * 1024 - 4096;
 
@@ -56,10 +62,14 @@ struct WArgs {
     int* err;
 };
 
-#define W_WAIT(bar, parity)                                   \
-    do {                                                      \
-        if (!mbar_wait_t((bar), (parity), a.err)) goto done;  \
+#define W_WAIT(bar, parity, code)                                     \
+    do {                                                              \
+        if (!mbar_wait_t((bar), (parity), a.err, (code))) goto done;  \
     } while (0)
+
+__device__ __forceinline__ void w_sts_zero16(uint32_t saddr) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(saddr), "r"(0u) : "memory");
+}
 
 template <int ROWB>
 __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t lbo) {
@@ -81,12 +91,11 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_persist_kernel(const WA
     __shared__ __align__(8) uint64_t full_bar[W_MAX_STAGES];
     __shared__ __align__(8) uint64_t empty_bar[W_MAX_STAGES];
     __shared__ __align__(8) uint64_t tbl_full[W_NTB], tbl_empty[W_NTB];
-    __shared__ __align__(8) uint64_t dout_empty[2];
+    __shared__ __align__(8) uint64_t dout_full[2], dout_empty[2];
     __shared__ __align__(8) uint64_t final_bar, meta_bar;
-    __shared__ int glist_s[W_NTB][MAXK_TC];
-    __shared__ int ng_s[W_NTB], tile_s[W_NTB];
+    __shared__ int tile_s[W_NTB];
     __shared__ uint32_t tmem_base_s;
-    __shared__ unsigned started_s;
+    __shared__ int started_s;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // this pass's slice of the kernel offsets (passes only when the accumulators of all groups exceed 512 TMEM columns)
@@ -103,25 +112,37 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_persist_kernel(const WA
     }
     if (tid == W_WARP_MMA * 32) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(&full_bar[s], W_PROD_THREADS);           // every producer thread (cp.async arrive)
+            // every producer thread of the stage's group (cp.async arrive) [+ one release arrive per warp for its zero stores]
+            mbar_init(&full_bar[s], 32 * W_PROD_WARPS + (VC_P_SKIP ? W_PROD_WARPS : 0));
             mbar_init(&empty_bar[s], 1);                       // tcgen05.commit
         }
         for (int b = 0; b < W_NTB; ++b) {
             mbar_init(&tbl_full[b], 1);                        // loader
-            mbar_init(&tbl_empty[b], W_PROD_WARPS + 1);        // producers + MMA warp
+            mbar_init(&tbl_empty[b], W_GROUPS * W_PROD_WARPS + 1);   // producers + MMA warp
         }
-        mbar_init(&dout_empty[0], 1);
-        mbar_init(&dout_empty[1], 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&dout_full[b], W_PROD_THREADS);          // every producer thread (cp.async arrive)
+            mbar_init(&dout_empty[b], 1);                      // tcgen05.commit
+        }
         mbar_init(&final_bar, 1);
         mbar_init(&meta_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        started_s = 0u;
+        started_s = 0;
     }
     pdl_wait();
     pdl_launch_dependents();
     const int n = a.n_dev != nullptr ? min(__ldg(a.n_dev), a.n_host) : a.n_host;
-    const int n_tiles = (n + TCM - 1) / TCM;
+    // a pipeline wait that timed out in an EARLIER launch left the (sticky) error flag set: do nothing, so that whatever went
+    // wrong costs one 2-second timeout, not one per launch
+    const bool dead = a.err != nullptr && *reinterpret_cast<volatile int*>(a.err) != 0;
+    const int n_tiles = dead ? 0 : (n + TCM - 1) / TCM;
     int* counter = a.tile_counter != nullptr ? a.tile_counter + blockIdx.y : nullptr;
+    int ntb = W_NTB;            // table buffers in use == tiles a CTA holds claimed at once (see conv_tc2.cu)
+    if (counter != nullptr) {
+        int d = n_tiles / (3 * (int)gridDim.x);
+        d = d < 1 ? 1 : (d > W_NTB - 1 ? W_NTB - 1 : d);
+        ntb = d + 1;
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -130,50 +151,40 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_persist_kernel(const WA
     if (warp == W_WARP_LOADER) {
         // ------------------------------------------------------------ tile scheduler + neighbour-table loader
         const bool vec_ok = (reinterpret_cast<uintptr_t>(a.nbr) & 15u) == 0 && (a.pitch & 3) == 0;
-        constexpr int PQ = W_AHEAD + W_PREF + 1;
-        int my_tile[PQ];
-        int claimed = 0, issued = 0;
+        const int lag = ntb - 1;
+        int tq0 = -1, tq1 = -1, tq2 = -1, tq3 = -1;
         bool stop = false;
-        auto claim = [&]() {
-            int tile;
-            if (counter != nullptr) {
-                tile = lane == 0 ? atomicAdd(counter, 1) : 0;
-                tile = __shfl_sync(0xffffffffu, tile, 0);
-            } else {
-                tile = blockIdx.x + claimed * gridDim.x;
-            }
-            if (tile >= n_tiles) {
-                tile = -1;
-                stop = true;
-            } else {
-                const int base = tile * TCM;
-                if (vec_ok && (long long)base + TCM <= a.pitch) {
-                    if (lane < k_count)
-                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.nbr + (size_t)(k_begin + lane) * a.pitch + base),
-                                     "r"(TCM * 4)
-                                     : "memory");
+        int claimed = 0;
+        for (int it = 0;; ++it) {
+            const int tb = it % ntb;
+            int tile = -1;
+            if (!stop) {
+                if (counter != nullptr) {
+                    tile = lane == 0 ? atomicAdd(counter, 1) : 0;
+                    tile = __shfl_sync(0xffffffffu, tile, 0);
                 } else {
-                    for (int i = lane; i < k_count * 5; i += 32) {
-                        const int k = i / 5, seg = i % 5;
-                        const long long row = (long long)base + seg * 32;
-                        if (row < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.nbr + (size_t)(k_begin + k) * a.pitch + row));
-                    }
+                    tile = blockIdx.x + claimed * gridDim.x;
+                }
+                ++claimed;
+                if (tile >= n_tiles) {
+                    tile = -1;
+                    stop = true;
                 }
             }
-            my_tile[claimed % PQ] = tile;
-            ++claimed;
-        };
-        auto issue = [&](int it) -> bool {
-            const int tb = it % W_NTB;
-            if (it >= W_NTB && !mbar_wait_t(&tbl_empty[tb], (uint32_t)(((it / W_NTB) - 1) & 1), a.err)) return false;
-            const int tile = my_tile[it % PQ];
+            switch (it & 3) {
+                case 0: tq0 = tile; break;
+                case 1: tq1 = tile; break;
+                case 2: tq2 = tile; break;
+                default: tq3 = tile; break;
+            }
+            if (it >= ntb) W_WAIT(&tbl_empty[tb], (uint32_t)(((it / ntb) - 1) & 1), 0x201);
             if (tile >= 0) {
                 int* dst = nbr_s + (size_t)tb * k_count * TCM;
                 const int base = tile * TCM;
                 if (vec_ok && (long long)base + TCM <= a.pitch) {
-                    const uint32_t d0 = smem_u32(dst) + lane * 16;
-                    const int32_t* s0 = a.nbr + (size_t)k_begin * a.pitch + base + lane * 4;
-                    for (int k = 0; k < k_count; ++k) cp_async16_s(d0 + k * (TCM * 4), s0 + (size_t)k * a.pitch, true);
+                    uint32_t d = smem_u32(dst) + lane * 16;
+                    const int32_t* sp = a.nbr + (size_t)k_begin * a.pitch + base + lane * 4;
+                    for (int k = 0; k < k_count; ++k, d += TCM * 4, sp += a.pitch) cp_async16_s(d, sp, true);
                 } else {
                     for (int k = 0; k < k_count; ++k) {
 #pragma unroll
@@ -190,56 +201,34 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_persist_kernel(const WA
                 }
             }
             cp_async_commit();
-            return true;
-        };
-        for (int it = 0;; ++it) {
-            while (!stop && claimed <= it + W_AHEAD + W_PREF - 1) claim();
-            while (issued < claimed && issued <= it + W_AHEAD - 1) {
-                if (!issue(issued)) goto done;
-                ++issued;
-            }
-            const int tb = it % W_NTB;
-            const int tile = my_tile[it % PQ];
-            if (issued - it - 1 >= 1) cp_async_wait<1>(); else cp_async_wait<0>();
-            __syncwarp();
-            if (tile < 0) {
-                if (lane == 0) {
-                    tile_s[tb] = -1;
-                    mbar_arrive(&tbl_full[tb]);
+            if (it >= lag) {
+                const int pi = it - lag;
+                if (lag == 3) cp_async_wait<3>(); else if (lag == 2) cp_async_wait<2>(); else cp_async_wait<1>();
+                __syncwarp();
+                const int ptb = pi % ntb;
+                const int ptile = (pi & 3) == 0 ? tq0 : (pi & 3) == 1 ? tq1 : (pi & 3) == 2 ? tq2 : tq3;
+                if (ptile >= 0 && ptile * TCM + TCM > n) {
+                    int* dst = nbr_s + (size_t)ptb * k_count * TCM;
+                    const int r0 = ptile * TCM + lane * 4;
+                    for (int k = 0; k < k_count; ++k) {
+                        int4 v = reinterpret_cast<const int4*>(dst + k * TCM)[lane];
+                        if (r0 + 0 >= n) v.x = -1;
+                        if (r0 + 1 >= n) v.y = -1;
+                        if (r0 + 2 >= n) v.z = -1;
+                        if (r0 + 3 >= n) v.w = -1;
+                        reinterpret_cast<int4*>(dst + k * TCM)[lane] = v;
+                    }
                 }
-                break;
+                if (lane == 0) tile_s[ptb] = ptile;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tbl_full[ptb]);
+                if (ptile < 0) break;
             }
-            int* dst = nbr_s + (size_t)tb * k_count * TCM;
-            const int base = tile * TCM;
-            const bool partial = base + TCM > n;
-            unsigned gm = 0u;
-            for (int k = 0; k < k_count; ++k) {
-                int4 v = reinterpret_cast<const int4*>(dst + k * TCM)[lane];
-                if (partial) {
-                    const int r0 = base + lane * 4;
-                    bool ch = false;
-                    if (r0 + 0 >= n && v.x != -1) { v.x = -1; ch = true; }
-                    if (r0 + 1 >= n && v.y != -1) { v.y = -1; ch = true; }
-                    if (r0 + 2 >= n && v.z != -1) { v.z = -1; ch = true; }
-                    if (r0 + 3 >= n && v.w != -1) { v.w = -1; ch = true; }
-                    if (ch) reinterpret_cast<int4*>(dst + k * TCM)[lane] = v;
-                }
-                const bool any = (v.x >= 0) | (v.y >= 0) | (v.z >= 0) | (v.w >= 0);
-                if (__any_sync(0xffffffffu, any)) gm |= 1u << (k / C::GW);
-            }
-            if (lane == 0) {
-                int c = 0;
-                for (int g = 0; g < g_count; ++g)
-                    if (gm >> g & 1u) glist_s[tb][c++] = g;
-                ng_s[tb] = c;
-                tile_s[tb] = tile;
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tbl_full[tb]);
         }
     } else if (warp >= W_WARP_PROD0) {
         // ------------------------------------------------------------ gather producers
-        const int pw = warp - W_WARP_PROD0, ptid = tid - W_WARP_PROD0 * 32;
+        const int grp = (warp - W_WARP_PROD0) / W_PROD_WARPS, pw = (warp - W_WARP_PROD0) % W_PROD_WARPS;
+        const int ptid = tid - W_WARP_PROD0 * 32;
         constexpr int CW = C::CPA < 4 ? C::CPA : 4;
         constexpr int RPI = 32 / CW;
         constexpr int NIT = W_ROWS_PER_PROD / RPI;
@@ -257,20 +246,17 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_persist_kernel(const WA
 #pragma unroll
         for (int cg = 0; cg < NCG; ++cg) ch_ok[cg] = (cg * CW + c_sub) * 8 < a.in_c;
         const uint32_t ring_s = smem_u32(ring);
-        int s = 0;
-        uint32_t ph = 0;
-        bool wrapped = false;
+        int s = 0, wr = 0, turn = 0;
         for (int it = 0;; ++it) {
-            const int tb = it % W_NTB, db = it & 1;
-            W_WAIT(&tbl_full[tb], (uint32_t)((it / W_NTB) & 1));
+            const int tb = it % ntb, db = it & 1;
+            W_WAIT(&tbl_full[tb], (uint32_t)((it / ntb) & 1), 0x211);
             const int tile = tile_s[tb];
             if (tile < 0) break;
-            const int ng = ng_s[tb];
             const int* tbl = nbr_s + (size_t)tb * k_count * TCM;
             const int base = tile * TCM;
-            // the tile of dout (second operand of every group of this tile): contiguous rows, swizzled image; its completion
-            // is covered by the first stage's `full` barrier (cp.async.mbarrier.arrive tracks ALL earlier copies of a thread)
-            if (it >= 2) W_WAIT(&dout_empty[db], (uint32_t)(((it >> 1) - 1) & 1));
+            // the tile of dout (second operand of every group of this tile): contiguous rows, swizzled image, loaded by all
+            // producer threads together
+            if (it >= 2) W_WAIT(&dout_empty[db], (uint32_t)(((it >> 1) - 1) & 1), 0x212);
             {
                 const uint32_t b_s = smem_u32(dout_s) + (uint32_t)db * C::B_BYTES;
                 for (int q = ptid; q < TCM * C::CPB; q += W_PROD_THREADS) {
@@ -278,37 +264,48 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_persist_kernel(const WA
                     const bool v = base + r < n && c * 8 < a.out_c;
                     cp_async16_s(b_s + swz_off<C::RB>(r, c), v ? a.dout + (size_t)(base + r) * a.out_c + c * 8 : a.dout, v);
                 }
+                cp_async_arrive_noinc(&dout_full[db]);
             }
-            for (int t = 0; t < ng; ++t) {
-                const int g = glist_s[tb][t];
-                int src[C::GW][NIT];
+            for (int g = 0; g < g_count; ++g) {
+                if (turn == grp) {
+                    int src[C::GW][NIT];
 #pragma unroll
-                for (int j = 0; j < C::GW; ++j) {
-                    const int kk = g * C::GW + j;
+                    for (int j = 0; j < C::GW; ++j) {
+                        const int kk = g * C::GW + j;
 #pragma unroll
-                    for (int i = 0; i < NIT; ++i) src[j][i] = kk < k_count ? tbl[kk * TCM + rows[i]] : -1;
-                }
-                if (wrapped) W_WAIT(&empty_bar[s], ph);
-                const uint32_t st_s = ring_s + (uint32_t)s * C::STAGE;
+                        for (int i = 0; i < NIT; ++i) src[j][i] = kk < k_count ? tbl[kk * TCM + rows[i]] : -1;
+                    }
+                    if (wr > 0) W_WAIT(&empty_bar[s], (uint32_t)((wr - 1) & 1), 0x213);
+                    const uint32_t st_s = ring_s + (uint32_t)s * C::STAGE;
 #pragma unroll
-                for (int j = 0; j < C::GW; ++j) {
-                    const uint32_t a_s = st_s + (uint32_t)j * C::A_BYTES;
+                    for (int j = 0; j < C::GW; ++j) {
+                        const uint32_t a_s = st_s + (uint32_t)j * C::A_BYTES;
 #pragma unroll
-                    for (int i = 0; i < NIT; ++i) {
-                        const bool v = src[j][i] >= 0;
-                        const __nv_bfloat16* srow = a.in + (size_t)(v ? src[j][i] : 0) * a.in_c + c_sub * 8;
+                        for (int i = 0; i < NIT; ++i) {
+                            const bool v = src[j][i] >= 0;
+                            const __nv_bfloat16* srow = a.in + (size_t)(v ? src[j][i] : 0) * a.in_c + c_sub * 8;
 #pragma unroll
-                        for (int cg = 0; cg < NCG; ++cg) {
-                            const bool vc = v && ch_ok[cg];
-                            cp_async16_s(a_s + dst_off[i][cg], vc ? srow + cg * CW * 8 : a.in, vc);
+                            for (int cg = 0; cg < NCG; ++cg) {
+                                const bool vc = v && ch_ok[cg];
+#if VC_P_SKIP
+                                if (vc) cp_async16_s(a_s + dst_off[i][cg], srow + cg * CW * 8, true);
+                                else w_sts_zero16(a_s + dst_off[i][cg]);
+#else
+                                cp_async16_s(a_s + dst_off[i][cg], vc ? srow + cg * CW * 8 : a.in, vc);
+#endif
+                            }
                         }
                     }
+                    cp_async_arrive_noinc(&full_bar[s]);
+#if VC_P_SKIP
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full_bar[s]);     // release: publishes the warp's zero stores
+#endif
                 }
-                cp_async_arrive_noinc(&full_bar[s]);
+                if (++turn == W_GROUPS) turn = 0;
                 if (++s == S) {
                     s = 0;
-                    if (wrapped) ph ^= 1u;
-                    wrapped = true;
+                    ++wr;
                 }
             }
             __syncwarp();
@@ -319,32 +316,27 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_persist_kernel(const WA
         constexpr uint32_t IDESC = umma_idesc(TCM, CO) | (1u << 15) | (1u << 16);     // both operands MN-major
         int s = 0;
         uint32_t ph = 0;
-        unsigned started = 0u;
+        int n_done = 0;
         for (int it = 0;; ++it) {
-            const int tb = it % W_NTB, db = it & 1;
-            W_WAIT(&tbl_full[tb], (uint32_t)((it / W_NTB) & 1));
+            const int tb = it % ntb, db = it & 1;
+            W_WAIT(&tbl_full[tb], (uint32_t)((it / ntb) & 1), 0x221);
             if (tile_s[tb] < 0) break;
-            const int ng = ng_s[tb];
-            int gl[MAXK_TC / 2];
-            for (int t = 0; t < ng; ++t) gl[t] = glist_s[tb][t];
             __syncwarp();
             if (lane == 0) mbar_arrive(&tbl_empty[tb]);
-            for (int t = 0; t < ng; ++t) {
-                W_WAIT(&full_bar[s], ph);
+            W_WAIT(&dout_full[db], (uint32_t)((it >> 1) & 1), 0x222);
+            for (int g = 0; g < g_count; ++g) {
+                W_WAIT(&full_bar[s], ph, 0x223);
                 fence_async_smem();
                 tc_fence_after();
                 if (lane == 0) {
-                    const int g = gl[t];
                     const uint32_t a0 = smem_u32(ring) + (uint32_t)s * C::STAGE;
                     const uint32_t b0 = smem_u32(dout_s) + (uint32_t)db * C::B_BYTES;
-                    const bool first = !(started >> g & 1u);
 #pragma unroll
                     for (int j = 0; j < 8; ++j)      // 16 rows (two 8-row groups) per MMA
                         umma_f16(tmem_base + (uint32_t)(g * CO), umma_desc_mn<C::RA>(a0 + j * 16 * C::RA, C::A_BYTES),
-                                 umma_desc_mn<C::RB>(b0 + j * 16 * C::RB, 0), IDESC, (first && j == 0) ? 0u : 1u);
-                    started |= 1u << g;
+                                 umma_desc_mn<C::RB>(b0 + j * 16 * C::RB, 0), IDESC, (it == 0 && j == 0) ? 0u : 1u);
                     umma_commit(&empty_bar[s]);
-                    if (t == ng - 1) umma_commit(&dout_empty[db]);
+                    if (g == g_count - 1) umma_commit(&dout_empty[db]);
                 }
                 __syncwarp();
                 if (++s == S) {
@@ -352,39 +344,39 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_persist_kernel(const WA
                     ph ^= 1u;
                 }
             }
-            if (ng == 0 && lane == 0) umma_commit(&dout_empty[db]);
-            __syncwarp();
+            ++n_done;
         }
         if (lane == 0) {
-            started_s = started;
-            umma_commit(&final_bar);           // arrives when every MMA of this CTA has completed
-            mbar_arrive(&meta_bar);            // publishes started_s (release)
+            started_s = n_done;
+            if (n_done > 0) umma_commit(&final_bar);   // arrives when every MMA of this CTA has completed
+            else mbar_arrive(&final_bar);              // (a CTA that was handed no tile has nothing in flight)
+            mbar_arrive(&meta_bar);                    // publishes started_s (release)
         }
     } else {
         // ------------------------------------------------------------ epilogue (once, at the end): TMEM -> vector reductions
-        W_WAIT(&meta_bar, 0u);
-        W_WAIT(&final_bar, 0u);
+        W_WAIT(&meta_bar, 0u, 0x231);
+        W_WAIT(&final_bar, 0u, 0x232);
         tc_fence_after();
-        const unsigned st = started_s;
         const int row = warp * 32 + lane;
         const int j = row / CI, ci = row % CI;
         const int oc = a.out_c, ic = a.in_c;
-        for (int g = 0; g < g_count; ++g) {
-            if (!(st >> g & 1u)) continue;               // warp-uniform: tcgen05.ld is warp-collective
-            const int kk = g * C::GW + j;
-            const bool mine = kk < k_count && ci < ic;
+        if (started_s > 0) {
+            for (int g = 0; g < g_count; ++g) {
+                const int kk = g * C::GW + j;
+                const bool mine = kk < k_count && ci < ic;
 #pragma unroll
-            for (int c0 = 0; c0 < CO; c0 += 16) {
-                float v[16];
-                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(g * CO + c0), v);
-                if (mine && c0 < oc) {
-                    float* dst = a.scratch + ((size_t)(k_begin + kk) * ic + ci) * oc + c0;
+                for (int c0 = 0; c0 < CO; c0 += 16) {
+                    float v[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(g * CO + c0), v);
+                    if (mine && c0 < oc) {
+                        float* dst = a.scratch + ((size_t)(k_begin + kk) * ic + ci) * oc + c0;
 #pragma unroll
-                    for (int i = 0; i < 16; i += 4)
-                        if (c0 + i < oc)
-                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "f"(v[i]), "f"(v[i + 1]),
-                                         "f"(v[i + 2]), "f"(v[i + 3])
-                                         : "memory");
+                        for (int i = 0; i < 16; i += 4)
+                            if (c0 + i < oc)
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "f"(v[i]), "f"(v[i + 1]),
+                                             "f"(v[i + 2]), "f"(v[i + 3])
+                                             : "memory");
+                    }
                 }
             }
         }

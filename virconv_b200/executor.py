@@ -192,26 +192,26 @@ def _pinned(device):
 ARENA_GRAIN = 64 << 20
 
 
-def _arena_bytes(plan, n0, device, training=True):
+def _arena_bytes(plan, n0, device, with_bwd=True):
     """Arena size for a step.  First use of a plan: a generous guess from the input row count (VirConv-L uses ~16 KB per
     input voxel, forward + backward; a forward alone about half).  Afterwards: the largest bytes-per-input-row an earlier
     step of the same plan really used (recorded by the backward / the eval forward) times this step's rows plus 30 %
     head-room — monotone per plan, so the caching allocator keeps handing back the same block, and an eval-only or
     small-batch user does not reserve the training worst case (rows*24 KB + 256 MB over-reserved ~2x)."""
-    key = (device.index, bool(training))
+    key = (device.index, bool(with_bwd))
     per_row = plan.arena_used.get(key, 0.0)
     if per_row:
         want = int(1.3 * per_row * int(n0)) + (32 << 20)
     else:
-        want = int(n0) * (24576 if training else 12288) + (128 << 20)
+        want = int(n0) * (24576 if with_bwd else 12288) + (128 << 20)
     want = max(want, plan.arena_bytes.get(key, 0))
     want = (want + ARENA_GRAIN - 1) // ARENA_GRAIN * ARENA_GRAIN
     plan.arena_bytes[key] = want
     return want
 
 
-def _note_arena_use(plan, device, training, used, n0):
-    key = (device.index, bool(training))
+def _note_arena_use(plan, device, with_bwd, used, n0):
+    key = (device.index, bool(with_bwd))
     plan.arena_used[key] = max(plan.arena_used.get(key, 0.0), float(used) / max(int(n0), 1))
 
 
@@ -440,7 +440,7 @@ class PlanFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, plan, holder, feats, coords, spatial_shape, batch_size, proj, training, precision, inputs_ready, static,
-                *params):
+                with_bwd, *params):
         lib = _lib.load()
         ctx.set_materialize_grads(False)     # published tensors the loss does not touch arrive as None, not as zeros
         dev = feats.device
@@ -462,7 +462,7 @@ class PlanFn(torch.autograd.Function):
             inflight = _throttle(plan, dev)
         tab = _layer_ptrs(plan)
         for attempt in range(3):
-            nbytes = _arena_bytes(plan, n0, dev, training)
+            nbytes = _arena_bytes(plan, n0, dev, with_bwd)
             if static is not None:
                 # (inside a capture: the graph's own pool.  No record_stream: the side / wgrad streams are forked from and
                 #  joined back into the calling stream inside vc_exec_forward / vc_exec_backward, so every later use of the
@@ -490,16 +490,16 @@ class PlanFn(torch.autograd.Function):
                 break
             # too small (first use of a plan on an unusually dense batch): the call is restartable — nothing it enqueued is
             # read by anyone — so take a bigger arena and run it again
-            plan.arena_bytes[(dev.index, bool(training))] = 2 * arena.numel()
+            plan.arena_bytes[(dev.index, bool(with_bwd))] = 2 * arena.numel()
         check(rc, 'vc_exec_forward')
         if inflight is not None:
             tail = torch.cuda.Event()
             tail.record()
             inflight.append(tail)
         run = _Run(plan, arena, state, precision)
-        run.static, run.n0, run.training = static, n0, bool(training)
+        run.static, run.n0, run.training, run.with_bwd = static, n0, bool(training), bool(with_bwd)
         holder.append(run)
-        if not training:
+        if not with_bwd:
             _note_arena_use(plan, dev, False, run.query(0, 0)[0], n0)
         if TIMING:
             global LAST_RUN
@@ -530,13 +530,14 @@ class PlanFn(torch.autograd.Function):
                                   ops.tc_error_flag(dev).data_ptr(), run.state.ctypes.data, ops._stream(),
                                   ws.cuda_stream if ws is not None else None)
         if rc == VC_ERR_WORKSPACE:
-            plan.arena_bytes[(dev.index, run.training)] = 2 * run.arena.numel()
+            # (a forward taken without autograd's knowledge of a later backward: the next step's arena is sized for it)
+            plan.arena_bytes[(dev.index, run.with_bwd)] = 2 * run.arena.numel()
         check(rc, 'vc_exec_backward')
-        _note_arena_use(plan, dev, run.training, run.query(0, 0)[0], run.n0)
+        _note_arena_use(plan, dev, run.with_bwd, run.query(0, 0)[0], run.n0)
         run.flat_grad = flat
         views = flat.split(sizes)
         out = [v.view_as(p) for v, p in zip(views, plan.params())]
-        return (None,) * 11 + tuple(out)
+        return (None,) * 12 + tuple(out)
 
 
 def run_plan(plan, feats, coords_i32, spatial_shape, batch_size, proj, training, precision, inputs_ready=False, static=None):
@@ -548,8 +549,10 @@ def run_plan(plan, feats, coords_i32, spatial_shape, batch_size, proj, training,
     ops._require_cuda(feats, coords_i32)
     assert coords_i32.dtype == torch.int32 and coords_i32.is_contiguous()
     holder = []
+    # the arena also holds what a backward saves / stages: sized for it whenever autograd will record this call
+    with_bwd = bool(training) or (torch.is_grad_enabled() and (feats.requires_grad or any(p.requires_grad for p in plan.params())))
     outs = PlanFn.apply(plan, holder, feats, coords_i32, list(spatial_shape), batch_size, proj, training, precision,
-                        bool(inputs_ready), static, *plan.params())
+                        bool(inputs_ready), static, with_bwd, *plan.params())
     run = holder[0]
     res = {}
     for (name, slot, iset), f in zip(plan.published, outs):
@@ -561,27 +564,36 @@ def run_plan(plan, feats, coords_i32, spatial_shape, batch_size, proj, training,
     return run, res
 
 
-_LAST_RUNS = weakref.WeakKeyDictionary()     # model -> weak reference to its most recent run record
+class RunCounts:
+    """What outlives a run record (whose arena goes back to the allocator with the step's tensors): the row count of every
+    strided conv's output set, for sizing a StaticSpec."""
+
+    def __init__(self, run):
+        self.rows = {}
+        if run.static is None:               # (a static run's counts live on the device)
+            for rb, (keys, ndim, i_in, i_out) in run.plan.rb_keys.items():
+                if i_out != i_in and i_out != 0:
+                    self.rows[i_out] = int(run.query(2, i_out)[1])
+
+
+_LAST_RUNS = weakref.WeakKeyDictionary()     # model -> RunCounts of its most recent exact-mode run
 
 
 def note_last_run(model, run):
-    _LAST_RUNS[model] = weakref.ref(run)
+    if run.static is None:
+        _LAST_RUNS[model] = RunCounts(run)
 
 
 def last_run(model):
-    r = _LAST_RUNS.get(model)
-    return r() if r is not None else None
+    return _LAST_RUNS.get(model)
 
 
 def measured_caps(run, margin=1.3, grain=1024):
-    """{index-set id: capacity} for a StaticSpec from an EXACT-mode run of the same plan on a representative batch: the
-    observed row count of every strided conv's output set times `margin`, rounded up to `grain` rows."""
-    caps = {}
-    for rb, (keys, ndim, i_in, i_out) in run.plan.rb_keys.items():
-        if i_out != i_in and i_out != 0:
-            n = run.query(2, i_out)[1]
-            caps[i_out] = (int(n * margin) + grain - 1) // grain * grain
-    return caps
+    """{index-set id: capacity} for a StaticSpec from an EXACT-mode run of the same plan on a representative batch (a run
+    record or the RunCounts `last_run(model)` keeps): the observed row count of every strided conv's output set times
+    `margin`, rounded up to `grain` rows."""
+    rows = run.rows if isinstance(run, RunCounts) else RunCounts(run).rows
+    return {i: (int(n * margin) + grain - 1) // grain * grain for i, n in rows.items()}
 
 
 def timing_start():

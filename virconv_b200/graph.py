@@ -39,6 +39,7 @@ class GraphedStep:
         self.model, self.loss_fn = model, loss_fn
         self.vox = dict(voxelizer) if voxelizer is not None else None
         self.params = list(model.parameters()) if params is None else list(params)
+        self.dev = self.params[0].device
         self.margin, self.grain, self.warmup = margin, grain, warmup
         self.check_overflow = check_overflow
         self.graph = None
