@@ -60,6 +60,7 @@ def parse():
                     help='graph = the whole step (forward + loss + backward) replayed as one CUDA graph (plan executor static '
                          'mode: device row counts, no host synchronisation); eager = exact-shape execution, one C-ABI call per '
                          'forward / backward, 4 data-dependent row counts read on the host')
+    ap.add_argument('--no-grid41', action='store_true', help='skip the extra [41,1600,1408]-grid measurement (N=1, graph mode)')
     ap.add_argument('--ncu-step', action='store_true',
                     help='profiling aid: W warm-up steps, then exactly one step between cudaProfilerStart/Stop; no JSON')
     return ap.parse_args()
@@ -440,6 +441,19 @@ def run_ours(args):
             loss = loss + masked_mean(t)
         return loss
 
+    ar_events = []
+
+    def reduce_grads():
+        """one flat fp32 bucket over NCCL / NVLink (no-op at N=1); runs on the main stream right after the backward, so its
+        whole duration is exposed — measured with events and reported as config.allreduce_ms_per_step"""
+        if world == 1:
+            return
+        a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        parallel.allreduce_gradients(params, average=True)
+        e.record()
+        ar_events.append((a, e))
+
     def step(vf, vc, b, sync_loss, resident=False):
         """exact-shape (eager) step: one C-ABI call per forward / backward"""
         for p in params:
@@ -452,7 +466,7 @@ def run_ours(args):
         out = model(bd)
         loss = loss_of(out)
         loss.backward()
-        parallel.allreduce_gradients(params, average=True)     # one flat fp32 bucket over NCCL/NVLink; no-op at N=1
+        reduce_grads()
         return float(loss.detach()) if sync_loss else loss
 
     graphed = GraphedStep(model, loss_of, params, margin=1.3, voxelizer=VOX) if args.mode == 'graph' else None
@@ -461,7 +475,7 @@ def run_ours(args):
         """graph step: the collated points (device or pinned-host tensor) are copied into the graph's input buffer, then ONE
         graph launch: voxelise + VFE -> rulebooks -> 20 x (conv, BN, ReLU) -> loss -> backward"""
         loss = graphed({'points': pts, 'batch_size': pb.batch_size, 'calib': pb.calib, 'aug_param': pb.aug_param})
-        parallel.allreduce_gradients(params, average=True)
+        reduce_grads()
         return loss
 
     # e2e upload targets: a ring of device buffers (what a prefetching loader keeps), so the timed loop allocates nothing
@@ -539,9 +553,11 @@ def run_ours(args):
     dev_allocs0 = torch.cuda.memory_stats(dev).get('num_device_alloc', 0)
     l0 = lib.vc_launch_count()
     t_wall = time.time()
+    del ar_events[:]
     ms_list = timed(args.steps, False)
     barrier()
     wall = time.time() - t_wall
+    ar_ms = sum(a.elapsed_time(e) for a, e in ar_events) / max(len(ar_events), 1) if ar_events else 0.0
     launches = (lib.vc_launch_count() - l0) / max(args.steps, 1)
     if graphed is not None:
         launches = graphed.launches_per_replay        # kernels of this library inside the captured step (counted at capture)
@@ -638,6 +654,39 @@ def run_ours(args):
                   'achieved_tflops': fl / (ms * 1e-3) / 1e12, 'peak_source': how,
                   'note': 'bytes = bf16 gathered rows + bf16 dout + P*8 + fp32 gradient; CUDA events inside the plan executor, kernels alone'}
 
+    # the same workload on BASELINE's wording of the grid, [41,1600,1408] (0.1 m z voxels; SURVEY §8d config 2 asks for both):
+    # its own model instance (sparse_shape is a model attribute) and captured step, N=1 only, same timing rules
+    grid41 = None
+    if world == 1 and graphed is not None and not args.no_grid41:
+        torch.manual_seed(666)
+        model41 = VirConvL8x(CFG, 8, [1408, 1600, 40], precision=args.precision).to(dev).train()
+        vs41 = (0.05, 0.05, 0.1)
+        vox41 = dict(VOX, voxel_size=vs41)
+        g41 = GraphedStep(model41, loss_of, list(model41.parameters()), margin=1.3, voxelizer=vox41)
+        pts41 = []
+        for i in range(POOL):
+            pb = scenes.make_points_batch(parallel.shard_scene_ids(i, rank, world, SCENES_PER_GPU), N_LIDAR, N_VIRTUAL, training=True,
+                                          voxel_size=vs41)
+            pts41.append((torch.from_numpy(pb.points).to(dev), pb))
+
+        def run41(n):
+            evs = []
+            for s_ in range(n):
+                flush_buf.zero_()
+                a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                pts, pb = pts41[s_ % POOL]
+                g41({'points': pts, 'batch_size': pb.batch_size, 'calib': pb.calib, 'aug_param': pb.aug_param})
+                e.record()
+                evs.append((a, e))
+            torch.cuda.synchronize()
+            return sum(a.elapsed_time(e) for a, e in evs) / n
+        run41(max(args.warmup, 3))
+        ms41 = run41(args.steps)
+        grid41 = {'value': scenes_per_step / (ms41 * 1e-3), 'unit': 'scenes/s', 'ms_per_step': ms41,
+                  'workload': WORKLOAD.replace('[81,1600,1408]', '[41,1600,1408]') + ' (z voxel 0.1 m)', 'captures': g41.recaptures}
+        del g41, model41, pts41
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -658,6 +707,7 @@ def run_ours(args):
             'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_step,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'scenes_per_step': scenes_per_step, 'parallelism': f'dp{world}',
+                       'allreduce_ms_per_step': ar_ms,       # gradient all-reduce (exposed: main stream, after the backward)
                        'host_path': ('whole step (forward + loss + backward) replayed as ONE CUDA graph: plan executor static mode, '
                                      'device row counts, no host synchronisation; %d capture(s)' % graphed.recaptures
                                      if graphed is not None else
@@ -676,8 +726,9 @@ def run_ours(args):
             'e2e': {'value': scenes_per_step / (ms_e2e * 1e-3), 'unit': 'scenes/s', 'ms_per_step': ms_e2e,
                     'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': 4 + 4 * 4, 'allocator_events_in_timed_region': e2e_allocs},
             'gpu_launches': launches, 'wall_s_timed_region': wall,
-            'value_wall_clock': scenes_per_step * args.steps / wall,      # includes the L2 flushes and inter-step gaps 'cuda_mallocs_in_timed_region': int(dev_allocs), 'clocks': clocks, 'roofline': roof,
-            'roofline_wgrad': roof_w, 'cpu_baseline': cpu_base}
+            'value_wall_clock': scenes_per_step * args.steps / wall,      # includes the L2 flushes and inter-step gaps
+            'cuda_mallocs_in_timed_region': int(dev_allocs), 'clocks': clocks, 'roofline': roof,
+            'roofline_wgrad': roof_w, 'value_grid41': grid41, 'cpu_baseline': cpu_base}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

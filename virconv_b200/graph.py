@@ -142,8 +142,13 @@ class GraphedStep:
     def _static_step(self, batch):
         out = self.model(self._static_batch(batch))
         loss = self.loss_fn(out)
-        loss.backward()
-        return loss
+        # torch.autograd.grad, not loss.backward(): no AccumulateGrad node takes part.  Those nodes remember the stream they
+        # were created on; one kept alive by an earlier eager step (created on the legacy default stream) would make the
+        # engine synchronise that stream with the capturing one — illegal during capture (cudaErrorStreamCaptureImplicit)
+        grads = torch.autograd.grad(loss, self.params, allow_unused=True)
+        for p, g in zip(self.params, grads):
+            p.grad = g
+        return loss.detach()
 
     def _capture(self, batch):
         torch.cuda.synchronize(self.dev)
