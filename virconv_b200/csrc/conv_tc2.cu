@@ -43,6 +43,7 @@ constexpr int P_THREADS = 32 * (P_WARP_PROD0 + P_GROUPS * P_PROD_WARPS);   // 73
 constexpr int P_MAX_STAGES = 16;
 constexpr int P_NTB = 4;                                        // neighbour-table buffers (<= 3 tiles loaded ahead)
 constexpr int P_ROWS_PER_PROD = TCM / P_PROD_WARPS;             // 16
+constexpr int P_INFLIGHT = 3;                                   // ring stages a producer warp keeps in flight (<= 3)
 constexpr int P_W_CHUNK = 16384;                                // bytes per bulk copy of the resident weight image
 constexpr int P_W_RESIDENT_MAX = 56 * 1024;
 constexpr int SMEM_BUDGET = 227 * 1024 - 4096;                  // dynamic shared memory per CTA (static part is small)
@@ -137,9 +138,10 @@ __global__ void __launch_bounds__(P_THREADS, 1) tc_conv_persist_kernel(const PAr
     }
     if (tid == P_WARP_MMA * 32) {
         for (int s = 0; s < S; ++s) {
-            // every producer thread of the stage's group (cp.async arrive) [+ one release arrive per producer warp for its
-            // zero stores] [+ the weight warp's expect_tx]
-            mbar_init(&full_bar[s], 32 * P_PROD_WARPS + (VC_P_SKIP ? P_PROD_WARPS : 0) + (wres ? 0 : 1));
+            // one arrive per producer WARP of the stage's group [+ the weight warp's expect_tx].  (Per-thread
+            // cp.async.mbarrier.arrive was the pipeline's bottleneck: 264 arrivals on one mbarrier cost ~550 ns per stage,
+            // whatever the copies themselves took — profiles/trace_tc2_r2_b.txt vs profiles/exp_gather_paths_r2.txt)
+            mbar_init(&full_bar[s], P_PROD_WARPS + (wres ? 0 : 1));
             mbar_init(&empty_bar[s], 1);                       // tcgen05.commit
         }
         for (int b = 0; b < P_NTB; ++b) {
@@ -288,9 +290,30 @@ __global__ void __launch_bounds__(P_THREADS, 1) tc_conv_persist_kernel(const PAr
         (void)leader;
         int s = 0, wr = 0;     // ring slot and wrap count of the NEXT stage in sequence (all groups count every stage)
         int turn = 0;          // whose stage it is: group `turn`
+        // Completion: each stage is one cp.async group of the warp; up to P_INFLIGHT groups stay in flight, the oldest is
+        // retired with cp.async.wait_group + __syncwarp + ONE release arrive by lane 0 (which also publishes the warp's zero
+        // stores).  A warp never blocks on a barrier while it holds unsignalled stages (flush first): no deadlock by
+        // construction, whatever the ring depth.
+        int pend0 = 0, pend1 = 0, pend2 = 0, pend3 = 0, n_pend = 0;
+        // in-flight depth: the oldest group is signalled after `depth` more of the warp's own groups, i.e. depth x groups ring
+        // stages later — it must stay below the ring depth or the producers would run into their own unsignalled stages
+        const int depth = max(1, min(P_INFLIGHT, S / P_GROUPS - 1));
+        auto retire = [&]() {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_bar[pend0]);
+            pend0 = pend1; pend1 = pend2; pend2 = pend3;
+            --n_pend;
+        };
+        auto flush = [&]() {
+            cp_async_wait<0>();
+            while (n_pend > 0) retire();
+        };
         for (int it = 0;; ++it) {
             const int tb = it % ntb;
-            P_WAIT(&tbl_full[tb], (uint32_t)((it / ntb) & 1), 0x111);
+            if (!mbar_try(&tbl_full[tb], (uint32_t)((it / ntb) & 1))) {
+                flush();
+                P_WAIT(&tbl_full[tb], (uint32_t)((it / ntb) & 1), 0x111);
+            }
             if (tile_s[tb] < 0) break;
             const int* tbl = nbr_s + (size_t)tb * K * TCM;
             for (int t0 = 0; t0 < K; t0 += C::G) {
@@ -302,7 +325,10 @@ __global__ void __launch_bounds__(P_THREADS, 1) tc_conv_persist_kernel(const PAr
 #pragma unroll
                         for (int i = 0; i < NIT; ++i) src[g][i] = g < cnt ? tbl[(t0 + g) * TCM + rows[i]] : -1;
                     }
-                    if (wr > 0) P_WAIT(&empty_bar[s], (uint32_t)((wr - 1) & 1), 0x112);
+                    if (wr > 0 && !mbar_try(&empty_bar[s], (uint32_t)((wr - 1) & 1))) {
+                        flush();
+                        P_WAIT(&empty_bar[s], (uint32_t)((wr - 1) & 1), 0x112);
+                    }
                     const uint32_t st_s = ring_s + (uint32_t)s * stage_bytes;
 #pragma unroll
                     for (int g = 0; g < C::G; ++g) {
@@ -325,12 +351,13 @@ __global__ void __launch_bounds__(P_THREADS, 1) tc_conv_persist_kernel(const PAr
                             }
                         }
                     }
-                    cp_async_arrive_noinc(&full_bar[s]);
-#if VC_P_SKIP
-                    // the zero stores are ordinary shared-memory writes: published by a release arrive of the warp
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&full_bar[s]);
-#endif
+                    cp_async_commit();
+                    if (n_pend == 0) pend0 = s; else if (n_pend == 1) pend1 = s; else if (n_pend == 2) pend2 = s; else pend3 = s;
+                    ++n_pend;
+                    if (n_pend > depth) {
+                        if (depth == 3) cp_async_wait<3>(); else if (depth == 2) cp_async_wait<2>(); else cp_async_wait<1>();
+                        retire();
+                    }
                     if (leader) P_TRACE(1, tr);
                 }
                 if (++turn == P_GROUPS) turn = 0;
@@ -342,6 +369,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) tc_conv_persist_kernel(const PAr
             __syncwarp();
             if (lane == 0) mbar_arrive(&tbl_empty[tb]);
         }
+        flush();
     } else if (warp == P_WARP_W) {
         // ------------------------------------------------------------ weight slices (TMA engine, linear bulk copies)
         if (wres) {

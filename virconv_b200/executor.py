@@ -203,7 +203,9 @@ def _arena_bytes(plan, n0, device, with_bwd=True):
     if per_row:
         want = int(1.3 * per_row * int(n0)) + (32 << 20)
     else:
-        want = int(n0) * (24576 if with_bwd else 12288) + (128 << 20)
+        # (fixed part: bitmaps / hash tables / weight images / per-layer scratch do not shrink with the batch — a 14 k-voxel
+        #  training step uses 540 MB, an 80 k-voxel one 1.1 GB)
+        want = int(n0) * (24576 if with_bwd else 12288) + ((384 if with_bwd else 192) << 20)
     want = max(want, plan.arena_bytes.get(key, 0))
     want = (want + ARENA_GRAIN - 1) // ARENA_GRAIN * ARENA_GRAIN
     plan.arena_bytes[key] = want
@@ -486,14 +488,6 @@ class PlanFn(torch.autograd.Function):
                                      static.caps_array().ctypes.data if static is not None else None,
                                      static.n_dev.data_ptr() if static is not None else None,
                                      static.overflow.data_ptr() if static is not None else None, side2)
-            if rc == 0 and with_bwd and attempt < 2 and (dev.index, True) not in plan.arena_used:
-                # first training step of a plan: the backward bump-allocates from the same arena (it cannot be restarted, the
-                # forward's tensors live there) and needs about as much again as the forward took — make sure of it now
-                out = (ctypes.c_longlong * 8)()
-                check(lib.vc_exec_query(state.ctypes.data, 0, 0, out), 'vc_exec_query')
-                if arena.numel() < 2 * int(out[0]) + (64 << 20):
-                    plan.arena_bytes[(dev.index, True)] = int(2.3 * int(out[0])) + (128 << 20)
-                    continue
             if rc != VC_ERR_WORKSPACE:
                 break
             # too small (first use of a plan on an unusually dense batch): the call is restartable — nothing it enqueued is
