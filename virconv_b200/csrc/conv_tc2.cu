@@ -299,6 +299,9 @@ __global__ void __launch_bounds__(P_THREADS, 1) tc_conv_persist_kernel(const PAr
         // stages later — it must stay below the ring depth or the producers would run into their own unsignalled stages
         const int depth = max(1, min(P_INFLIGHT, S / P_GROUPS - 1));
         auto retire = [&]() {
+            // the WRITER makes its generic-proxy writes (cp.async, st.shared) visible to the tensor core's async proxy, then
+            // signals: the MMA warp needs no proxy fence of its own (one there sat in the pipeline's critical path)
+            fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&full_bar[pend0]);
             pend0 = pend1; pend1 = pend2; pend2 = pend3;
@@ -341,7 +344,12 @@ __global__ void __launch_bounds__(P_THREADS, 1) tc_conv_persist_kernel(const PAr
 #pragma unroll
                                 for (int cg = 0; cg < NCG; ++cg) {
                                     const bool vc = v && ch_ok[cg];
-#if VC_P_SKIP
+#if defined(VC_DBG_NO_COPY)
+                                    if (!vc) sts_zero16(a_s + dst_off[i][cg]);
+#elif defined(VC_DBG_LINEAR_DST)
+                                    if (vc) cp_async16_s(a_s + (uint32_t)((rows[i] * C::CPR + cg * CW + c_sub) * 16), srow + cg * CW * 8, true);
+                                    else sts_zero16(a_s + dst_off[i][cg]);
+#elif VC_P_SKIP
                                     if (vc) cp_async16_s(a_s + dst_off[i][cg], srow + cg * CW * 8, true);
                                     else sts_zero16(a_s + dst_off[i][cg]);
 #else
@@ -426,7 +434,9 @@ __global__ void __launch_bounds__(P_THREADS, 1) tc_conv_persist_kernel(const PAr
             for (int t0 = 0; t0 < K; t0 += C::G) {
                 const int cnt = min(C::G, K - t0);
                 P_WAIT(&full_bar[s], ph, 0x134);
-                fence_async_smem();     // generic-proxy (cp.async, st.shared) writes -> visible to the tensor core's async proxy
+#ifdef VC_DBG_FENCE_IN_MMA
+                fence_async_smem();
+#endif
                 tc_fence_after();
                 if (lane == 0) {
                     const uint32_t st_s = smem_u32(ring) + (uint32_t)s * stage_bytes;
@@ -434,6 +444,9 @@ __global__ void __launch_bounds__(P_THREADS, 1) tc_conv_persist_kernel(const PAr
                         const uint32_t a0 = st_s + (uint32_t)g * C::A_BYTES;
                         const uint32_t b0 = wres ? smem_u32(wimg_s) + (uint32_t)((t0 + g) * C::B_BYTES)
                                                  : st_s + C::G * C::A_BYTES + (uint32_t)g * C::B_BYTES;
+#ifdef VC_DBG_NO_MMA
+                        if (t0 == 0 && g == 0)
+#endif
 #pragma unroll
                         for (int m = 0; m < KC / 16; ++m)
                             umma_f16(acc, umma_desc_sw<C::ROWB>(a0 + m * 32), umma_desc_sw<C::ROWB>(b0 + m * 32), IDESC,

@@ -255,6 +255,9 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_persist_kernel(const WA
         // stages later — it must stay below the ring depth or the producers would run into their own unsignalled stages
         const int depth = max(1, min(W_INFLIGHT, S / W_GROUPS - 1));
         auto retire = [&]() {
+            // the WRITER makes its generic-proxy writes (cp.async, st.shared) visible to the tensor core's async proxy, then
+            // signals: the MMA warp needs no proxy fence of its own (one there sat in the pipeline's critical path)
+            fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(pend0 >= 16 ? &dout_full[pend0 - 16] : &full_bar[pend0]);
             pend0 = pend1; pend1 = pend2; pend2 = pend3;
@@ -358,7 +361,6 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_persist_kernel(const WA
             W_WAIT(&dout_full[db], (uint32_t)((it >> 1) & 1), 0x222);
             for (int g = 0; g < g_count; ++g) {
                 W_WAIT(&full_bar[s], ph, 0x223);
-                fence_async_smem();
                 tc_fence_after();
                 if (lane == 0) {
                     const uint32_t a0 = smem_u32(ring) + (uint32_t)s * C::STAGE;
