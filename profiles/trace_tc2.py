@@ -39,16 +39,25 @@ for li in [int(x) for x in os.environ.get('LAYERS', '2,6,10').split(',')]:
     fb = ops.cast_bf16(feats)
     ops.conv_forward(feats, weight, rb, None, prec, fb)
     for cold in (1, 0):
-        trace = torch.zeros(7 * 256, dtype=torch.int64, device=dev)
+        trace = torch.zeros(9 * 256, dtype=torch.int64, device=dev)
         if cold:
             flush.zero_()
         assert lib.vc_debug_set_trace2(trace.data_ptr()) == 0
         ops.conv_forward(feats, weight, rb, None, prec, fb)
         torch.cuda.synchronize()
         lib.vc_debug_set_trace2(None)
-        t = trace.cpu().numpy().reshape(7, 256)
+        t = trace.cpu().numpy().reshape(9, 256)
         t0 = t[6][0]
         print(f'layer {li}: {weight.shape[-1]}->{weight.shape[0]} K={rb.K} N={rb.n_out} {"L2 flushed" if cold else "warm"} (ns since CTA 0 start)')
         for r in range(7):
             v = t[r][t[r] > 0] - t0
             print(f'  {names[r]:16s} n={len(v):3d}: ' + ' '.join(str(int(x)) for x in v[:40]))
+        # SM-clock phase stamps inside a stage (cycles since the role's first stamp)
+        for r, nph, what in ((7, 4, 'producer leader [top, slot free, copies issued, retired]'), (8, 3, 'MMA thread [before wait, landed, issued]')):
+            v = t[r][t[r] > 0]
+            if len(v):
+                v = v - v[0]
+                rows = [' '.join('%6d' % int(x) for x in v[i:i + nph]) for i in range(0, min(len(v), nph * 24), nph)]
+                print(f'  cycles, {what}:')
+                for row in rows:
+                    print('      ' + row)

@@ -91,9 +91,18 @@ __device__ __forceinline__ void ptrace(int role, int& idx) {
         ++idx;
     }
 }
+// roles 7 (producer leader) and 8 (MMA thread): SM-clock stamps of the phases inside one ring stage
+__device__ __forceinline__ void pclock(int role, int& idx) {
+    if (g_trace2 != nullptr && blockIdx.x == 0 && idx < 256) {
+        g_trace2[role * 256 + idx] = clock64();
+        ++idx;
+    }
+}
 #define P_TRACE(role, idx) ptrace(role, idx)
+#define P_CLOCK(role, idx) pclock(role, idx)
 #else
 #define P_TRACE(role, idx) do { } while (0)
+#define P_CLOCK(role, idx) do { } while (0)
 #endif
 
 #define P_WAIT(bar, parity, code)                                     \
@@ -127,8 +136,8 @@ __global__ void __launch_bounds__(P_THREADS, 1) tc_conv_persist_kernel(const PAr
     __shared__ double red_s[2][TCM];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    int tr = 0, tr2 = 0;      // trace cursors (debug build)
-    (void)tr; (void)tr2;
+    int tr = 0, tr2 = 0, tr3 = 0;      // trace cursors (debug build)
+    (void)tr; (void)tr2; (void)tr3;
     if (tid == 0) P_TRACE(6, tr);
 
     if (warp == 0) {
@@ -321,6 +330,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) tc_conv_persist_kernel(const PAr
             const int* tbl = nbr_s + (size_t)tb * K * TCM;
             for (int t0 = 0; t0 < K; t0 += C::G) {
                 if (turn == grp) {
+                    if (leader) P_CLOCK(7, tr3);                                  // phase 0: stage loop top
                     const int cnt = min(C::G, K - t0);
                     int src[C::G][NIT];
 #pragma unroll
@@ -332,6 +342,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) tc_conv_persist_kernel(const PAr
                         flush();
                         P_WAIT(&empty_bar[s], (uint32_t)((wr - 1) & 1), 0x112);
                     }
+                    if (leader) P_CLOCK(7, tr3);                                  // phase 1: ring slot free
                     const uint32_t st_s = ring_s + (uint32_t)s * stage_bytes;
 #pragma unroll
                     for (int g = 0; g < C::G; ++g) {
@@ -359,6 +370,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) tc_conv_persist_kernel(const PAr
                             }
                         }
                     }
+                    if (leader) P_CLOCK(7, tr3);                                  // phase 2: copies issued
                     cp_async_commit();
                     if (n_pend == 0) pend0 = s; else if (n_pend == 1) pend1 = s; else if (n_pend == 2) pend2 = s; else pend3 = s;
                     ++n_pend;
@@ -366,6 +378,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) tc_conv_persist_kernel(const PAr
                         if (depth == 3) cp_async_wait<3>(); else if (depth == 2) cp_async_wait<2>(); else cp_async_wait<1>();
                         retire();
                     }
+                    if (leader) P_CLOCK(7, tr3);                                  // phase 3: oldest group retired
                     if (leader) P_TRACE(1, tr);
                 }
                 if (++turn == P_GROUPS) turn = 0;
@@ -433,7 +446,9 @@ __global__ void __launch_bounds__(P_THREADS, 1) tc_conv_persist_kernel(const PAr
             const uint32_t acc = tmem_base + (uint32_t)(ab * NR);
             for (int t0 = 0; t0 < K; t0 += C::G) {
                 const int cnt = min(C::G, K - t0);
+                if (lane == 0) P_CLOCK(8, tr3);                                       // phase 0: before the wait
                 P_WAIT(&full_bar[s], ph, 0x134);
+                if (lane == 0) P_CLOCK(8, tr3);                                       // phase 1: stage landed
 #ifdef VC_DBG_FENCE_IN_MMA
                 fence_async_smem();
 #endif
@@ -453,6 +468,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) tc_conv_persist_kernel(const PAr
                                      (t0 > 0 || g > 0 || m > 0) ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[s]);
+                    P_CLOCK(8, tr3);                                                  // phase 2: MMAs + commit issued
                     P_TRACE(2, tr);
                     if (t0 + cnt >= K) {
                         umma_commit(&acc_full[ab]);

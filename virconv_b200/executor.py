@@ -424,8 +424,10 @@ class StaticSpec:
     (the feature / coordinate tensors passed to the plan are then CAPACITY sized), `caps` {index-set id: row capacity} for
     the strided convs' output sets, `overflow` int32[1] device tensor receiving the largest row count that did not fit."""
 
-    def __init__(self, n_dev, caps, overflow):
+    def __init__(self, n_dev, caps, overflow, alias_params=False):
         self.n_dev, self.caps, self.overflow = n_dev, dict(caps), overflow
+        self.alias_params = alias_params      # differentiate w.r.t. per-call leaf aliases of the parameters (run_plan)
+        self.param_aliases = {}
         self._arr = None
 
     def caps_array(self):
@@ -553,8 +555,17 @@ def run_plan(plan, feats, coords_i32, spatial_shape, batch_size, proj, training,
     holder = []
     # the arena also holds what a backward saves / stages: sized for it whenever autograd will record this call
     with_bwd = bool(training) or (torch.is_grad_enabled() and (feats.requires_grad or any(p.requires_grad for p in plan.params())))
+    params = plan.params()
+    if static is not None and with_bwd and static.alias_params:
+        # Fresh leaf aliases of the parameters (same storage) for this call.  autograd keeps ONE AccumulateGrad node per leaf
+        # alive as long as any earlier graph is, and that node remembers the stream it was created on: a node born in an eager
+        # step on the legacy default stream makes the engine synchronise that stream with the capturing one — illegal during
+        # CUDA-graph capture (cudaErrorStreamCaptureImplicit).  graph.GraphedStep differentiates w.r.t. the aliases.
+        aliases = [p.detach().requires_grad_(True) for p in params]
+        static.param_aliases = {id(p): a for p, a in zip(params, aliases)}
+        params = aliases
     outs = PlanFn.apply(plan, holder, feats, coords_i32, list(spatial_shape), batch_size, proj, training, precision,
-                        bool(inputs_ready), static, with_bwd, *plan.params())
+                        bool(inputs_ready), static, with_bwd, *params)
     run = holder[0]
     res = {}
     for (name, slot, iset), f in zip(plan.published, outs):

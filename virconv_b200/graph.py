@@ -100,7 +100,7 @@ class GraphedStep:
         self.ovf_host = torch.zeros(8, dtype=torch.int32).pin_memory()
         self.err_host = torch.zeros(8, dtype=torch.int32).pin_memory()
         self._pending, self._slot = [], 0
-        self.spec = executor.StaticSpec(self.n_dev, self.caps, self.overflow)
+        self.spec = executor.StaticSpec(self.n_dev, self.caps, self.overflow, alias_params=True)
 
     def _load(self, batch):
         """Copy one batch into the graph's input buffers (asynchronous, current stream)."""
@@ -142,10 +142,10 @@ class GraphedStep:
     def _static_step(self, batch):
         out = self.model(self._static_batch(batch))
         loss = self.loss_fn(out)
-        # torch.autograd.grad, not loss.backward(): no AccumulateGrad node takes part.  Those nodes remember the stream they
-        # were created on; one kept alive by an earlier eager step (created on the legacy default stream) would make the
-        # engine synchronise that stream with the capturing one — illegal during capture (cudaErrorStreamCaptureImplicit)
-        grads = torch.autograd.grad(loss, self.params, allow_unused=True)
+        # torch.autograd.grad w.r.t. the per-call leaf aliases the executor made of the parameters (executor.run_plan): no
+        # long-lived AccumulateGrad node (which remembers the stream it was created on) takes part in a captured backward
+        alias = getattr(self.spec, 'param_aliases', {})
+        grads = torch.autograd.grad(loss, [alias.get(id(p), p) for p in self.params], allow_unused=True)
         for p, g in zip(self.params, grads):
             p.grad = g
         return loss.detach()
