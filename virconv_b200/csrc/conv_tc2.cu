@@ -453,7 +453,8 @@ __global__ void __launch_bounds__(P_THREADS, 1) tc_conv_persist_kernel(const PAr
                 fence_async_smem();
 #endif
                 tc_fence_after();
-                if (lane == 0) {
+                {
+                    // all 32 lanes run this block converged (uniform values -> uniform registers); one elected lane issues
                     const uint32_t st_s = smem_u32(ring) + (uint32_t)s * stage_bytes;
                     for (int g = 0; g < cnt; ++g) {
                         const uint32_t a0 = st_s + (uint32_t)g * C::A_BYTES;
@@ -464,15 +465,17 @@ __global__ void __launch_bounds__(P_THREADS, 1) tc_conv_persist_kernel(const PAr
 #endif
 #pragma unroll
                         for (int m = 0; m < KC / 16; ++m)
-                            umma_f16(acc, umma_desc_sw<C::ROWB>(a0 + m * 32), umma_desc_sw<C::ROWB>(b0 + m * 32), IDESC,
-                                     (t0 > 0 || g > 0 || m > 0) ? 1u : 0u);
+                            umma_f16_elect(acc, umma_desc_sw<C::ROWB>(a0 + m * 32), umma_desc_sw<C::ROWB>(b0 + m * 32), IDESC,
+                                           (t0 > 0 || g > 0 || m > 0) ? 1u : 0u);
                     }
-                    umma_commit(&empty_bar[s]);
-                    P_CLOCK(8, tr3);                                                  // phase 2: MMAs + commit issued
-                    P_TRACE(2, tr);
+                    umma_commit_elect(&empty_bar[s]);
+                    if (lane == 0) {
+                        P_CLOCK(8, tr3);                                              // phase 2: MMAs + commit issued
+                        P_TRACE(2, tr);
+                    }
                     if (t0 + cnt >= K) {
-                        umma_commit(&acc_full[ab]);
-                        P_TRACE(3, tr2);
+                        umma_commit_elect(&acc_full[ab]);
+                        if (lane == 0) P_TRACE(3, tr2);
                     }
                 }
                 __syncwarp();

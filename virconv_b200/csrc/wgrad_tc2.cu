@@ -362,17 +362,17 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_persist_kernel(const WA
             for (int g = 0; g < g_count; ++g) {
                 W_WAIT(&full_bar[s], ph, 0x223);
                 tc_fence_after();
-                if (lane == 0) {
+                {
+                    // all lanes converged, one elected lane issues (see umma_f16_elect)
                     const uint32_t a0 = smem_u32(ring) + (uint32_t)s * C::STAGE;
                     const uint32_t b0 = smem_u32(dout_s) + (uint32_t)db * C::B_BYTES;
 #pragma unroll
                     for (int j = 0; j < 8; ++j)      // 16 rows (two 8-row groups) per MMA
-                        umma_f16(tmem_base + (uint32_t)(g * CO), umma_desc_mn<C::RA>(a0 + j * 16 * C::RA, C::A_BYTES),
-                                 umma_desc_mn<C::RB>(b0 + j * 16 * C::RB, 0), IDESC, (it == 0 && j == 0) ? 0u : 1u);
-                    umma_commit(&empty_bar[s]);
-                    if (g == g_count - 1) umma_commit(&dout_empty[db]);
+                        umma_f16_elect(tmem_base + (uint32_t)(g * CO), umma_desc_mn<C::RA>(a0 + j * 16 * C::RA, C::A_BYTES),
+                                       umma_desc_mn<C::RB>(b0 + j * 16 * C::RB, 0), IDESC, (it == 0 && j == 0) ? 0u : 1u);
+                    umma_commit_elect(&empty_bar[s]);
+                    if (g == g_count - 1) umma_commit_elect(&dout_empty[db]);
                 }
-                __syncwarp();
                 if (++s == S) {
                     s = 0;
                     ph ^= 1u;
@@ -380,11 +380,11 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_persist_kernel(const WA
             }
             ++n_done;
         }
+        if (n_done > 0) umma_commit_elect(&final_bar);     // arrives when every MMA of this CTA has completed
         if (lane == 0) {
             started_s = n_done;
-            if (n_done > 0) umma_commit(&final_bar);   // arrives when every MMA of this CTA has completed
-            else mbar_arrive(&final_bar);              // (a CTA that was handed no tile has nothing in flight)
-            mbar_arrive(&meta_bar);                    // publishes started_s (release)
+            if (n_done == 0) mbar_arrive(&final_bar);       // (a CTA that was handed no tile has nothing in flight)
+            mbar_arrive(&meta_bar);                         // publishes started_s (release)
         }
     } else {
         // ------------------------------------------------------------ epilogue (once, at the end): TMEM -> vector reductions

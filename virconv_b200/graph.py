@@ -95,8 +95,14 @@ class GraphedStep:
         self.n_dev = torch.zeros(1, dtype=torch.int32, device=dev)
         self.overflow = torch.zeros(1, dtype=torch.int32, device=dev)
         self.proj = torch.zeros((B, 28), dtype=torch.float32, device=dev)
-        self.proj_host = torch.zeros((B, 28), dtype=torch.float32).pin_memory()
-        self.n_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        # pinned staging for the small per-step host values: a ring of slots, each guarded by an event recorded after its
+        # upload — the host runs several replays ahead of the GPU, and rewriting ONE pinned buffer before the previous
+        # step's asynchronous copy has executed would hand that step the next step's row count / projection
+        self.STAGE_SLOTS = 8
+        self.proj_host = torch.zeros((self.STAGE_SLOTS, B, 28), dtype=torch.float32).pin_memory()
+        self.n_host = torch.zeros((self.STAGE_SLOTS, 1), dtype=torch.int32).pin_memory()
+        self._stage_ev = [None] * self.STAGE_SLOTS
+        self._stage = 0
         self.ovf_host = torch.zeros(8, dtype=torch.int32).pin_memory()
         self.err_host = torch.zeros(8, dtype=torch.int32).pin_memory()
         self._pending, self._slot = [], 0
@@ -118,13 +124,21 @@ class GraphedStep:
             n = vf.shape[0]
             if n > self.cap0:
                 return False
+        slot = self._stage
+        self._stage = (slot + 1) % self.STAGE_SLOTS
+        if self._stage_ev[slot] is not None:
+            self._stage_ev[slot].synchronize()         # (8 steps back: has long completed unless the GPU is far behind)
+        if self.vox is None:
             self.vf[:n].copy_(vf, non_blocking=True)
             self.vc[:n].copy_(vc, non_blocking=True)
-            self.n_host[0] = n
-            self.n_dev.copy_(self.n_host, non_blocking=True)
+            self.n_host[slot, 0] = n
+            self.n_dev.copy_(self.n_host[slot], non_blocking=True)
         trans = batch.get('aug_param')
-        self.proj_host.copy_(torch.from_numpy(ops.projection_params_host(batch['calib'], trans, self.B)))
-        self.proj.copy_(self.proj_host, non_blocking=True)
+        self.proj_host[slot].copy_(torch.from_numpy(ops.projection_params_host(batch['calib'], trans, self.B)))
+        self.proj.copy_(self.proj_host[slot], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._stage_ev[slot] = ev
         return True
 
     def _static_batch(self, batch):
@@ -133,10 +147,12 @@ class GraphedStep:
             v = self.vox
             f, c, num, n_dev = ops.voxelize_mean(self.pts, self.B, v['point_cloud_range'], v['voxel_size'], v['max_points_per_voxel'],
                                                  v['max_voxels'], v['vfe_model'], static=True)
-            spec = executor.StaticSpec(n_dev, self.caps, self.overflow)
+            spec = executor.StaticSpec(n_dev, self.caps, self.overflow, alias_params=True)
             bd.update(voxel_features=f, voxel_coords=c, voxel_num_points=num, virconv_static=spec, virconv_proj=self.proj)
         else:
-            bd.update(voxel_features=self.vf, voxel_coords=self.vc, virconv_static=self.spec, virconv_proj=self.proj)
+            spec = self.spec
+            bd.update(voxel_features=self.vf, voxel_coords=self.vc, virconv_static=spec, virconv_proj=self.proj)
+        self._cur_spec = spec
         return bd
 
     def _static_step(self, batch):
@@ -144,7 +160,7 @@ class GraphedStep:
         loss = self.loss_fn(out)
         # torch.autograd.grad w.r.t. the per-call leaf aliases the executor made of the parameters (executor.run_plan): no
         # long-lived AccumulateGrad node (which remembers the stream it was created on) takes part in a captured backward
-        alias = getattr(self.spec, 'param_aliases', {})
+        alias = self._cur_spec.param_aliases
         grads = torch.autograd.grad(loss, [alias.get(id(p), p) for p in self.params], allow_unused=True)
         for p, g in zip(self.params, grads):
             p.grad = g
