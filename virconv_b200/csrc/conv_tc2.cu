@@ -43,7 +43,13 @@ constexpr int P_THREADS = 32 * (P_WARP_PROD0 + P_GROUPS * P_PROD_WARPS);   // 73
 constexpr int P_MAX_STAGES = 16;
 constexpr int P_NTB = 4;                                        // neighbour-table buffers (<= 3 tiles loaded ahead)
 constexpr int P_ROWS_PER_PROD = TCM / P_PROD_WARPS;             // 16
-constexpr int P_INFLIGHT = 3;                                   // ring stages a producer warp keeps in flight (<= 3)
+#ifndef VC_P_ARRIVE
+#define VC_P_ARRIVE 0            // 0: cp.async.mbarrier.arrive.noinc per producer thread (hardware-tracked completion, no lag)
+#endif                           // 1: one arrive per warp after cp.async.wait_group (VC_P_INFLIGHT own stages of lag)
+#ifndef VC_P_INFLIGHT
+#define VC_P_INFLIGHT 1
+#endif
+constexpr int P_INFLIGHT = VC_P_INFLIGHT;                       // (mode 1) ring stages a producer warp keeps in flight (<= 3)
 constexpr int P_W_CHUNK = 16384;                                // bytes per bulk copy of the resident weight image
 constexpr int P_W_RESIDENT_MAX = 56 * 1024;
 constexpr int SMEM_BUDGET = 227 * 1024 - 4096;                  // dynamic shared memory per CTA (static part is small)
@@ -150,7 +156,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) tc_conv_persist_kernel(const PAr
             // one arrive per producer WARP of the stage's group [+ the weight warp's expect_tx].  (Per-thread
             // cp.async.mbarrier.arrive was the pipeline's bottleneck: 264 arrivals on one mbarrier cost ~550 ns per stage,
             // whatever the copies themselves took — profiles/trace_tc2_r2_b.txt vs profiles/exp_gather_paths_r2.txt)
-            mbar_init(&full_bar[s], P_PROD_WARPS + (wres ? 0 : 1));
+            mbar_init(&full_bar[s], (VC_P_ARRIVE ? P_PROD_WARPS : 32 * P_PROD_WARPS + (VC_P_SKIP ? P_PROD_WARPS : 0)) + (wres ? 0 : 1));
             mbar_init(&empty_bar[s], 1);                       // tcgen05.commit
         }
         for (int b = 0; b < P_NTB; ++b) {
@@ -317,8 +323,10 @@ __global__ void __launch_bounds__(P_THREADS, 1) tc_conv_persist_kernel(const PAr
             --n_pend;
         };
         auto flush = [&]() {
+#if VC_P_ARRIVE
             cp_async_wait<0>();
             while (n_pend > 0) retire();
+#endif
         };
         for (int it = 0;; ++it) {
             const int tb = it % ntb;
@@ -371,6 +379,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) tc_conv_persist_kernel(const PAr
                         }
                     }
                     if (leader) P_CLOCK(7, tr3);                                  // phase 2: copies issued
+#if VC_P_ARRIVE
                     cp_async_commit();
                     if (n_pend == 0) pend0 = s; else if (n_pend == 1) pend1 = s; else if (n_pend == 2) pend2 = s; else pend3 = s;
                     ++n_pend;
@@ -378,6 +387,13 @@ __global__ void __launch_bounds__(P_THREADS, 1) tc_conv_persist_kernel(const PAr
                         if (depth == 3) cp_async_wait<3>(); else if (depth == 2) cp_async_wait<2>(); else cp_async_wait<1>();
                         retire();
                     }
+#else
+                    cp_async_arrive_noinc(&full_bar[s]);       // fires when this thread's copies of the stage have landed
+#if VC_P_SKIP
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full_bar[s]);  // release: publishes the warp's zero stores
+#endif
+#endif
                     if (leader) P_CLOCK(7, tr3);                                  // phase 3: oldest group retired
                     if (leader) P_TRACE(1, tr);
                 }
@@ -449,8 +465,8 @@ __global__ void __launch_bounds__(P_THREADS, 1) tc_conv_persist_kernel(const PAr
                 if (lane == 0) P_CLOCK(8, tr3);                                       // phase 0: before the wait
                 P_WAIT(&full_bar[s], ph, 0x134);
                 if (lane == 0) P_CLOCK(8, tr3);                                       // phase 1: stage landed
-#ifdef VC_DBG_FENCE_IN_MMA
-                fence_async_smem();
+#if !VC_P_ARRIVE
+                fence_async_smem();     // generic-proxy (cp.async, st.shared) writes -> visible to the tensor core's async proxy
 #endif
                 tc_fence_after();
                 {
