@@ -444,6 +444,10 @@ __global__ void __launch_bounds__(P_THREADS, 1) tc_conv_persist_kernel(const PAr
     } else if (warp == P_WARP_MMA) {
         // ------------------------------------------------------------ MMA issuer
         constexpr uint32_t IDESC = umma_idesc(TCM, NR);
+        constexpr uint32_t DHI = umma_desc_hi<C::ROWB>();
+        // shared-window addresses once, outside the loops (see tc_common.cuh: the MMA warp's instruction count is the budget)
+        const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]), accf0 = smem_u32(&acc_full[0]);
+        const uint32_t ring_a = smem_u32(ring), wimg_a = smem_u32(wimg_s);
         int s = 0;
         uint32_t ph = 0;
         bool w_ready = !wres;
@@ -463,38 +467,36 @@ __global__ void __launch_bounds__(P_THREADS, 1) tc_conv_persist_kernel(const PAr
             for (int t0 = 0; t0 < K; t0 += C::G) {
                 const int cnt = min(C::G, K - t0);
                 if (lane == 0) P_CLOCK(8, tr3);                                       // phase 0: before the wait
-                P_WAIT(&full_bar[s], ph, 0x134);
+                if (!mbar_spin(full0 + 8u * s, ph, 4096u) && !mbar_wait_t_addr(full0 + 8u * s, ph, a.err, 0x134)) goto done;
                 if (lane == 0) P_CLOCK(8, tr3);                                       // phase 1: stage landed
 #if !VC_P_ARRIVE
                 fence_async_smem();     // generic-proxy (cp.async, st.shared) writes -> visible to the tensor core's async proxy
 #endif
                 tc_fence_after();
                 {
-                    // all 32 lanes run this block converged (uniform values -> uniform registers); one elected lane issues
-                    const uint32_t st_s = smem_u32(ring) + (uint32_t)s * stage_bytes;
-                    for (int g = 0; g < cnt; ++g) {
-                        const uint32_t a0 = st_s + (uint32_t)g * C::A_BYTES;
-                        const uint32_t b0 = wres ? smem_u32(wimg_s) + (uint32_t)((t0 + g) * C::B_BYTES)
-                                                 : st_s + C::G * C::A_BYTES + (uint32_t)g * C::B_BYTES;
+                    // all 32 lanes converged; per kernel offset ONE asm block with one elect issues its KC/16 MMAs
+                    const uint32_t st_s = ring_a + (uint32_t)s * stage_bytes;
+                    const uint32_t a_lo = st_s >> 4;
+                    const uint32_t b_lo = (wres ? wimg_a + (uint32_t)(t0 * C::B_BYTES) : st_s + C::G * C::A_BYTES) >> 4;
+#pragma unroll
+                    for (int g = 0; g < C::G; ++g) {
 #ifdef VC_DBG_NO_MMA
                         if (t0 == 0 && g == 0)
 #endif
-#pragma unroll
-                        for (int m = 0; m < KC / 16; ++m)
-                            umma_f16_elect(acc, umma_desc_sw<C::ROWB>(a0 + m * 32), umma_desc_sw<C::ROWB>(b0 + m * 32), IDESC,
-                                           (t0 > 0 || g > 0 || m > 0) ? 1u : 0u);
+                        if (g < cnt)
+                            umma_series<KC / 16, 2, 2>(acc, a_lo + (uint32_t)(g * (C::A_BYTES >> 4)), b_lo + (uint32_t)(g * (C::B_BYTES >> 4)), DHI,
+                                                       DHI, IDESC, (t0 > 0 || g > 0) ? 1u : 0u);
                     }
-                    umma_commit_elect(&empty_bar[s]);
+                    umma_commit_elect_addr(empty0 + 8u * s);
                     if (lane == 0) {
                         P_CLOCK(8, tr3);                                              // phase 2: MMAs + commit issued
                         P_TRACE(2, tr);
                     }
                     if (t0 + cnt >= K) {
-                        umma_commit_elect(&acc_full[ab]);
+                        umma_commit_elect_addr(accf0 + 8u * ab);
                         if (lane == 0) P_TRACE(3, tr2);
                     }
                 }
-                __syncwarp();
                 if (++s == S) {
                     s = 0;
                     ph ^= 1u;

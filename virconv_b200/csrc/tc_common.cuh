@@ -151,6 +151,121 @@ __device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
         ::"r"(smem_u32(bar))
         : "memory");
 }
+// ---- lean issue path for the MMA warp of the persistent kernels -----------------------------------------------------------
+// The MMA warp is ONE instruction stream per SM: at ~200 SASS instructions per ring stage (inlined timed wait, 64-bit
+// descriptor arithmetic in vector registers, five R2UR per MMA, address re-derivation for every barrier) it needed ~900 cycles
+// per 16 KB stage and was the bottleneck of the whole kernel (ncu source view, profiles/ncu_conv2_r2.txt).  These helpers keep
+// the hot path short: barrier addresses are precomputed shared-window offsets, the wait spins inside one asm block (the
+// time-bounded wait is the cold fall-back), and all MMAs of one kernel offset go out in one asm block with one elect.
+
+// up to `tries` probes inside one asm block; 1 when the phase completed
+__device__ __forceinline__ uint32_t mbar_spin(uint32_t bar_addr, uint32_t parity, uint32_t tries) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .u32 c;\n\t"
+        "mov.u32 c, 0;\n"
+        "VC_SPIN:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "@p bra VC_SPIN_DONE;\n\t"
+        "add.u32 c, c, 1;\n\t"
+        "setp.lt.u32 q, c, %3;\n\t"
+        "@q bra VC_SPIN;\n"
+        "VC_SPIN_DONE:\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar_addr), "r"(parity), "r"(tries)
+        : "memory");
+    return ok;
+}
+// time-bounded wait on a precomputed shared-window address (cold path behind mbar_spin)
+__device__ __forceinline__ bool mbar_wait_t_addr(uint32_t addr, uint32_t parity, int* err, int code) {
+    uint32_t done = 0;
+    unsigned long long t0 = 0;
+    for (unsigned spin = 0;; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return true;
+        if ((spin & 255u) == 255u) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 2000000000ULL) break;
+        }
+    }
+    if (err) atomicCAS(err, 0, code);
+    return false;
+}
+__device__ __forceinline__ void umma_commit_elect_addr(uint32_t bar_addr) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(bar_addr)
+        : "memory");
+}
+// high words of the shared-memory descriptors (constants of the layout): SBO | version | layout type
+template <int ROWB>
+__host__ __device__ constexpr uint32_t umma_desc_hi() {
+    return (uint32_t)((8 * ROWB) >> 4) | (1u << 14) | ((ROWB == 128 ? 2u : ROWB == 64 ? 4u : 6u) << 29);
+}
+// NK MMAs of one series from a converged warp (one elect): descriptor low words a_lo / b_lo (start address >> 4, plus the LBO
+// field where the layout has one) advance by STEP_A / STEP_B per MMA; the first MMA accumulates iff acc_first != 0
+template <int NK, int STEP_A, int STEP_B>
+__device__ __forceinline__ void umma_series(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t a_hi, uint32_t b_hi, uint32_t idesc,
+                                            uint32_t acc_first) {
+    static_assert(NK == 1 || NK == 2 || NK == 4 || NK == 8, "series length");
+#define VC_MMA_NEXT(I)                                                  \
+    "add.u32 al, %1, " #I "*%7;\n\tadd.u32 bl, %2, " #I "*%8;\n\t"      \
+    "mov.b64 da, {al, %3};\n\tmov.b64 db, {bl, %4};\n\t"               \
+    "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, t;\n\t"
+    if constexpr (NK == 1) {
+        asm volatile(
+            "{\n\t.reg .pred q, p;\n\t.reg .b64 da, db;\n\t"
+            "elect.sync _|q, 0xffffffff;\n\t"
+            "setp.ne.b32 p, %6, 0;\n\t"
+            "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %4};\n\t"
+            "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+            ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(a_hi), "r"(b_hi), "r"(idesc), "r"(acc_first), "n"(STEP_A), "n"(STEP_B)
+            : "memory");
+    } else if constexpr (NK == 2) {
+        asm volatile(
+            "{\n\t.reg .pred q, p, t;\n\t.reg .b64 da, db;\n\t.reg .b32 al, bl;\n\t"
+            "elect.sync _|q, 0xffffffff;\n\t"
+            "setp.ne.b32 p, %6, 0;\n\tsetp.eq.u32 t, 0, 0;\n\t"
+            "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %4};\n\t"
+            "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+            VC_MMA_NEXT(1) "}"
+            ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(a_hi), "r"(b_hi), "r"(idesc), "r"(acc_first), "n"(STEP_A), "n"(STEP_B)
+            : "memory");
+    } else if constexpr (NK == 4) {
+        asm volatile(
+            "{\n\t.reg .pred q, p, t;\n\t.reg .b64 da, db;\n\t.reg .b32 al, bl;\n\t"
+            "elect.sync _|q, 0xffffffff;\n\t"
+            "setp.ne.b32 p, %6, 0;\n\tsetp.eq.u32 t, 0, 0;\n\t"
+            "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %4};\n\t"
+            "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+            VC_MMA_NEXT(1) VC_MMA_NEXT(2) VC_MMA_NEXT(3) "}"
+            ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(a_hi), "r"(b_hi), "r"(idesc), "r"(acc_first), "n"(STEP_A), "n"(STEP_B)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred q, p, t;\n\t.reg .b64 da, db;\n\t.reg .b32 al, bl;\n\t"
+            "elect.sync _|q, 0xffffffff;\n\t"
+            "setp.ne.b32 p, %6, 0;\n\tsetp.eq.u32 t, 0, 0;\n\t"
+            "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %4};\n\t"
+            "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+            VC_MMA_NEXT(1) VC_MMA_NEXT(2) VC_MMA_NEXT(3) VC_MMA_NEXT(4) VC_MMA_NEXT(5) VC_MMA_NEXT(6) VC_MMA_NEXT(7) "}"
+            ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(a_hi), "r"(b_hi), "r"(idesc), "r"(acc_first), "n"(STEP_A), "n"(STEP_B)
+            : "memory");
+    }
+#undef VC_MMA_NEXT
+}
+
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     uint32_t r[16];
     asm volatile(

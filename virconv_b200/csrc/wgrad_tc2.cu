@@ -34,7 +34,6 @@ constexpr int W_THREADS = 32 * (W_WARP_PROD0 + W_GROUPS * W_PROD_WARPS);   // 70
 constexpr int W_PROD_THREADS = 32 * W_PROD_WARPS * W_GROUPS;
 constexpr int W_MAX_STAGES = 8;
 constexpr int W_NTB = 4;
-constexpr int W_INFLIGHT = 3;                                   // cp.async groups a producer warp keeps in flight (<= 3)
 constexpr int W_ROWS_PER_PROD = TCM / W_PROD_WARPS;             // 16
 constexpr int W_SMEM_BUDGET = 227 * 1024 - 4096;
 
@@ -113,8 +112,9 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_persist_kernel(const WA
     }
     if (tid == W_WARP_MMA * 32) {
         for (int s = 0; s < S; ++s) {
-            // one arrive per producer warp of the stage's group (see conv_tc2.cu: per-thread arrivals were the bottleneck)
-            mbar_init(&full_bar[s], W_PROD_WARPS);
+            // every producer thread of the stage's group (cp.async.mbarrier.arrive.noinc: fires when the thread's copies have
+            // landed) + one release arrive per warp for its zero stores
+            mbar_init(&full_bar[s], 32 * W_PROD_WARPS + (VC_P_SKIP ? W_PROD_WARPS : 0));
             mbar_init(&empty_bar[s], 1);                       // tcgen05.commit
         }
         for (int b = 0; b < W_NTB; ++b) {
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_persist_kernel(const WA
             mbar_init(&tbl_empty[b], W_GROUPS * W_PROD_WARPS + 1);   // producers + MMA warp
         }
         for (int b = 0; b < 2; ++b) {
-            mbar_init(&dout_full[b], W_GROUPS * W_PROD_WARPS); // every producer warp
+            mbar_init(&dout_full[b], W_PROD_THREADS);          // every producer thread (cp.async arrive)
             mbar_init(&dout_empty[b], 1);                      // tcgen05.commit
         }
         mbar_init(&final_bar, 1);
@@ -248,50 +248,16 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_persist_kernel(const WA
         for (int cg = 0; cg < NCG; ++cg) ch_ok[cg] = (cg * CW + c_sub) * 8 < a.in_c;
         const uint32_t ring_s = smem_u32(ring);
         int s = 0, wr = 0, turn = 0;
-        // completion signalling as in conv_tc2.cu: one cp.async group per ring stage (code = stage) or dout tile (code = 16 + db),
-        // up to W_INFLIGHT groups in flight per warp, ONE release arrive per warp when a group has landed
-        int pend0 = 0, pend1 = 0, pend2 = 0, pend3 = 0, n_pend = 0;
-        // in-flight depth: the oldest group is signalled after `depth` more of the warp's own groups, i.e. depth x groups ring
-        // stages later — it must stay below the ring depth or the producers would run into their own unsignalled stages
-        const int depth = max(1, min(W_INFLIGHT, S / W_GROUPS - 1));
-        auto retire = [&]() {
-            // the WRITER makes its generic-proxy writes (cp.async, st.shared) visible to the tensor core's async proxy, then
-            // signals: the MMA warp needs no proxy fence of its own (one there sat in the pipeline's critical path)
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(pend0 >= 16 ? &dout_full[pend0 - 16] : &full_bar[pend0]);
-            pend0 = pend1; pend1 = pend2; pend2 = pend3;
-            --n_pend;
-        };
-        auto flush = [&]() {
-            cp_async_wait<0>();
-            while (n_pend > 0) retire();
-        };
-        auto push = [&](int code) {
-            cp_async_commit();
-            if (n_pend == 0) pend0 = code; else if (n_pend == 1) pend1 = code; else if (n_pend == 2) pend2 = code; else pend3 = code;
-            ++n_pend;
-            if (n_pend > depth) {
-                if (depth == 3) cp_async_wait<3>(); else if (depth == 2) cp_async_wait<2>(); else cp_async_wait<1>();
-                retire();
-            }
-        };
         for (int it = 0;; ++it) {
             const int tb = it % ntb, db = it & 1;
-            if (!mbar_try(&tbl_full[tb], (uint32_t)((it / ntb) & 1))) {
-                flush();
-                W_WAIT(&tbl_full[tb], (uint32_t)((it / ntb) & 1), 0x211);
-            }
+            W_WAIT(&tbl_full[tb], (uint32_t)((it / ntb) & 1), 0x211);
             const int tile = tile_s[tb];
             if (tile < 0) break;
             const int* tbl = nbr_s + (size_t)tb * k_count * TCM;
             const int base = tile * TCM;
             // the tile of dout (second operand of every group of this tile): contiguous rows, swizzled image, loaded by all
             // producer threads together
-            if (it >= 2 && !mbar_try(&dout_empty[db], (uint32_t)(((it >> 1) - 1) & 1))) {
-                flush();
-                W_WAIT(&dout_empty[db], (uint32_t)(((it >> 1) - 1) & 1), 0x212);
-            }
+            if (it >= 2) W_WAIT(&dout_empty[db], (uint32_t)(((it >> 1) - 1) & 1), 0x212);
             {
                 const uint32_t b_s = smem_u32(dout_s) + (uint32_t)db * C::B_BYTES;
                 for (int q = ptid; q < TCM * C::CPB; q += W_PROD_THREADS) {
@@ -299,7 +265,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_persist_kernel(const WA
                     const bool v = base + r < n && c * 8 < a.out_c;
                     cp_async16_s(b_s + swz_off<C::RB>(r, c), v ? a.dout + (size_t)(base + r) * a.out_c + c * 8 : a.dout, v);
                 }
-                push(16 + db);
+                cp_async_arrive_noinc(&dout_full[db]);
             }
             for (int g = 0; g < g_count; ++g) {
                 if (turn == grp) {
@@ -310,10 +276,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_persist_kernel(const WA
 #pragma unroll
                         for (int i = 0; i < NIT; ++i) src[j][i] = kk < k_count ? tbl[kk * TCM + rows[i]] : -1;
                     }
-                    if (wr > 0 && !mbar_try(&empty_bar[s], (uint32_t)((wr - 1) & 1))) {
-                        flush();
-                        W_WAIT(&empty_bar[s], (uint32_t)((wr - 1) & 1), 0x213);
-                    }
+                    if (wr > 0) W_WAIT(&empty_bar[s], (uint32_t)((wr - 1) & 1), 0x213);
                     const uint32_t st_s = ring_s + (uint32_t)s * C::STAGE;
 #pragma unroll
                     for (int j = 0; j < C::GW; ++j) {
@@ -334,7 +297,11 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_persist_kernel(const WA
                             }
                         }
                     }
-                    push(s);
+                    cp_async_arrive_noinc(&full_bar[s]);
+#if VC_P_SKIP
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full_bar[s]);     // release: publishes the warp's zero stores
+#endif
                 }
                 if (++turn == W_GROUPS) turn = 0;
                 if (++s == S) {
@@ -345,10 +312,15 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_persist_kernel(const WA
             __syncwarp();
             if (lane == 0) mbar_arrive(&tbl_empty[tb]);
         }
-        flush();
     } else if (warp == W_WARP_MMA) {
         // ------------------------------------------------------------ MMA issuer
         constexpr uint32_t IDESC = umma_idesc(TCM, CO) | (1u << 15) | (1u << 16);     // both operands MN-major
+        // Major-MN descriptors: low word = start >> 4 | (LBO >> 4) << 16, high word constant (tc_common.cuh umma_series)
+        constexpr uint32_t A_HI = umma_desc_hi<C::RA>(), B_HI = umma_desc_hi<C::RB>();
+        constexpr uint32_t A_LBO = (uint32_t)(C::A_BYTES >> 4) << 16;
+        const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]), doutf0 = smem_u32(&dout_full[0]),
+                       doute0 = smem_u32(&dout_empty[0]);
+        const uint32_t ring_a = smem_u32(ring), dout_a = smem_u32(dout_s);
         int s = 0;
         uint32_t ph = 0;
         int n_done = 0;
@@ -358,21 +330,19 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_persist_kernel(const WA
             if (tile_s[tb] < 0) break;
             __syncwarp();
             if (lane == 0) mbar_arrive(&tbl_empty[tb]);
-            W_WAIT(&dout_full[db], (uint32_t)((it >> 1) & 1), 0x222);
+            if (!mbar_spin(doutf0 + 8u * db, (uint32_t)((it >> 1) & 1), 4096u) &&
+                !mbar_wait_t_addr(doutf0 + 8u * db, (uint32_t)((it >> 1) & 1), a.err, 0x222))
+                goto done;
+            const uint32_t b_lo = (dout_a + (uint32_t)db * C::B_BYTES) >> 4;
             for (int g = 0; g < g_count; ++g) {
-                W_WAIT(&full_bar[s], ph, 0x223);
+                if (!mbar_spin(full0 + 8u * s, ph, 4096u) && !mbar_wait_t_addr(full0 + 8u * s, ph, a.err, 0x223)) goto done;
+                fence_async_smem();     // generic-proxy (cp.async, st.shared) writes -> visible to the tensor core's async proxy
                 tc_fence_after();
-                {
-                    // all lanes converged, one elected lane issues (see umma_f16_elect)
-                    const uint32_t a0 = smem_u32(ring) + (uint32_t)s * C::STAGE;
-                    const uint32_t b0 = smem_u32(dout_s) + (uint32_t)db * C::B_BYTES;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)      // 16 rows (two 8-row groups) per MMA
-                        umma_f16_elect(tmem_base + (uint32_t)(g * CO), umma_desc_mn<C::RA>(a0 + j * 16 * C::RA, C::A_BYTES),
-                                       umma_desc_mn<C::RB>(b0 + j * 16 * C::RB, 0), IDESC, (it == 0 && j == 0) ? 0u : 1u);
-                    umma_commit_elect(&empty_bar[s]);
-                    if (g == g_count - 1) umma_commit_elect(&dout_empty[db]);
-                }
+                // all lanes converged; the 8 MMAs of the stage (16 rows = two 8-row groups each) in one asm block
+                umma_series<8, C::RA, C::RB>(tmem_base + (uint32_t)(g * CO), ((ring_a + (uint32_t)s * C::STAGE) >> 4) | A_LBO, b_lo, A_HI, B_HI,
+                                             IDESC, it == 0 ? 0u : 1u);
+                umma_commit_elect_addr(empty0 + 8u * s);
+                if (g == g_count - 1) umma_commit_elect_addr(doute0 + 8u * db);
                 if (++s == S) {
                     s = 0;
                     ph ^= 1u;
