@@ -60,6 +60,8 @@ def parse():
                     help='graph = the whole step (forward + loss + backward) replayed as one CUDA graph (plan executor static '
                          'mode: device row counts, no host synchronisation); eager = exact-shape execution, one C-ABI call per '
                          'forward / backward, 4 data-dependent row counts read on the host')
+    ap.add_argument('--tc-variant', type=int, default=int(os.environ.get('VIRCONV_TC_VARIANT', '1')), choices=[0, 1],
+                    help='A/B aid: 1 = persistent tensor-core kernels (default), 0 = the round-1 kernels')
     ap.add_argument('--no-grid41', action='store_true', help='skip the extra [41,1600,1408]-grid measurement (N=1, graph mode)')
     ap.add_argument('--ncu-step', action='store_true',
                     help='profiling aid: W warm-up steps, then exactly one step between cudaProfilerStart/Stop; no JSON')
@@ -400,6 +402,7 @@ def run_ours(args):
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=dev)
     lib = _lib.load()
+    _lib.check(lib.vc_set_tc_variant(int(args.tc_variant)), 'vc_set_tc_variant')
 
     torch.manual_seed(666)
     model = VirConvL8x(CFG, 8, [1408, 1600, 80], precision=args.precision).to(dev).train()

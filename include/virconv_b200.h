@@ -55,6 +55,9 @@ int vc_set_pdl(int enable);
  * (csrc/conv_tc2.cu; C in {8,16,32,64}); 0 = the round-1 one-tile-per-CTA kernel (csrc/conv_tc.cu; C in {16,32,64}).
  * A/B measurements only — weight images built under one variant are not valid under the other. */
 int vc_set_tc_variant(int variant);
+/* A/B aid for the persistent tensor-core conv kernel (conv_tc2.cu): CTAs per SM, 0 = automatic (two when each still gets a
+ * ring of >= 2 stages in half the shared memory), 1 or 2 = forced. */
+int vc_conv_tc2_config(int ctas_per_sm);
 /* CTAs of the persistent tensor-core wgrad kernel (csrc/wgrad_tc2.cu): 0 (default) = one per SM.  Every CTA adds one
  * [K, C_in, C_out] partial with L2 vector reductions, so fewer CTAs trade main-loop parallelism for reduction traffic. */
 int vc_conv_wgrad_tc2_config(int max_ctas);

@@ -10,6 +10,7 @@ from virconv_b200.backbone import VirConvL8x
 
 dev = torch.device('cuda:0')
 lib = _lib.load()
+_lib.check(lib.vc_conv_tc2_config(int(os.environ.get('VIRCONV_TC2_CTAS', '0'))), 'vc_conv_tc2_config')
 torch.manual_seed(666)
 model = VirConvL8x(bench.CFG, 8, [1408, 1600, 80], precision='bf16').to(dev).train()
 executor.ENABLED = False

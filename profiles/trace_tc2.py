@@ -31,6 +31,7 @@ with torch.no_grad():
            'batch_size': 2, 'calib': b.calib, 'aug_param': b.aug_param})
 ops.conv_forward = orig
 lib = _lib.load()
+_lib.check(lib.vc_conv_tc2_config(int(os.environ.get('VIRCONV_TC2_CTAS', '0'))), 'vc_conv_tc2_config')
 lib.vc_debug_set_trace2.argtypes = [ctypes.c_void_p]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 names = ['table published', 'stage issued', 'stage consumed', 'tile committed', 'epilogue start', 'epilogue end', 'misc']

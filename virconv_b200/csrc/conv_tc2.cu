@@ -32,7 +32,7 @@ int g_tc_variant = 1;   // 1: this kernel; 0: the round-1 kernel (conv_tc.cu) â€
 namespace {
 
 #ifndef VC_P_GROUPS
-#define VC_P_GROUPS 2            // producer groups of 8 warps; consecutive ring stages go to consecutive groups
+#define VC_P_GROUPS 1            // producer groups of 8 warps; consecutive ring stages go to consecutive groups (1: two CTAs fit an SM)
 #endif
 #ifndef VC_P_SKIP
 #define VC_P_SKIP 1              // 1: missing neighbours cost a shared-memory zero store, not a (zero-fill) cp.async
@@ -63,7 +63,7 @@ struct PCfg {
     static constexpr int B_BYTES = NR * ROWB;                // one offset's weight slice
     static constexpr int TMEM_COLS = 2 * NR < 32 ? 32 : 2 * NR;   // two accumulators
     static constexpr int STG_LD = NR + 1;                    // staging row pitch (floats)
-    static constexpr int STG_BYTES = TCM * STG_LD * 4;
+    static constexpr int STG_BYTES = (TCM / 2) * STG_LD * 4;   // half a tile at a time
 };
 
 struct PArgs {
@@ -81,6 +81,7 @@ struct PArgs {
     int* tile_counter;         // optional (zeroed by the caller): dynamic tile scheduling; NULL: tile = blockIdx.x + i * gridDim.x
     int K, S;
     int w_resident;            // all K weight slices stay in shared memory for the whole launch (else: streamed with the ring)
+    int ntb_alloc;             // neighbour-table buffers in shared memory (2 when two CTAs share an SM, else P_NTB)
     int* err;
 };
 
@@ -89,8 +90,8 @@ struct PArgs {
 // role 0 loader (table published), 1 producer leader (stage issued), 2 MMA (stage consumed), 3 MMA (tile committed),
 // 4 epilogue (tile start), 5 epilogue (tile end), 6 misc (kernel start / roles start / end)
 __device__ long long* g_trace2 = nullptr;
-__device__ __forceinline__ void ptrace(int role, int& idx) {
-    if (g_trace2 != nullptr && blockIdx.x == 0 && idx < 256) {
+__device__ __forceinline__ void ptrace(long long* g_trace2, int role, int& idx) {
+    if (g_trace2 != nullptr && idx < 256) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
         g_trace2[role * 256 + idx] = (long long)t;
@@ -98,14 +99,14 @@ __device__ __forceinline__ void ptrace(int role, int& idx) {
     }
 }
 // roles 7 (producer leader) and 8 (MMA thread): SM-clock stamps of the phases inside one ring stage
-__device__ __forceinline__ void pclock(int role, int& idx) {
-    if (g_trace2 != nullptr && blockIdx.x == 0 && idx < 256) {
+__device__ __forceinline__ void pclock(long long* g_trace2, int role, int& idx) {
+    if (g_trace2 != nullptr && idx < 256) {
         g_trace2[role * 256 + idx] = clock64();
         ++idx;
     }
 }
-#define P_TRACE(role, idx) ptrace(role, idx)
-#define P_CLOCK(role, idx) pclock(role, idx)
+#define P_TRACE(role, idx) ptrace(trc, role, idx)
+#define P_CLOCK(role, idx) pclock(trc, role, idx)
 #else
 #define P_TRACE(role, idx) do { } while (0)
 #define P_CLOCK(role, idx) do { } while (0)
@@ -121,7 +122,7 @@ __device__ __forceinline__ void sts_zero16(uint32_t saddr) {
 }
 
 template <int KC, int NR>
-__global__ void __launch_bounds__(P_THREADS, 1) tc_conv_persist_kernel(const PArgs a) {
+__global__ void __launch_bounds__(P_THREADS, P_GROUPS == 1 ? 2 : 1) tc_conv_persist_kernel(const PArgs a) {
     using C = PCfg<KC, NR>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int S = a.S, K = a.K;
@@ -131,7 +132,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) tc_conv_persist_kernel(const PAr
     unsigned char* ring = smem_raw;                                              // [S][G x A (| G x B)]
     unsigned char* wimg_s = smem_raw + (size_t)S * stage_bytes;                  // [K][B] when resident
     int* nbr_s = reinterpret_cast<int*>(wimg_s + wres_bytes);                    // [P_NTB][K][128]
-    float* stg = reinterpret_cast<float*>(nbr_s + (size_t)P_NTB * K * TCM);      // [128][STG_LD]
+    float* stg = reinterpret_cast<float*>(nbr_s + (size_t)a.ntb_alloc * K * TCM); // [64][STG_LD]
     __shared__ __align__(8) uint64_t full_bar[P_MAX_STAGES];
     __shared__ __align__(8) uint64_t empty_bar[P_MAX_STAGES];
     __shared__ __align__(8) uint64_t tbl_full[P_NTB], tbl_empty[P_NTB];
@@ -142,6 +143,9 @@ __global__ void __launch_bounds__(P_THREADS, 1) tc_conv_persist_kernel(const PAr
     __shared__ double red_s[2][TCM];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef VC_TC_TRACE
+    long long* const trc = blockIdx.x == 0 ? g_trace2 : nullptr;      // (read once: a stamp must not cost a global load)
+#endif
     int tr = 0, tr2 = 0, tr3 = 0;      // trace cursors (debug build)
     (void)tr; (void)tr2; (void)tr3;
     if (tid == 0) P_TRACE(6, tr);
@@ -179,10 +183,10 @@ __global__ void __launch_bounds__(P_THREADS, 1) tc_conv_persist_kernel(const PAr
     const int n_tiles = dead ? 0 : (n + TCM - 1) / TCM;
     // Table buffers in use == how many tiles a CTA holds claimed at once.  With dynamic scheduling a deep look-ahead
     // unbalances short launches (the first CTAs would grab every tile), so it grows with the tiles per CTA.
-    int ntb = P_NTB;
+    int ntb = a.ntb_alloc;
     if (a.tile_counter != nullptr) {
         int d = n_tiles / (3 * (int)gridDim.x);
-        d = d < 1 ? 1 : (d > P_NTB - 1 ? P_NTB - 1 : d);
+        d = d < 1 ? 1 : (d > a.ntb_alloc - 1 ? a.ntb_alloc - 1 : d);
         ntb = d + 1;
     }
     tc_fence_before();
@@ -344,7 +348,11 @@ __global__ void __launch_bounds__(P_THREADS, 1) tc_conv_persist_kernel(const PAr
 #pragma unroll
                     for (int g = 0; g < C::G; ++g) {
 #pragma unroll
+#ifdef VC_DBG_NO_TBL
+                        for (int i = 0; i < NIT; ++i) src[g][i] = g < cnt ? rows[i] + (int)((uintptr_t)tbl & 1) : -1;
+#else
                         for (int i = 0; i < NIT; ++i) src[g][i] = g < cnt ? tbl[(t0 + g) * TCM + rows[i]] : -1;
+#endif
                     }
                     if (wr > 0 && !mbar_try(&empty_bar[s], (uint32_t)((wr - 1) & 1))) {
                         flush();
@@ -363,7 +371,9 @@ __global__ void __launch_bounds__(P_THREADS, 1) tc_conv_persist_kernel(const PAr
 #pragma unroll
                                 for (int cg = 0; cg < NCG; ++cg) {
                                     const bool vc = v && ch_ok[cg];
-#if defined(VC_DBG_NO_COPY)
+#if defined(VC_DBG_NO_COPY) && defined(VC_DBG_NO_ZERO)
+                                    (void)vc; (void)srow;
+#elif defined(VC_DBG_NO_COPY)
                                     if (!vc) sts_zero16(a_s + dst_off[i][cg]);
 #elif defined(VC_DBG_LINEAR_DST)
                                     if (vc) cp_async16_s(a_s + (uint32_t)((rows[i] * C::CPR + cg * CW + c_sub) * 16), srow + cg * CW * 8, true);
@@ -469,7 +479,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) tc_conv_persist_kernel(const PAr
                 if (lane == 0) P_CLOCK(8, tr3);                                       // phase 0: before the wait
                 if (!mbar_spin(full0 + 8u * s, ph, 4096u) && !mbar_wait_t_addr(full0 + 8u * s, ph, a.err, 0x134)) goto done;
                 if (lane == 0) P_CLOCK(8, tr3);                                       // phase 1: stage landed
-#if !VC_P_ARRIVE
+#if !VC_P_ARRIVE && !defined(VC_DBG_NO_FENCE)
                 fence_async_smem();     // generic-proxy (cp.async, st.shared) writes -> visible to the tensor core's async proxy
 #endif
                 tc_fence_after();
@@ -519,48 +529,63 @@ __global__ void __launch_bounds__(P_THREADS, 1) tc_conv_persist_kernel(const PAr
             P_WAIT(&acc_full[ab], (uint32_t)((it >> 1) & 1), 0x142);
             tc_fence_after();
             if (tid == 0) P_TRACE(4, tr);
-            const int r = warp * 32 + lane;
-#pragma unroll
-            for (int c0 = 0; c0 < NR; c0 += 16) {
-                float v[16];
-                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(ab * NR + c0), v);
-                if (c0 < oc) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        if (c0 + i < oc) stg[r * C::STG_LD + c0 + i] = v[i];
-                }
-            }
+#ifdef VC_DBG_NO_EPI
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[ab]);      // the accumulator may be overwritten by tile it + 2
-            named_bar_sync(1, 128);
-            // coalesced fp32 stores: consecutive threads -> consecutive float4 of the [128, out_c] tile
+            if (lane == 0) mbar_arrive(&acc_empty[ab]);
+            (void)base; (void)ch; (void)rg; (void)n_rg;
+            continue;
+#endif
+            // two halves of 64 rows through a [64][NR + 1] staging buffer (half the shared memory of a full-tile buffer: what
+            // lets two CTAs share an SM): the two warps owning the half's TMEM lanes unload it, then all four warps store it
             const int oc4 = oc >> 2;
-            for (int q = e; q < TCM * oc4; q += 128) {
-                const int rr = q / oc4, c4 = q % oc4;
-                if (base + rr < n) {
-                    const float* sp = stg + rr * C::STG_LD + c4 * 4;
-                    float4 v = make_float4(sp[0], sp[1], sp[2], sp[3]);
-                    const size_t o = (size_t)(base + rr) * oc + c4 * 4;
-                    if (a.addend != nullptr) {      // same element read and written by this thread only: aliasing `out` is safe
-                        const float4 w = *reinterpret_cast<const float4*>(a.addend + o);
-                        v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                if ((warp >> 1) == half) {
+                    const int r = (warp & 1) * 32 + lane;          // row inside the half
+#pragma unroll
+                    for (int c0 = 0; c0 < NR; c0 += 16) {
+                        float v[16];
+                        tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(ab * NR + c0), v);
+                        if (c0 < oc) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (c0 + i < oc) stg[r * C::STG_LD + c0 + i] = v[i];
+                        }
                     }
-                    *reinterpret_cast<float4*>(a.out + o) = v;
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[ab]);      // (4 arrivals per tile: the accumulator is free for tile it + 2)
                 }
-            }
-            if (a.bn_sums != nullptr) {
-                const int rows_valid = min(TCM, n - base);
-                float ts = 0.f, tq = 0.f;
-                for (int rr = rg; rr < rows_valid; rr += n_rg) {
-                    const float x = stg[rr * C::STG_LD + ch];
-                    ts += x;
-                    tq = fmaf(x, x, tq);
+                named_bar_sync(1, 128);
+                const int hbase = base + half * 64;
+                // coalesced fp32 stores: consecutive threads -> consecutive float4 of the [64, out_c] half tile
+                for (int q = e; q < 64 * oc4; q += 128) {
+                    const int rr = q / oc4, c4 = q % oc4;
+                    if (hbase + rr < n) {
+                        const float* sp = stg + rr * C::STG_LD + c4 * 4;
+                        float4 v = make_float4(sp[0], sp[1], sp[2], sp[3]);
+                        const size_t o = (size_t)(hbase + rr) * oc + c4 * 4;
+                        if (a.addend != nullptr) {      // same element read and written by this thread only: aliasing `out` is safe
+                            const float4 w = *reinterpret_cast<const float4*>(a.addend + o);
+                            v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+                        }
+                        *reinterpret_cast<float4*>(a.out + o) = v;
+                    }
                 }
-                bs += (double)ts;
-                bq += (double)tq;
+                if (a.bn_sums != nullptr) {
+                    const int rows_valid = max(0, min(64, n - hbase));
+                    float ts = 0.f, tq = 0.f;
+                    for (int rr = rg; rr < rows_valid; rr += n_rg) {
+                        const float x = stg[rr * C::STG_LD + ch];
+                        ts += x;
+                        tq = fmaf(x, x, tq);
+                    }
+                    bs += (double)ts;
+                    bq += (double)tq;
+                }
+                named_bar_sync(1, 128);
             }
-            named_bar_sync(1, 128);
             if (tid == 0) P_TRACE(5, tr2);
         }
     }
@@ -610,25 +635,57 @@ int num_sms() {
     return sms;
 }
 
+#ifndef VC_P_MIN_STAGES2
+#define VC_P_MIN_STAGES2 2       // two CTAs per SM are used when each still gets a ring of at least this many stages
+#endif
+int g_p_ctas = 0;                // 0: automatic; 1 / 2: forced CTAs per SM (vc_conv_tc2_config, A/B runs)
+
+struct PPlan {
+    int S, resident, ntb;
+    size_t smem;
+};
+
+// shared-memory plan of one CTA under a budget: weights resident if they fit beside a ring of >= min_stages, else streamed
+template <int KC, int NR>
+bool plan_smem(int K, size_t budget, int ntb, size_t resident_max, int min_stages, PPlan& p) {
+    using C = PCfg<KC, NR>;
+    const size_t fixed = (size_t)ntb * K * TCM * 4 + C::STG_BYTES;
+    const size_t wbytes = ((size_t)K * C::B_BYTES + 1023) & ~(size_t)1023;
+    if (fixed + (size_t)min_stages * C::G * C::A_BYTES > budget) return false;
+    int s_res = 0;
+    if (wbytes <= resident_max && fixed + wbytes < budget) s_res = (int)((budget - fixed - wbytes) / ((size_t)C::G * C::A_BYTES));
+    const size_t stage_str = (size_t)C::G * (C::A_BYTES + C::B_BYTES);
+    int s_str = (int)((budget - fixed) / stage_str);
+    const bool resident = s_res >= min_stages && s_res >= s_str - 1;
+    int S = resident ? s_res : s_str;
+    if (S < min_stages) return false;
+    if (S > P_MAX_STAGES) S = P_MAX_STAGES;
+    p.S = S;
+    p.resident = resident ? 1 : 0;
+    p.ntb = ntb;
+    p.smem = (size_t)S * (resident ? (size_t)C::G * C::A_BYTES : stage_str) + (resident ? wbytes : 0) + fixed;
+    return true;
+}
+
 template <int KC, int NR>
 int launch_persist(const PArgs& a0, int n_cap, cudaStream_t stream) {
-    using C = PCfg<KC, NR>;
     PArgs a = a0;
-    const size_t fixed = (size_t)P_NTB * a.K * TCM * 4 + C::STG_BYTES;
-    const size_t wbytes = ((size_t)a.K * C::B_BYTES + 1023) & ~(size_t)1023;
-    // small weight sets stay in shared memory for the whole launch; large ones travel with the ring stages
-    const bool resident = wbytes <= (size_t)P_W_RESIDENT_MAX && (SMEM_BUDGET - fixed - wbytes) / (C::G * C::A_BYTES) >= 4;
-    const size_t stage = (size_t)C::G * C::A_BYTES + (resident ? 0 : (size_t)C::G * C::B_BYTES);
-    const size_t wres = resident ? wbytes : 0;
-    int S = (int)((SMEM_BUDGET - fixed - wres) / stage);
-    if (S > P_MAX_STAGES) S = P_MAX_STAGES;
-    if (S < 2) {
+    // Two CTAs per SM (half the shared memory each, 2 table buffers) when the ring still has VC_P_MIN_STAGES2 stages: two
+    // independent pipelines per SM â€” the per-stage cost of ONE pipeline is a serial chain through its single MMA-issuing
+    // warp (barrier wait -> fences -> MMA issue -> commit, ~1000 cycles per 16 KB stage measured) â€” and room for CTAs of
+    // another stream's kernel.  Otherwise one CTA with the whole SM.
+    PPlan p;
+    int ctas = 1;
+    const size_t budget2 = (size_t)(227 * 1024) / 2 - 5 * 1024;      // static shared memory + 1 KB/CTA reserved by the driver
+    if (P_GROUPS == 1 && g_p_ctas != 1 && plan_smem<KC, NR>(a.K, budget2, 2, 28 * 1024, VC_P_MIN_STAGES2, p)) {
+        ctas = 2;
+    } else if (!plan_smem<KC, NR>(a.K, SMEM_BUDGET, P_NTB, P_W_RESIDENT_MAX, 2, p)) {
         set_error("tensor-core conv: no room for the operand ring (K=%d, %d->%d)", a.K, KC, NR);
         return VC_ERR_UNSUPPORTED;
     }
-    a.S = S;
-    a.w_resident = resident ? 1 : 0;
-    const size_t smem = (size_t)S * stage + wres + fixed;
+    a.S = p.S;
+    a.w_resident = p.resident;
+    a.ntb_alloc = p.ntb;
     auto kern = tc_conv_persist_kernel<KC, NR>;
     static bool attr_done = false;            // per instantiation
     if (!attr_done) {
@@ -636,8 +693,9 @@ int launch_persist(const PArgs& a0, int n_cap, cudaStream_t stream) {
         attr_done = true;
     }
     const int tiles = cdiv(n_cap, TCM);
-    const int grid = tiles < num_sms() ? (tiles < 1 ? 1 : tiles) : num_sms();
-    VC_LAUNCH_CHAIN(kern, dim3(grid), dim3(P_THREADS), smem, stream, a);
+    const int slots = ctas * num_sms();
+    const int grid = tiles < slots ? (tiles < 1 ? 1 : tiles) : slots;
+    VC_LAUNCH_CHAIN(kern, dim3(grid), dim3(P_THREADS), p.smem, stream, a);
     return VC_OK;
 }
 
@@ -709,7 +767,7 @@ int tc2_conv(int kc, int nr, const void* in_bf16, const void* wimg, const int32_
     PArgs a;
     a.in = (const __nv_bfloat16*)in_bf16; a.in_c = kc; a.wimg = (const unsigned char*)wimg; a.nbr = nbr; a.pitch = pitch;
     a.out = out; a.out_c = nr; a.addend = addend; a.bn_sums = bn_sums; a.n_dev = n_dev; a.n_host = n_rows; a.tile_counter = tile_counter;
-    a.K = K; a.S = 0; a.w_resident = 0;
+    a.K = K; a.S = 0; a.w_resident = 0; a.ntb_alloc = P_NTB;
     a.err = err;
     const int kcp = tc_pad16(kc), nrp = tc_pad16(nr);
 #define VC_P_CASE(A, B) \
@@ -728,6 +786,12 @@ extern "C" int vc_debug_set_trace2(long long* buf) {
     return cudaMemcpyToSymbol(vc::g_trace2, &buf, sizeof(buf)) == cudaSuccess ? 0 : -2;
 }
 #endif
+
+extern "C" int vc_conv_tc2_config(int ctas_per_sm) {
+    VC_CHECK_ARG(ctas_per_sm >= 0 && ctas_per_sm <= 2, "CTAs per SM must be 0 (automatic), 1 or 2");
+    vc::g_p_ctas = ctas_per_sm;
+    return VC_OK;
+}
 
 extern "C" int vc_set_tc_variant(int variant) {
     VC_CHECK_ARG(variant == 0 || variant == 1, "tensor-core conv variant must be 0 (round-1 kernel) or 1 (persistent)");
