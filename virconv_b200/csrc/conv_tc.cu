@@ -463,10 +463,10 @@ int tc_scatter_with_image(int kc, int nr, const void* dout_bf16, const void* wim
 // variant 0: the round-1 kernel above (core-matrix images, C >= 16, host row count, dense table pitch)
 int tc_conv_with_image(int kc, int nr, const void* in_bf16, const void* wimg, const int32_t* nbr, long long pitch, float* out,
                        int n_rows, const int* n_dev, int K, double* bn_sums, int* err, cudaStream_t stream, const float* addend,
-                       int* tile_counter) {
+                       int* tile_counter, int sparse_k) {
     if (n_rows == 0) return VC_OK;
     if (g_tc_variant == 1)
-        return tc2_conv(kc, nr, in_bf16, wimg, nbr, pitch, out, n_rows, n_dev, K, bn_sums, err, stream, addend, tile_counter);
+        return tc2_conv(kc, nr, in_bf16, wimg, nbr, pitch, out, n_rows, n_dev, K, bn_sums, err, stream, addend, tile_counter, sparse_k);
     if (n_dev != nullptr || pitch != n_rows) {
         set_error("round-1 tensor-core conv kernel needs a host row count and a dense table");
         return VC_ERR_UNSUPPORTED;
@@ -520,7 +520,8 @@ static int tc_common(const void* feats_bf16, const float* w, const int32_t* nbr,
     int rc = tc_one_image(w, ws, cin, cout, K, mode, mirror, g_tc_variant, stream);
     if (rc) return rc;
     int kc = mode == 0 ? cin : cout, nr = mode == 0 ? cout : cin;
-    return tc_conv_with_image(kc, nr, feats_bf16, ws, nbr, n_rows, out, n_rows, nullptr, K, bn_sums, err, stream, nullptr);
+    return tc_conv_with_image(kc, nr, feats_bf16, ws, nbr, n_rows, out, n_rows, nullptr, K, bn_sums, err, stream, nullptr, nullptr,
+                              (mode == 1 && !mirror) ? 1 : 0);
 }
 
 extern "C" int vc_conv_fwd_tc(const void* in_bf16, const float* w, const int32_t* nbr, float* out, int n_out, int cin,

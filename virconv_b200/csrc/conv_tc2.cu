@@ -81,6 +81,7 @@ struct PArgs {
     int* tile_counter;         // optional (zeroed by the caller): dynamic tile scheduling; NULL: tile = blockIdx.x + i * gridDim.x
     int K, S;
     int w_resident;            // all K weight slices stay in shared memory for the whole launch (else: streamed with the ring)
+    int scan_k;                // the loader lists the kernel offsets that touch each tile (strided-conv dgrad: most do not)
     int ntb_alloc;             // neighbour-table buffers in shared memory (2 when two CTAs share an SM, else P_NTB)
     int* err;
 };
@@ -138,7 +139,8 @@ __global__ void __launch_bounds__(P_THREADS, P_GROUPS == 1 ? 2 : 1) tc_conv_pers
     __shared__ __align__(8) uint64_t tbl_full[P_NTB], tbl_empty[P_NTB];
     __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
     __shared__ __align__(8) uint64_t wres_bar;
-    __shared__ int tile_s[P_NTB];
+    __shared__ int tile_s[P_NTB], nk_s[P_NTB];
+    __shared__ int klist_s[P_NTB][MAXK_TC];
     __shared__ uint32_t tmem_base_s;
     __shared__ double red_s[2][TCM];
 
@@ -275,6 +277,28 @@ __global__ void __launch_bounds__(P_THREADS, P_GROUPS == 1 ? 2 : 1) tc_conv_pers
                         reinterpret_cast<int4*>(dst + k * TCM)[lane] = v;
                     }
                 }
+                if (ptile >= 0) {
+                    // the kernel offsets the tile's stages walk.  By default all of them (a slice without a single neighbour costs
+                    // 128 zero stores and one MMA group, less than finding out); with scan_k — the dgrad of a strided conv,
+                    // where a tile's rows share their (z, y) parity and 3 of 4 offsets cannot reach any output — lane k ORs
+                    // table row k (rotated 16-byte chunks: conflict free) and the empty offsets are dropped
+                    unsigned km = K >= 32 ? 0xffffffffu : ((1u << K) - 1u);
+                    if (a.scan_k) {
+                        __syncwarp();
+                        bool any = false;
+                        if (lane < K) {
+                            const int4* row = reinterpret_cast<const int4*>(nbr_s + (size_t)ptb * K * TCM + (size_t)lane * TCM);
+#pragma unroll 4
+                            for (int j = 0; j < 32; ++j) {
+                                const int4 v = row[(j + lane) & 31];
+                                any |= (v.x & v.y & v.z & v.w) >= 0;      // some entry without the sign bit
+                            }
+                        }
+                        km = __ballot_sync(0xffffffffu, any);
+                    }
+                    if (km >> lane & 1u) klist_s[ptb][__popc(km & ((1u << lane) - 1u))] = lane;
+                    if (lane == 0) nk_s[ptb] = __popc(km);
+                }
                 if (lane == 0) tile_s[ptb] = ptile;
                 __syncwarp();
                 if (lane == 0) {
@@ -340,18 +364,20 @@ __global__ void __launch_bounds__(P_THREADS, P_GROUPS == 1 ? 2 : 1) tc_conv_pers
             }
             if (tile_s[tb] < 0) break;
             const int* tbl = nbr_s + (size_t)tb * K * TCM;
-            for (int t0 = 0; t0 < K; t0 += C::G) {
+            const int nk = nk_s[tb];
+            for (int t0 = 0; t0 < nk; t0 += C::G) {
                 if (turn == grp) {
                     if (leader) P_CLOCK(7, tr3);                                  // phase 0: stage loop top
-                    const int cnt = min(C::G, K - t0);
+                    const int cnt = min(C::G, nk - t0);
                     int src[C::G][NIT];
 #pragma unroll
                     for (int g = 0; g < C::G; ++g) {
 #pragma unroll
+                        const int kk = g < cnt ? klist_s[tb][t0 + g] : 0;
 #ifdef VC_DBG_NO_TBL
-                        for (int i = 0; i < NIT; ++i) src[g][i] = g < cnt ? rows[i] + (int)((uintptr_t)tbl & 1) : -1;
+                        for (int i = 0; i < NIT; ++i) src[g][i] = g < cnt ? rows[i] + (int)((uintptr_t)tbl & 1) + 0 * kk : -1;
 #else
-                        for (int i = 0; i < NIT; ++i) src[g][i] = g < cnt ? tbl[(t0 + g) * TCM + rows[i]] : -1;
+                        for (int i = 0; i < NIT; ++i) src[g][i] = g < cnt ? tbl[kk * TCM + rows[i]] : -1;
 #endif
                     }
                     if (wr > 0 && !mbar_try(&empty_bar[s], (uint32_t)((wr - 1) & 1))) {
@@ -432,17 +458,18 @@ __global__ void __launch_bounds__(P_THREADS, P_GROUPS == 1 ? 2 : 1) tc_conv_pers
                 const int tb = it % ntb;
                 P_WAIT(&tbl_full[tb], (uint32_t)((it / ntb) & 1), 0x121);
                 if (tile_s[tb] < 0) break;
+                const int nk = nk_s[tb];
+                int kl = lane < nk ? klist_s[tb][lane] : 0;      // lane j: the j-th offset of the tile
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tbl_empty[tb]);
-                for (int t0 = 0; t0 < K; t0 += C::G) {
-                    const int cnt = min(C::G, K - t0);
+                for (int t0 = 0; t0 < nk; t0 += C::G) {
+                    const int cnt = min(C::G, nk - t0);
                     if (wr > 0) P_WAIT(&empty_bar[s], (uint32_t)((wr - 1) & 1), 0x122);
-                    if (lane == 0) {
-                        // the slices of consecutive offsets are contiguous in the image and in the stage: one copy
-                        mbar_expect_tx(&full_bar[s], (uint32_t)(cnt * C::B_BYTES));
-                        bulk_g2s(smem_u32(ring) + (uint32_t)s * stage_bytes + C::G * C::A_BYTES, a.wimg + (size_t)t0 * C::B_BYTES,
-                                 (uint32_t)(cnt * C::B_BYTES), &full_bar[s]);
-                    }
+                    if (lane == 0) mbar_expect_tx(&full_bar[s], (uint32_t)(cnt * C::B_BYTES));
+                    __syncwarp();
+                    if (lane >= t0 && lane < t0 + cnt)
+                        bulk_g2s(smem_u32(ring) + (uint32_t)s * stage_bytes + C::G * C::A_BYTES + (uint32_t)(lane - t0) * C::B_BYTES,
+                                 a.wimg + (size_t)kl * C::B_BYTES, (uint32_t)C::B_BYTES, &full_bar[s]);
                     __syncwarp();
                     if (++s == S) {
                         s = 0;
@@ -465,8 +492,6 @@ __global__ void __launch_bounds__(P_THREADS, P_GROUPS == 1 ? 2 : 1) tc_conv_pers
             const int tb = it % ntb, ab = it & 1;
             P_WAIT(&tbl_full[tb], (uint32_t)((it / ntb) & 1), 0x131);
             if (tile_s[tb] < 0) break;
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tbl_empty[tb]);
             if (!w_ready) {
                 P_WAIT(&wres_bar, 0u, 0x132);
                 w_ready = true;
@@ -474,8 +499,10 @@ __global__ void __launch_bounds__(P_THREADS, P_GROUPS == 1 ? 2 : 1) tc_conv_pers
             if (it >= 2) P_WAIT(&acc_empty[ab], (uint32_t)(((it >> 1) - 1) & 1), 0x133);
             tc_fence_after();
             const uint32_t acc = tmem_base + (uint32_t)(ab * NR);
-            for (int t0 = 0; t0 < K; t0 += C::G) {
-                const int cnt = min(C::G, K - t0);
+            const int nk = nk_s[tb];
+            if (nk == 0) umma_commit_elect_addr(accf0 + 8u * ab);      // (no neighbour at all: the epilogue writes zeros)
+            for (int t0 = 0; t0 < nk; t0 += C::G) {
+                const int cnt = min(C::G, nk - t0);
                 if (lane == 0) P_CLOCK(8, tr3);                                       // phase 0: before the wait
                 if (!mbar_spin(full0 + 8u * s, ph, 4096u) && !mbar_wait_t_addr(full0 + 8u * s, ph, a.err, 0x134)) goto done;
                 if (lane == 0) P_CLOCK(8, tr3);                                       // phase 1: stage landed
@@ -487,22 +514,25 @@ __global__ void __launch_bounds__(P_THREADS, P_GROUPS == 1 ? 2 : 1) tc_conv_pers
                     // all 32 lanes converged; per kernel offset ONE asm block with one elect issues its KC/16 MMAs
                     const uint32_t st_s = ring_a + (uint32_t)s * stage_bytes;
                     const uint32_t a_lo = st_s >> 4;
-                    const uint32_t b_lo = (wres ? wimg_a + (uint32_t)(t0 * C::B_BYTES) : st_s + C::G * C::A_BYTES) >> 4;
+                    const uint32_t b_str = (st_s + C::G * C::A_BYTES) >> 4;
 #pragma unroll
                     for (int g = 0; g < C::G; ++g) {
 #ifdef VC_DBG_NO_MMA
                         if (t0 == 0 && g == 0)
 #endif
-                        if (g < cnt)
-                            umma_series<KC / 16, 2, 2>(acc, a_lo + (uint32_t)(g * (C::A_BYTES >> 4)), b_lo + (uint32_t)(g * (C::B_BYTES >> 4)), DHI,
-                                                       DHI, IDESC, (t0 > 0 || g > 0) ? 1u : 0u);
+                        if (g < cnt) {
+                            const uint32_t b_lo = wres ? (wimg_a + (uint32_t)(klist_s[tb][t0 + g] * C::B_BYTES)) >> 4
+                                                       : b_str + (uint32_t)(g * (C::B_BYTES >> 4));
+                            umma_series<KC / 16, 2, 2>(acc, a_lo + (uint32_t)(g * (C::A_BYTES >> 4)), b_lo, DHI, DHI, IDESC,
+                                                       (t0 > 0 || g > 0) ? 1u : 0u);
+                        }
                     }
                     umma_commit_elect_addr(empty0 + 8u * s);
                     if (lane == 0) {
                         P_CLOCK(8, tr3);                                              // phase 2: MMAs + commit issued
                         P_TRACE(2, tr);
                     }
-                    if (t0 + cnt >= K) {
+                    if (t0 + cnt >= nk) {
                         umma_commit_elect_addr(accf0 + 8u * ab);
                         if (lane == 0) P_TRACE(3, tr2);
                     }
@@ -512,6 +542,8 @@ __global__ void __launch_bounds__(P_THREADS, P_GROUPS == 1 ? 2 : 1) tc_conv_pers
                     ph ^= 1u;
                 }
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tbl_empty[tb]);      // (the offset list of the tile was read until here)
         }
     } else {
         // ------------------------------------------------------------ epilogue (warps 0-3 == TMEM lane quarters)
@@ -524,6 +556,7 @@ __global__ void __launch_bounds__(P_THREADS, P_GROUPS == 1 ? 2 : 1) tc_conv_pers
             const int tile = tile_s[tb];
             if (tile < 0) break;
             const int base = tile * TCM;
+            const bool empty_tile = nk_s[tb] == 0;
             __syncwarp();
             if (lane == 0) mbar_arrive(&tbl_empty[tb]);
             P_WAIT(&acc_full[ab], (uint32_t)((it >> 1) & 1), 0x142);
@@ -550,7 +583,7 @@ __global__ void __launch_bounds__(P_THREADS, P_GROUPS == 1 ? 2 : 1) tc_conv_pers
                         if (c0 < oc) {
 #pragma unroll
                             for (int i = 0; i < 16; ++i)
-                                if (c0 + i < oc) stg[r * C::STG_LD + c0 + i] = v[i];
+                                if (c0 + i < oc) stg[r * C::STG_LD + c0 + i] = empty_tile ? 0.f : v[i];
                         }
                     }
                     tc_fence_before();
@@ -758,7 +791,7 @@ bool tc2_ch_ok(int c) { return c == 8 || c == 16 || c == 32 || c == 64; }
 // (layout 1).  n_dev (optional) overrides n_rows on the device; n_rows is then the capacity the grid is sized for.
 int tc2_conv(int kc, int nr, const void* in_bf16, const void* wimg, const int32_t* nbr, long long pitch, float* out,
              int n_rows, const int* n_dev, int K, double* bn_sums, int* err, cudaStream_t stream, const float* addend,
-             int* tile_counter) {
+             int* tile_counter, int sparse_k) {
     if (n_rows == 0) return VC_OK;
     if (!tc2_ch_ok(kc) || !tc2_ch_ok(nr) || K < 1 || K > MAXK_TC) {
         set_error("tensor-core conv: unsupported shape (%d -> %d channels, K=%d)", kc, nr, K);
@@ -767,7 +800,7 @@ int tc2_conv(int kc, int nr, const void* in_bf16, const void* wimg, const int32_
     PArgs a;
     a.in = (const __nv_bfloat16*)in_bf16; a.in_c = kc; a.wimg = (const unsigned char*)wimg; a.nbr = nbr; a.pitch = pitch;
     a.out = out; a.out_c = nr; a.addend = addend; a.bn_sums = bn_sums; a.n_dev = n_dev; a.n_host = n_rows; a.tile_counter = tile_counter;
-    a.K = K; a.S = 0; a.w_resident = 0; a.ntb_alloc = P_NTB;
+    a.K = K; a.S = 0; a.w_resident = 0; a.ntb_alloc = P_NTB; a.scan_k = sparse_k;
     a.err = err;
     const int kcp = tc_pad16(kc), nrp = tc_pad16(nr);
 #define VC_P_CASE(A, B) \

@@ -845,7 +845,7 @@ extern "C" int vc_exec_backward(const int32_t* ops_i, const float* ops_f, int n_
             VC_TRY(contribute_fused(C, X, [&](float* dst, const float* addend) -> int {
                 Timed t(3, li, st);
                 return tc_conv_with_image(L.cout, L.cin, dxb, L.wimg_dgrad, table, R.n_in, dst, R.n_in, R.n_in_dev, R.K, nullptr, C.err, st,
-                                          addend, L.tile_ctr + 1);
+                                          addend, L.tile_ctr + 1, R.subm ? 0 : 1);
             }));
         } else {
             const size_t wsb = vc_conv_ws_bytes(L.cin, L.cout, R.K);
