@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 T=${1:-a}
 timeout 300 python profiles/microbench_conv2.py > gpurun_out/micro2_$T.txt 2>&1; echo "== micro conv rc=$?"; tail -3 gpurun_out/micro2_$T.txt
-timeout 300 python profiles/microbench_wgrad2.py > gpurun_out/microw_$T.txt 2>&1; echo "== micro wgrad rc=$?"; tail -3 gpurun_out/microw_$T.txt
+for i in 1 2 3; do timeout 300 python -m pytest tests/test_gpu_graph.py -m gpu -q -k rotating 2>&1 | grep -E "passed|failed|^E    .*assert [0-9]" | head -3; done
 timeout 900 python -m pytest tests -m gpu -q --maxfail=12 > gpurun_out/pytest_r2$T.log 2>&1; echo "== pytest rc=$?"; grep -E "^(FAILED|ERROR)|passed|failed" gpurun_out/pytest_r2$T.log | tail -20
 timeout 400 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_r2$T.json 2> gpurun_out/bench_r2$T.err; echo "== bench graph rc=$?"; cat gpurun_out/bench_r2$T.json | cut -c1-260; tail -2 gpurun_out/bench_r2$T.err
 timeout 400 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --mode eager --no-grid41 > gpurun_out/bench_r2${T}_eager.json 2> gpurun_out/bench_r2${T}_eager.err; echo "== bench eager rc=$?"; cat gpurun_out/bench_r2${T}_eager.json | cut -c1-260; tail -2 gpurun_out/bench_r2${T}_eager.err

@@ -500,6 +500,9 @@ __global__ void __launch_bounds__(P_THREADS, P_GROUPS == 1 ? 2 : 1) tc_conv_pers
             tc_fence_after();
             const uint32_t acc = tmem_base + (uint32_t)(ab * NR);
             const int nk = nk_s[tb];
+            const int kl = lane < nk ? klist_s[tb][lane] : 0;          // lane j: the j-th offset of the tile
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tbl_empty[tb]);                // (the table buffer is not needed by this warp any more)
             if (nk == 0) umma_commit_elect_addr(accf0 + 8u * ab);      // (no neighbour at all: the epilogue writes zeros)
             for (int t0 = 0; t0 < nk; t0 += C::G) {
                 const int cnt = min(C::G, nk - t0);
@@ -521,7 +524,7 @@ __global__ void __launch_bounds__(P_THREADS, P_GROUPS == 1 ? 2 : 1) tc_conv_pers
                         if (t0 == 0 && g == 0)
 #endif
                         if (g < cnt) {
-                            const uint32_t b_lo = wres ? (wimg_a + (uint32_t)(klist_s[tb][t0 + g] * C::B_BYTES)) >> 4
+                            const uint32_t b_lo = wres ? (wimg_a + (uint32_t)(__shfl_sync(0xffffffffu, kl, t0 + g) * C::B_BYTES)) >> 4
                                                        : b_str + (uint32_t)(g * (C::B_BYTES >> 4));
                             umma_series<KC / 16, 2, 2>(acc, a_lo + (uint32_t)(g * (C::A_BYTES >> 4)), b_lo, DHI, DHI, IDESC,
                                                        (t0 > 0 || g > 0) ? 1u : 0u);
@@ -542,8 +545,6 @@ __global__ void __launch_bounds__(P_THREADS, P_GROUPS == 1 ? 2 : 1) tc_conv_pers
                     ph ^= 1u;
                 }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tbl_empty[tb]);      // (the offset list of the tile was read until here)
         }
     } else {
         // ------------------------------------------------------------ epilogue (warps 0-3 == TMEM lane quarters)
