@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(P_THREADS, P_GROUPS == 1 ? 2 : 1) tc_conv_pers
                         }
                         km = __ballot_sync(0xffffffffu, any);
                     }
-                    if (km >> lane & 1u) klist_s[ptb][__popc(km & ((1u << lane) - 1u))] = lane;
+                    if (a.scan_k && (km >> lane & 1u)) klist_s[ptb][__popc(km & ((1u << lane) - 1u))] = lane;
                     if (lane == 0) nk_s[ptb] = __popc(km);
                 }
                 if (lane == 0) tile_s[ptb] = ptile;
@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(P_THREADS, P_GROUPS == 1 ? 2 : 1) tc_conv_pers
 #pragma unroll
                     for (int g = 0; g < C::G; ++g) {
 #pragma unroll
-                        const int kk = g < cnt ? klist_s[tb][t0 + g] : 0;
+                        const int kk = g < cnt ? (a.scan_k ? klist_s[tb][t0 + g] : t0 + g) : 0;
 #ifdef VC_DBG_NO_TBL
                         for (int i = 0; i < NIT; ++i) src[g][i] = g < cnt ? rows[i] + (int)((uintptr_t)tbl & 1) + 0 * kk : -1;
 #else
@@ -459,7 +459,7 @@ __global__ void __launch_bounds__(P_THREADS, P_GROUPS == 1 ? 2 : 1) tc_conv_pers
                 P_WAIT(&tbl_full[tb], (uint32_t)((it / ntb) & 1), 0x121);
                 if (tile_s[tb] < 0) break;
                 const int nk = nk_s[tb];
-                int kl = lane < nk ? klist_s[tb][lane] : 0;      // lane j: the j-th offset of the tile
+                int kl = lane < nk ? (a.scan_k ? klist_s[tb][lane] : lane) : 0;      // lane j: the j-th offset of the tile
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tbl_empty[tb]);
                 for (int t0 = 0; t0 < nk; t0 += C::G) {
@@ -500,7 +500,7 @@ __global__ void __launch_bounds__(P_THREADS, P_GROUPS == 1 ? 2 : 1) tc_conv_pers
             tc_fence_after();
             const uint32_t acc = tmem_base + (uint32_t)(ab * NR);
             const int nk = nk_s[tb];
-            const int kl = lane < nk ? klist_s[tb][lane] : 0;          // lane j: the j-th offset of the tile
+            const int kl = lane < nk ? (a.scan_k ? klist_s[tb][lane] : lane) : 0;      // lane j: the j-th offset of the tile
             __syncwarp();
             if (lane == 0) mbar_arrive(&tbl_empty[tb]);                // (the table buffer is not needed by this warp any more)
             if (nk == 0) umma_commit_elect_addr(accf0 + 8u * ab);      // (no neighbour at all: the epilogue writes zeros)
@@ -524,7 +524,8 @@ __global__ void __launch_bounds__(P_THREADS, P_GROUPS == 1 ? 2 : 1) tc_conv_pers
                         if (t0 == 0 && g == 0)
 #endif
                         if (g < cnt) {
-                            const uint32_t b_lo = wres ? (wimg_a + (uint32_t)(__shfl_sync(0xffffffffu, kl, t0 + g) * C::B_BYTES)) >> 4
+                            const int kk = a.scan_k ? __shfl_sync(0xffffffffu, kl, t0 + g) : t0 + g;
+                            const uint32_t b_lo = wres ? (wimg_a + (uint32_t)(kk * C::B_BYTES)) >> 4
                                                        : b_str + (uint32_t)(g * (C::B_BYTES >> 4));
                             umma_series<KC / 16, 2, 2>(acc, a_lo + (uint32_t)(g * (C::A_BYTES >> 4)), b_lo, DHI, DHI, IDESC,
                                                        (t0 > 0 || g > 0) ? 1u : 0u);
