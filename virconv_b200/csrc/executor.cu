@@ -54,10 +54,12 @@ struct RBk {
     const int *n_in_dev, *n_out_dev;   // static mode (see ISet); table pitches are n_out (nbr) and n_in (nbr_bwd)
     int K, n_in, n_out, subm, unique, ev, prod;
 };
+constexpr int CTR_PER_LAYER = 8;   // forward, dgrad, up to 6 wgrad passes (wgrad2_passes: at most 4 today)
+
 struct Layer {
     float *x, *y, *stats;
     double* sums;          // [4*cout]: forward sums, backward sums
-    int* tile_ctr;         // [4] tile-scheduler counters of the persistent kernels (forward, dgrad, wgrad pass 0 / 1), zeroed with the sums
+    int* tile_ctr;         // [CTR_PER_LAYER] tile-scheduler counters of the persistent kernels (forward, dgrad, wgrad passes), zeroed with the sums
     float* wscratch;       // [K][cin][cout] fp32 accumulator of the persistent wgrad kernel (zeroed with the sums), or NULL
     void *wimg_fwd, *wimg_dgrad;
     int in_slot, out_slot, rb, use_tc, use_tc_w, cin, cout, need_dgrad;   // use_tc: conv fwd / gather dgrad; use_tc_w: wgrad / scatter dgrad
@@ -384,10 +386,10 @@ extern "C" int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_o
             if (training && precision == 1 && g_tc_variant == 1 && tc2_ch_ok(o[F_CIN]) && tc2_ch_ok(o[F_COUT]))
                 wg_floats += ((size_t)rb_K[o[F_C]] * o[F_CIN] * o[F_COUT] + 63) / 64 * 64;
         }
-    const size_t zero_bytes = sums_doubles * 8 + n_cbr * 4 * sizeof(int) + wg_floats * 4;
+    const size_t zero_bytes = sums_doubles * 8 + n_cbr * CTR_PER_LAYER * sizeof(int) + wg_floats * 4;
     VC_ALLOC(sums_all, double*, zero_bytes);
     int* ctr_all = reinterpret_cast<int*>(sums_all + sums_doubles);
-    float* wg_all = reinterpret_cast<float*>(ctr_all + n_cbr * 4);
+    float* wg_all = reinterpret_cast<float*>(ctr_all + n_cbr * CTR_PER_LAYER);
     if (zero_bytes) VC_CUDA(cudaMemsetAsync(sums_all, 0, zero_bytes, C.st[0]));
     size_t wg_cur = 0;
     size_t sums_cur = 0, ctr_cur = 0;
@@ -403,7 +405,7 @@ extern "C" int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_o
         L.use_tc_w = precision == 1 && tc_ok(L.cin) && tc_ok(L.cout);
         L.sums = sums_all + sums_cur;
         sums_cur += 4 * (size_t)L.cout;
-        L.tile_ctr = ctr_all + 4 * ctr_cur++;
+        L.tile_ctr = ctr_all + CTR_PER_LAYER * ctr_cur++;
         L.wscratch = nullptr;
         if (training && precision == 1 && g_tc_variant == 1 && tc2_ch_ok(L.cin) && tc2_ch_ok(L.cout)) {
             L.wscratch = wg_all + wg_cur;
