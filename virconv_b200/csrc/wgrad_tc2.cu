@@ -23,30 +23,27 @@
 namespace vc {
 namespace {
 
+#ifndef VC_W_GROUPS
+#define VC_W_GROUPS 2            // producer groups of 8 warps; consecutive ring stages go to consecutive groups
+#endif
 #ifndef VC_P_SKIP
 #define VC_P_SKIP 1              // 1: missing neighbours cost a shared-memory zero store, not a (zero-fill) cp.async
 #endif
-// Two CTAs per SM (like conv_tc2.cu: one pipeline's speed is a serial chain through its single MMA-issuing warp, and a CTA
-// that leaves half the SM free can share it with the dgrad kernels of the main stream).  A ring stage is HALF a tile (64 rows)
-// of the GW offsets of one accumulator group: 16 KB; the two producer groups (4 warps each) own the two halves.
-constexpr int W_WARP_LOADER = 4, W_WARP_MMA = 5, W_WARP_PROD0 = 6, W_GROUPS = 2, W_GROUP_WARPS = 4;
-constexpr int W_PROD_WARPS = W_GROUPS * W_GROUP_WARPS;             // 8
-constexpr int W_THREADS = 32 * (W_WARP_PROD0 + W_PROD_WARPS);      // 448
-constexpr int W_PROD_THREADS = 32 * W_PROD_WARPS;
+constexpr int W_WARP_LOADER = 4, W_WARP_MMA = 5, W_WARP_PROD0 = 6, W_PROD_WARPS = 8, W_GROUPS = VC_W_GROUPS;
+constexpr int W_THREADS = 32 * (W_WARP_PROD0 + W_GROUPS * W_PROD_WARPS);   // 704 with two groups
+constexpr int W_PROD_THREADS = 32 * W_PROD_WARPS * W_GROUPS;
 constexpr int W_MAX_STAGES = 8;
-constexpr int W_NTB = 2;
-constexpr int W_HROWS = TCM / 2;                                   // rows of a ring stage
-constexpr int W_ROWS_PER_PROD = W_HROWS / W_GROUP_WARPS;           // 16
-constexpr int W_TMEM_MAX = 256;                                    // accumulator columns per CTA (two CTAs share 512)
-constexpr int W_SMEM_BUDGET = (227 * 1024) / 2 - 5 * 1024;
+constexpr int W_NTB = 4;
+constexpr int W_ROWS_PER_PROD = TCM / W_PROD_WARPS;             // 16
+constexpr int W_SMEM_BUDGET = 227 * 1024 - 4096;
 
 template <int CI, int CO>
 struct WCfg2 {
     static constexpr int RA = CI * 2, RB = CO * 2;           // row bytes of a gathered tile / of the dout tile (= swizzle spans)
     static constexpr int CPA = CI / 8, CPB = CO / 8;         // 16-byte chunks per row
     static constexpr int GW = 128 / CI;                      // kernel offsets stacked along M (one accumulator group)
-    static constexpr int A_BYTES = W_HROWS * RA;             // one offset's half tile
-    static constexpr int STAGE = GW * A_BYTES;               // 16 KB for every C_in
+    static constexpr int A_BYTES = TCM * RA;
+    static constexpr int STAGE = GW * A_BYTES;               // 32 KB for every C_in
     static constexpr int B_BYTES = TCM * RB;
 };
 
@@ -84,11 +81,11 @@ __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t lbo) {
 }
 
 template <int CI, int CO>
-__global__ void __launch_bounds__(W_THREADS, 2) tc_wgrad_persist_kernel(const WArgs a) {
+__global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_persist_kernel(const WArgs a) {
     using C = WCfg2<CI, CO>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int S = a.S, K = a.K;
-    unsigned char* ring = smem_raw;                                              // [S][GW x A half tile]
+    unsigned char* ring = smem_raw;                                              // [S][GW x A tile]
     unsigned char* dout_s = smem_raw + (size_t)S * C::STAGE;                     // [2][B tile]
     int* nbr_s = reinterpret_cast<int*>(dout_s + 2 * C::B_BYTES);                // [W_NTB][kcount][128]
     __shared__ __align__(8) uint64_t full_bar[W_MAX_STAGES];
@@ -101,7 +98,7 @@ __global__ void __launch_bounds__(W_THREADS, 2) tc_wgrad_persist_kernel(const WA
     __shared__ int started_s;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // this pass's slice of the kernel offsets (passes only when the accumulators of all groups exceed W_TMEM_MAX columns)
+    // this pass's slice of the kernel offsets (passes only when the accumulators of all groups exceed 512 TMEM columns)
     const int n_groups_total = (K + C::GW - 1) / C::GW;
     const int g_begin = blockIdx.y * a.groups_per_pass;
     const int g_count = min(a.groups_per_pass, n_groups_total - g_begin);
@@ -117,12 +114,12 @@ __global__ void __launch_bounds__(W_THREADS, 2) tc_wgrad_persist_kernel(const WA
         for (int s = 0; s < S; ++s) {
             // every producer thread of the stage's group (cp.async.mbarrier.arrive.noinc: fires when the thread's copies have
             // landed) + one release arrive per warp for its zero stores
-            mbar_init(&full_bar[s], 32 * W_GROUP_WARPS + (VC_P_SKIP ? W_GROUP_WARPS : 0));
+            mbar_init(&full_bar[s], 32 * W_PROD_WARPS + (VC_P_SKIP ? W_PROD_WARPS : 0));
             mbar_init(&empty_bar[s], 1);                       // tcgen05.commit
         }
         for (int b = 0; b < W_NTB; ++b) {
             mbar_init(&tbl_full[b], 1);                        // loader
-            mbar_init(&tbl_empty[b], W_PROD_WARPS + 1);        // producers + MMA warp
+            mbar_init(&tbl_empty[b], W_GROUPS * W_PROD_WARPS + 1);   // producers + MMA warp
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&dout_full[b], W_PROD_THREADS);          // every producer thread (cp.async arrive)
@@ -231,7 +228,7 @@ __global__ void __launch_bounds__(W_THREADS, 2) tc_wgrad_persist_kernel(const WA
         }
     } else if (warp >= W_WARP_PROD0) {
         // ------------------------------------------------------------ gather producers
-        const int grp = (warp - W_WARP_PROD0) / W_GROUP_WARPS, pw = (warp - W_WARP_PROD0) % W_GROUP_WARPS;   // grp = half of the tile
+        const int grp = (warp - W_WARP_PROD0) / W_PROD_WARPS, pw = (warp - W_WARP_PROD0) % W_PROD_WARPS;
         const int ptid = tid - W_WARP_PROD0 * 32;
         constexpr int CW = C::CPA < 4 ? C::CPA : 4;
         constexpr int RPI = 32 / CW;
@@ -270,15 +267,14 @@ __global__ void __launch_bounds__(W_THREADS, 2) tc_wgrad_persist_kernel(const WA
                 }
                 cp_async_arrive_noinc(&dout_full[db]);
             }
-            for (int gs = 0; gs < 2 * g_count; ++gs) {         // stage (group g, half h) = 2 g + h; half h belongs to producer group h
-                const int g = gs >> 1;
+            for (int g = 0; g < g_count; ++g) {
                 if (turn == grp) {
                     int src[C::GW][NIT];
 #pragma unroll
                     for (int j = 0; j < C::GW; ++j) {
                         const int kk = g * C::GW + j;
 #pragma unroll
-                        for (int i = 0; i < NIT; ++i) src[j][i] = kk < k_count ? tbl[kk * TCM + grp * W_HROWS + rows[i]] : -1;
+                        for (int i = 0; i < NIT; ++i) src[j][i] = kk < k_count ? tbl[kk * TCM + rows[i]] : -1;
                     }
                     if (wr > 0) W_WAIT(&empty_bar[s], (uint32_t)((wr - 1) & 1), 0x213);
                     const uint32_t st_s = ring_s + (uint32_t)s * C::STAGE;
@@ -338,16 +334,15 @@ __global__ void __launch_bounds__(W_THREADS, 2) tc_wgrad_persist_kernel(const WA
                 !mbar_wait_t_addr(doutf0 + 8u * db, (uint32_t)((it >> 1) & 1), a.err, 0x222))
                 goto done;
             const uint32_t b_lo = (dout_a + (uint32_t)db * C::B_BYTES) >> 4;
-            for (int gs = 0; gs < 2 * g_count; ++gs) {
-                const int g = gs >> 1, h = gs & 1;
+            for (int g = 0; g < g_count; ++g) {
                 if (!mbar_spin(full0 + 8u * s, ph, 4096u) && !mbar_wait_t_addr(full0 + 8u * s, ph, a.err, 0x223)) goto done;
                 fence_async_smem();     // generic-proxy (cp.async, st.shared) writes -> visible to the tensor core's async proxy
                 tc_fence_after();
-                // all lanes converged; the 4 MMAs of the half tile (16 rows = two 8-row groups each) in one asm block
-                umma_series<4, C::RA, C::RB>(tmem_base + (uint32_t)(g * CO), ((ring_a + (uint32_t)s * C::STAGE) >> 4) | A_LBO,
-                                             b_lo + (uint32_t)(h * ((W_HROWS * C::RB) >> 4)), A_HI, B_HI, IDESC, (it == 0 && h == 0) ? 0u : 1u);
+                // all lanes converged; the 8 MMAs of the stage (16 rows = two 8-row groups each) in one asm block
+                umma_series<8, C::RA, C::RB>(tmem_base + (uint32_t)(g * CO), ((ring_a + (uint32_t)s * C::STAGE) >> 4) | A_LBO, b_lo, A_HI, B_HI,
+                                             IDESC, it == 0 ? 0u : 1u);
                 umma_commit_elect_addr(empty0 + 8u * s);
-                if (gs == 2 * g_count - 1) umma_commit_elect_addr(doute0 + 8u * db);
+                if (g == g_count - 1) umma_commit_elect_addr(doute0 + 8u * db);
                 if (++s == S) {
                     s = 0;
                     ph ^= 1u;
@@ -417,7 +412,7 @@ int launch_wgrad2(const WArgs& a0, int n_cap, cudaStream_t stream) {
     using C = WCfg2<CI, CO>;
     WArgs a = a0;
     const int n_groups = (a.K + C::GW - 1) / C::GW;
-    const int max_groups = W_TMEM_MAX / CO;
+    const int max_groups = 512 / CO;
     int passes = (n_groups + max_groups - 1) / max_groups;
     int gpp = (n_groups + passes - 1) / passes;
     int cols = 32;
@@ -441,7 +436,7 @@ int launch_wgrad2(const WArgs& a0, int n_cap, cudaStream_t stream) {
         attr_done = true;
     }
     const int tiles = cdiv(n_cap, TCM);
-    int cap = g_wgrad2_ctas > 0 ? g_wgrad2_ctas : 2 * wg_num_sms();
+    int cap = g_wgrad2_ctas > 0 ? g_wgrad2_ctas : wg_num_sms();
     const int grid = tiles < cap ? (tiles < 1 ? 1 : tiles) : cap;
     VC_LAUNCH_CHAIN(kern, dim3(grid, passes), dim3(W_THREADS), smem, stream, a);
     return VC_OK;
@@ -502,7 +497,7 @@ int tc2_wgrad(int cin, int cout, const void* in_bf16, const void* dout_bf16, con
 int wgrad2_passes(int cin, int cout, int K) {
     const int ci = tc_pad16(cin), co = tc_pad16(cout);
     const int n_groups = (K + 128 / ci - 1) / (128 / ci);
-    const int max_groups = W_TMEM_MAX / co;
+    const int max_groups = 512 / co;
     return (n_groups + max_groups - 1) / max_groups;
 }
 
