@@ -185,6 +185,10 @@ int tc2_conv(int kc, int nr, const void* in_bf16, const void* wimg, const int32_
              const int* n_dev, int K, double* bn_sums, int* err, cudaStream_t stream, const float* addend,
              int* tile_counter = nullptr, int sparse_k = 0);
 
+// ---- wgrad_tc3.cu (half-tile-stage variant of the persistent wgrad, A/B) ----
+extern int g_wgrad_variant;
+int tc3_wgrad(int cin, int cout, const void* in_bf16, const void* dout_bf16, const int32_t* nbr, long long pitch, float* scratch,
+              int n_rows, const int* n_dev, int K, int* err, cudaStream_t stream, int* tile_counter);
 // ---- wgrad_tc2.cu (persistent tensor-core wgrad) ----
 struct WgradFinEntry {
     const float* scratch;   // [K][cin][cout] accumulated by tc2_wgrad

@@ -808,8 +808,8 @@ extern "C" int vc_exec_backward(const int32_t* ops_i, const float* ops_f, int n_
         }
         if (L.wscratch != nullptr) {
             Timed t(6, li, wst);
-            VC_TRY(tc2_wgrad(L.cin, L.cout, X.bf16, dxb, R.nbr, R.n_out, L.wscratch, R.n_out, R.n_out_dev, R.K, C.err, wst,
-                             L.tile_ctr + 2));
+            VC_TRY((g_wgrad_variant ? tc3_wgrad : tc2_wgrad)(L.cin, L.cout, X.bf16, dxb, R.nbr, R.n_out, L.wscratch, R.n_out, R.n_out_dev,
+                                                              R.K, C.err, wst, L.tile_ctr + 2));
             if (fin.n == WGRAD_FIN_MAX) {
                 VC_TRY(wgrad_finalize(fin, wst));
                 fin.n = 0;
