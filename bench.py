@@ -62,8 +62,8 @@ def parse():
                          'forward / backward, 4 data-dependent row counts read on the host')
     ap.add_argument('--tc-variant', type=int, default=int(os.environ.get('VIRCONV_TC_VARIANT', '1')), choices=[0, 1],
                     help='A/B aid: 1 = persistent tensor-core kernels (default), 0 = the round-1 kernels')
-    ap.add_argument('--wgrad-variant', type=int, default=int(os.environ.get('VIRCONV_WGRAD_VARIANT', '0')), choices=[0, 1],
-                    help='A/B aid: 0 = wgrad_tc2.cu (one CTA per SM), 1 = wgrad_tc3.cu (half-tile stages, can share an SM)')
+    ap.add_argument('--wgrad-variant', type=int, default=int(os.environ.get('VIRCONV_WGRAD_VARIANT', '1')), choices=[0, 1],
+                    help='A/B aid: 1 = wgrad_tc3.cu (half-tile stages, shares SMs with the dgrad kernels; default), 0 = wgrad_tc2.cu')
     ap.add_argument('--wgrad-ctas', type=int, default=0)
     ap.add_argument('--no-grid41', action='store_true', help='skip the extra [41,1600,1408]-grid measurement (N=1, graph mode)')
     ap.add_argument('--ncu-step', action='store_true',

@@ -58,9 +58,9 @@ int vc_set_tc_variant(int variant);
 /* A/B aid for the persistent tensor-core conv kernel (conv_tc2.cu): CTAs per SM, 0 = automatic (two when each still gets a
  * ring of >= 2 stages in half the shared memory), 1 or 2 = forced. */
 int vc_conv_tc2_config(int ctas_per_sm);
-/* A/B aid for the plan executor's weight-gradient kernel: variant 0 (default) = wgrad_tc2.cu (one CTA per SM, 32 KB ring stages),
- * 1 = wgrad_tc3.cu (half-tile stages, <= 111 KB shared memory and <= 256 TMEM columns per CTA: can share an SM with the dgrad
- * kernels of the main stream); max_ctas > 0 caps the CTAs of variant 1 (default 148). */
+/* The plan executor's weight-gradient kernel: variant 1 (default) = wgrad_tc3.cu (half-tile ring stages, <= 111 KB shared memory
+ * and <= 256 TMEM columns per CTA: shares an SM with the dgrad kernels of the main stream), 0 = wgrad_tc2.cu (one CTA per SM,
+ * 32 KB stages); max_ctas caps the CTAs of variant 1 (0 = half the SMs, the measured optimum). */
 int vc_conv_wgrad_tc3_config(int variant, int max_ctas);
 /* CTAs of the persistent tensor-core wgrad kernel (csrc/wgrad_tc2.cu): 0 (default) = one per SM.  Every CTA adds one
  * [K, C_in, C_out] partial with L2 vector reductions, so fewer CTAs trade main-loop parallelism for reduction traffic. */

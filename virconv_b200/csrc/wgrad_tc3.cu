@@ -24,7 +24,7 @@
 
 namespace vc {
 
-int g_wgrad_variant = 0;    // 0: wgrad_tc2.cu (one CTA per SM), 1: this file
+int g_wgrad_variant = 1;    // plan executor: 1 = this file (default), 0 = wgrad_tc2.cu (one CTA per SM, 32 KB stages)
 
 namespace {
 
@@ -405,7 +405,9 @@ done:
     }
 }
 
-int g_wgrad3_ctas = 148;    // CTA cap of this variant (<= 2 per SM fit): 148 keeps the reduction traffic of the one-CTA kernel
+int g_wgrad3_ctas = 0;      // CTA cap; 0 = half the SMs: the kernel runs on its own stream BESIDE the main stream's dgrad (a CTA of
+                            // each fits an SM), fewer CTAs halve the [K,C_in,C_out] reduction traffic, and 74 measured best
+                            // (profiles/sweep_wgrad_ctas_r2.txt: 3.21 ms/step with wgrad_tc2, 3.11 at 148, 3.04 at 74, 3.34 at 37)
 
 int wg_num_sms() {
     static int sms = 0;
@@ -446,7 +448,7 @@ int launch_wgrad3(const WArgs& a0, int n_cap, cudaStream_t stream) {
         attr_done = true;
     }
     const int tiles = cdiv(n_cap, TCM);
-    int cap = g_wgrad3_ctas > 0 ? g_wgrad3_ctas : 2 * wg_num_sms();
+    int cap = g_wgrad3_ctas > 0 ? g_wgrad3_ctas : (wg_num_sms() + 1) / 2;
     const int grid = tiles < cap ? (tiles < 1 ? 1 : tiles) : cap;
     VC_LAUNCH_CHAIN(kern, dim3(grid, passes), dim3(W_THREADS), smem, stream, a);
     return VC_OK;
@@ -489,6 +491,6 @@ extern "C" int vc_conv_wgrad_tc3_config(int variant, int max_ctas) {
     VC_CHECK_ARG(variant == 0 || variant == 1, "wgrad variant must be 0 (one CTA per SM, 32 KB stages) or 1 (half-tile stages, <= 111 KB)");
     VC_CHECK_ARG(max_ctas >= 0 && max_ctas <= 1024, "wgrad CTA cap out of range (%d)", max_ctas);
     vc::g_wgrad_variant = variant;
-    if (max_ctas > 0) vc::g_wgrad3_ctas = max_ctas;
+    vc::g_wgrad3_ctas = max_ctas;
     return VC_OK;
 }
