@@ -37,7 +37,11 @@ namespace {
 #ifndef VC_P_SKIP
 #define VC_P_SKIP 1              // 1: missing neighbours cost a shared-memory zero store, not a (zero-fill) cp.async
 #endif
-constexpr int P_WARP_LOADER = 4, P_WARP_MMA = 5, P_WARP_W = 6, P_WARP_PROD0 = 7;
+#ifndef VC_P_MMAS
+#define VC_P_MMAS 2              // MMA-issuing warps per CTA: a tile's ring stages go to them round robin, each accumulates into its
+#endif                           // own TMEM columns, the epilogue adds them up — the issue chain (wait, fence, issue, commit) is per warp
+constexpr int P_MMAS = VC_P_MMAS;
+constexpr int P_WARP_LOADER = 4, P_WARP_MMA = 5, P_WARP_W = P_WARP_MMA + P_MMAS, P_WARP_PROD0 = P_WARP_W + 1;
 constexpr int P_GROUPS = VC_P_GROUPS, P_PROD_WARPS = 8;
 constexpr int P_THREADS = 32 * (P_WARP_PROD0 + P_GROUPS * P_PROD_WARPS);   // 736 with two groups
 constexpr int P_MAX_STAGES = 16;
@@ -61,7 +65,7 @@ struct PCfg {
     static constexpr int G = 64 / KC;                        // kernel offsets per ring stage: 16 KB of gathered rows per stage
     static constexpr int A_BYTES = TCM * ROWB;               // one offset's gathered tile
     static constexpr int B_BYTES = NR * ROWB;                // one offset's weight slice
-    static constexpr int TMEM_COLS = 2 * NR < 32 ? 32 : 2 * NR;   // two accumulators
+    static constexpr int TMEM_COLS = 2 * P_MMAS * NR < 32 ? 32 : 2 * P_MMAS * NR;   // (two tiles in flight) x (one accumulator per MMA warp)
     static constexpr int STG_LD = NR + 1;                    // staging row pitch (floats)
     static constexpr int STG_BYTES = (TCM / 2) * STG_LD * 4;   // half a tile at a time
 };
@@ -167,10 +171,10 @@ __global__ void __launch_bounds__(P_THREADS, P_GROUPS == 1 ? 2 : 1) tc_conv_pers
         }
         for (int b = 0; b < P_NTB; ++b) {
             mbar_init(&tbl_full[b], 1);                        // loader
-            mbar_init(&tbl_empty[b], P_GROUPS * P_PROD_WARPS + 1 + 4 + (wres ? 0 : 1));   // producers, MMA, epilogue, weights
+            mbar_init(&tbl_empty[b], P_GROUPS * P_PROD_WARPS + P_MMAS + 4 + (wres ? 0 : 1));   // producers, MMA warps, epilogue, weights
         }
         for (int b = 0; b < 2; ++b) {
-            mbar_init(&acc_full[b], 1);                        // tcgen05.commit
+            mbar_init(&acc_full[b], P_MMAS);                   // tcgen05.commit (or a plain arrive) of every MMA warp
             mbar_init(&acc_empty[b], 4);                       // epilogue warps
         }
         mbar_init(&wres_bar, 1);
@@ -478,8 +482,9 @@ __global__ void __launch_bounds__(P_THREADS, P_GROUPS == 1 ? 2 : 1) tc_conv_pers
                 }
             }
         }
-    } else if (warp == P_WARP_MMA) {
-        // ------------------------------------------------------------ MMA issuer
+    } else if (warp >= P_WARP_MMA && warp < P_WARP_MMA + P_MMAS) {
+        // ------------------------------------------------------------ MMA issuers (stage j of a tile belongs to warp j % P_MMAS)
+        const int mw = warp - P_WARP_MMA;
         constexpr uint32_t IDESC = umma_idesc(TCM, NR);
         constexpr uint32_t DHI = umma_desc_hi<C::ROWB>();
         // shared-window addresses once, outside the loops (see tc_common.cuh: the MMA warp's instruction count is the budget)
@@ -498,14 +503,26 @@ __global__ void __launch_bounds__(P_THREADS, P_GROUPS == 1 ? 2 : 1) tc_conv_pers
             }
             if (it >= 2) P_WAIT(&acc_empty[ab], (uint32_t)(((it >> 1) - 1) & 1), 0x133);
             tc_fence_after();
-            const uint32_t acc = tmem_base + (uint32_t)(ab * NR);
+            const uint32_t acc = tmem_base + (uint32_t)((ab * P_MMAS + mw) * NR);
             const int nk = nk_s[tb];
             const int kl = lane < nk ? (a.scan_k ? klist_s[tb][lane] : lane) : 0;      // lane j: the j-th offset of the tile
             __syncwarp();
             if (lane == 0) mbar_arrive(&tbl_empty[tb]);                // (the table buffer is not needed by this warp any more)
-            if (nk == 0) umma_commit_elect_addr(accf0 + 8u * ab);      // (no neighbour at all: the epilogue writes zeros)
-            for (int t0 = 0; t0 < nk; t0 += C::G) {
+            // this warp's share of the tile: stages mw, mw + P_MMAS, ...; a warp without a stage just reports in
+            const int nst = (nk + C::G - 1) / C::G;
+            if (nst <= mw) {
+                if (lane == 0) mbar_arrive(&acc_full[ab]);
+            }
+            int j = 0;
+            for (int t0 = 0; t0 < nk; t0 += C::G, ++j) {
                 const int cnt = min(C::G, nk - t0);
+                if (j % P_MMAS != mw) {
+                    if (++s == S) {
+                        s = 0;
+                        ph ^= 1u;
+                    }
+                    continue;
+                }
                 if (lane == 0) P_CLOCK(8, tr3);                                       // phase 0: before the wait
                 if (!mbar_spin(full0 + 8u * s, ph, 4096u) && !mbar_wait_t_addr(full0 + 8u * s, ph, a.err, 0x134)) goto done;
                 if (lane == 0) P_CLOCK(8, tr3);                                       // phase 1: stage landed
@@ -528,7 +545,7 @@ __global__ void __launch_bounds__(P_THREADS, P_GROUPS == 1 ? 2 : 1) tc_conv_pers
                             const uint32_t b_lo = wres ? (wimg_a + (uint32_t)(kk * C::B_BYTES)) >> 4
                                                        : b_str + (uint32_t)(g * (C::B_BYTES >> 4));
                             umma_series<KC / 16, 2, 2>(acc, a_lo + (uint32_t)(g * (C::A_BYTES >> 4)), b_lo, DHI, DHI, IDESC,
-                                                       (t0 > 0 || g > 0) ? 1u : 0u);
+                                                       (j >= P_MMAS || g > 0) ? 1u : 0u);
                         }
                     }
                     umma_commit_elect_addr(empty0 + 8u * s);
@@ -536,7 +553,7 @@ __global__ void __launch_bounds__(P_THREADS, P_GROUPS == 1 ? 2 : 1) tc_conv_pers
                         P_CLOCK(8, tr3);                                              // phase 2: MMAs + commit issued
                         P_TRACE(2, tr);
                     }
-                    if (t0 + cnt >= nk) {
+                    if (j + P_MMAS >= nst) {         // this warp's last stage of the tile
                         umma_commit_elect_addr(accf0 + 8u * ab);
                         if (lane == 0) P_TRACE(3, tr2);
                     }
@@ -559,6 +576,7 @@ __global__ void __launch_bounds__(P_THREADS, P_GROUPS == 1 ? 2 : 1) tc_conv_pers
             if (tile < 0) break;
             const int base = tile * TCM;
             const bool empty_tile = nk_s[tb] == 0;
+            const int n_acc = min(P_MMAS, (nk_s[tb] + C::G - 1) / C::G);      // accumulators that hold a part of this tile
             __syncwarp();
             if (lane == 0) mbar_arrive(&tbl_empty[tb]);
             P_WAIT(&acc_full[ab], (uint32_t)((it >> 1) & 1), 0x142);
@@ -581,7 +599,16 @@ __global__ void __launch_bounds__(P_THREADS, P_GROUPS == 1 ? 2 : 1) tc_conv_pers
 #pragma unroll
                     for (int c0 = 0; c0 < NR; c0 += 16) {
                         float v[16];
-                        tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(ab * NR + c0), v);
+                        tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(ab * P_MMAS * NR + c0), v);
+#pragma unroll
+                        for (int m = 1; m < P_MMAS; ++m) {
+                            if (m < n_acc) {         // warp-uniform
+                                float w[16];
+                                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)((ab * P_MMAS + m) * NR + c0), w);
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) v[i] += w[i];
+                            }
+                        }
                         if (c0 < oc) {
 #pragma unroll
                             for (int i = 0; i < 16; ++i)
