@@ -38,8 +38,10 @@ namespace {
 #define VC_P_SKIP 1              // 1: missing neighbours cost a shared-memory zero store, not a (zero-fill) cp.async
 #endif
 #ifndef VC_P_MMAS
-#define VC_P_MMAS 2              // MMA-issuing warps per CTA: a tile's ring stages go to them round robin, each accumulates into its
-#endif                           // own TMEM columns, the epilogue adds them up — the issue chain (wait, fence, issue, commit) is per warp
+#define VC_P_MMAS 1              // MMA-issuing warps per CTA: a tile's ring stages go to them round robin, each accumulates into its
+#endif                           // own TMEM columns, the epilogue adds them up.  Measured with 2 (on top of two CTAs per SM): fwd 633 ->
+                                 // 629 us, dgrad 471 -> 461 us, step unchanged (profiles/microbench_conv2_r2_2mma.txt) — not worth the
+                                 // TMEM columns, so 1
 constexpr int P_MMAS = VC_P_MMAS;
 constexpr int P_WARP_LOADER = 4, P_WARP_MMA = 5, P_WARP_W = P_WARP_MMA + P_MMAS, P_WARP_PROD0 = P_WARP_W + 1;
 constexpr int P_GROUPS = VC_P_GROUPS, P_PROD_WARPS = 8;
