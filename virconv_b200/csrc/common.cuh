@@ -175,7 +175,7 @@ int tc_scatter_with_image(int kc, int nr, const void* dout_bf16, const void* wim
                           int K, int* err, cudaStream_t stream);
 int tc_conv_with_image(int kc, int nr, const void* in_bf16, const void* wimg, const int32_t* nbr, long long pitch, float* out,
                        int n_rows, const int* n_dev, int K, double* bn_sums, int* err, cudaStream_t stream, const float* addend,
-                       int* tile_counter = nullptr, int sparse_k = 0);
+                       int* tile_counter = nullptr, int flags = 0);   // flags: bit 0 sparse offsets (strided dgrad), bit 1 early tables
 bool tc_conv_ch_ok(int c);
 // ---- conv_tc2.cu (persistent tensor-core conv) ----
 extern int g_tc_variant;

@@ -87,6 +87,7 @@ struct PArgs {
     int* tile_counter;         // optional (zeroed by the caller): dynamic tile scheduling; NULL: tile = blockIdx.x + i * gridDim.x
     int K, S;
     int w_resident;            // all K weight slices stay in shared memory for the whole launch (else: streamed with the ring)
+    int early_tables;          // the neighbour table (and row count) do not come from the immediately preceding kernel of the stream
     int scan_k;                // the loader lists the kernel offsets that touch each tile (strided-conv dgrad: most do not)
     int ntb_alloc;             // neighbour-table buffers in shared memory (2 when two CTAs share an SM, else P_NTB)
     int* err;
@@ -182,8 +183,13 @@ __global__ void __launch_bounds__(P_THREADS, P_GROUPS == 1 ? 2 : 1) tc_conv_pers
         mbar_init(&wres_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    pdl_wait();                 // everything below reads what the previous kernel of the chain wrote
+    // Programmatic dependent launch: this grid may have started while its predecessor in the stream still runs.  What the
+    // roles read BEFORE their griddepcontrol.wait must not come from that predecessor: the row count, the tile counter and —
+    // when the caller vouches for it (early_tables: the plan executor builds its rulebooks on other streams and joins them with
+    // events) — the neighbour table, so that TMEM allocation, barrier set-up and the first table loads overlap the
+    // predecessor's tail.  Features, weights, addend and outputs are only touched after the wait.
     pdl_launch_dependents();
+    if (!a.early_tables) pdl_wait();
     const int n = a.n_dev != nullptr ? min(__ldg(a.n_dev), a.n_host) : a.n_host;
     // a pipeline wait that timed out in an EARLIER launch left the (sticky) error flag set: do nothing, so that whatever went
     // wrong costs one 2-second timeout, not one per launch
@@ -317,6 +323,7 @@ __global__ void __launch_bounds__(P_THREADS, P_GROUPS == 1 ? 2 : 1) tc_conv_pers
     } else if (warp >= P_WARP_PROD0) {
         // ------------------------------------------------------------ gather producers
         const int grp = (warp - P_WARP_PROD0) / P_PROD_WARPS, pw = (warp - P_WARP_PROD0) % P_PROD_WARPS;
+        pdl_wait();                                         // the gathered rows are the predecessor's output
         constexpr int CW = C::CPR < 4 ? C::CPR : 4;         // chunks of one row handled by adjacent lanes (full sectors)
         constexpr int RPI = 32 / CW;                        // rows per warp instruction
         constexpr int NIT = P_ROWS_PER_PROD / RPI;          // row groups per offset and warp
@@ -451,6 +458,7 @@ __global__ void __launch_bounds__(P_THREADS, P_GROUPS == 1 ? 2 : 1) tc_conv_pers
         flush();
     } else if (warp == P_WARP_W) {
         // ------------------------------------------------------------ weight slices (TMA engine, linear bulk copies)
+        pdl_wait();                                         // (the weight images may come from the kernel just before this one)
         if (wres) {
             if (lane == 0) {
                 const uint32_t total = (uint32_t)(K * C::B_BYTES);
@@ -568,6 +576,7 @@ __global__ void __launch_bounds__(P_THREADS, P_GROUPS == 1 ? 2 : 1) tc_conv_pers
         }
     } else {
         // ------------------------------------------------------------ epilogue (warps 0-3 == TMEM lane quarters)
+        pdl_wait();                              // addend / out / bn_sums
         const int e = tid;                       // 0..127
         const int oc = a.out_c;
         const int ch = e % oc, rg = e / oc, n_rg = TCM / oc;
@@ -831,7 +840,7 @@ int tc2_conv(int kc, int nr, const void* in_bf16, const void* wimg, const int32_
     PArgs a;
     a.in = (const __nv_bfloat16*)in_bf16; a.in_c = kc; a.wimg = (const unsigned char*)wimg; a.nbr = nbr; a.pitch = pitch;
     a.out = out; a.out_c = nr; a.addend = addend; a.bn_sums = bn_sums; a.n_dev = n_dev; a.n_host = n_rows; a.tile_counter = tile_counter;
-    a.K = K; a.S = 0; a.w_resident = 0; a.ntb_alloc = P_NTB; a.scan_k = sparse_k;
+    a.K = K; a.S = 0; a.w_resident = 0; a.ntb_alloc = P_NTB; a.scan_k = sparse_k & 1; a.early_tables = (sparse_k >> 1) & 1;
     a.err = err;
     const int kcp = tc_pad16(kc), nrp = tc_pad16(nr);
 #define VC_P_CASE(A, B) \

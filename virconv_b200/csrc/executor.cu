@@ -615,8 +615,10 @@ extern "C" int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_o
                         X.bf16 = xb;
                     }
                     Timed t(1, li, st);
+                    // (flag bit 1: the rulebook was built on another stream and joined by an event, so the kernel may load its first
+                    //  table slices before its griddepcontrol.wait — conv_tc2.cu)
                     VC_TRY(tc_conv_with_image(L.cin, L.cout, X.bf16, L.wimg_fwd, R.nbr, R.n_out, x, R.n_out, R.n_out_dev, R.K, sums, C.err, st,
-                                              nullptr, L.tile_ctr));
+                                              nullptr, L.tile_ctr, C.st[R.prod] != C.st[s] ? 2 : 0));
                 } else {
                     const size_t wsb = vc_conv_ws_bytes(L.cin, L.cout, R.K);
                     VC_ALLOC(ws, void*, wsb);
@@ -847,7 +849,7 @@ extern "C" int vc_exec_backward(const int32_t* ops_i, const float* ops_f, int n_
             VC_TRY(contribute_fused(C, X, [&](float* dst, const float* addend) -> int {
                 Timed t(3, li, st);
                 return tc_conv_with_image(L.cout, L.cin, dxb, L.wimg_dgrad, table, R.n_in, dst, R.n_in, R.n_in_dev, R.K, nullptr, C.err, st,
-                                          addend, L.tile_ctr + 1, R.subm ? 0 : 1);
+                                          addend, L.tile_ctr + 1, (R.subm ? 0 : 1) | 2);      // (tables from the forward call: early loads allowed)
             }));
         } else {
             const size_t wsb = vc_conv_ws_bytes(L.cin, L.cout, R.K);
