@@ -257,8 +257,7 @@ def run_ours_t(args):
     dev = torch.device('cuda', local)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
-            os.environ['NCCL_DEBUG'] = 'WARN'
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')   # (NCCL's version banner must not land on stdout, next to the one JSON line)
         dist.init_process_group('nccl', device_id=dev)
     lib = _lib.load()
     torch.manual_seed(666)
@@ -405,8 +404,7 @@ def run_ours(args):
     dev = torch.device('cuda', local)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
-            os.environ['NCCL_DEBUG'] = 'WARN'          # (VERSION prints a banner on stdout, next to the one JSON line)
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')   # (NCCL's version banner must not land on stdout, next to the one JSON line)
         dist.init_process_group('nccl', device_id=dev)
     lib = _lib.load()
     _lib.check(lib.vc_set_tc_variant(int(args.tc_variant)), 'vc_set_tc_variant')
