@@ -346,6 +346,17 @@ int vc_exec_query(const void* state, int what, int id, long long* out);
 int vc_exec_timing(int enable);
 int vc_exec_timing_read(float* ms_out, int32_t* kind_layer_out, int max_records);
 
+/* ---- gradient all-reduce over NVLink peer memory (replaces DistributedDataParallel's NCCL all-reduce of
+ * tools/train.py:140-141 for the backbone's one flat 1.7 MB gradient buffer) ----
+ * Every rank owns a SYMMETRIC fp32 buffer of 2 * n_pad floats and a symmetric array of vc_allreduce_peer_flag_words(world)
+ * zero-initialised uint32 flags, both mapped into every peer (torch.distributed._symmetric_memory); peer_bufs / peer_flags are
+ * HOST arrays of `world` device addresses: where rank r's buffer / flags are mapped in THIS process.  One call per step on every
+ * rank with the same, strictly increasing `epoch` (first call: 1): grads[i] <- scale * sum over ranks of grads[i], in place.
+ * A peer that does not show up within 4 s sets *err_flag (0x400 + peer) instead of hanging the GPU. */
+int vc_allreduce_peer_flag_words(int world);
+int vc_allreduce_peer_f32(const uint64_t* peer_bufs, const uint64_t* peer_flags, int rank, int world, float* grads, long long n,
+                          long long n_pad, unsigned epoch, float scale, int32_t* err_flag, vc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -73,6 +73,8 @@ SIGNATURES = {
     'vc_exec_query': (_I, [_P, _I, _I, _P]),
     'vc_exec_timing': (_I, [_I]),
     'vc_exec_timing_read': (_I, [_P, _P, _I]),
+    'vc_allreduce_peer_flag_words': (_I, [_I]),
+    'vc_allreduce_peer_f32': (_I, [_P, _P, _I, _I, _P, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_uint, _F, _P, _P]),
 }
 
 _lib = None
