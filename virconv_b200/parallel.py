@@ -34,8 +34,11 @@ def _as_one_buffer(grads):
 class PeerAllReduce:
     """One-kernel all-reduce of a flat fp32 gradient buffer over NVLink peer memory (csrc/allreduce.cu): every rank publishes
     its gradients in a symmetric buffer (torch.distributed._symmetric_memory: mapped into all peers of the node), signals,
-    and sums all peers' copies straight out of their memory.  For the backbone's 1.7 MB message this takes a fraction of an
-    NCCL all-reduce (latency-bound either way).  Construction is collective (every rank, same `numel`)."""
+    and sums all peers' copies straight out of their memory.  Bit-identical to NCCL's result at 2 ranks; measured back to back
+    on the backbone's 1.7 MB message it is NOT faster than NCCL 2.28 on the NVSwitch box (24.5 vs 18.2 us at 2 GPUs,
+    profiles/check_peer_allreduce_n2.txt) — what bench.py reports as all-reduce time (84 us at 2 GPUs, 176 us at 8) is mostly
+    the skew between the ranks' backward passes, which no collective removes — so it is opt-in (VIRCONV_PEER_ALLREDUCE=1).
+    Construction is collective (every rank, same `numel`)."""
 
     def __init__(self, numel: int, device, group=None):
         import ctypes
@@ -74,7 +77,7 @@ _PEER = {}      # (device index, numel, group id) -> PeerAllReduce, or None wher
 
 def _peer_allreduce(flat, group):
     import os
-    if os.environ.get('VIRCONV_PEER_ALLREDUCE', '1') == '0' or dist.get_backend(group) != 'nccl':
+    if os.environ.get('VIRCONV_PEER_ALLREDUCE', '0') != '1' or dist.get_backend(group) != 'nccl':
         return None
     key = (flat.device.index, flat.numel(), id(group))
     if key not in _PEER:
