@@ -140,12 +140,13 @@ def cpu_step(model, batch):
 
 def cpu_threads():
     """Threads for the CPU legs: the per-offset mm / index_add_ of the Native algorithm stop scaling (and then slow
-    down) beyond a few tens of threads, so 'all the threads it can use' is capped at 32 (sweep on the B200 box's host:
-    profiles/cpu_thread_sweep_r2.txt, `python bench.py --cpu-thread-sweep`).  VIRCONV_CPU_THREADS overrides."""
+    down) beyond a few tens of threads, so 'all the threads it can use' is the count that is FASTEST on the B200 box's
+    128-core host: 16 (sweep, profiles/cpu_thread_sweep_r2.txt from `python bench.py --cpu-thread-sweep`: 0.98 scenes/s at
+    4 threads, 1.28 at 8, 1.50 at 16, 1.05 at 32, 0.39 at 64, 0.01 at 128).  VIRCONV_CPU_THREADS overrides."""
     env = os.environ.get('VIRCONV_CPU_THREADS')
     if env:
         return max(1, int(env))
-    return max(1, min(os.cpu_count() or 1, 32))
+    return max(1, min(os.cpu_count() or 1, 16))
 
 
 def run_cpu_thread_sweep():
@@ -154,7 +155,7 @@ def run_cpu_thread_sweep():
     cm = make_cpu_model()
     b = scenes.make_batch([0, 1], N_LIDAR, N_VIRTUAL, MAX_VOXELS, training=True)
     n = os.cpu_count() or 1
-    for t in [c for c in (4, 8, 16, 32, 64, 128, 256) if c <= n] + ([n] if n not in (4, 8, 16, 32, 64, 128, 256) else []):
+    for t in [c for c in (4, 8, 16, 32, 64) if c <= n]:          # (128 threads: 200 s per step on the B200 box's host)
         torch.set_num_threads(t)
         cpu_step(cm, b)
         ts = []
