@@ -40,6 +40,24 @@ WORKLOAD = ('VirConv-L 3D backbone fwd+bwd, synthetic KITTI scenes 16k LiDAR + 8
             '40000-voxel cap/scene, grid [81,1600,1408], batch 2/GPU')
 
 
+class _StdoutToStderr:
+    """OS-level redirect of fd 1 to fd 2 while NCCL initialises: with NCCL_DEBUG=VERSION|WARN in the environment the library
+    prints its version banner on stdout, where the driver expects exactly one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+        return False
+
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -258,8 +276,9 @@ def run_ours_t(args):
     dev = torch.device('cuda', local)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')   # (NCCL's version banner must not land on stdout, next to the one JSON line)
-        dist.init_process_group('nccl', device_id=dev)
+        with _StdoutToStderr():
+            dist.init_process_group('nccl', device_id=dev)
+            dist.barrier()
     lib = _lib.load()
     torch.manual_seed(666)
     model = VirConv8x(CFG_T, 8, [1408, 1600, 80], precision=args.precision).to(dev).train()
@@ -405,8 +424,9 @@ def run_ours(args):
     dev = torch.device('cuda', local)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')   # (NCCL's version banner must not land on stdout, next to the one JSON line)
-        dist.init_process_group('nccl', device_id=dev)
+        with _StdoutToStderr():
+            dist.init_process_group('nccl', device_id=dev)
+            dist.barrier()                      # (communicator creation — and NCCL's banner — happen here)
     lib = _lib.load()
     _lib.check(lib.vc_set_tc_variant(int(args.tc_variant)), 'vc_set_tc_variant')
     _lib.check(lib.vc_conv_wgrad_tc3_config(int(args.wgrad_variant), int(args.wgrad_ctas)), 'vc_conv_wgrad_tc3_config')
