@@ -356,3 +356,32 @@ def test_virconv8x_forward_backward_vs_oracle(lib_built):
     # shared rulebooks: conv_input / conv1 use one 'subm1' table
     d = pub['multi_scale_3d_features:x_conv1'].indice_dict
     assert d['subm1'] is not None and len([k for k in d if isinstance(k, str)]) == 8   # subm1-4, spconv2-4, spconv_down2
+
+
+def test_wgrad_kernel_variants_agree(lib_built):
+    """The plan executor's two weight-gradient kernels (vc_conv_wgrad_tc3_config: half-tile stages on half the SMs — the default —
+    and the one-CTA-per-SM kernel) accumulate the same bf16 products in fp32: parameter gradients agree up to summation order."""
+    from virconv_b200 import _lib, scenes
+    from virconv_b200 import spconv_compat as spc
+    lib = _lib.load()
+    batch = scenes.make_batch([51, 52], n_lidar=4096, n_virtual=9000, max_voxels=7000, training=True)
+    model, _ = _models()
+    spc.set_precision(model, 'bf16')
+    model.train()
+    grads = []
+    try:
+        for variant in (0, 1):
+            _lib.check(lib.vc_conv_wgrad_tc3_config(variant, 0), 'vc_conv_wgrad_tc3_config')
+            for p in model.parameters():
+                p.grad = None
+            named, out = _run_gpu(model, batch.voxel_features, batch.voxel_coords, 2, batch.calib, batch.aug_param)
+            loss = sum(t.features.mean() for t in named.values())
+            loss.backward()
+            torch.cuda.synchronize()
+            assert int(ops_err_flag()) == 0
+            grads.append({k: v.grad.detach().clone() for k, v in model.named_parameters() if k.endswith('0.weight')})
+    finally:
+        _lib.check(lib.vc_conv_wgrad_tc3_config(1, 0), 'vc_conv_wgrad_tc3_config')
+    for k in grads[0]:
+        a, b = grads[0][k].double(), grads[1][k].double()
+        assert float((a - b).norm() / b.norm().clamp_min(1e-30)) < 1e-2, k      # (bf16 run-to-run noise of the chain: see test_gpu_graph._grad_close)

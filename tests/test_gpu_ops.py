@@ -315,7 +315,7 @@ def _bf(t):
     return t.bfloat16().float()
 
 
-@pytest.mark.parametrize('cin,cout', [(16, 16), (32, 16), (16, 32), (32, 32), (64, 32), (32, 64), (64, 64), (16, 64), (64, 16)])
+@pytest.mark.parametrize('cin,cout', [(8, 8), (16, 16), (32, 16), (16, 32), (32, 32), (64, 32), (32, 64), (64, 64), (16, 64), (64, 16)])
 def test_tc_subm3d_conv_fwd_dgrad(lib_built, cin, cout):
     """tcgen05 path: exact-operand check (oracle fed the same bf16-rounded operands, fp32 accumulate) at 1e-4, and
     the bf16-precision check against the full-fp32 oracle at 2e-2; pipeline-timeout flag must stay 0."""
@@ -372,6 +372,43 @@ def test_tc_strided_conv_fwd_dgrad(lib_built, cin, cout, geo):
     assert rel_err(f.grad.cpu(), rdf) < TOL
     _, _, rdw = _oracle_conv(_bf(feats), weight, nf, oi.shape[0], False, _bf(dout))
     assert rel_err(w.grad.cpu(), rdw) < TOL
+
+
+@pytest.mark.parametrize('ctas', [1, 2])
+def test_tc2_one_and_two_ctas_per_sm(lib_built, ctas):
+    """The persistent conv kernel in both of its shared-memory plans (vc_conv_tc2_config: one CTA with the whole SM, two CTAs
+    with half each — automatic choice elsewhere): forward, gather dgrad of a submanifold conv and the offset-scanning dgrad of a
+    strided conv against the oracle fed the same bf16-rounded operands."""
+    from virconv_b200 import _lib, ops
+    lib = _lib.load()
+    _lib.check(lib.vc_conv_tc2_config(ctas), 'vc_conv_tc2_config')
+    try:
+        rng = np.random.default_rng(77 + ctas)
+        shape = [21, 40, 36]
+        c = _coords(rng, 6000, 2, shape)
+        n = c.shape[0]
+        torch.manual_seed(5)
+        for cin, cout, strided in ((32, 32, False), (16, 32, True), (64, 64, True)):
+            if strided:
+                rb = ops.build_conv_rulebook(torch.from_numpy(c).to(_dev()), 2, shape, 3, 2, 1)
+                oi, _, nf, _ = orb.conv_rulebook(c, shape, 3, 2, 1)
+                nbr, n_out = nf, oi.shape[0]
+            else:
+                rb = ops.build_subm_rulebook(torch.from_numpy(c).to(_dev()), 2, shape, 3)
+                nbr, n_out = orb.subm_rulebook(c, shape, 3), n
+            feats, weight, dout = torch.randn(n, cin), torch.randn(cout, 3, 3, 3, cin) * 0.1, torch.randn(n_out, cout)
+            f = feats.to(_dev()).requires_grad_(True)
+            w = weight.to(_dev()).requires_grad_(True)
+            out = ops.SparseConvFn.apply(f, w, rb, 'bf16')
+            out.backward(dout.to(_dev()))
+            torch.cuda.synchronize()
+            assert int(ops.tc_error_flag(_dev()).item()) == 0
+            ro, _, _ = _oracle_conv(_bf(feats), _bf(weight), nbr, n_out, not strided, dout)
+            assert rel_err(out.detach().cpu(), ro) < TOL, (cin, cout, strided)
+            _, rdf, _ = _oracle_conv(feats, _bf(weight), nbr, n_out, not strided, _bf(dout))
+            assert rel_err(f.grad.cpu(), rdf) < TOL, (cin, cout, strided)
+    finally:
+        _lib.check(lib.vc_conv_tc2_config(0), 'vc_conv_tc2_config')
 
 
 def test_tc_subm2d_duplicates_and_tails(lib_built):
