@@ -678,7 +678,9 @@ def run_ours(args):
     if rank == 0 and roof is not None and kern.get('conv_wgrad_tc'):
         c, ms, by, fl = kern['conv_wgrad_tc']
         peak, how = peaks()
-        roof_w = {'bound': 'hbm', 'kernel': 'tc_wgrad_persist_kernel<CI,CO> (persistent tcgen05 weight gradient)',
+        roof_w = {'bound': 'hbm', 'kernel': ('tc_wgrad_half_kernel<CI,CO> (persistent tcgen05 weight gradient, half-tile stages, 74 CTAs: sized to '
+                                            'run beside the main stream, timed alone here)' if args.wgrad_variant == 1 else
+                                            'tc_wgrad_persist_kernel<CI,CO> (persistent tcgen05 weight gradient, one CTA per SM)'),
                   'achieved': by / (ms * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s', 'frac': by / (ms * 1e-3) / 1e9 / peak,
                   'launches_per_step': c / nprof, 'avg_launch_ms': ms / max(c, 1), 'alg_bytes_per_launch': by / max(c, 1),
                   'achieved_tflops': fl / (ms * 1e-3) / 1e12, 'peak_source': how,
