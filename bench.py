@@ -83,6 +83,7 @@ def parse():
     ap.add_argument('--wgrad-variant', type=int, default=int(os.environ.get('VIRCONV_WGRAD_VARIANT', '1')), choices=[0, 1],
                     help='A/B aid: 1 = wgrad_tc3.cu (half-tile stages, shares SMs with the dgrad kernels; default), 0 = wgrad_tc2.cu')
     ap.add_argument('--wgrad-ctas', type=int, default=0)
+    ap.add_argument('--bn-fused', type=int, default=1, choices=[0, 1], help='A/B aid: BatchNorm backward as one cooperative launch (1) or two (0)')
     ap.add_argument('--no-grid41', action='store_true', help='skip the extra [41,1600,1408]-grid measurement (N=1, graph mode)')
     ap.add_argument('--ncu-step', action='store_true',
                     help='profiling aid: W warm-up steps, then exactly one step between cudaProfilerStart/Stop; no JSON')
@@ -430,6 +431,7 @@ def run_ours(args):
     lib = _lib.load()
     _lib.check(lib.vc_set_tc_variant(int(args.tc_variant)), 'vc_set_tc_variant')
     _lib.check(lib.vc_conv_wgrad_tc3_config(int(args.wgrad_variant), int(args.wgrad_ctas)), 'vc_conv_wgrad_tc3_config')
+    _lib.check(lib.vc_set_bn_fused(int(args.bn_fused)), 'vc_set_bn_fused')
 
     torch.manual_seed(666)
     model = VirConvL8x(CFG, 8, [1408, 1600, 80], precision=args.precision).to(dev).train()

@@ -51,6 +51,8 @@ long long vc_launch_count(void);
 /* Programmatic dependent launch for the kernels of the conv / BN chain (default on): each starts while its predecessor
  * drains and blocks in `griddepcontrol.wait` before touching dependent data.  0 = plain stream-ordered launches. */
 int vc_set_pdl(int enable);
+/* BatchNorm backward as ONE cooperative launch (reduction, grid-wide barrier, apply; default on) or as two launches (0). */
+int vc_set_bn_fused(int enable);
 /* Tensor-core conv forward / gather-dgrad kernel: 1 (default) = persistent kernel with a deep cp.async operand ring
  * (csrc/conv_tc2.cu; C in {8,16,32,64}); 0 = the round-1 one-tile-per-CTA kernel (csrc/conv_tc.cu; C in {16,32,64}).
  * A/B measurements only — weight images built under one variant are not valid under the other. */

@@ -25,6 +25,7 @@ SIGNATURES = {
     'vc_last_error': (c_char_p, []),
     'vc_launch_count': (ctypes.c_longlong, []),
     'vc_set_pdl': (_I, [_I]),
+    'vc_set_bn_fused': (_I, [_I]),
     'vc_set_tc_variant': (_I, [_I]),
     'vc_conv_tc2_config': (_I, [_I]),
     'vc_conv_wgrad_tc3_config': (_I, [_I, _I]),

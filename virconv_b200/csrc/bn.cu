@@ -9,6 +9,7 @@
 // kernels: a reduce that accumulates (sum g, sum g*xhat) the same way, and an apply that derives its per-channel
 // coefficients from those sums.  The float64 accumulators make the fp32-rounded results independent of the
 // atomic arrival order for all practical purposes (each addend is an fp32 tile partial, < 2^12 of them).
+#include <cooperative_groups.h>
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -216,6 +217,107 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float4* __restr
     }
 }
 
+// backward, both passes in ONE cooperative launch (grid-wide barrier between the reduction and the apply): 20 launches fewer per
+// step than reduce + apply, and the second read of dy / x comes out of L2.  Same arithmetic as the two kernels above.
+__global__ void __launch_bounds__(256) bn_bwd_fused_kernel(const float4* __restrict__ dy, int dy_ld4, const float4* __restrict__ x,
+                                                           const float* __restrict__ gamma, const float* __restrict__ stats,
+                                                           double* __restrict__ bsums, int n_rows, const int* __restrict__ n_dev, int c,
+                                                           int training, float4* __restrict__ dx, uint2* __restrict__ dx_bf16,
+                                                           float* __restrict__ dgamma, float* __restrict__ dbeta, int tail_zero) {
+    extern __shared__ float shf[];  // [rowlanes][2][c]
+    const int cap_rows = n_rows;
+    if (n_dev != nullptr) n_rows = min(n_rows, __ldg(n_dev));
+    const int c4 = c / 4;
+    {
+        const int cg = threadIdx.x % c4, rl = threadIdx.x / c4, rowlanes = blockDim.x / c4;
+        const float4 sc = reinterpret_cast<const float4*>(stats)[cg];
+        const float4 sh = reinterpret_cast<const float4*>(stats + c)[cg];
+        const float4 m = reinterpret_cast<const float4*>(stats + 2 * c)[cg];
+        const float4 is = reinterpret_cast<const float4*>(stats + 3 * c)[cg];
+        float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+        for (int row = blockIdx.x * rowlanes + rl; row < n_rows; row += gridDim.x * rowlanes) {
+            size_t i = (size_t)row * c4 + cg;
+            float4 g = dy[(size_t)row * dy_ld4 + cg], xx = x[i];
+            g.x = fmaf(xx.x, sc.x, sh.x) > 0.f ? g.x : 0.f; g.y = fmaf(xx.y, sc.y, sh.y) > 0.f ? g.y : 0.f;
+            g.z = fmaf(xx.z, sc.z, sh.z) > 0.f ? g.z : 0.f; g.w = fmaf(xx.w, sc.w, sh.w) > 0.f ? g.w : 0.f;
+            s[0] += g.x; s[1] += g.y; s[2] += g.z; s[3] += g.w;
+            q[0] = fmaf(g.x, (xx.x - m.x) * is.x, q[0]); q[1] = fmaf(g.y, (xx.y - m.y) * is.y, q[1]);
+            q[2] = fmaf(g.z, (xx.z - m.z) * is.z, q[2]); q[3] = fmaf(g.w, (xx.w - m.w) * is.w, q[3]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            shf[(rl * 2 + 0) * c + cg * 4 + j] = s[j];
+            shf[(rl * 2 + 1) * c + cg * 4 + j] = q[j];
+        }
+        __syncthreads();
+        if (threadIdx.x < 2 * c) {
+            int which = threadIdx.x / c, ch = threadIdx.x % c;
+            float v = 0.f;
+            for (int l = 0; l < rowlanes; ++l) v += shf[(l * 2 + which) * c + ch];
+            atomicAdd(bsums + which * c + ch, (double)v);
+        }
+    }
+    __threadfence();
+    cooperative_groups::this_grid().sync();
+    const size_t n4 = (size_t)n_rows * c4;
+    const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const int cg = (int)(i0 % c4);
+    float* a_s = shf;                 // (the reduction's staging is dead: reuse it)
+    float* b_s = shf + 128;
+    float* d_s = shf + 256;
+    __syncthreads();
+    if (threadIdx.x < c) {
+        const int ch = threadIdx.x;
+        const double S = __ldcg(bsums + ch), Q = __ldcg(bsums + c + ch);
+        const float mean = stats[2 * c + ch], invstd = stats[3 * c + ch];
+        const float gi = gamma[ch] * invstd;
+        if (training) {
+            const double nn = (double)(n_rows > 0 ? n_rows : 1);
+            const float k1 = (float)(Q / nn) * invstd;
+            a_s[ch] = gi;
+            b_s[ch] = -gi * k1;
+            d_s[ch] = gi * (k1 * mean - (float)(S / nn));
+        } else {
+            a_s[ch] = gi;
+            b_s[ch] = 0.f;
+            d_s[ch] = 0.f;
+        }
+        if (blockIdx.x == 0) {
+            dbeta[ch] = (float)S;
+            dgamma[ch] = (float)Q;
+        }
+    }
+    __syncthreads();
+    float a[4], b[4], d[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        a[j] = a_s[cg * 4 + j];
+        b[j] = b_s[cg * 4 + j];
+        d[j] = d_s[cg * 4 + j];
+    }
+    const float4 sc = reinterpret_cast<const float4*>(stats)[cg];
+    const float4 sh = reinterpret_cast<const float4*>(stats + c)[cg];
+    for (size_t i = i0; i < n4; i += stride) {
+        float4 g = dy[dy_ld4 == c4 ? i : (i / c4) * dy_ld4 + cg], xx = x[i], r;
+        g.x = fmaf(xx.x, sc.x, sh.x) > 0.f ? g.x : 0.f; g.y = fmaf(xx.y, sc.y, sh.y) > 0.f ? g.y : 0.f;
+        g.z = fmaf(xx.z, sc.z, sh.z) > 0.f ? g.z : 0.f; g.w = fmaf(xx.w, sc.w, sh.w) > 0.f ? g.w : 0.f;
+        r.x = fmaf(a[0], g.x, fmaf(b[0], xx.x, d[0])); r.y = fmaf(a[1], g.y, fmaf(b[1], xx.y, d[1]));
+        r.z = fmaf(a[2], g.z, fmaf(b[2], xx.z, d[2])); r.w = fmaf(a[3], g.w, fmaf(b[3], xx.w, d[3]));
+        if (dx != nullptr) dx[i] = r;
+        if (dx_bf16 != nullptr) dx_bf16[i] = pack_bf16x4(r);
+    }
+    if (tail_zero && cap_rows > n_rows) {
+        const size_t t4 = (size_t)cap_rows * c4;
+        for (size_t i = n4 + i0; i < t4; i += stride) {
+            if (dx != nullptr) dx[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (dx_bf16 != nullptr) dx_bf16[i] = make_uint2(0u, 0u);
+        }
+    }
+}
+
+int g_bn_fused = 1;     // 1: reduce + apply in one cooperative launch; 0: two launches (vc_set_bn_fused)
+
 static bool c_ok(int c) { return c > 0 && c % 4 == 0 && c <= 128; }
 
 static int ew_blocks(size_t n4) {
@@ -251,6 +353,32 @@ int vc::bn_relu_bwd_dev(const float* dy, int dy_ld, const float* x, const float*
     VC_CHECK_ARG(c_ok(c) && n >= 0, "bad args n=%d c=%d", n, c);
     VC_CHECK_ARG(dgamma && dbeta && bsums && stats && gamma, "null pointer");
     VC_CHECK_ARG(dy_ld % 4 == 0 && dy_ld >= c, "bad gradient pitch");
+    if (n > 0 && g_bn_fused) {
+        VC_CHECK_ARG(dy && x && (dx || dx_bf16), "null pointer");
+        // the grid must be co-resident for the grid-wide barrier: <= 2 blocks per SM (the row loop and the apply loop stride)
+        static int max_blocks = 0;
+        if (max_blocks == 0) {
+            int dev = 0, sms = 148, per_sm = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bn_bwd_fused_kernel, 256, 8192) != cudaSuccess || per_sm < 1) per_sm = 1;
+            max_blocks = sms * (per_sm < 2 ? per_sm : 2);
+        }
+        const int c4 = c / 4, rowlanes = 256 / c4;
+        int blocks = (n + rowlanes - 1) / rowlanes;
+        if (blocks > max_blocks) blocks = max_blocks;
+        const size_t smem = (size_t)rowlanes * 2 * c * sizeof(float) < 3 * 128 * sizeof(float) ? 3 * 128 * sizeof(float)
+                                                                                               : (size_t)rowlanes * 2 * c * sizeof(float);
+        const float4* dy4 = (const float4*)dy;
+        const float4* x4 = (const float4*)x;
+        int dy_ld4 = dy_ld / 4;
+        float4* dx4 = (float4*)dx;
+        uint2* dxb = (uint2*)dx_bf16;
+        void* args[] = {&dy4, &dy_ld4, &x4, &gamma, &stats, &bsums, &n, &n_dev, &c, &training, &dx4, &dxb, &dgamma, &dbeta, &tail_zero};
+        vc::count_launch();
+        VC_CUDA(cudaLaunchCooperativeKernel((const void*)bn_bwd_fused_kernel, dim3(blocks), dim3(256), args, smem, stream));
+        return VC_OK;
+    }
     if (n > 0) {
         VC_CHECK_ARG(dy && x && (dx || dx_bf16), "null pointer");
         int c4 = c / 4;
@@ -284,4 +412,9 @@ extern "C" int vc_bn_relu_bwd_f32(const float* dy, const float* x, const float* 
     VC_CHECK_ARG(n == 0 || dx, "null pointer");
     return vc::bn_relu_bwd_dev(dy, c, x, gamma, stats, dx, dx_bf16, dgamma, dbeta, n, nullptr, c, training, bsums, 0,
                                (cudaStream_t)stream_);
+}
+
+extern "C" int vc_set_bn_fused(int enable) {
+    vc::g_bn_fused = enable ? 1 : 0;
+    return VC_OK;
 }
