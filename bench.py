@@ -721,6 +721,30 @@ def run_ours(args):
                   'workload': WORKLOAD.replace('[81,1600,1408]', '[41,1600,1408]') + ' (z voxel 0.1 m)', 'captures': g41.recaptures}
         del g41, model41, pts41
 
+    # the same captured step WITHOUT the voxeliser inside (device-resident voxel features / coordinates, what round 1's `value`
+    # timed and what the reference's dataloader hands the model): N=1 only, same timing rules
+    from_voxels = None
+    if world == 1 and graphed is not None and not args.no_grid41:
+        gv = GraphedStep(model, loss_of, params, margin=1.3)
+
+        def runv(n):
+            evs = []
+            for s_ in range(n):
+                flush_buf.zero_()
+                a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                vf, vc, b = devb[s_ % POOL]
+                gv({'voxel_features': vf, 'voxel_coords': vc, 'batch_size': b.batch_size, 'calib': b.calib, 'aug_param': b.aug_param})
+                e.record()
+                evs.append((a, e))
+            torch.cuda.synchronize()
+            return sum(a.elapsed_time(e) for a, e in evs) / n
+        runv(max(args.warmup, 3))
+        msv = runv(args.steps)
+        from_voxels = {'value': scenes_per_step / (msv * 1e-3), 'unit': 'scenes/s', 'ms_per_step': msv, 'captures': gv.recaptures,
+                       'what': 'the graph-replayed step starting from pre-voxelised device-resident inputs (no voxeliser inside)'}
+        del gv
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -762,7 +786,7 @@ def run_ours(args):
             'gpu_launches': launches, 'wall_s_timed_region': wall,
             'value_wall_clock': scenes_per_step * args.steps / wall,      # includes the L2 flushes and inter-step gaps
             'cuda_mallocs_in_timed_region': int(dev_allocs), 'clocks': clocks, 'roofline': roof,
-            'roofline_wgrad': roof_w, 'value_grid41': grid41, 'cpu_baseline': cpu_base}
+            'roofline_wgrad': roof_w, 'value_grid41': grid41, 'value_from_voxels': from_voxels, 'cpu_baseline': cpu_base}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
