@@ -218,7 +218,9 @@ def _note_arena_use(plan, device, with_bwd, used, n0):
 
 
 MAX_STEPS_AHEAD = 4          # the host never enqueues more than this many forwards of a plan beyond the GPU
-ARENAS_IN_FLIGHT = MAX_STEPS_AHEAD + 1
+ARENAS_IN_FLIGHT = MAX_STEPS_AHEAD + 3   # (+1 for the step being enqueued, +2: a block handed to three streams with record_stream
+                                         #  returns to the pool only after all of them passed it — one cudaMalloc of a 2.3 GB arena in a
+                                         #  timed loop costs 46 ms, profiles/bench_r2_eager_bf16.json vs its e2e outlier run)
 
 
 def _throttle(plan, dev):
