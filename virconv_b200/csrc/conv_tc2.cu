@@ -1,26 +1,30 @@
 // bf16 tensor-core sparse convolution, forward and dgrad — PERSISTENT variant (round 2), tcgen05 / TMEM, sm_100a only.
 //
 // Same contraction as conv_tc.cu (output-stationary 128-row tiles, per kernel offset one [128 x C_in] x [C_in x C_out]
-// UMMA accumulating in TMEM), restructured around what the round-1 profiles and profiles/exp_gather4_r2.txt measured:
-//   * a launch of the old kernel was ONE wave of short-lived CTAs, each a chain of <= 27 dependent
-//     {table read -> gather round trip -> MMA -> commit} links on a 2-deep ring: latency bound at 6-9 % of the HBM peak;
-//   * the gather throughput of an SM is set by how many independent 16-byte cp.async a producer warp can keep in flight
-//     (1.2+ row slots/clk/SM with 16 warps and a deep ring); TMA tile::gather4 tops out at 0.35 row slots/clk/SM with all
-//     rows in bounds and 0.11 with the rulebooks' 57 % missing neighbours, so the gather stays on cp.async and the TMA
-//     engine carries the weight slices.
-// One CTA per SM lives for the whole launch and walks its tiles (tile = blockIdx.x + i * gridDim.x):
-//   warps 0-3   epilogue: TMEM -> registers -> shared staging -> coalesced fp32 stores (+ addend), BatchNorm channel sums
-//               kept in registers across ALL tiles of the CTA (one set of float64 atomics per CTA, not per tile);
-//   warp  4     table loader: the NEXT tile's slice of the neighbour table (K x 128 int32) into a double-buffered shared
-//               copy, plus the list of kernel offsets that touch the tile — producers never wait for global memory;
-//   warp  5     MMA issuer: C_in/16 tcgen05.mma per (tile, offset) into one of TWO TMEM accumulators, so the epilogue of
-//               tile i overlaps the main loop of tile i+1; tcgen05.commit frees the operand stage;
-//   warps 6-13  gather producers: 16 rows each, 16-byte cp.async (zero fill for missing neighbours and for the padded
-//               channels of the C = 8 layers) straight into the 32/64/128-byte-swizzled K-major operand image, completion
-//               through cp.async.mbarrier.arrive.noinc on the stage's `full` barrier; the ring is as deep as shared memory
-//               allows (6-32 stages) and runs ACROSS tile boundaries, so there is no per-tile pipeline fill or drain.
+// UMMA accumulating in TMEM).  A launch of the round-1 kernel was one wave of short-lived CTAs, each a chain of <= 27 dependent
+// {table read -> gather round trip -> MMA -> commit} links on a 2-deep ring.  Here CTAs live for the whole launch, claim
+// tiles from a counter and run a warp-specialised pipeline; what bounds it, and every design decision below, was measured —
+// DESIGN.md section 4 has the account (gather paths, barrier chain, build variants VC_P_* / VC_DBG_* of this file).
+// TWO CTAs per SM by default (<= 111 KB shared memory, <= 128 TMEM columns each; one CTA with the whole SM where a two-stage
+// ring would not fit), 480 threads per CTA:
+//   warps 0-3   epilogue: TMEM -> registers -> half-tile shared staging -> coalesced fp32 stores (+ addend); BatchNorm channel
+//               sums per tile in fp32 over fixed row groups, accumulated per CTA in float64 (scheduling independent), one set
+//               of atomics per CTA;
+//   warp  4     tile scheduler + table loader: claims a tile, cp.async's its K x 128 slice of the neighbour table into one of
+//               2-4 shared buffers one tile ahead, fixes rows beyond the (device) row count to -1 and — for the dgrad of a
+//               strided conv — lists the kernel offsets that reach the tile at all (lane-parallel scan);
+//   warp  5     MMA issuer (converged warp; one asm block with one elect per kernel offset): C_in/16 tcgen05.mma per offset
+//               into one of two TMEM accumulators, so the epilogue of tile i overlaps the main loop of tile i+1;
+//               tcgen05.commit frees the ring stage;
+//   warp  6     weights: all K slices resident in shared memory for the launch (one bulk copy) when they fit beside >= 3 ring
+//               stages, else one cp.async.bulk per stage with complete_tx on the stage's `full` barrier;
+//   warps 7-14  gather producers: 16 rows each; a present neighbour is a 16-byte cp.async straight into the 32/64/128-byte-
+//               swizzled K-major operand image, a missing one (and the padded channels of the C = 8 layers) a 16-byte zero
+//               store; completion through cp.async.mbarrier.arrive.noinc per thread + one release arrive per warp.
+// A ring stage holds 64 / C_in kernel offsets (16 KB of gathered rows); the ring runs ACROSS tile boundaries.
 // The row count may come from device memory (n_dev): the grid is sized from a host-side capacity and every role derives
 // its tile list from *n_dev, which is what makes the plan executor CUDA-graph capturable (no host read of a row count).
+// Every mbarrier wait is time-bounded (2 s): a wedged pipeline stores a code in the error flag and the roles leave their loops.
 // Replaces spconv `ops.indice_conv` / `indice_conv_backward` (input gradient) behind spconv_backbone.py:89,92-93,113,563-564.
 // Algorithmic bytes per launch: N_in*C_in*2 + N_out*C_out*4 + P*8 + K*C_in*C_out*2;  FLOPs 2*P*C_in*C_out.
 #include "tc_common.cuh"
@@ -216,9 +220,7 @@ __global__ void __launch_bounds__(P_THREADS, P_GROUPS == 1 ? 2 : 1) tc_conv_pers
         // ------------------------------------------------------------ tile scheduler + neighbour-table loader
         // Table slices travel global -> shared with cp.async (no register staging), ntb - 1 tiles in flight: producers never
         // wait for global memory, and the loader's own latency (DRAM-cold table rows: 1-1.5 us under load) is pipelined
-        // across tiles.  Every kernel offset of a tile is processed (no per-tile scan for empty offsets: a slice without a
-        // single neighbour costs the producers 128 zero stores and the tensor core one MMA group — cheaper than the scan,
-        // which was the pipeline's bottleneck at 3.3 us per tile, profiles/trace_tc2_r2_a.txt).
+        // across tiles.
         const bool vec_ok = (reinterpret_cast<uintptr_t>(a.nbr) & 15u) == 0 && (a.pitch & 3) == 0;
         const int lag = ntb - 1;
         int tq0 = -1, tq1 = -1, tq2 = -1, tq3 = -1;      // tiles of the last four iterations (it & 3)

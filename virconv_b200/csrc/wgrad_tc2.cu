@@ -2,10 +2,12 @@
 //
 //   dW[k] (C_in x C_out) = sum over output rows o of  in[nbr[k,o], :]^T (x) dout[o, :]
 //
+// (The plan executor's default weight-gradient kernel is the half-tile-stage variant of this one, wgrad_tc3.cu, launched on
+//  half the SMs beside the main stream; this file serves the per-operator C ABI — vc_conv_wgrad_tc — and the A/B switch.)
 // Same machinery as the persistent forward kernel (conv_tc2.cu): one CTA per SM walks 128-row output tiles (dynamic tile
-// counter), a loader warp stages the tile's neighbour-table slice (L2 prefetch several tiles ahead, cp.async into a
-// 4-deep shared ring), 8 producer warps gather the rows with 16-byte cp.async into 32/64/128-byte-swizzled tiles, one
-// thread issues the MMAs.  What differs:
+// counter), a loader warp stages the tile's neighbour-table slice (cp.async into 2-4 shared buffers, one to three tiles
+// ahead), two groups of 8 producer warps gather the rows with 16-byte cp.async into 32/64/128-byte-swizzled tiles, one
+// converged warp issues the MMAs.  What differs:
 //   * the gathered tile is used MN-MAJOR (the reduction runs over the 128 rows): the row-major swizzled tile the forward
 //     kernel builds is exactly the canonical Major-MN layout (profiles/exp_mnmajor.cu), and G = 128 / C_in kernel offsets
 //     are stacked along the UMMA M dimension through the descriptor's leading-byte offset (one ring stage = G tiles);
