@@ -134,8 +134,14 @@ def test_plan_executor_matches_module_path(lib_built, precision, training):
     gm = dict(mm.named_parameters())
     for name, p in pm.named_parameters():
         assert p.grad is not None, name
-        # bf16: the scatter-dgrad atomics' order differs run to run and a 1-ulp change can flip a bf16 rounding downstream
-        assert rel_err(p.grad.cpu(), gm[name].grad.cpu()) < (1e-2 if precision == 'bf16' else 2e-4), name
+        if precision == 'bf16':
+            # the scatter-dgrad / weight-gradient atomics' order differs run to run and a 1-ulp change can flip a bf16 rounding
+            # downstream: two runs of the SAME path differ by up to 6e-3 of the largest element (profiles/diag_graph_vs_exact_r2.txt)
+            a, b = p.grad.double().cpu(), gm[name].grad.double().cpu()
+            assert float((a - b).norm() / b.norm().clamp_min(1e-30)) < 1e-2, name
+            assert rel_err(p.grad.cpu(), gm[name].grad.cpu()) < 3e-2, name
+        else:
+            assert rel_err(p.grad.cpu(), gm[name].grad.cpu()) < 2e-4, name
     bm = dict(mm.named_buffers())
     for name, b in pm.named_buffers():
         assert torch.allclose(b.float().cpu(), bm[name].float().cpu(), rtol=1e-5, atol=1e-7), name

@@ -106,10 +106,12 @@ def test_static_mode_matches_exact_mode(lib_built, precision):
         if k != 'x_conv1':
             assert bool((t.indices[rows:] == -1).all()), k
     assert abs(float(loss) - l0) < 1e-5 * max(1.0, abs(l0))
-    tol = 1e-2 if precision == 'bf16' else 2e-4        # order of the scatter / float64 atomics differs run to run
     for name, p in model.named_parameters():
         assert p.grad is not None and bool(torch.isfinite(p.grad).all()), name
-        assert rel_err(p.grad.cpu(), g0[name].cpu()) < tol, name
+        if precision == 'bf16':
+            assert _grad_close(p.grad, g0[name]), name
+        else:
+            assert rel_err(p.grad.cpu(), g0[name].cpu()) < 2e-4, name     # order of the scatter / float64 atomics differs run to run
 
 
 def test_static_mode_reports_overflow(lib_built):
