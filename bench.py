@@ -85,6 +85,8 @@ def parse():
     ap.add_argument('--wgrad-ctas', type=int, default=0)
     ap.add_argument('--bn-fused', type=int, default=1, choices=[0, 1], help='A/B aid: BatchNorm backward as one cooperative launch (1) or two (0)')
     ap.add_argument('--no-grid41', action='store_true', help='skip the extra [41,1600,1408]-grid measurement (N=1, graph mode)')
+    ap.add_argument('--graph-pipeline', type=int, default=int(os.environ.get('VIRCONV_GRAPH_PIPELINE', '0')), choices=[0, 1],
+                    help='graph mode: 1 = graph.PipelinedStep (index graph of step t+1 beside the feature graph of step t), 0 = one graph per step')
     ap.add_argument('--ncu-step', action='store_true',
                     help='profiling aid: W warm-up steps, then exactly one step between cudaProfilerStart/Stop; no JSON')
     return ap.parse_args()
@@ -501,7 +503,11 @@ def run_ours(args):
         reduce_grads()
         return float(loss.detach()) if sync_loss else loss
 
-    graphed = GraphedStep(model, loss_of, params, margin=1.3, voxelizer=VOX) if args.mode == 'graph' else None
+    if args.mode == 'graph' and args.graph_pipeline:
+        from virconv_b200.graph import PipelinedStep
+        graphed = PipelinedStep(model, loss_of, params, margin=1.3, voxelizer=VOX)
+    else:
+        graphed = GraphedStep(model, loss_of, params, margin=1.3, voxelizer=VOX) if args.mode == 'graph' else None
 
     def gstep(pts, pb):
         """graph step: the collated points (device or pinned-host tensor) are copied into the graph's input buffer, then ONE

@@ -210,3 +210,37 @@ def test_graph_with_in_graph_voxeliser(lib_built):
         assert abs(float(got[s][0]) - l0) < 1e-5 * max(1.0, abs(l0)), s
         for k in params:
             assert _grad_close(got[s][1][k], g0[k]), (s, k)
+
+
+@pytest.mark.parametrize('with_voxeliser', [False, True])
+def test_pipelined_step_matches_eager(lib_built, with_voxeliser):
+    """graph.PipelinedStep: every step as an index graph + a feature graph over two alternating buffer sets, the index graph of
+    step t+1 running beside the feature graph of step t.  Losses and parameter gradients of 8 back-to-back steps over rotating
+    batches against the synchronous exact-mode execution of the same batches."""
+    from virconv_b200 import scenes
+    from virconv_b200.graph import PipelinedStep
+    model = _model('bf16')
+    ids = [[61, 62], [63, 64], [65, 66]]
+    kw = dict(n_lidar=4096, n_virtual=9000)
+    ref = [_exact(model, _batch(i, max_voxels=7000, **kw))[:2] for i in ids]
+    vox = dict(point_cloud_range=(0, -40, -3, 70.4, 40, 1), voxel_size=(0.05, 0.05, 0.05), max_points_per_voxel=5,
+               max_voxels=7000, vfe_model='max') if with_voxeliser else None
+    step = PipelinedStep(model, _loss, margin=1.35, grain=256, voxelizer=vox)
+    params = dict(model.named_parameters())
+    got = []
+    for s in range(8):
+        if with_voxeliser:
+            pb = scenes.make_points_batch(ids[s % 3], training=True, **kw)
+            b = {'points': torch.from_numpy(pb.points).cuda(), 'batch_size': pb.batch_size, 'calib': pb.calib,
+                 'aug_param': torch.from_numpy(pb.aug_param)}
+        else:
+            b = _batch(ids[s % 3], max_voxels=7000, **kw)
+        loss = step(b)
+        got.append((loss.detach().clone(), {k: v.grad.detach().clone() for k, v in params.items()}))
+    torch.cuda.synchronize()
+    assert _err_flag() == 0 and step.recaptures == 2          # one capture per buffer set
+    for s in range(8):
+        l0, g0 = ref[s % 3]
+        assert abs(float(got[s][0]) - l0) < 1e-5 * max(1.0, abs(l0)), s
+        for k in params:
+            assert _grad_close(got[s][1][k], g0[k]), (s, k)

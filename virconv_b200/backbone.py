@@ -212,6 +212,20 @@ class VirConvL8x(nn.Module):
         mode = plan.layers[0][1].training
         return all(bn.training == mode for _, bn in plan.layers)
 
+    def index_phase(self, batch_dict):
+        """Phased static execution (graph.PipelinedStep), phase 1: everything of the forward that depends on the voxel
+        COORDINATES only — int32 coordinates, rulebooks of every stage, voxel -> pixel projections — enqueued into
+        batch_dict['virconv_static'].arena.  forward() with the same batch_dict and `static.phase = 2` then runs the
+        feature operators over it."""
+        feats, coords = batch_dict['voxel_features'], batch_dict['voxel_coords']
+        static = batch_dict['virconv_static']
+        assert static.phase == 1 and self._use_plan(feats)
+        ci = spconv._as_i32(coords)
+        executor.run_index(self._plan(), feats, ci, self.sparse_shape, batch_dict['batch_size'], batch_dict['virconv_proj'],
+                           self.conv_out[1].training, self.conv_out[0].precision, static)
+        batch_dict['virconv_ci'] = ci
+        return batch_dict
+
     def forward(self, batch_dict):
         rot_num = batch_dict['transform_param'].shape[1] if 'transform_param' in batch_dict else 1
         batch_size = batch_dict['batch_size']
@@ -232,7 +246,9 @@ class VirConvL8x(nn.Module):
                 side = ops.side(feats.device).stream if executor.TWO_STREAMS else None
                 static = batch_dict.get('virconv_static')
                 ready = side is not None and static is None and bool(batch_dict.get('virconv_inputs_ready', False))
-                if ready and (coords.dtype != torch.int32 or not coords.is_contiguous()):
+                if static is not None and static.phase == 2:
+                    ci = batch_dict['virconv_ci']           # (built by index_phase for this very batch)
+                elif ready and (coords.dtype != torch.int32 or not coords.is_contiguous()):
                     executor.reserve_blocks('coords_i32', 4 * coords.numel(), feats.device, side)
                     with torch.cuda.stream(side):
                         ci = spconv._as_i32(coords)

@@ -334,6 +334,14 @@ extern "C" int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_o
     // capacities and report an overflow through *overflow_flag (the largest row count that did not fit).
     const bool is_static = n0_dev != nullptr;
     VC_CHECK_ARG(!is_static || (caps && overflow_flag), "static mode needs capacities and an overflow flag");
+    // Phased execution (static mode only; bits 8-9 of want_pair_num): 1 = enqueue ONLY the index operators (voxel -> rulebooks,
+    // projection), 2 = ONLY the feature operators (weight images, conv + BN + ReLU, concat).  Both phases walk the whole plan with
+    // the same deterministic bump allocation, so they agree on every address and leave the same state blob: graph.GraphedStep
+    // captures them as two graphs and runs the index graph of step t+1 beside the feature graph of step t.
+    const int phase = (want_pair_num >> 8) & 3;
+    want_pair_num &= 0xff;
+    VC_CHECK_ARG(phase == 0 || (is_static && phase <= 2), "phased execution needs static mode");
+    const bool do_idx = phase != 2, do_feat = phase != 1;
     VC_TRY(check_plan(ops_i, n_ops, n_layers));
     VC_CHECK_ARG(state && state_bytes >= sizeof(State), "state blob too small (%zu < %zu)", state_bytes, sizeof(State));
     VC_CHECK_ARG(feats0 && idx0 && n0 > 0 && shape0 && batch_size > 0 && arena && pinned_host && ops_f && layer_ptrs && layer_f,
@@ -390,7 +398,7 @@ extern "C" int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_o
     VC_ALLOC(sums_all, double*, zero_bytes);
     int* ctr_all = reinterpret_cast<int*>(sums_all + sums_doubles);
     float* wg_all = reinterpret_cast<float*>(ctr_all + n_cbr * CTR_PER_LAYER);
-    if (zero_bytes) VC_CUDA(cudaMemsetAsync(sums_all, 0, zero_bytes, C.st[0]));
+    if (zero_bytes && do_feat) VC_CUDA(cudaMemsetAsync(sums_all, 0, zero_bytes, C.st[0]));
     size_t wg_cur = 0;
     size_t sums_cur = 0, ctr_cur = 0;
 
@@ -430,7 +438,7 @@ extern "C" int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_o
                 VC_ALLOC(img, void*, tc_image_bytes(L.cin, L.cout, K, layout));
                 (mode == 0 ? L.wimg_fwd : L.wimg_dgrad) = img;
                 if (T.n == TC_PREP_MAX) {
-                    VC_TRY(tc_prep_images(T, C.st[0]));
+                    if (do_feat) VC_TRY(tc_prep_images(T, C.st[0]));
                     T.n = 0;
                 }
                 TcPrepEntry& e = T.e[T.n++];
@@ -439,7 +447,7 @@ extern "C" int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_o
                 e.layout = layout;
             }
         }
-        VC_TRY(tc_prep_images(T, C.st[0]));
+        if (do_feat) VC_TRY(tc_prep_images(T, C.st[0]));
     }
 
     // the side stream starts after everything already queued on main (the caller's inputs) — unless the caller vouches
@@ -482,8 +490,9 @@ extern "C" int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_o
         if (is_static) {
             n_out = caps[o[F_B]];
             VC_CHECK_ARG(n_out > 0, "op %d: static mode needs a capacity for index set %d", j, o[F_B]);
-            VC_TRY(conv_rulebook_count_dev(I.idx, I.n, I.n_dev, I.ndim, batch_size, I.shape, o + F_KS, o + F_ST, o + F_PD, o + F_DL,
-                                           n_dev, n_out, overflow_flag, ws, wsb, st));
+            if (do_idx)
+                VC_TRY(conv_rulebook_count_dev(I.idx, I.n, I.n_dev, I.ndim, batch_size, I.shape, o + F_KS, o + F_ST, o + F_PD, o + F_DL,
+                                               n_dev, n_out, overflow_flag, ws, wsb, st));
         } else {
             VC_TRY(conv_rulebook_count_dev(I.idx, I.n, nullptr, I.ndim, batch_size, I.shape, o + F_KS, o + F_ST, o + F_PD, o + F_DL,
                                            n_dev, 0, nullptr, ws, wsb, st));
@@ -506,9 +515,10 @@ extern "C" int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_o
         for (int d = 0; d < 3; ++d) O.shape[d] = oshape[d];
         VC_ALLOC(oidx, int32_t*, (size_t)(n_out > 0 ? n_out : 1) * (1 + I.ndim) * 4);
         O.idx = oidx;
-        if (is_static) VC_CUDA(cudaMemsetAsync(oidx, 0xFF, (size_t)n_out * (1 + I.ndim) * 4, st));   // defined tail (-1) for the published indices
-        VC_TRY(conv_rulebook_fill_phases(I.idx, I.n, I.n_dev, I.ndim, batch_size, I.shape, o + F_KS, o + F_ST, o + F_PD, o + F_DL, n_out, O.idx,
-                                         nullptr, nullptr, nullptr, ws, wsb, st, 1));
+        if (is_static && do_idx) VC_CUDA(cudaMemsetAsync(oidx, 0xFF, (size_t)n_out * (1 + I.ndim) * 4, st));   // defined tail (-1) for the published indices
+        if (do_idx)
+            VC_TRY(conv_rulebook_fill_phases(I.idx, I.n, I.n_dev, I.ndim, batch_size, I.shape, o + F_KS, o + F_ST, o + F_PD, o + F_DL, n_out, O.idx,
+                                             nullptr, nullptr, nullptr, ws, wsb, st, 1));
         O.prod = s;
         O.ev = side_ev(s);
         chain_ws[j] = ws; chain_wsb[j] = wsb; chain_done[j] = true;
@@ -536,7 +546,7 @@ extern "C" int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_o
                 }
                 const size_t wsb = vc_subm_rulebook_ws_bytes(I.n);
                 VC_ALLOC(ws, void*, wsb);
-                VC_TRY(subm_rulebook_dev(I.idx, I.n, I.n_dev, I.ndim, batch_size, I.shape, o + F_KS, o + F_DL, R.nbr, R.pair_num, ws, wsb, st));
+                if (do_idx) VC_TRY(subm_rulebook_dev(I.idx, I.n, I.n_dev, I.ndim, batch_size, I.shape, o + F_KS, o + F_DL, R.nbr, R.pair_num, ws, wsb, st));
                 R.prod = s;
                 R.ev = side_ev(s);
                 break;
@@ -569,8 +579,9 @@ extern "C" int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_o
                     VC_ALLOC(pn, int32_t*, (size_t)R.K * 4);
                     R.pair_num = pn;
                 }
-                VC_TRY(conv_rulebook_fill_phases(I.idx, I.n, I.n_dev, I.ndim, batch_size, I.shape, o + F_KS, o + F_ST, o + F_PD, o + F_DL,
-                                                 R.n_out, O.idx, R.nbr, R.nbr_bwd, R.pair_num, chain_ws[i], chain_wsb[i], st, 2));
+                if (do_idx)
+                    VC_TRY(conv_rulebook_fill_phases(I.idx, I.n, I.n_dev, I.ndim, batch_size, I.shape, o + F_KS, o + F_ST, o + F_PD, o + F_DL,
+                                                     R.n_out, O.idx, R.nbr, R.nbr_bwd, R.pair_num, chain_ws[i], chain_wsb[i], st, 2));
                 R.prod = s;
                 R.ev = side_ev(s);
                 break;
@@ -582,7 +593,7 @@ extern "C" int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_o
                 VC_TRY(wait_for(C, I.ev, I.prod, s));
                 VC_ALLOC(uv, int32_t*, (size_t)I.n * 3 * 4);
                 O.idx = uv; O.n = I.n; O.ndim = 2; O.shape[0] = o[F_KS]; O.shape[1] = o[F_KS + 1]; O.shape[2] = 0; O.n_dev = I.n_dev;
-                VC_TRY(index2uv_dev(I.idx, I.n, I.n_dev, batch_size, proj_params, fo, o[F_X0], o[F_X1], o[F_X2], uv, st));
+                if (do_idx) VC_TRY(index2uv_dev(I.idx, I.n, I.n_dev, batch_size, proj_params, fo, o[F_X0], o[F_X1], o[F_X2], uv, st));
                 O.prod = s;
                 O.ev = side_ev(s);
                 break;
@@ -611,23 +622,25 @@ extern "C" int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_o
                 if (L.use_tc && R.n_out > 0) {
                     if (!X.bf16) {   // no producer wrote a shadow (network input): cast once
                         VC_ALLOC(xb, void*, (size_t)X.rows * X.c * 2);
-                        VC_TRY(vc_cast_f32_bf16(X.f32, xb, (long long)X.rows * X.c, st));
+                        if (do_feat) VC_TRY(vc_cast_f32_bf16(X.f32, xb, (long long)X.rows * X.c, st));
                         X.bf16 = xb;
                     }
                     Timed t(1, li, st);
                     // (flag bit 1: the rulebook was built on another stream and joined by an event, so the kernel may load its first
                     //  table slices before its griddepcontrol.wait — conv_tc2.cu)
-                    VC_TRY(tc_conv_with_image(L.cin, L.cout, X.bf16, L.wimg_fwd, R.nbr, R.n_out, x, R.n_out, R.n_out_dev, R.K, sums, C.err, st,
-                                              nullptr, L.tile_ctr, C.st[R.prod] != C.st[s] ? 2 : 0));
+                    if (do_feat)
+                        VC_TRY(tc_conv_with_image(L.cin, L.cout, X.bf16, L.wimg_fwd, R.nbr, R.n_out, x, R.n_out, R.n_out_dev, R.K, sums, C.err, st,
+                                                  nullptr, L.tile_ctr, (phase == 2 || C.st[R.prod] != C.st[s]) ? 2 : 0));
                 } else {
                     const size_t wsb = vc_conv_ws_bytes(L.cin, L.cout, R.K);
                     VC_ALLOC(ws, void*, wsb);
                     Timed t(0, li, st);
-                    VC_TRY(vc_conv_fwd_f32(X.f32, C.P<const float>(li, P_W), R.nbr, x, R.n_out, L.cin, L.cout, R.K, sums, ws, wsb, st));
+                    if (do_feat) VC_TRY(vc_conv_fwd_f32(X.f32, C.P<const float>(li, P_W), R.nbr, x, R.n_out, L.cin, L.cout, R.K, sums, ws, wsb, st));
                 }
-                VC_TRY(bn_apply_relu_dev(x, L.sums, R.n_out, R.n_out_dev, L.cout, C.P<const float>(li, P_GAMMA), C.P<const float>(li, P_BETA),
-                                         C.P<float>(li, P_RM), C.P<float>(li, P_RV), C.P<long long>(li, P_NBT), C.lf[2 * li + 1],
-                                         C.lf[2 * li], training, y, L.cout, yb, L.cout, stats, 1, is_static, st));
+                if (do_feat)
+                    VC_TRY(bn_apply_relu_dev(x, L.sums, R.n_out, R.n_out_dev, L.cout, C.P<const float>(li, P_GAMMA), C.P<const float>(li, P_BETA),
+                                             C.P<float>(li, P_RM), C.P<float>(li, P_RV), C.P<long long>(li, P_NBT), C.lf[2 * li + 1],
+                                             C.lf[2 * li], training, y, L.cout, yb, L.cout, stats, 1, is_static, st));
                 Y.f32 = y; Y.bf16 = yb; Y.rows = R.n_out; Y.c = L.cout; Y.prod = s; Y.n_dev = R.n_out_dev;
                 Y.ev = side_ev(s);
                 break;
@@ -646,7 +659,7 @@ extern "C" int vc_exec_forward(const int32_t* ops_i, const float* ops_f, int n_o
                     VC_ALLOC(ob_, void*, elems * 2);
                     ob = ob_;
                 }
-                VC_TRY(cat2_dev(Aa.f32, Bb.f32, out, ob, Aa.rows, Aa.n_dev, Aa.c, Bb.c, st));
+                if (do_feat) VC_TRY(cat2_dev(Aa.f32, Bb.f32, out, ob, Aa.rows, Aa.n_dev, Aa.c, Bb.c, st));
                 O.f32 = out; O.bf16 = ob; O.rows = Aa.rows; O.c = Aa.c + Bb.c; O.prod = s; O.n_dev = Aa.n_dev;
                 O.ev = side_ev(s);
                 break;

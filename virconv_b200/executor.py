@@ -430,6 +430,9 @@ class StaticSpec:
         self.n_dev, self.caps, self.overflow = n_dev, dict(caps), overflow
         self.alias_params = alias_params      # differentiate w.r.t. per-call leaf aliases of the parameters (run_plan)
         self.param_aliases = {}
+        # phased execution (graph.PipelinedStep): 1 = only the index operators (run_index), 2 = only the feature operators
+        # (run_plan), both in the caller-owned `arena` (deterministic bump allocation: the two phases agree on every address)
+        self.phase, self.arena = 0, None
         self._arr = None
 
     def caps_array(self):
@@ -469,7 +472,9 @@ class PlanFn(torch.autograd.Function):
         tab = _layer_ptrs(plan)
         for attempt in range(3):
             nbytes = _arena_bytes(plan, n0, dev, with_bwd)
-            if static is not None:
+            if static is not None and static.arena is not None:
+                arena = static.arena              # phased execution: the index phase already built its part in there
+            elif static is not None:
                 # (inside a capture: the graph's own pool.  No record_stream: the side / wgrad streams are forked from and
                 #  joined back into the calling stream inside vc_exec_forward / vc_exec_backward, so every later use of the
                 #  block in the calling stream's order comes after all of this step's uses)
@@ -486,7 +491,8 @@ class PlanFn(torch.autograd.Function):
             rc = lib.vc_exec_forward(oi.ctypes.data, of.ctypes.data, oi.shape[0], tab.ctypes.data, lf.ctypes.data, len(plan.layers),
                                      feats.data_ptr(), feats.shape[1], coords.data_ptr(), n0, _lib.host_i32(spatial_shape),
                                      int(batch_size), proj.data_ptr() if proj is not None else None, int(training),
-                                     int(precision == 'bf16'), 1, arena.data_ptr(), arena.numel(),
+                                     int(precision == 'bf16'), 1 | ((static.phase if static is not None else 0) << 8), arena.data_ptr(),
+                                     arena.numel(),
                                      _pinned(dev).data_ptr(), ops.tc_error_flag(dev).data_ptr(), state.ctypes.data, state.size,
                                      main, side, 0 if (inputs_ready and side is not None) else 1,
                                      static.caps_array().ctypes.data if static is not None else None,
@@ -544,6 +550,28 @@ class PlanFn(torch.autograd.Function):
         views = flat.split(sizes)
         out = [v.view_as(p) for v, p in zip(views, plan.params())]
         return (None,) * 12 + tuple(out)
+
+
+def run_index(plan, feats, coords_i32, spatial_shape, batch_size, proj, training, precision, static):
+    """Phase 1 of a phased static execution: enqueue ONLY the index operators of the plan (rulebooks, projection) into
+    `static.arena`; `run_plan` with `static.phase == 2` later enqueues the feature operators over the same arena."""
+    ops._require_cuda(feats, coords_i32)
+    assert static is not None and static.arena is not None and static.phase == 1
+    lib = _lib.load()
+    dev = feats.device
+    oi, of, lf, sizes, offs = plan.finalize()
+    tab = _layer_ptrs(plan)
+    side_obj = ops.side(dev).stream if TWO_STREAMS else None
+    side2_obj = ops.side2(dev) if (side_obj is not None and THREE_STREAMS) else None
+    state = np.zeros(lib.vc_exec_state_bytes(), dtype=np.uint8)
+    rc = lib.vc_exec_forward(oi.ctypes.data, of.ctypes.data, oi.shape[0], tab.ctypes.data, lf.ctypes.data, len(plan.layers),
+                             feats.data_ptr(), feats.shape[1], coords_i32.data_ptr(), feats.shape[0], _lib.host_i32(spatial_shape),
+                             int(batch_size), proj.data_ptr(), int(training), int(precision == 'bf16'), 1 | (1 << 8),
+                             static.arena.data_ptr(), static.arena.numel(), _pinned(dev).data_ptr(), ops.tc_error_flag(dev).data_ptr(),
+                             state.ctypes.data, state.size, ops._stream(), side_obj.cuda_stream if side_obj is not None else None, 1,
+                             static.caps_array().ctypes.data, static.n_dev.data_ptr(), static.overflow.data_ptr(),
+                             side2_obj.cuda_stream if side2_obj is not None else None)
+    check(rc, 'vc_exec_forward (index phase)')
 
 
 def run_plan(plan, feats, coords_i32, spatial_shape, batch_size, proj, training, precision, inputs_ready=False, static=None):
