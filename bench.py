@@ -503,11 +503,12 @@ def run_ours(args):
         reduce_grads()
         return float(loss.detach()) if sync_loss else loss
 
+    MARGIN = float(os.environ.get('VIRCONV_GRAPH_MARGIN', '1.3'))      # capacity head-room of the captured step's buffers
     if args.mode == 'graph' and args.graph_pipeline:
         from virconv_b200.graph import PipelinedStep
-        graphed = PipelinedStep(model, loss_of, params, margin=1.3, voxelizer=VOX)
+        graphed = PipelinedStep(model, loss_of, params, margin=MARGIN, voxelizer=VOX)
     else:
-        graphed = GraphedStep(model, loss_of, params, margin=1.3, voxelizer=VOX) if args.mode == 'graph' else None
+        graphed = GraphedStep(model, loss_of, params, margin=MARGIN, voxelizer=VOX) if args.mode == 'graph' else None
 
     def gstep(pts, pb):
         """graph step: the collated points (device or pinned-host tensor) are copied into the graph's input buffer, then ONE
