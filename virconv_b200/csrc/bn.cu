@@ -375,9 +375,14 @@ int vc::bn_relu_bwd_dev(const float* dy, int dy_ld, const float* x, const float*
         float4* dx4 = (float4*)dx;
         uint2* dxb = (uint2*)dx_bf16;
         void* args[] = {&dy4, &dy_ld4, &x4, &gamma, &stats, &bsums, &n, &n_dev, &c, &training, &dx4, &dxb, &dgamma, &dbeta, &tail_zero};
-        vc::count_launch();
-        VC_CUDA(cudaLaunchCooperativeKernel((const void*)bn_bwd_fused_kernel, dim3(blocks), dim3(256), args, smem, stream));
-        return VC_OK;
+        const cudaError_t ce = cudaLaunchCooperativeKernel((const void*)bn_bwd_fused_kernel, dim3(blocks), dim3(256), args, smem, stream);
+        if (ce == cudaSuccess) {
+            vc::count_launch();
+            return VC_OK;
+        }
+        // (a device / driver configuration without cooperative launches: fall back to the two-kernel form for good)
+        cudaGetLastError();
+        g_bn_fused = 0;
     }
     if (n > 0) {
         VC_CHECK_ARG(dy && x && (dx || dx_bf16), "null pointer");
